@@ -1,0 +1,198 @@
+/*
+ * mvsnet_b200.h -- C ABI of the B200-native MVSNet cost-volume hot path.
+ *
+ * The reference (ubiquity6/MVSNet) has no FFI of its own: the path is a set of
+ * Python functions in mvsnet/homography_warping.py and mvsnet/model.py that build
+ * TensorFlow ops.  Each entry point below replaces the TF ops behind one of those
+ * functions (cited as file:line under the reference root).  The Python mirror in
+ * mvsnet_b200/ re-creates the reference names on top of this ABI via ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - tensors are dense, channels-last, fp32 unless a *_dtype argument says otherwise;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*, NULL =
+ *     legacy default stream) except the *_host entry points, which synchronise;
+ *   - return 0 on success, a negative MVSB200_ERR_* otherwise; the message of the last
+ *     error on the calling thread is mvsb200_last_error();
+ *   - no hidden allocation on the hot path: workspaces are caller-owned and sized by the
+ *     *_workspace_bytes queries.  There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef MVSNET_B200_H_
+#define MVSNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVSB200_OK 0
+#define MVSB200_ERR_INVALID (-1)     /* bad argument (shape, enum, null pointer) */
+#define MVSB200_ERR_CUDA (-2)        /* CUDA runtime error; see mvsb200_last_error() */
+#define MVSB200_ERR_UNSUPPORTED (-3) /* valid in the reference but not built here */
+#define MVSB200_ERR_WORKSPACE (-4)   /* workspace too small */
+
+/* variance op order: model.py:458-461 (inference_mem) vs model.py:330-332 (inference) */
+#define MVSB200_ORDER_MEM 0
+#define MVSB200_ORDER_TRAIN 1
+/* sampler: tf.contrib.image.transform zero-fill (homography_warping.py:251) vs the
+ * legacy clamp-gather `interpolate` (homography_warping.py:131-174) */
+#define MVSB200_SAMPLER_TRANSFORM 0
+#define MVSB200_SAMPLER_LEGACY 1
+/* storage types */
+#define MVSB200_F32 0
+#define MVSB200_BF16 1
+/* regularizer arithmetic: fp32 CUDA-core direct convolution (parity mode) or bf16 operands
+ * with fp32 accumulation on the tcgen05 tensor cores (product mode) */
+#define MVSB200_PRECISION_FP32 0
+#define MVSB200_PRECISION_BF16 1
+
+/* RegNetUS0 layers in execution order (mvsnetworks.py:131-158). */
+#define MVSB200_REGNET_LAYERS 11
+enum {
+  MVSB200_L_3DCONV1_0 = 0, MVSB200_L_3DCONV2_0 = 1, MVSB200_L_3DCONV3_0 = 2,
+  MVSB200_L_3DCONV0_1 = 3, MVSB200_L_3DCONV1_1 = 4, MVSB200_L_3DCONV2_1 = 5,
+  MVSB200_L_3DCONV3_1 = 6, MVSB200_L_3DCONV4_0 = 7, MVSB200_L_3DCONV5_0 = 8,
+  MVSB200_L_3DCONV6_0 = 9, MVSB200_L_3DCONV6_2 = 10
+};
+
+/* Weights of RegNetUS0 in TF variable layout, fp32, device memory.
+ * kernel[l]: conv `<layer>/kernel` [3,3,3,Cin,Cout]; deconv (layers 7..9) [3,3,3,Cout,Cin].
+ * gamma/beta[l]: `<layer>/bn/{gamma,beta}` [Cout]; NULL for 3dconv6_2 (no BN, mvsnetworks.py:158). */
+typedef struct mvsb200_regnet_params {
+  const float* kernel[MVSB200_REGNET_LAYERS];
+  const float* gamma[MVSB200_REGNET_LAYERS];
+  const float* beta[MVSB200_REGNET_LAYERS];
+} mvsb200_regnet_params;
+
+const char* mvsb200_last_error(void);
+int mvsb200_version(void);
+/* sm count / compute capability of the current device; fails unless it is sm_100. */
+int mvsb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* get_homographies (homography_warping.py:10-58) and get_homographies_inv_depth (:60-106)
+ * for every source view of one reference view.
+ *   cams            [n_views,2,4,4] (view 0 = reference; layout mvs_cluster.py:103-111)
+ *   depth_step      depth_interval, or depth_end when inverse_depth != 0
+ *   homographies    out [(n_views-1), depth_num, 9]  image-coordinate H (may be NULL)
+ *   transforms      out [(n_views-1), depth_num, 8]  pixel-coordinate coefficients of
+ *                   tf_transform_homography (homography_warping.py:216-250) (may be NULL) */
+int mvsb200_homographies(const float* cams, int n_views, int depth_num, float depth_start,
+                         float depth_step, int inverse_depth, float* homographies,
+                         float* transforms, void* stream);
+
+/* Coefficient conversion alone (homography_warping.py:216-250): H [count,9] -> T [count,8]. */
+int mvsb200_transform_coefs(const float* homographies, int count, float* transforms, void* stream);
+
+/* tf_transform_homography (homography_warping.py:211-253, sampler TRANSFORM) or the legacy
+ * homography_warping (:176-210, sampler LEGACY).
+ *   image [image_count,H,W,C]; homographies [hom_count,9]; out [hom_count,H,W,C].
+ *   image_count must equal hom_count, or be 1 (the one image is warped by every homography). */
+int mvsb200_warp(const float* image, int image_count, const float* homographies, int hom_count,
+                 int height, int width, int channels, int sampler, float* out, void* stream);
+
+/* Legacy interpolate (homography_warping.py:131-174) on caller-supplied image coordinates:
+ * image [B,H,W,C], xs/ys [B*H*W] -> out [B*H*W, C]. */
+int mvsb200_interpolate(const float* image, const float* xs, const float* ys, int batch, int height,
+                        int width, int channels, float* out, void* stream);
+
+/* get_pixel_grids (homography_warping.py:108-117): out [3*H*W] = concat(x, y, 1) at pixel centres. */
+int mvsb200_pixel_grids(int height, int width, float* out, void* stream);
+
+/* Sample coordinates only (parity gate "sample coordinates bit-exact"): for sampler TRANSFORM the
+ * pixel coordinates (ix,iy) of the contrib kernel, for LEGACY the image coordinates (x,y) fed to
+ * interpolate().  out [hom_count,H,W,2]. */
+int mvsb200_sample_coords(const float* homographies, int hom_count, int height, int width,
+                          int sampler, float* out, void* stream);
+
+/* Fused warp + N-view variance cost volume (model.py:423-463 / :315-334).  The warped
+ * volume is never materialised.
+ *   feats [n_views,Hf,Wf,C]; homographies [(n_views-1),depth_num,9];
+ *   out   [depth_num,Hf,Wf,C] of out_dtype (MVSB200_F32 / MVSB200_BF16).
+ *   variant: 0 = automatic; other values select a specific kernel (tests / tuning). */
+int mvsb200_cost_volume(const float* feats, const float* homographies, int n_views, int depth_num,
+                        int hf, int wf, int channels, int order, int sampler, int out_dtype,
+                        void* out, int variant, void* stream);
+
+/* One layer of the regularizer: y_raw = conv3d(act(x) [+ act(skip)], kernel) with TF SAME padding
+ * (network.py:210 conv, :327 transposed), where act(t) = relu(t*scale + shift) per channel when
+ * scale/shift are given and identity when NULL; plus per-channel sum / sum-of-squares of the fp32
+ * result (network.py:496 batch statistics) accumulated into stats[2*Cout] (double, must be zeroed
+ * by the caller).  stats may be NULL.  Output extents: conv ceil(in/stride); deconv 2*in. */
+int mvsb200_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const float* x_shift,
+                         const void* skip, const float* skip_scale, const float* skip_shift,
+                         const float* kernel_tf, int depth, int height, int width, int cin, int cout,
+                         int stride, int transposed, int precision, void* y_raw, int y_dtype,
+                         double* stats, void* stream);
+
+/* Batch-norm finalise: stats[2*C] (sum, sumsq over `count` voxels) -> scale = gamma*rsqrt(var+eps),
+ * shift = beta - mean*scale (network.py:496-506, Appendix A.6). */
+int mvsb200_bn_finalize(const double* stats, const float* gamma, const float* beta, int channels,
+                        double count, float eps, float* scale, float* shift, void* stream);
+
+size_t mvsb200_regnet_workspace_bytes(int depth, int hf, int wf, int in_channels, int base_filter,
+                                      int precision);
+
+/* RegNetUS0 forward (mvsnetworks.py:122-158): cost [D,Hf,Wf,Cin] -> filtered [D,Hf,Wf] fp32.
+ * D, Hf, Wf must be multiples of 8 (the reference graph does not close otherwise). */
+int mvsb200_regnet_forward(const void* cost, int cost_dtype, const mvsb200_regnet_params* params,
+                           int depth, int hf, int wf, int in_channels, int base_filter, float bn_eps,
+                           int precision, float* filtered, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* After mvsb200_regnet_forward: address of a layer's raw (pre-BN) output inside the workspace and
+ * of its BN scale/shift (tests, layer-wise parity).  Returns NULL for an invalid layer. */
+const void* mvsb200_regnet_layer_raw(const void* workspace, int depth, int hf, int wf, int in_channels,
+                                     int base_filter, int precision, int layer, const float** scale,
+                                     const float** shift);
+
+/* softmax(-F) over depth, soft-argmin and the 4-neighbour probability map
+ * (model.py:472-498, 45-144).  filtered [D,Hf,Wf] -> depth_map [Hf,Wf], prob_map [Hf,Wf];
+ * prob_volume [D,Hf,Wf] is written when non-NULL.  depth_interval is the plane spacing. */
+int mvsb200_depth_regress(const float* filtered, int depth_num, int hf, int wf, float depth_start,
+                          float depth_interval, int inverse_depth, int num_buckets, float* depth_map,
+                          float* prob_map, float* prob_volume, void* stream);
+
+/* get_probability_map_slice alone (model.py:45-144): prob_volume [D,H,W], depth_map [H,W]. */
+int mvsb200_probability_map(const float* prob_volume, const float* depth_map, int depth_num, int height,
+                            int width, float depth_start, float depth_interval, int inverse_depth,
+                            int num_buckets, float* prob_map, void* stream);
+
+size_t mvsb200_infer_workspace_bytes(int n_views, int depth_num, int hf, int wf, int channels,
+                                     int base_filter, int precision);
+
+/* Whole hot path for one reference view, device buffers (model.py:407-502 after the feature
+ * towers): feats [n_views,Hf,Wf,C], cams [n_views,2,4,4] -> depth_map, prob_map [Hf,Wf]. */
+int mvsb200_infer(const float* feats, const float* cams, int n_views, int depth_num, int hf, int wf,
+                  int channels, float depth_start, float depth_interval, int inverse_depth, int order,
+                  int sampler, const mvsb200_regnet_params* params, int base_filter, float bn_eps,
+                  int precision, float* depth_map, float* prob_map, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* Same with HOST buffers for feats / cams / outputs (the sess.run feed/fetch boundary of
+ * inference.py:105-112): copies in, runs, copies out, synchronises.  `params` and `workspace`
+ * stay device-resident (weights are loaded once per model, predictlib.py:69-76).  When
+ * staging_dev is non-NULL it must hold mvsb200_infer_host_staging_bytes() bytes. */
+size_t mvsb200_infer_host_staging_bytes(int n_views, int hf, int wf, int channels);
+int mvsb200_infer_host(const float* feats_host, const float* cams_host, int n_views, int depth_num,
+                       int hf, int wf, int channels, float depth_start, float depth_interval,
+                       int inverse_depth, int order, int sampler, const mvsb200_regnet_params* params,
+                       int base_filter, float bn_eps, int precision, float* depth_map_host,
+                       float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* Diagnostic (not on the product path): one 128 x n x (16*kblocks) tcgen05.mma tile computed from
+ * caller-built shared-memory images of the A and B operands (no-swizzle K-major core-matrix
+ * layout).  Pins the descriptor semantics conv3d_umma.cu relies on.  d_out [128*n] fp32. */
+int mvsb200_umma_probe(const void* a_image, int a_bytes, const void* b_image, int b_bytes, int n,
+                       int kblocks, int a_kblock_stride, int a_start, int a_lbo, int a_sbo,
+                       int b_kblock_stride, int b_lbo, int b_sbo, float* d_out, void* stream);
+
+/* Number of kernel launches issued through this library by the calling process so far. */
+uint64_t mvsb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSNET_B200_H_ */

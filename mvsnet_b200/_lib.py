@@ -1,0 +1,112 @@
+"""ctypes binding of libmvsnet_b200.so (include/mvsnet_b200.h).
+
+There is no fallback: if the library has not been built, or a call fails, this
+raises.  PyTorch is used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint64, c_void_p
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmvsnet_b200.so")
+
+OK = 0
+ORDER_MEM, ORDER_TRAIN = 0, 1
+SAMPLER_TRANSFORM, SAMPLER_LEGACY = 0, 1
+F32, BF16 = 0, 1
+PRECISION_FP32, PRECISION_BF16 = 0, 1
+REGNET_LAYERS = 11
+REGNET_LAYER_NAMES = ["3dconv1_0", "3dconv2_0", "3dconv3_0", "3dconv0_1", "3dconv1_1", "3dconv2_1",
+                      "3dconv3_1", "3dconv4_0", "3dconv5_0", "3dconv6_0", "3dconv6_2"]
+
+
+class MVSB200Error(RuntimeError):
+    """A call into libmvsnet_b200.so returned a non-zero status."""
+
+
+class RegnetParams(ctypes.Structure):
+    _fields_ = [("kernel", c_void_p * REGNET_LAYERS), ("gamma", c_void_p * REGNET_LAYERS),
+                ("beta", c_void_p * REGNET_LAYERS)]
+
+
+# name -> (restype, argtypes); every symbol include/mvsnet_b200.h declares
+_P = c_void_p
+SIGNATURES = {
+    "mvsb200_last_error": (c_char_p, []),
+    "mvsb200_version": (c_int, []),
+    "mvsb200_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "mvsb200_homographies": (c_int, [_P, c_int, c_int, c_float, c_float, c_int, _P, _P, _P]),
+    "mvsb200_transform_coefs": (c_int, [_P, c_int, _P, _P]),
+    "mvsb200_warp": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "mvsb200_interpolate": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "mvsb200_pixel_grids": (c_int, [c_int, c_int, _P, _P]),
+    "mvsb200_sample_coords": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
+    "mvsb200_cost_volume": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    "mvsb200_conv3d_layer": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, _P, c_int, _P, _P]),
+    "mvsb200_bn_finalize": (c_int, [_P, _P, _P, c_int, c_double, c_float, _P, _P, _P]),
+    "mvsb200_regnet_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mvsb200_regnet_forward": (c_int, [_P, c_int, POINTER(RegnetParams), c_int, c_int, c_int, c_int, c_int, c_float,
+                                       c_int, _P, _P, c_size_t, _P]),
+    "mvsb200_regnet_layer_raw": (c_void_p, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p),
+                                            POINTER(c_void_p)]),
+    "mvsb200_depth_regress": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P, _P, _P]),
+    "mvsb200_probability_map": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P]),
+    "mvsb200_infer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mvsb200_infer": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
+                              POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
+    "mvsb200_infer_host_staging_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "mvsb200_infer_host": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
+                                   POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "mvsb200_umma_probe": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, _P, _P]),
+    "mvsb200_launch_count": (c_uint64, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m mvsnet_b200.build` "
+            "(nvcc, sm_100a).  mvsnet_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().mvsb200_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != OK:
+        raise MVSB200Error(f"{what or 'mvsb200 call'} failed ({rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device (or host) address of a tensor / None."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MVSB200Error("mvsnet_b200 needs CUDA tensors: there is no CPU path")

@@ -1,0 +1,75 @@
+// Shared host/device helpers for the mvsnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/mvsnet_b200.h"
+
+namespace mvsb200 {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+inline void count_launch(int n = 1) { g_launch_count.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define MVS_CHECK_ARG(cond, ...)                         \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      ::mvsb200::set_error(__VA_ARGS__);                 \
+      return MVSB200_ERR_INVALID;                        \
+    }                                                    \
+  } while (0)
+
+#define MVS_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      ::mvsb200::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,              \
+                           cudaGetErrorString(e__));                                         \
+      return MVSB200_ERR_CUDA;                                                               \
+    }                                                                                        \
+  } while (0)
+
+#define MVS_LAUNCH_CHECK(name)                                                               \
+  do {                                                                                       \
+    ::mvsb200::count_launch();                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) {                                                                \
+      ::mvsb200::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));        \
+      return MVSB200_ERR_CUDA;                                                               \
+    }                                                                                        \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// TF SAME padding before the first element: out=ceil(in/s); total=max((out-1)s+k-in,0); before=total/2.
+static inline int tf_same_pad_before(int size, int k, int s) {
+  int out = (size + s - 1) / s;
+  int total = (out - 1) * s + k - size;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+// internal launchers shared between translation units -------------------------------------------
+int launch_homographies(const float* cams, int n_views, int depth_num, float depth_start, float depth_step,
+                        int inverse_depth, float* homographies, float* transforms, cudaStream_t s);
+int launch_cost_volume(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
+                       int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
+                       cudaStream_t s);
+int launch_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const float* x_shift,
+                        const void* skip, const float* skip_scale, const float* skip_shift,
+                        const float* kernel_tf, int depth, int height, int width, int cin, int cout,
+                        int stride, int transposed, int precision, void* y_raw, int y_dtype, double* stats,
+                        cudaStream_t s);
+int launch_bn_finalize(const double* stats, const float* gamma, const float* beta, int channels,
+                       double count, float eps, float* scale, float* shift, cudaStream_t s);
+int launch_depth_regress(const float* filtered, int depth_num, int hf, int wf, float depth_start,
+                         float depth_interval, int inverse_depth, int num_buckets, float* depth_map,
+                         float* prob_map, float* prob_volume, cudaStream_t s);
+
+}  // namespace mvsb200

@@ -1,0 +1,292 @@
+// Kernel 2: fused homography warp + N-view variance cost volume.
+// Replaces the D x (N-1) tf_transform_homography launches and the running-sum ops of
+// model.py:423-463 (inference_mem) / model.py:315-334 (inference).  The (N-1) x D x H x W x C
+// warped volume is never written: each thread keeps the running sum and squared sum of its
+// voxels in registers across views and stores only the variance.
+//
+// Transform coefficients live in __constant__ memory (one 8-float row per (view, plane),
+// written once per call by prepare_table_kernel + a device-to-device symbol copy).
+#include "geometry.cuh"
+
+namespace mvsb200 {
+
+constexpr int kTableFloats = 14336;  // 56 KB: (N-1)*D*8 for N=8, D=256 (inference.py:29-31 defaults)
+__constant__ float c_table[kTableFloats];
+__device__ float g_table[kTableFloats];  // staging copy in global memory (generic kernel reads this one)
+
+__global__ void prepare_table_kernel(const float* __restrict__ homographies, int count) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  float h[9], t[8];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h[i] = homographies[idx * 9 + i];
+  transform_coefs(h, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g_table[idx * 8 + i] = t[i];
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float variance(float S, float Q, float n_f, float nn_f, int order) {
+  if (order == MVSB200_ORDER_MEM) {
+    float A = (S * S) / nn_f;       // model.py:458
+    return Q / n_f - A;             // model.py:460
+  }
+  float mean = S / n_f, mean2 = Q / n_f;   // model.py:330-331
+  return mean2 - mean * mean;              // model.py:332
+}
+
+__device__ __forceinline__ void store_cost4(void* out, size_t elem, float4 c, bool bf16) {
+  if (bf16) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(c.x, c.y), hi = __floats2bfloat162_rn(c.z, c.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + elem) = pk;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem) = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path, C = 32: block = 32 reference pixels x 8 channel groups (float4), DC = 8 planes per
+// thread.  The 8 lanes of a pixel each compute the sample position of a different plane and
+// broadcast it with a shuffle, so the coordinate math (2 IEEE divisions) is done once per voxel
+// and view instead of once per channel group.  Taps are 128-bit loads through L1 (features are
+// L2-resident: 5 x 216 x 288 x 32 fp32 = 40 MB at config 2); consecutive planes move the footprint
+// by ~0.35 px, so with REUSE the four taps stay in registers until the 2x2 corner changes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDC = 8;
+constexpr int kMaxSrcViews = 7;
+
+template <bool BF16OUT, bool REUSE, int TX, int TY>
+__global__ void __launch_bounds__(256, 2)
+cost_volume_c32_kernel(const float* __restrict__ feats, int n_views, int D, int Hf, int Wf, int order,
+                       void* __restrict__ out) {
+  static_assert(TX * TY == 32, "tile must hold 32 pixels");
+  __shared__ float s_coef[kMaxSrcViews * kDC * 8];
+  const int tid = threadIdx.x;
+  const int g = tid & 7;            // channel group (4 channels) and plane slot for coordinates
+  const int p = tid >> 3;           // pixel within the tile
+  const int x = blockIdx.x * TX + (p % TX);
+  const int y = blockIdx.y * TY + (p / TX);
+  const int d0 = blockIdx.z * kDC;
+  const int n_src = n_views - 1;
+  for (int i = tid; i < n_src * kDC * 8; i += 256) {
+    int v = i / (kDC * 8), r = i - v * (kDC * 8);
+    int d = min(d0 + (r >> 3), D - 1);
+    s_coef[i] = c_table[(v * D + d) * 8 + (r & 7)];
+  }
+  __syncthreads();
+  const bool active = (x < Wf) && (y < Hf);
+  const int xc = min(x, Wf - 1), yc = min(y, Hf - 1);
+  const size_t plane = (size_t)Hf * Wf * 32;
+  const float4 r = ldg4(feats + ((size_t)yc * Wf + xc) * 32 + g * 4);
+  float4 S[kDC], Q[kDC];
+#pragma unroll
+  for (int dd = 0; dd < kDC; ++dd) {
+    S[dd] = r;
+    Q[dd] = make_float4(r.x * r.x, r.y * r.y, r.z * r.z, r.w * r.w);
+  }
+  const unsigned lane_base = (threadIdx.x & 31) & ~7u;
+  for (int v = 0; v < n_src; ++v) {
+    const float* img = feats + (size_t)(v + 1) * plane + g * 4;
+    float ix_l, iy_l;
+    transform_coords(&s_coef[(v * kDC + g) * 8], (float)xc, (float)yc, ix_l, iy_l);
+    float4 p00 = make_float4(0.f, 0.f, 0.f, 0.f), p01 = p00, p10 = p00, p11 = p00;
+    int px0 = -0x7fffffff, py0 = -0x7fffffff;
+#pragma unroll
+    for (int dd = 0; dd < kDC; ++dd) {
+      float ix = __shfl_sync(0xffffffffu, ix_l, lane_base | dd);
+      float iy = __shfl_sync(0xffffffffu, iy_l, lane_base | dd);
+      Footprint f = make_footprint(ix, iy, Wf, Hf);
+      if (!REUSE || f.x0 != px0 || f.y0 != py0) {
+        const float* base = img + ((int64_t)f.y0 * Wf + f.x0) * 32;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        p00 = (f.vy0 && f.vx0) ? ldg4(base) : z;
+        p01 = (f.vy0 && f.vx1) ? ldg4(base + 32) : z;
+        p10 = (f.vy1 && f.vx0) ? ldg4(base + (int64_t)Wf * 32) : z;
+        p11 = (f.vy1 && f.vx1) ? ldg4(base + (int64_t)Wf * 32 + 32) : z;
+        px0 = f.x0; py0 = f.y0;
+      }
+      float4 w;
+      w.x = f.wyl * (f.wxl * p00.x + f.wxr * p01.x) + f.wyr * (f.wxl * p10.x + f.wxr * p11.x);
+      w.y = f.wyl * (f.wxl * p00.y + f.wxr * p01.y) + f.wyr * (f.wxl * p10.y + f.wxr * p11.y);
+      w.z = f.wyl * (f.wxl * p00.z + f.wxr * p01.z) + f.wyr * (f.wxl * p10.z + f.wxr * p11.z);
+      w.w = f.wyl * (f.wxl * p00.w + f.wxr * p01.w) + f.wyr * (f.wxl * p10.w + f.wxr * p11.w);
+      S[dd].x += w.x; S[dd].y += w.y; S[dd].z += w.z; S[dd].w += w.w;
+      Q[dd].x += w.x * w.x; Q[dd].y += w.y * w.y; Q[dd].z += w.z * w.z; Q[dd].w += w.w * w.w;
+    }
+  }
+  if (!active) return;
+  const float n_f = (float)n_views, nn_f = (float)(n_views * n_views);
+#pragma unroll
+  for (int dd = 0; dd < kDC; ++dd) {
+    const int d = d0 + dd;
+    if (d < D) {
+      float4 c;
+      c.x = variance(S[dd].x, Q[dd].x, n_f, nn_f, order);
+      c.y = variance(S[dd].y, Q[dd].y, n_f, nn_f, order);
+      c.z = variance(S[dd].z, Q[dd].z, n_f, nn_f, order);
+      c.w = variance(S[dd].w, Q[dd].w, n_f, nn_f, order);
+      store_cost4(out, (((size_t)d * Hf + y) * Wf + x) * 32 + g * 4, c, BF16OUT);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic path: any channel count, both samplers.  One thread per (plane, pixel, channel group).
+// ------------------------------------------------------------------------------------------------
+template <int VEC, int SAMPLER, bool BF16OUT>
+__global__ void __launch_bounds__(256)
+cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restrict__ homographies, int n_views,
+                           int D, int Hf, int Wf, int C, int order, void* __restrict__ out) {
+  const int groups = C / VEC;
+  const size_t total = (size_t)D * Hf * Wf * groups;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  size_t vox = idx / groups;
+  const int x = (int)(vox % Wf);
+  const int y = (int)((vox / Wf) % Hf);
+  const int d = (int)(vox / ((size_t)Wf * Hf));
+  const size_t plane = (size_t)Hf * Wf * C;
+  const int c0 = g * VEC;
+  float S[VEC], Q[VEC];
+  const float* ref = feats + ((size_t)y * Wf + x) * C + c0;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { float r = __ldg(ref + k); S[k] = r; Q[k] = r * r; }
+  for (int v = 0; v < n_views - 1; ++v) {
+    const float* img = feats + (size_t)(v + 1) * plane;
+    float w[VEC];
+    if (SAMPLER == MVSB200_SAMPLER_TRANSFORM) {
+      float ix, iy;
+      transform_coords(&g_table[(v * D + d) * 8], (float)x, (float)y, ix, iy);
+      Footprint f = make_footprint(ix, iy, Wf, Hf);
+      const float* base = img + ((int64_t)f.y0 * Wf + f.x0) * C + c0;
+      const int64_t row = (int64_t)Wf * C;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        float p00 = (f.vy0 && f.vx0) ? __ldg(base + k) : 0.f;
+        float p01 = (f.vy0 && f.vx1) ? __ldg(base + C + k) : 0.f;
+        float p10 = (f.vy1 && f.vx0) ? __ldg(base + row + k) : 0.f;
+        float p11 = (f.vy1 && f.vx1) ? __ldg(base + row + C + k) : 0.f;
+        w[k] = f.wyl * (f.wxl * p00 + f.wxr * p01) + f.wyr * (f.wxl * p10 + f.wxr * p11);
+      }
+    } else {
+      // legacy sampler: every op rounded separately (Appendix A.3 cancellations)
+      float h[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) h[i] = __ldg(homographies + ((size_t)v * D + d) * 9 + i);
+      float xw, yw;
+      legacy_coords(h, x, y, Wf, Hf, xw, yw);
+      float xs = sub_(xw, 0.5f), ys = sub_(yw, 0.5f);
+      int x0 = floor_to_int(xs), y0 = floor_to_int(ys);
+      int x1 = x0 + 1, y1 = y0 + 1;
+      x0 = min(max(x0, 0), Wf - 1); x1 = min(max(x1, 0), Wf - 1);
+      y0 = min(max(y0, 0), Hf - 1); y1 = min(max(y1, 0), Hf - 1);
+      float wa = mul_(sub_((float)y1, ys), sub_((float)x1, xs));
+      float wb = mul_(sub_((float)y1, ys), sub_(xs, (float)x0));
+      float wc = mul_(sub_(ys, (float)y0), sub_((float)x1, xs));
+      float wd = mul_(sub_(ys, (float)y0), sub_(xs, (float)x0));
+      const float* pa = img + ((size_t)y0 * Wf + x0) * C + c0;
+      const float* pb = img + ((size_t)y0 * Wf + x1) * C + c0;
+      const float* pc = img + ((size_t)y1 * Wf + x0) * C + c0;
+      const float* pd = img + ((size_t)y1 * Wf + x1) * C + c0;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        w[k] = add_(add_(add_(mul_(wa, __ldg(pa + k)), mul_(wb, __ldg(pb + k))), mul_(wc, __ldg(pc + k))),
+                    mul_(wd, __ldg(pd + k)));
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { S[k] += w[k]; Q[k] += w[k] * w[k]; }
+  }
+  const float n_f = (float)n_views, nn_f = (float)(n_views * n_views);
+  const size_t o = vox * C + c0;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    float c = variance(S[k], Q[k], n_f, nn_f, order);
+    if (BF16OUT) reinterpret_cast<__nv_bfloat16*>(out)[o + k] = __float2bfloat16_rn(c);
+    else reinterpret_cast<float*>(out)[o + k] = c;
+  }
+}
+
+int launch_cost_volume(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
+                       int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
+                       cudaStream_t s) {
+  MVS_CHECK_ARG(feats && homographies && out, "cost_volume: NULL pointer");
+  MVS_CHECK_ARG(n_views >= 2 && depth_num >= 1 && hf >= 1 && wf >= 1 && channels >= 1,
+                "cost_volume: bad shape N=%d D=%d %dx%dx%d", n_views, depth_num, hf, wf, channels);
+  MVS_CHECK_ARG(order == MVSB200_ORDER_MEM || order == MVSB200_ORDER_TRAIN, "cost_volume: bad order %d", order);
+  MVS_CHECK_ARG(sampler == MVSB200_SAMPLER_TRANSFORM || sampler == MVSB200_SAMPLER_LEGACY,
+                "cost_volume: bad sampler %d", sampler);
+  MVS_CHECK_ARG(out_dtype == MVSB200_F32 || out_dtype == MVSB200_BF16, "cost_volume: bad out_dtype %d", out_dtype);
+  const int rows = (n_views - 1) * depth_num;
+  const bool bf16 = out_dtype == MVSB200_BF16;
+  if (sampler == MVSB200_SAMPLER_TRANSFORM) {
+    if (rows * 8 > kTableFloats) {
+      set_error("cost_volume: (n_views-1)*depth_num = %d exceeds the %d-row coefficient table", rows,
+                kTableFloats / 8);
+      return MVSB200_ERR_UNSUPPORTED;
+    }
+    prepare_table_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(homographies, rows);
+    MVS_LAUNCH_CHECK("prepare_table_kernel");
+  }
+  // variant: 0 auto, 1 generic, 2 c32 (always reload taps), 3 c32 with tap reuse, 4/5 = 2/3 with a 16x2 tile
+  bool fast_ok = sampler == MVSB200_SAMPLER_TRANSFORM && channels == 32 && n_views - 1 <= kMaxSrcViews;
+  if (variant == 0) variant = fast_ok ? 3 : 1;
+  MVS_CHECK_ARG(variant >= 1 && variant <= 5, "cost_volume: bad variant %d", variant);
+  if (variant >= 2 && !fast_ok) {
+    set_error("cost_volume: variant %d needs sampler=transform, C=32, n_views<=8", variant);
+    return MVSB200_ERR_UNSUPPORTED;
+  }
+  if (variant >= 2) {
+    void* g_ptr = nullptr;
+    MVS_CUDA(cudaGetSymbolAddress(&g_ptr, g_table));
+    MVS_CUDA(cudaMemcpyToSymbolAsync(c_table, g_ptr, (size_t)rows * 8 * sizeof(float), 0,
+                                     cudaMemcpyDeviceToDevice, s));
+    const bool wide = variant <= 3;
+    const int tx = wide ? 32 : 16, ty = wide ? 1 : 2;
+    dim3 grid(ceil_div(wf, tx), ceil_div(hf, ty), ceil_div(depth_num, kDC));
+    MVS_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "cost_volume: grid too large");
+#define CV_FAST(BF, RE, TX_, TY_) \
+  cost_volume_c32_kernel<BF, RE, TX_, TY_><<<grid, 256, 0, s>>>(feats, n_views, depth_num, hf, wf, order, out)
+    const bool reuse = (variant == 3 || variant == 5);
+    if (wide) {
+      if (bf16) { if (reuse) CV_FAST(true, true, 32, 1); else CV_FAST(true, false, 32, 1); }
+      else      { if (reuse) CV_FAST(false, true, 32, 1); else CV_FAST(false, false, 32, 1); }
+    } else {
+      if (bf16) { if (reuse) CV_FAST(true, true, 16, 2); else CV_FAST(true, false, 16, 2); }
+      else      { if (reuse) CV_FAST(false, true, 16, 2); else CV_FAST(false, false, 16, 2); }
+    }
+#undef CV_FAST
+    MVS_LAUNCH_CHECK("cost_volume_c32_kernel");
+    return MVSB200_OK;
+  }
+  const int vec = channels % 4 == 0 ? 4 : 1;
+  size_t total = (size_t)depth_num * hf * wf * (channels / vec);
+  MVS_CHECK_ARG((total + 255) / 256 <= 0x7fffffffu, "cost_volume: problem too large for one launch");
+  unsigned blocks = (unsigned)((total + 255) / 256);
+#define CV_GEN(V, SM, BF)                                                                                  \
+  cost_volume_generic_kernel<V, SM, BF><<<blocks, 256, 0, s>>>(feats, homographies, n_views, depth_num, hf, \
+                                                               wf, channels, order, out)
+  if (sampler == MVSB200_SAMPLER_TRANSFORM) {
+    if (vec == 4) { if (bf16) CV_GEN(4, MVSB200_SAMPLER_TRANSFORM, true); else CV_GEN(4, MVSB200_SAMPLER_TRANSFORM, false); }
+    else          { if (bf16) CV_GEN(1, MVSB200_SAMPLER_TRANSFORM, true); else CV_GEN(1, MVSB200_SAMPLER_TRANSFORM, false); }
+  } else {
+    if (vec == 4) { if (bf16) CV_GEN(4, MVSB200_SAMPLER_LEGACY, true); else CV_GEN(4, MVSB200_SAMPLER_LEGACY, false); }
+    else          { if (bf16) CV_GEN(1, MVSB200_SAMPLER_LEGACY, true); else CV_GEN(1, MVSB200_SAMPLER_LEGACY, false); }
+  }
+#undef CV_GEN
+  MVS_LAUNCH_CHECK("cost_volume_generic_kernel");
+  return MVSB200_OK;
+}
+
+}  // namespace mvsb200
+
+extern "C" int mvsb200_cost_volume(const float* feats, const float* homographies, int n_views, int depth_num,
+                                   int hf, int wf, int channels, int order, int sampler, int out_dtype, void* out,
+                                   int variant, void* stream) {
+  return mvsb200::launch_cost_volume(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler,
+                                     out_dtype, out, variant, (cudaStream_t)stream);
+}

@@ -1,0 +1,324 @@
+// RegNetUS0 forward (mvsnetworks.py:122-158) and the whole-path entry points.
+//
+// Data flow: every conv / deconv layer writes its RAW (pre-BN) output plus per-channel
+// sum / sum-of-squares; bn_finalize turns those into (scale, shift); the consumer applies
+// relu(raw*scale+shift) (and the skip add) while reading its input.  No normalised tensor is
+// ever written back to HBM.  BN uses batch statistics, as the reference does at inference
+// (network.py:54,64; model.py:337-338; SURVEY.md "facts").
+#include "common.cuh"
+
+namespace mvsb200 {
+
+int launch_conv3d_direct(const void* x, int x_dtype, const float* xs, const float* xb, const void* skip,
+                         const float* ss, const float* sb, const float* kernel_tf, int D, int H, int W, int cin,
+                         int cout, int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);
+int launch_conv3d_umma(const void* x, int x_dtype, const float* xs, const float* xb, const void* skip,
+                       const float* ss, const float* sb, const float* kernel_tf, int D, int H, int W, int cin,
+                       int cout, int stride, int transposed, void* y, int y_dtype, double* stats, void* scratch,
+                       cudaStream_t s);
+size_t conv3d_umma_scratch_bytes(int cin, int cout, int transposed);
+
+int launch_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const float* x_shift, const void* skip,
+                        const float* skip_scale, const float* skip_shift, const float* kernel_tf, int depth,
+                        int height, int width, int cin, int cout, int stride, int transposed, int precision,
+                        void* y_raw, int y_dtype, double* stats, cudaStream_t s) {
+  MVS_CHECK_ARG(x && kernel_tf && y_raw, "conv3d_layer: NULL pointer");
+  MVS_CHECK_ARG(depth > 0 && height > 0 && width > 0 && cin > 0 && cout > 0, "conv3d_layer: bad shape");
+  MVS_CHECK_ARG(x_dtype == MVSB200_F32 || x_dtype == MVSB200_BF16, "conv3d_layer: bad x_dtype %d", x_dtype);
+  MVS_CHECK_ARG(y_dtype == MVSB200_F32 || y_dtype == MVSB200_BF16, "conv3d_layer: bad y_dtype %d", y_dtype);
+  MVS_CHECK_ARG((x_scale == nullptr) == (x_shift == nullptr), "conv3d_layer: x_scale/x_shift must come together");
+  MVS_CHECK_ARG(!skip || ((skip_scale == nullptr) == (skip_shift == nullptr)),
+                "conv3d_layer: skip_scale/skip_shift must come together");
+  if (transposed) MVS_CHECK_ARG(stride == 2, "conv3d_layer: transposed conv supports stride 2 only (got %d)", stride);
+  else MVS_CHECK_ARG(stride == 1 || stride == 2, "conv3d_layer: stride must be 1 or 2 (got %d)", stride);
+  if (precision == MVSB200_PRECISION_FP32)
+    return launch_conv3d_direct(x, x_dtype, x_scale, x_shift, skip, skip_scale, skip_shift, kernel_tf, depth, height,
+                                width, cin, cout, stride, transposed, y_raw, y_dtype, stats, s);
+  if (precision == MVSB200_PRECISION_BF16)
+    return launch_conv3d_umma(x, x_dtype, x_scale, x_shift, skip, skip_scale, skip_shift, kernel_tf, depth, height,
+                              width, cin, cout, stride, transposed, y_raw, y_dtype, stats, nullptr, s);
+  set_error("conv3d_layer: bad precision %d", precision);
+  return MVSB200_ERR_INVALID;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------
+struct LayerDesc {
+  int cin, cout, stride, transposed;
+  int in_level, out_level;     // U-Net level of input / output volume (0 = full resolution)
+  int src;                     // producing layer of the input, -1 = cost volume
+  int skip;                    // layer added to the input (skip connection), -1 = none
+};
+
+struct RegnetPlan {
+  LayerDesc layer[MVSB200_REGNET_LAYERS];
+  size_t raw_off[MVSB200_REGNET_LAYERS];     // raw output of each layer (layer 10 writes `filtered` instead)
+  size_t stats_off, scale_off, shift_off, scratch_off;
+  size_t stats_bytes, total;
+  int elem;                                  // bytes per activation element
+  size_t vox[4];
+  int dims[4][3];
+};
+
+static void make_plan(int D, int H, int W, int cin, int b, int precision, RegnetPlan* p) {
+  // mvsnetworks.py:131-158
+  const LayerDesc L[MVSB200_REGNET_LAYERS] = {
+      {cin, 2 * b, 2, 0, 0, 1, -1, -1},                                     // 3dconv1_0
+      {2 * b, 4 * b, 2, 0, 1, 2, MVSB200_L_3DCONV1_0, -1},                  // 3dconv2_0
+      {4 * b, 8 * b, 2, 0, 2, 3, MVSB200_L_3DCONV2_0, -1},                  // 3dconv3_0
+      {cin, b, 1, 0, 0, 0, -1, -1},                                         // 3dconv0_1
+      {2 * b, 2 * b, 1, 0, 1, 1, MVSB200_L_3DCONV1_0, -1},                  // 3dconv1_1
+      {4 * b, 4 * b, 1, 0, 2, 2, MVSB200_L_3DCONV2_0, -1},                  // 3dconv2_1
+      {8 * b, 8 * b, 1, 0, 3, 3, MVSB200_L_3DCONV3_0, -1},                  // 3dconv3_1
+      {8 * b, 4 * b, 2, 1, 3, 2, MVSB200_L_3DCONV3_1, -1},                  // 3dconv4_0
+      {4 * b, 2 * b, 2, 1, 2, 1, MVSB200_L_3DCONV4_0, MVSB200_L_3DCONV2_1}, // 3dconv5_0 (input 3dconv4_1 = add)
+      {2 * b, b, 2, 1, 1, 0, MVSB200_L_3DCONV5_0, MVSB200_L_3DCONV1_1},     // 3dconv6_0 (input 3dconv5_1 = add)
+      {b, 1, 1, 0, 0, 0, MVSB200_L_3DCONV6_0, MVSB200_L_3DCONV0_1},         // 3dconv6_2 (input 3dconv6_1 = add)
+  };
+  for (int l = 0; l < 4; ++l) {
+    p->dims[l][0] = D >> l; p->dims[l][1] = H >> l; p->dims[l][2] = W >> l;
+    p->vox[l] = (size_t)(D >> l) * (H >> l) * (W >> l);
+  }
+  p->elem = precision == MVSB200_PRECISION_BF16 ? 2 : 4;
+  size_t off = 0;
+  int max_c = 0;
+  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+    p->layer[i] = L[i];
+    p->raw_off[i] = off;
+    if (i != MVSB200_L_3DCONV6_2) off += align_up(p->vox[L[i].out_level] * L[i].cout * p->elem, 256);
+    if (L[i].cout > max_c) max_c = L[i].cout;
+  }
+  const int cpad = (max_c + 63) / 64 * 64;
+  p->stats_off = off;  p->stats_bytes = (size_t)MVSB200_REGNET_LAYERS * 2 * cpad * sizeof(double); off += align_up(p->stats_bytes, 256);
+  p->scale_off = off;  off += align_up((size_t)MVSB200_REGNET_LAYERS * cpad * sizeof(float), 256);
+  p->shift_off = off;  off += align_up((size_t)MVSB200_REGNET_LAYERS * cpad * sizeof(float), 256);
+  p->scratch_off = off;
+  size_t scratch = 0;
+  if (precision == MVSB200_PRECISION_BF16)
+    for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+      size_t s = conv3d_umma_scratch_bytes(L[i].cin, L[i].cout, L[i].transposed);
+      if (s > scratch) scratch = s;
+    }
+  off += align_up(scratch, 256);
+  p->total = off;
+}
+
+static inline int plan_cpad(const RegnetPlan& p) {
+  return (int)(p.stats_bytes / (MVSB200_REGNET_LAYERS * 2 * sizeof(double)));
+}
+
+static int check_regnet_shape(int D, int H, int W, int cin, int b) {
+  MVS_CHECK_ARG(D > 0 && H > 0 && W > 0 && cin > 0 && b > 0, "regnet: bad shape D=%d H=%d W=%d Cin=%d base=%d", D, H, W,
+                cin, b);
+  // the reference graph only closes when every extent halves three times (mvsnetworks.py:148,152,156)
+  MVS_CHECK_ARG(D % 8 == 0 && H % 8 == 0 && W % 8 == 0,
+                "regnet: D, Hf, Wf must be multiples of 8 (got %d, %d, %d): the skip adds of RegNetUS0 do not "
+                "line up otherwise", D, H, W);
+  return MVSB200_OK;
+}
+
+int regnet_forward_impl(const void* cost, int cost_dtype, const mvsb200_regnet_params* params, int D, int H, int W,
+                        int cin, int b, float eps, int precision, float* filtered, void* workspace,
+                        size_t workspace_bytes, cudaStream_t s) {
+  MVS_CHECK_ARG(cost && params && filtered && workspace, "regnet_forward: NULL pointer");
+  int rc = check_regnet_shape(D, H, W, cin, b);
+  if (rc) return rc;
+  MVS_CHECK_ARG(precision == MVSB200_PRECISION_FP32 || precision == MVSB200_PRECISION_BF16,
+                "regnet_forward: bad precision %d", precision);
+  RegnetPlan p;
+  make_plan(D, H, W, cin, b, precision, &p);
+  if (workspace_bytes < p.total) {
+    set_error("regnet_forward: workspace %zu < required %zu bytes", workspace_bytes, p.total);
+    return MVSB200_ERR_WORKSPACE;
+  }
+  char* ws = (char*)workspace;
+  const int cpad = plan_cpad(p);
+  double* stats = (double*)(ws + p.stats_off);
+  float* scale = (float*)(ws + p.scale_off);
+  float* shift = (float*)(ws + p.shift_off);
+  const int act_dtype = precision == MVSB200_PRECISION_BF16 ? MVSB200_BF16 : MVSB200_F32;
+  MVS_CUDA(cudaMemsetAsync(stats, 0, p.stats_bytes, s));
+  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+    const LayerDesc& L = p.layer[i];
+    MVS_CHECK_ARG(params->kernel[i] != nullptr, "regnet_forward: kernel[%d] is NULL", i);
+    const bool last = i == MVSB200_L_3DCONV6_2;
+    if (!last) MVS_CHECK_ARG(params->gamma[i] && params->beta[i], "regnet_forward: gamma/beta[%d] is NULL", i);
+    const void* x = L.src < 0 ? cost : (const void*)(ws + p.raw_off[L.src]);
+    const int x_dtype = L.src < 0 ? cost_dtype : act_dtype;
+    const float* xs = L.src < 0 ? nullptr : scale + (size_t)L.src * cpad;
+    const float* xb = L.src < 0 ? nullptr : shift + (size_t)L.src * cpad;
+    const void* sk = L.skip < 0 ? nullptr : (const void*)(ws + p.raw_off[L.skip]);
+    const float* ss = L.skip < 0 ? nullptr : scale + (size_t)L.skip * cpad;
+    const float* sb = L.skip < 0 ? nullptr : shift + (size_t)L.skip * cpad;
+    if (L.src < 0 && precision == MVSB200_PRECISION_BF16)
+      MVS_CHECK_ARG(cost_dtype == MVSB200_BF16, "regnet_forward: precision bf16 needs a bf16 cost volume");
+    void* y = last ? (void*)filtered : (void*)(ws + p.raw_off[i]);
+    const int y_dtype = last ? MVSB200_F32 : act_dtype;
+    double* st = last ? nullptr : stats + (size_t)i * 2 * cpad;
+    const int* d = p.dims[L.in_level];
+    if (precision == MVSB200_PRECISION_FP32)
+      rc = launch_conv3d_direct(x, x_dtype, xs, xb, sk, ss, sb, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout,
+                                L.stride, L.transposed, y, y_dtype, st ? st : nullptr, s);
+    else
+      rc = launch_conv3d_umma(x, x_dtype, xs, xb, sk, ss, sb, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout,
+                              L.stride, L.transposed, y, y_dtype, st, ws + p.scratch_off, s);
+    if (rc) return rc;
+    if (!last) {
+      // stats hold sum over L.cout channels laid out [sum(cout) | sumsq(cout)]
+      rc = launch_bn_finalize(st, params->gamma[i], params->beta[i], L.cout, (double)p.vox[L.out_level], eps,
+                              scale + (size_t)i * cpad, shift + (size_t)i * cpad, s);
+      if (rc) return rc;
+    }
+  }
+  return MVSB200_OK;
+}
+
+}  // namespace mvsb200
+
+using namespace mvsb200;
+
+extern "C" int mvsb200_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const float* x_shift,
+                                    const void* skip, const float* skip_scale, const float* skip_shift,
+                                    const float* kernel_tf, int depth, int height, int width, int cin, int cout,
+                                    int stride, int transposed, int precision, void* y_raw, int y_dtype,
+                                    double* stats, void* stream) {
+  return launch_conv3d_layer(x, x_dtype, x_scale, x_shift, skip, skip_scale, skip_shift, kernel_tf, depth, height,
+                             width, cin, cout, stride, transposed, precision, y_raw, y_dtype, stats,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int mvsb200_bn_finalize(const double* stats, const float* gamma, const float* beta, int channels,
+                                   double count, float eps, float* scale, float* shift, void* stream) {
+  return launch_bn_finalize(stats, gamma, beta, channels, count, eps, scale, shift, (cudaStream_t)stream);
+}
+
+extern "C" size_t mvsb200_regnet_workspace_bytes(int depth, int hf, int wf, int in_channels, int base_filter,
+                                                 int precision) {
+  if (depth <= 0 || hf <= 0 || wf <= 0 || in_channels <= 0 || base_filter <= 0) return 0;
+  RegnetPlan p;
+  make_plan(depth, hf, wf, in_channels, base_filter, precision, &p);
+  return p.total;
+}
+
+extern "C" int mvsb200_regnet_forward(const void* cost, int cost_dtype, const mvsb200_regnet_params* params,
+                                      int depth, int hf, int wf, int in_channels, int base_filter, float bn_eps,
+                                      int precision, float* filtered, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  return regnet_forward_impl(cost, cost_dtype, params, depth, hf, wf, in_channels, base_filter, bn_eps, precision,
+                             filtered, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" const void* mvsb200_regnet_layer_raw(const void* workspace, int depth, int hf, int wf, int in_channels,
+                                                int base_filter, int precision, int layer, const float** scale,
+                                                const float** shift) {
+  if (!workspace || layer < 0 || layer >= MVSB200_REGNET_LAYERS) return nullptr;
+  RegnetPlan p;
+  make_plan(depth, hf, wf, in_channels, base_filter, precision, &p);
+  const char* ws = (const char*)workspace;
+  const int cpad = plan_cpad(p);
+  if (scale) *scale = (const float*)(ws + p.scale_off) + (size_t)layer * cpad;
+  if (shift) *shift = (const float*)(ws + p.shift_off) + (size_t)layer * cpad;
+  if (layer == MVSB200_L_3DCONV6_2) return nullptr;
+  return ws + p.raw_off[layer];
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole path
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct InferPlan {
+  size_t hom_off, cost_off, filtered_off, regnet_off, total;
+  size_t regnet_bytes;
+};
+void make_infer_plan(int n_views, int D, int hf, int wf, int C, int b, int precision, InferPlan* ip) {
+  size_t off = 0;
+  ip->hom_off = off;      off += align_up((size_t)(n_views - 1) * D * 9 * sizeof(float), 256);
+  ip->cost_off = off;     off += align_up((size_t)D * hf * wf * C * (precision == MVSB200_PRECISION_BF16 ? 2 : 4), 256);
+  ip->filtered_off = off; off += align_up((size_t)D * hf * wf * sizeof(float), 256);
+  ip->regnet_off = off;
+  ip->regnet_bytes = mvsb200_regnet_workspace_bytes(D, hf, wf, C, b, precision);
+  off += ip->regnet_bytes;
+  ip->total = off;
+}
+}  // namespace
+
+extern "C" size_t mvsb200_infer_workspace_bytes(int n_views, int depth_num, int hf, int wf, int channels,
+                                                int base_filter, int precision) {
+  if (n_views < 2 || depth_num <= 0 || hf <= 0 || wf <= 0 || channels <= 0 || base_filter <= 0) return 0;
+  InferPlan ip;
+  make_infer_plan(n_views, depth_num, hf, wf, channels, base_filter, precision, &ip);
+  return ip.total;
+}
+
+extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views, int depth_num, int hf, int wf,
+                             int channels, float depth_start, float depth_interval, int inverse_depth, int order,
+                             int sampler, const mvsb200_regnet_params* params, int base_filter, float bn_eps,
+                             int precision, float* depth_map, float* prob_map, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  MVS_CHECK_ARG(feats && cams && params && depth_map && prob_map && workspace, "infer: NULL pointer");
+  MVS_CHECK_ARG(n_views >= 2, "infer: n_views must be >= 2 (got %d)", n_views);
+  int rc = check_regnet_shape(depth_num, hf, wf, channels, base_filter);
+  if (rc) return rc;
+  InferPlan ip;
+  make_infer_plan(n_views, depth_num, hf, wf, channels, base_filter, precision, &ip);
+  if (workspace_bytes < ip.total) {
+    set_error("infer: workspace %zu < required %zu bytes", workspace_bytes, ip.total);
+    return MVSB200_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* homs = (float*)(ws + ip.hom_off);
+  void* cost = ws + ip.cost_off;
+  float* filtered = (float*)(ws + ip.filtered_off);
+  // model.py:378-379: depth_end = depth_start + (float(depth_num) - 1) * depth_interval (fp32)
+  volatile float dm1 = (float)depth_num - 1.0f;
+  volatile float prod = dm1 * depth_interval;
+  volatile float depth_end = depth_start + prod;
+  rc = launch_homographies(cams, n_views, depth_num, depth_start, inverse_depth ? (float)depth_end : depth_interval,
+                           inverse_depth, homs, nullptr, s);
+  if (rc) return rc;
+  const int cost_dtype = precision == MVSB200_PRECISION_BF16 ? MVSB200_BF16 : MVSB200_F32;
+  rc = launch_cost_volume(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cost_dtype, cost, 0, s);
+  if (rc) return rc;
+  rc = regnet_forward_impl(cost, cost_dtype, params, depth_num, hf, wf, channels, base_filter, bn_eps, precision,
+                           filtered, ws + ip.regnet_off, ip.regnet_bytes, s);
+  if (rc) return rc;
+  return launch_depth_regress(filtered, depth_num, hf, wf, depth_start, depth_interval, inverse_depth, 4, depth_map,
+                              prob_map, nullptr, s);
+}
+
+extern "C" size_t mvsb200_infer_host_staging_bytes(int n_views, int hf, int wf, int channels) {
+  if (n_views < 2 || hf <= 0 || wf <= 0 || channels <= 0) return 0;
+  return align_up((size_t)n_views * hf * wf * channels * sizeof(float), 256) +
+         align_up((size_t)n_views * 32 * sizeof(float), 256) + 2 * align_up((size_t)hf * wf * sizeof(float), 256);
+}
+
+extern "C" int mvsb200_infer_host(const float* feats_host, const float* cams_host, int n_views, int depth_num,
+                                  int hf, int wf, int channels, float depth_start, float depth_interval,
+                                  int inverse_depth, int order, int sampler, const mvsb200_regnet_params* params,
+                                  int base_filter, float bn_eps, int precision, float* depth_map_host,
+                                  float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  MVS_CHECK_ARG(feats_host && cams_host && depth_map_host && prob_map_host && staging_dev, "infer_host: NULL pointer");
+  MVS_CHECK_ARG(n_views >= 2 && hf > 0 && wf > 0 && channels > 0, "infer_host: bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* st = (char*)staging_dev;
+  const size_t feat_bytes = (size_t)n_views * hf * wf * channels * sizeof(float);
+  const size_t cam_bytes = (size_t)n_views * 32 * sizeof(float);
+  const size_t map_bytes = (size_t)hf * wf * sizeof(float);
+  float* d_feats = (float*)st;
+  float* d_cams = (float*)(st + align_up(feat_bytes, 256));
+  float* d_depth = (float*)((char*)d_cams + align_up(cam_bytes, 256));
+  float* d_prob = (float*)((char*)d_depth + align_up(map_bytes, 256));
+  MVS_CUDA(cudaMemcpyAsync(d_feats, feats_host, feat_bytes, cudaMemcpyHostToDevice, s));
+  MVS_CUDA(cudaMemcpyAsync(d_cams, cams_host, cam_bytes, cudaMemcpyHostToDevice, s));
+  int rc = mvsb200_infer(d_feats, d_cams, n_views, depth_num, hf, wf, channels, depth_start, depth_interval,
+                         inverse_depth, order, sampler, params, base_filter, bn_eps, precision, d_depth, d_prob,
+                         workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  MVS_CUDA(cudaMemcpyAsync(depth_map_host, d_depth, map_bytes, cudaMemcpyDeviceToHost, s));
+  MVS_CUDA(cudaMemcpyAsync(prob_map_host, d_prob, map_bytes, cudaMemcpyDeviceToHost, s));
+  MVS_CUDA(cudaStreamSynchronize(s));
+  return MVSB200_OK;
+}

@@ -1,0 +1,93 @@
+"""Whole hot path on the GPU against the oracle: depth within 0.1 depth-interval on >= 99.9 % of pixels in
+fp32 parity mode and >= 95 % in bf16 product mode (north_star gates), through the device and the host-buffer
+C-ABI entry points and the reference-named Python API."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from conftest import to_dev  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def oracle_small(small_problem):
+    import oracle as O
+    p = small_problem
+    depth, prob, allr = O.inference_from_features(p["feats"], p["cams"], p["depth_num"], p["depth_start"],
+                                                  p["depth_interval"], p["weights"], return_all=True)
+    return depth, prob, allr
+
+
+def _frac_within(depth, ref, interval, tol=0.1):
+    return float(np.mean(np.abs(depth - ref) <= tol * interval))
+
+
+def test_fp32_path_vs_oracle(small_problem, oracle_small):
+    from mvsnet_b200.engine import HotPath
+    p = small_problem
+    rd, rp, _ = oracle_small
+    eng = HotPath(p["n_views"], p["depth_num"], p["hf"], p["wf"], p["weights"], precision="fp32")
+    d, pm = eng.infer(to_dev(p["feats"]), to_dev(p["cams"]), p["depth_start"], p["depth_interval"])
+    frac = _frac_within(d.cpu().numpy(), rd, p["depth_interval"])
+    assert frac >= 0.999, frac
+    assert np.mean(np.abs(pm.cpu().numpy() - rp) <= 1e-2) >= 0.99
+
+
+def test_bf16_path_vs_oracle(small_problem, oracle_small):
+    from mvsnet_b200.engine import HotPath
+    p = small_problem
+    rd, rp, _ = oracle_small
+    eng = HotPath(p["n_views"], p["depth_num"], p["hf"], p["wf"], p["weights"], precision="bf16")
+    d, pm = eng.infer(to_dev(p["feats"]), to_dev(p["cams"]), p["depth_start"], p["depth_interval"])
+    frac = _frac_within(d.cpu().numpy(), rd, p["depth_interval"])
+    assert frac >= 0.95, frac
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_host_entry_point_matches_device(small_problem, precision):
+    from mvsnet_b200.engine import HotPath
+    p = small_problem
+    eng = HotPath(p["n_views"], p["depth_num"], p["hf"], p["wf"], p["weights"], precision=precision)
+    d, pm = eng.infer(to_dev(p["feats"]), to_dev(p["cams"]), p["depth_start"], p["depth_interval"])
+    d, pm = d.clone(), pm.clone()
+    fh = torch.from_numpy(p["feats"]).pin_memory()
+    ch = torch.from_numpy(p["cams"]).pin_memory()
+    dh = torch.empty((p["hf"], p["wf"])).pin_memory()
+    ph = torch.empty((p["hf"], p["wf"])).pin_memory()
+    eng.infer_host(fh, ch, p["depth_start"], p["depth_interval"], dh, ph)
+    # batch-statistic BN sums use atomics: allow last-bit noise
+    assert np.allclose(dh.numpy(), d.cpu().numpy(), rtol=1e-4, atol=1e-2)
+    assert np.allclose(ph.numpy(), pm.cpu().numpy(), atol=1e-2)
+
+
+def test_reference_named_inference(small_problem, oracle_small):
+    from mvsnet_b200 import model
+    from mvsnet_b200.cnn_wrapper import mvsnetworks
+    p = small_problem
+    rd, _, allr = oracle_small
+    mvsnetworks.set_variables(p["weights"])
+    model.FLAGS.view_num = p["n_views"]
+    model.FLAGS.precision = "fp32"
+    feats = to_dev(p["feats"])[None]
+    cams = to_dev(p["cams"])[None]
+    depth, prob = model.inference_mem(feats, cams, p["depth_num"], torch.tensor([p["depth_start"]]),
+                                      torch.tensor([p["depth_interval"]]), "normal")
+    assert depth.shape == (1, p["hf"], p["wf"], 1) and prob.shape == depth.shape
+    assert _frac_within(depth[0, :, :, 0].cpu().numpy(), rd, p["depth_interval"]) >= 0.999
+    depth2, _ = model.inference(feats, cams, p["depth_num"], torch.tensor([p["depth_start"]]),
+                                torch.tensor([p["depth_interval"]]), "normal")
+    assert _frac_within(depth2[0, :, :, 0].cpu().numpy(), rd, p["depth_interval"]) >= 0.99
+    with pytest.raises(TypeError):
+        model.inference_mem(feats, cams, torch.tensor(32), torch.tensor([425.0]), torch.tensor([10.0]), "normal")
+    with pytest.raises(RuntimeError):
+        model.inference_mem(torch.zeros((1, 5, 8, 8, 3), device="cuda"), cams, 32, torch.tensor([425.0]),
+                            torch.tensor([10.0]), "normal")
+    # RegNetUS0 by its reference name
+    mvsnetworks.RegNetUS0.precision = "fp32"
+    out = mvsnetworks.RegNetUS0({"data": to_dev(allr["cost"])[None]}, trainable=True, training=True,
+                                mode="normal", reuse=False).get_output()
+    assert out.shape == (1,) + allr["filtered"].shape + (1,)
+    assert np.abs(out[0, ..., 0].cpu().numpy() - allr["filtered"]).max() <= 2e-3 * np.abs(allr["filtered"]).max()
+    mvsnetworks.RegNetUS0.precision = "bf16"
+    model.FLAGS.precision = "bf16"

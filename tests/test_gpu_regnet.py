@@ -1,0 +1,166 @@
+"""GPU parity of the regularizer: single layers and the whole RegNetUS0 in fp32 parity mode (CUDA-core
+direct conv) and bf16 product mode (tcgen05), against the oracle (torch-CPU fp32 conv3d)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from conftest import to_dev  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def O():
+    import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mvsnet_b200 import ops
+    return ops
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+
+
+LAYER_CASES = [
+    # (D, H, W, Cin, Cout, stride, transposed)
+    (8, 16, 24, 32, 8, 1, False),      # 3dconv0_1
+    (8, 16, 24, 32, 16, 2, False),     # 3dconv1_0
+    (8, 8, 16, 16, 16, 1, False),      # 3dconv1_1
+    (8, 8, 16, 16, 32, 2, False),      # 3dconv2_0
+    (4, 8, 8, 32, 32, 1, False),       # 3dconv2_1
+    (4, 8, 8, 32, 64, 2, False),       # 3dconv3_0
+    (3, 5, 6, 64, 64, 1, False),       # 3dconv3_1 (odd extents)
+    (3, 5, 6, 64, 32, 2, True),        # 3dconv4_0
+    (4, 8, 8, 32, 16, 2, True),        # 3dconv5_0
+    (8, 8, 16, 16, 8, 2, True),        # 3dconv6_0
+    (8, 16, 24, 8, 1, 1, False),       # 3dconv6_2
+    (7, 9, 11, 32, 16, 2, False),      # stride 2 on odd extents: TF SAME pads (1,1)
+]
+
+
+def _layer_ref(O, x, w, stride, transposed):
+    return O.conv3d_transpose_same(x, w) if transposed else O.conv3d_same(x, w, stride)
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_fp32_layer_vs_oracle(ops, O, case):
+    D, H, W, cin, cout, stride, tr = case
+    rng = np.random.RandomState(21)
+    x = rng.randn(D, H, W, cin).astype(np.float32)
+    w = (rng.randn(*((3, 3, 3, cout, cin) if tr else (3, 3, 3, cin, cout))) * 0.1).astype(np.float32)
+    y, stats = ops.conv3d_layer(to_dev(x), to_dev(w), stride, tr, "fp32")
+    ref = _layer_ref(O, x, w, stride, tr)
+    assert tuple(y.shape) == ref.shape
+    err = np.abs(y.cpu().numpy() - ref).max()
+    assert err <= 2e-4 * max(1.0, np.abs(ref).max()), err
+    st = stats.cpu().numpy()
+    r64 = ref.reshape(-1, cout).astype(np.float64)
+    np.testing.assert_allclose(st[:cout], r64.sum(0), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(st[cout:], (r64 ** 2).sum(0), rtol=1e-4, atol=1e-2)
+
+
+def test_fp32_layer_with_affine_relu_and_skip(ops, O):
+    rng = np.random.RandomState(22)
+    D, H, W, cin, cout = 4, 8, 8, 16, 8
+    x = rng.randn(D, H, W, cin).astype(np.float32)
+    sk = rng.randn(D, H, W, cin).astype(np.float32)
+    xs, xb, ss, sb = (rng.uniform(0.5, 1.5, cin).astype(np.float32) for _ in range(4))
+    w = (rng.randn(3, 3, 3, cout, cin) * 0.1).astype(np.float32)
+    inp = np.maximum(x * xs + xb, 0) + np.maximum(sk * ss + sb, 0)
+    ref = O.conv3d_transpose_same(inp.astype(np.float32), w)
+    y, _ = ops.conv3d_layer(to_dev(x), to_dev(w), 2, True, "fp32", x_affine=(to_dev(xs), to_dev(xb)),
+                            skip=to_dev(sk), skip_affine=(to_dev(ss), to_dev(sb)))
+    assert np.abs(y.cpu().numpy() - ref).max() <= 3e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_bn_finalize(ops, O):
+    rng = np.random.RandomState(23)
+    x = (rng.randn(4, 6, 8, 5) * 2 + 0.5).astype(np.float32)
+    g = rng.uniform(0.5, 1.5, 5).astype(np.float32)
+    b = rng.randn(5).astype(np.float32)
+    x64 = x.reshape(-1, 5).astype(np.float64)
+    stats = to_dev(np.concatenate([x64.sum(0), (x64 ** 2).sum(0)]))
+    scale, shift = ops.bn_finalize(stats, to_dev(g), to_dev(b), x64.shape[0])
+    y = np.maximum(x * scale.cpu().numpy() + shift.cpu().numpy(), 0)
+    np.testing.assert_allclose(y, O.batch_norm_train(x, g, b), rtol=1e-5, atol=1e-5)
+
+
+def _regnet(precision, p, cost):
+    from mvsnet_b200.engine import HotPath
+    eng = HotPath(p["n_views"], cost.shape[0], cost.shape[1], cost.shape[2], p["weights"], precision=precision)
+    c = to_dev(cost)
+    if precision == "bf16":
+        c = c.to(torch.bfloat16)
+    return eng.regnet(c).cpu().numpy()
+
+
+@pytest.mark.parametrize("which", ["tiny", "small"])
+def test_regnet_fp32_vs_oracle(O, tiny_problem, small_problem, golden_tiny, which):
+    p = tiny_problem if which == "tiny" else small_problem
+    H = np.stack([O.get_homographies(p["cams"][0:1], p["cams"][v:v + 1], p["depth_num"], p["depth_start"],
+                                     p["depth_interval"])[0] for v in range(1, p["n_views"])])
+    cost = O.cost_volume(p["feats"], H)
+    ref = O.regnet_us0(cost, p["weights"])
+    out = _regnet("fp32", p, cost)
+    scale = np.abs(ref).max()
+    assert np.abs(out - ref).max() <= 2e-3 * scale, (np.abs(out - ref).max(), scale)
+    if which == "tiny":
+        assert np.abs(out - golden_tiny["filtered"]).max() <= 2e-3 * scale
+
+
+def test_regnet_rejects_bad_extents(tiny_problem):
+    from mvsnet_b200._lib import MVSB200Error
+    from mvsnet_b200.engine import HotPath
+    p = tiny_problem
+    eng = HotPath(3, 16, 24, 32, p["weights"], precision="fp32")
+    with pytest.raises(MVSB200Error, match="multiples of 8"):
+        eng.regnet(torch.zeros((12, 24, 32, 32), device="cuda"))
+
+
+# ---- bf16 / tcgen05 product mode ----------------------------------------------------------------------------
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_bf16_layer_vs_oracle(ops, O, case):
+    D, H, W, cin, cout, stride, tr = case
+    rng = np.random.RandomState(31)
+    x = bf16_round(rng.randn(D, H, W, cin))
+    w = (rng.randn(*((3, 3, 3, cout, cin) if tr else (3, 3, 3, cin, cout))) * 0.1).astype(np.float32)
+    y, stats = ops.conv3d_layer(to_dev(x).to(torch.bfloat16), to_dev(w), stride, tr, "bf16", out_dtype=torch.float32)
+    ref = _layer_ref(O, x, bf16_round(w), stride, tr)             # same bf16 operands, fp32 accumulation
+    assert tuple(y.shape) == ref.shape
+    err = np.abs(y.cpu().numpy() - ref).max()
+    assert err <= 1e-3 * max(1.0, np.abs(ref).max()), f"{case}: max abs err {err}"
+    st = stats.cpu().numpy()
+    r64 = ref.reshape(-1, cout).astype(np.float64)
+    np.testing.assert_allclose(st[:cout], r64.sum(0), rtol=1e-3, atol=0.5)
+    np.testing.assert_allclose(st[cout:], (r64 ** 2).sum(0), rtol=1e-3, atol=0.5)
+
+
+def test_bf16_layer_with_affine_relu_and_skip(ops, O):
+    rng = np.random.RandomState(32)
+    D, H, W, cin, cout = 4, 8, 8, 16, 8
+    x = bf16_round(rng.randn(D, H, W, cin))
+    sk = bf16_round(rng.randn(D, H, W, cin))
+    xs, xb, ss, sb = (rng.uniform(0.5, 1.5, cin).astype(np.float32) for _ in range(4))
+    w = (rng.randn(3, 3, 3, cout, cin) * 0.1).astype(np.float32)
+    inp = bf16_round(np.maximum(x * xs + xb, 0) + np.maximum(sk * ss + sb, 0))
+    ref = O.conv3d_transpose_same(inp, bf16_round(w))
+    y, _ = ops.conv3d_layer(to_dev(x).to(torch.bfloat16), to_dev(w), 2, True, "bf16",
+                            x_affine=(to_dev(xs), to_dev(xb)), skip=to_dev(sk).to(torch.bfloat16),
+                            skip_affine=(to_dev(ss), to_dev(sb)), out_dtype=torch.float32)
+    assert np.abs(y.cpu().numpy() - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max())
+
+
+def test_regnet_bf16_vs_oracle(O, small_problem):
+    p = small_problem
+    H = np.stack([O.get_homographies(p["cams"][0:1], p["cams"][v:v + 1], p["depth_num"], p["depth_start"],
+                                     p["depth_interval"])[0] for v in range(1, p["n_views"])])
+    cost = O.cost_volume(p["feats"], H)
+    ref = O.regnet_us0(cost, p["weights"])
+    out = _regnet("bf16", p, cost)
+    rel = np.abs(out - ref).max() / np.abs(ref).max()
+    assert rel <= 0.08, rel
+    assert np.corrcoef(out.ravel(), ref.ravel())[0, 1] >= 0.999

@@ -129,6 +129,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_c
     s_aff[2 * p.Cin + i] = p.ss ? p.ss[i] : 1.0f;
     s_aff[3 * p.Cin + i] = p.sb ? p.sb[i] : 0.0f;
   }
+  // Every cell of the ring starts finite: halo rows of the GEMM read a few cells past the loaded
+  // area (their results are dropped, but 0 * NaN from stale shared memory must not reach a zero-
+  // weighted K half of a valid row).
+  for (int i = threadIdx.x; i < p.R * p.slot_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.R; ++i) { mbar_init(&bar_full[i], kLoadThreads); mbar_init(&bar_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kEpiThreads / 32); }
@@ -278,7 +284,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_c
               }
               if (p.y_is_f32) {
                 float* yo = reinterpret_cast<float*>(p.y) + vox * p.Cout + p.cout_base;
-                for (int k = 0; k < p.cout_n; ++k) yo[k] = __uint_as_float(r[k]);
+#pragma unroll
+                for (int k = 0; k < CP; ++k)
+                  if (k < p.cout_n) yo[k] = __uint_as_float(r[k]);
               } else {
                 __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + vox * p.Cout + p.cout_base;
                 if ((p.cout_n & 7) == 0) {
@@ -294,7 +302,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_c
                     }
                   }
                 } else {
-                  for (int k = 0; k < p.cout_n; ++k) yo[k] = __float2bfloat16_rn(__uint_as_float(r[k]));
+#pragma unroll
+                  for (int k = 0; k < CP; ++k)
+                    if (k < p.cout_n) yo[k] = __float2bfloat16_rn(__uint_as_float(r[k]));
                 }
               }
             }

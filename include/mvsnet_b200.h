@@ -170,6 +170,11 @@ int mvsb200_infer(const float* feats, const float* cams, int n_views, int depth_
                   int precision, float* depth_map, float* prob_map, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Optional instrumentation: five cudaEvent_t handles recorded by mvsb200_infer on its stream at the
+ * stage boundaries (start, after homographies, after cost volume, after regularizer, after regression);
+ * NULL switches it off.  Per calling thread. */
+int mvsb200_infer_set_stage_events(void* const* events);
+
 /* Same with HOST buffers for feats / cams / outputs (the sess.run feed/fetch boundary of
  * inference.py:105-112): copies in, runs, copies out, synchronises.  `params` and `workspace`
  * stay device-resident (weights are loaded once per model, predictlib.py:69-76).  When

@@ -11,7 +11,7 @@
 //
 //   warps 0-3  epilogue: tcgen05.ld accumulators -> bf16/fp32 store + per-channel batch statistics
 //   warp  4    TMEM allocation; one thread issues every tcgen05.mma and the commits
-//   warps 5-8  loaders: global -> (BN scale/shift + ReLU + skip add of the producers) -> bf16 cells
+//   warps 5-12 loaders: global -> (BN scale/shift + ReLU + skip add of the producers) -> bf16 cells
 //
 // The three layer kinds of RegNetUS0 are all "tap GEMMs" over such planes:
 //   conv s=1 (network.py:210)   27 taps, plane z-1..z+1, cell offset kh*PX+kw
@@ -21,20 +21,25 @@
 // one bulk async copy (TMA engine) per CTA.
 #include "common.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace mvsb200 {
 using namespace umma;
 
 constexpr int kMaxOps = 108;            // 27 taps x (64 channels / 16)
-constexpr int kEpiThreads = 128, kLoadThreads = 128;
+constexpr int kEpiThreads = 128, kLoadThreads = 256;
 constexpr int kThreads = kEpiThreads + 32 + kLoadThreads;
-constexpr int kMaxRing = 5;
+constexpr int kMaxRing = 8;
+constexpr int kLoadBatch = 4;            // 16-byte loads in flight per loader thread
 
 enum { MODE_CONV1 = 0, MODE_CONV2 = 1, MODE_DECONV = 2 };
 
+// Pre-baked descriptor words of one MMA (read from the constant bank with a uniform index):
 struct UmmaOp {
-  uint32_t a;   // [0,14) a_off>>4 (within slot) | [14,28) a_lbo>>4 | [28,30) dz | [30] first (overwrite)
-  uint32_t b;   // [0,14) b_off>>4 | [14,24) tmem column offset within the block
+  uint32_t a_lo;   // A descriptor low word relative to the slot: [0,14) a_off>>4 | [16,30) a_lbo>>4
+  uint32_t b_lo;   // B descriptor low word relative to the B image: [0,14) b_off>>4 | [16,30) b_lbo>>4
+  uint32_t meta;   // [0,16) tmem column offset in the block | [16] first (overwrite) | [20,22) dz
+  uint32_t pad;
 };
 
 // host-side description of the two K halves of an op, consumed by the weight pack kernel
@@ -56,6 +61,7 @@ struct ConvParams {
   int NCH, PS, slot_bytes, R;
   int MB, NB, CP;                // blocks per step, TMEM columns per block, padded channels per MMA
   int nops, b_bytes, tmem_cols;
+  int dbg;                       // development switches (env MVSB200_UMMA_DBG): 1 no global loads, 2 no MMA, 4 no stores
   UmmaOp ops[kMaxOps];
 };
 
@@ -98,10 +104,12 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 template <int CP>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: [B image][R slots][4*Cin floats][barriers][tmem ptr]
+  // layout: [B image][R slots][cell table][op table][4*Cin floats][barriers][tmem ptr]
   unsigned char* s_b = smem;
   unsigned char* s_slots = smem + p.b_bytes;
-  float* s_aff = reinterpret_cast<float*>(s_slots + (size_t)p.R * p.slot_bytes);
+  const int ncells = p.nsub * p.RY * p.PX;
+  int2* s_cells = reinterpret_cast<int2*>(s_slots + (size_t)p.R * p.slot_bytes);   // {offset in plane | -1, cell}
+  float* s_aff = reinterpret_cast<float*>(s_cells + ((ncells + 1) & ~1));
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_aff + 4 * p.Cin);
   uint64_t* bar_full = bars;                    // [R]   loaders -> MMA
   uint64_t* bar_empty = bars + kMaxRing;        // [R]   MMA (commit) -> loaders
@@ -129,6 +137,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_c
     s_aff[2 * p.Cin + i] = p.ss ? p.ss[i] : 1.0f;
     s_aff[3 * p.Cin + i] = p.sb ? p.sb[i] : 0.0f;
   }
+  // loop-invariant loader addressing: one entry per cell of a slot
+  for (int i = threadIdx.x; i < ncells; i += blockDim.x) {
+    const int c = i % p.PX;
+    int rest = i / p.PX;
+    const int r = rest % p.RY, sub = rest / p.RY;
+    const int ix = p.xstep * (x0 + c) + p.xoff + (sub & 1);
+    const int iy = p.xstep * (y0 + r) + p.yoff + (sub >> 1);
+    const bool ok = ix >= 0 && ix < p.W && iy >= 0 && iy < p.H;
+    s_cells[i] = make_int2(ok ? (iy * p.W + ix) * p.Cin : -1, sub * p.SUBP + r * p.PX + c);
+  }
   // Every cell of the ring starts finite: halo rows of the GEMM read a few cells past the loaded
   // area (their results are dropped, but 0 * NaN from stale shared memory must not reach a zero-
   // weighted K half of a valid row).
@@ -155,34 +173,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_c
       // ===================================== loaders =====================================
       const int lt = threadIdx.x - (kEpiThreads + 32);
       const bool x_act = p.xs != nullptr, has_skip = p.skip != nullptr, s_act = p.ss != nullptr;
-      const int items = p.nsub * p.RY * p.PX * p.NCH;
-      const size_t row_elems = (size_t)p.W * p.Cin, plane_elems = (size_t)p.H * row_elems;
+      const bool transform = x_act || has_skip;
+      const int items = ncells * p.NCH;
+      const int nch_shift = (p.NCH & (p.NCH - 1)) == 0 ? __ffs(p.NCH) - 1 : -1;
+      const size_t plane_elems = (size_t)p.H * p.W * p.Cin;
       for (int seq = 0; seq < nplanes; ++seq) {
         const int slot = seq % p.R;
         if (seq >= p.R) mbar_wait(&bar_empty[slot], (uint32_t)((seq / p.R) - 1) & 1u);
         unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
         const int iz = p.zstep * zb + p.zoff + seq;
         const bool zok = iz >= 0 && iz < p.D;
-        for (int i = lt; i < items; i += kLoadThreads) {
-          const int ch = i % p.NCH;
-          int rest = i / p.NCH;
-          const int c = rest % p.PX; rest /= p.PX;
-          const int r = rest % p.RY;
-          const int s = rest / p.RY;
-          const int ix = p.xstep * (x0 + c) + p.xoff + (s & 1);
-          const int iy = p.xstep * (y0 + r) + p.yoff + (s >> 1);
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (zok && ix >= 0 && ix < p.W && iy >= 0 && iy < p.H) {
-            const size_t off = (size_t)iz * plane_elems + (size_t)iy * row_elems + (size_t)ix * p.Cin + ch * 8;
-            v = __ldg(reinterpret_cast<const uint4*>(p.x + off));
-            if (x_act || has_skip) {
-              uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
-              uint4 sv = make_uint4(0u, 0u, 0u, 0u);
-              if (has_skip) sv = __ldg(reinterpret_cast<const uint4*>(p.skip + off));
-              const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sv);
+        const __nv_bfloat16* xp = p.x + (size_t)(zok ? iz : 0) * plane_elems;
+        const __nv_bfloat16* kp = has_skip ? p.skip + (size_t)(zok ? iz : 0) * plane_elems : nullptr;
+        for (int base = 0; base < items; base += kLoadThreads * kLoadBatch) {
+          uint4 v[kLoadBatch], sv[kLoadBatch];
+          int dst[kLoadBatch], chn[kLoadBatch];
+          bool live[kLoadBatch];
+#pragma unroll
+          for (int u = 0; u < kLoadBatch; ++u) {
+            const int i = base + u * kLoadThreads + lt;
+            const bool in = i < items;
+            const int cell = nch_shift >= 0 ? (i >> nch_shift) : (i / p.NCH);
+            const int ch = i - cell * p.NCH;
+            const int2 e = in ? s_cells[cell] : make_int2(-1, 0);
+            chn[u] = ch;
+            dst[u] = in ? ch * p.PS + e.y * 16 : -1;
+            live[u] = in && zok && e.x >= 0 && !(p.dbg & 1);
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            sv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (live[u]) {
+              v[u] = __ldg(reinterpret_cast<const uint4*>(xp + e.x + ch * 8));
+              if (has_skip) sv[u] = __ldg(reinterpret_cast<const uint4*>(kp + e.x + ch * 8));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kLoadBatch; ++u) {
+            if (dst[u] < 0) continue;
+            if (live[u] && transform) {
+              uint32_t* vw = reinterpret_cast<uint32_t*>(&v[u]);
+              const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sv[u]);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const int cc = ch * 8 + 2 * k;
+                const int cc = chn[u] * 8 + 2 * k;
                 float2 f = unpack_bf16x2(vw[k]);
                 if (x_act) {
                   f.x = fmaxf(fmaf(f.x, s_aff[cc], s_aff[p.Cin + cc]), 0.0f);
@@ -199,55 +231,81 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_c
                 vw[k] = pack_bf16x2(f.x, f.y);
               }
             }
+            *reinterpret_cast<uint4*>(sl + dst[u]) = v[u];
           }
-          const int pos = s * p.SUBP + r * p.PX + c;
-          *reinterpret_cast<uint4*>(sl + (size_t)ch * p.PS + (size_t)pos * 16) = v;
         }
         fence_proxy_async_smem();
         mbar_arrive(&bar_full[slot]);
       }
     } else if (warp == 4) {
       // ===================================== MMA issuer =====================================
-      if (lane == 0) {
+      // The whole warp walks the loop with uniform control flow (descriptor words come from the
+      // constant bank and loop counters, i.e. the uniform datapath); one elected lane issues.
+      if (elect_one()) {
         // weights: one bulk async copy (TMA engine) in <= 32 KB pieces
         mbar_arrive_expect_tx(bar_b, (uint32_t)p.b_bytes);
         for (int off = 0; off < p.b_bytes; off += 32768) {
           int n = min(32768, p.b_bytes - off);
           bulk_g2s(s_b + off, reinterpret_cast<const unsigned char*>(p.wpacked) + off, (uint32_t)n, bar_b);
         }
-        mbar_wait(bar_b, 0);
-        const uint32_t idesc = make_idesc_bf16_f32(128, CP);
-        const uint32_t sb_addr = smem_u32(s_b), slots_addr = smem_u32(s_slots);
-        const uint32_t b_lbo = (uint32_t)CP * 16u;
-        int waited = 0;
-        for (int t = 0; t < nsteps; ++t) {
-          const int seq_lo = p.zstep * t, seq_hi = seq_lo + p.span - 1;
-          while (waited <= seq_hi) {
-            mbar_wait(&bar_full[waited % p.R], (uint32_t)(waited / p.R) & 1u);
-            ++waited;
-          }
-          const int stage = t & 1;
-          mbar_wait(&bar_acc_empty[stage], ((uint32_t)(t >> 1) & 1u) ^ 1u);
-          tc_fence_after();
-          for (int b = 0; b < p.MB; ++b) {
-            const uint32_t d_col = tmem_base + (uint32_t)((stage * p.MB + b) * p.NB);
+      }
+      __syncwarp();
+      mbar_wait(bar_b, 0);
+      const uint32_t idesc = make_idesc_bf16_f32(128, CP);
+      const uint32_t slots16 = smem_u32(s_slots) >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
+      const uint32_t b16 = smem_u32(s_b) >> 4;
+      const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;   // version 1, SBO = 128 B
+      int waited = 0, wslot = 0;
+      uint32_t wphase = 0;
+      int slot_lo = 0;                                  // ring slot of plane seq_lo
+      for (int t = 0; t < nsteps; ++t) {
+        const int seq_lo = p.zstep * t, seq_hi = seq_lo + p.span - 1;
+        while (waited <= seq_hi) {
+          mbar_wait(&bar_full[wslot], wphase);
+          ++waited;
+          if (++wslot == p.R) { wslot = 0; wphase ^= 1u; }
+        }
+        const int stage = t & 1;
+        mbar_wait(&bar_acc_empty[stage], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        int s1 = slot_lo + 1; if (s1 >= p.R) s1 -= p.R;
+        int s2 = s1 + 1; if (s2 >= p.R) s2 -= p.R;
+        const uint32_t sl0 = slots16 + (uint32_t)slot_lo * slot16;
+        const uint32_t sl1 = slots16 + (uint32_t)s1 * slot16;
+        const uint32_t sl2 = slots16 + (uint32_t)s2 * slot16;
+        if (elect_one()) {
+          if (!(p.dbg & 2)) {
+            // op-major order: the descriptor words of an op are formed once and reused for all MB
+            // row blocks (start address + 2 KB, next TMEM column group)
+            const uint32_t d_base = tmem_base + (uint32_t)(stage * p.MB * p.NB);
+#pragma unroll 2
             for (int o = 0; o < p.nops; ++o) {
-              const UmmaOp op = p.ops[o];
-              const uint32_t a_off = (op.a & 0x3FFFu) << 4, a_lbo = ((op.a >> 14) & 0x3FFFu) << 4;
-              const int dz = (op.a >> 28) & 3;
-              const uint32_t first = (op.a >> 30) & 1u;
-              const int slot = (seq_lo + dz) % p.R;
-              const uint32_t a_addr = slots_addr + (uint32_t)slot * p.slot_bytes + a_off + (uint32_t)b * 2048u;
-              const uint64_t da = make_smem_desc(a_addr, a_lbo, 128u);
-              const uint64_t db = make_smem_desc(sb_addr + ((op.b & 0x3FFFu) << 4), b_lbo, 128u);
-              mma_bf16(d_col + ((op.b >> 14) & 0x3FFu), da, db, idesc, first ? 0u : 1u);
+              const UmmaOp e = p.ops[o];
+              const uint32_t dz = e.meta >> 20;
+              const uint32_t sl = dz == 0 ? sl0 : (dz == 1 ? sl1 : sl2);
+              uint32_t a_lo = e.a_lo + sl;
+              uint32_t d_col = d_base + (e.meta & 0xFFFFu);
+              const uint64_t db = desc_hi | (uint64_t)(e.b_lo + b16);
+              const uint32_t acc = ((e.meta >> 16) & 1u) ^ 1u;
+#pragma unroll 4
+              for (int b = 0; b < p.MB; ++b) {
+                mma_bf16(d_col, desc_hi | (uint64_t)a_lo, db, idesc, acc);
+                a_lo += 2048u >> 4;
+                d_col += (uint32_t)p.NB;
+              }
             }
           }
           mma_commit(&bar_acc_full[stage]);
           // planes no later step needs go back to the loaders
-          const int next_lo = p.zstep * (t + 1);
-          for (int s = seq_lo; s < min(next_lo, nplanes); ++s) mma_commit(&bar_empty[s % p.R]);
+          int rs = slot_lo;
+          for (int s = seq_lo; s < min(p.zstep * (t + 1), nplanes); ++s) {
+            mma_commit(&bar_empty[rs]);
+            if (++rs == p.R) rs = 0;
+          }
         }
+        __syncwarp();
+        slot_lo += p.zstep;
+        if (slot_lo >= p.R) slot_lo -= p.R;
       }
     } else {
       // ===================================== epilogue =====================================
@@ -263,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_c
         for (int b = 0; b < p.MB; ++b) {
           const int m = b * 128 + warp * 32 + lane;
           const int yy = m / p.PX, xx = m - yy * p.PX;
-          const bool valid = xx < TXe && yy < TYe;
+          const bool valid = xx < TXe && yy < TYe && !(p.dbg & 4);
           for (int cls = 0; cls < ncls; ++cls) {
             uint32_t r[CP];
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
@@ -341,6 +399,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const __grid_c
 // host-side planning
 // ---------------------------------------------------------------------------------------------
 namespace {
+
+constexpr size_t kSmemBudget = 225 * 1024;
 
 struct Plan {
   ConvParams cp;
@@ -428,8 +488,10 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   const int b_op_bytes = 2 * CP * 16;
   auto add_op = [&](int dz, uint32_t a_off, uint32_t a_lbo, int col, bool first, int tap0, int cb0, int tap1, int cb1) {
     UmmaOp& o = c.ops[nops];
-    o.a = (a_off >> 4) | ((a_lbo >> 4) << 14) | ((uint32_t)dz << 28) | ((first ? 1u : 0u) << 30);
-    o.b = (uint32_t)((nops * b_op_bytes) >> 4) | ((uint32_t)col << 14);
+    o.a_lo = (a_off >> 4) | ((a_lbo >> 4) << 16);
+    o.b_lo = (uint32_t)((nops * b_op_bytes) >> 4) | (((uint32_t)CP * 16u >> 4) << 16);
+    o.meta = (uint32_t)col | ((first ? 1u : 0u) << 16) | ((uint32_t)dz << 20);
+    o.pad = 0;
     pk.ops[nops].tap[0] = (int16_t)tap0; pk.ops[nops].cbase[0] = (int16_t)cb0;
     pk.ops[nops].tap[1] = (int16_t)tap1; pk.ops[nops].cbase[1] = (int16_t)cb1;
     ++nops;
@@ -469,12 +531,14 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   c.b_bytes = nops * b_op_bytes;
   pk.nops = nops; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
   pk.transposed = mode == MODE_DECONV;
-  pl->smem = (size_t)c.b_bytes + (size_t)c.R * c.slot_bytes + (size_t)4 * cin * sizeof(float) +
-             (2 * kMaxRing + 5) * sizeof(uint64_t) + 16;
+  const int ncells = c.nsub * c.RY * c.PX;
+  const size_t fixed = (size_t)c.b_bytes + (size_t)((ncells + 1) & ~1) * sizeof(int2) +
+                       (size_t)4 * cin * sizeof(float) + (2 * kMaxRing + 5) * sizeof(uint64_t) + 16;
+  // deepen the ring while shared memory allows: more planes in flight hide the L2 / HBM latency
+  while (c.R < kMaxRing && fixed + (size_t)(c.R + 1) * c.slot_bytes <= kSmemBudget) ++c.R;
+  pl->smem = fixed + (size_t)c.R * c.slot_bytes;
   return c.slot_bytes < (1 << 18) && (size_t)c.PS < (1u << 18);
 }
-
-constexpr size_t kSmemBudget = 225 * 1024;
 
 }  // namespace
 
@@ -554,6 +618,13 @@ int launch_conv3d_umma(const void* x, int x_dtype, const float* xs, const float*
     c.x = (const __nv_bfloat16*)x; c.skip = (const __nv_bfloat16*)skip;
     c.xs = xs; c.xb = xb; c.ss = ss; c.sb = sb;
     c.y = y; c.stats = stats; c.y_is_f32 = y_dtype == MVSB200_F32;
+    {
+      const char* dbg = getenv("MVSB200_UMMA_DBG");
+      c.dbg = dbg ? atoi(dbg) : 0;
+      if (getenv("MVSB200_UMMA_VERBOSE"))
+        fprintf(stderr, "[umma] mode=%d Cin=%d Cout=%d(+%d) tile %dx%d PX=%d MB=%d R=%d zsplit=%d grid=%d smem=%zu nops=%d\n", mode,
+                cin, cn, cb, c.TX, c.TY, c.PX, c.MB, c.R, c.zsplit, c.tiles_x * c.tiles_y * c.zsplit, best.smem, c.nops);
+    }
     unsigned char* wp = (unsigned char*)scratch + (size_t)(launch_idx & 1) * align_up((size_t)kMaxOps * 2 * 32 * 16, 256);
     c.wpacked = (const uint4*)wp;
     best.pp.kernel_tf = kernel_tf;

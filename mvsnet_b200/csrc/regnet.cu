@@ -243,6 +243,21 @@ void make_infer_plan(int n_views, int D, int hf, int wf, int C, int b, int preci
 }
 }  // namespace
 
+// optional stage-boundary events (bench.py measures the dominant kernel live with these)
+static thread_local cudaEvent_t t_stage_events[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static thread_local bool t_stage_events_on = false;
+
+extern "C" int mvsb200_infer_set_stage_events(void* const* events) {
+  t_stage_events_on = events != nullptr;
+  for (int i = 0; i < 5; ++i) t_stage_events[i] = events ? (cudaEvent_t)events[i] : nullptr;
+  return MVSB200_OK;
+}
+
+#define MVS_STAGE_EVENT(i)                                                        \
+  do {                                                                            \
+    if (t_stage_events_on && t_stage_events[i]) MVS_CUDA(cudaEventRecord(t_stage_events[i], s)); \
+  } while (0)
+
 extern "C" size_t mvsb200_infer_workspace_bytes(int n_views, int depth_num, int hf, int wf, int channels,
                                                 int base_filter, int precision) {
   if (n_views < 2 || depth_num <= 0 || hf <= 0 || wf <= 0 || channels <= 0 || base_filter <= 0) return 0;
@@ -275,17 +290,24 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   volatile float dm1 = (float)depth_num - 1.0f;
   volatile float prod = dm1 * depth_interval;
   volatile float depth_end = depth_start + prod;
+  MVS_STAGE_EVENT(0);
   rc = launch_homographies(cams, n_views, depth_num, depth_start, inverse_depth ? (float)depth_end : depth_interval,
                            inverse_depth, homs, nullptr, s);
   if (rc) return rc;
+  MVS_STAGE_EVENT(1);
   const int cost_dtype = precision == MVSB200_PRECISION_BF16 ? MVSB200_BF16 : MVSB200_F32;
   rc = launch_cost_volume(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cost_dtype, cost, 0, s);
   if (rc) return rc;
+  MVS_STAGE_EVENT(2);
   rc = regnet_forward_impl(cost, cost_dtype, params, depth_num, hf, wf, channels, base_filter, bn_eps, precision,
                            filtered, ws + ip.regnet_off, ip.regnet_bytes, s);
   if (rc) return rc;
-  return launch_depth_regress(filtered, depth_num, hf, wf, depth_start, depth_interval, inverse_depth, 4, depth_map,
-                              prob_map, nullptr, s);
+  MVS_STAGE_EVENT(3);
+  rc = launch_depth_regress(filtered, depth_num, hf, wf, depth_start, depth_interval, inverse_depth, 4, depth_map,
+                            prob_map, nullptr, s);
+  if (rc) return rc;
+  MVS_STAGE_EVENT(4);
+  return MVSB200_OK;
 }
 
 extern "C" size_t mvsb200_infer_host_staging_bytes(int n_views, int hf, int wf, int channels) {

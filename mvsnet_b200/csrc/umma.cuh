@@ -37,6 +37,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// true on exactly one lane of a converged warp (ptxas treats the guarded region as single-lane, so
+// uniform-register operands of tcgen05 instructions need no divergence handling)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -112,8 +124,9 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :
-      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
+  // no "memory" clobber: operand visibility is ordered by the mbarrier wait + tcgen05 fence that precede the
+  // issue loop and by the commit that follows it; volatile keeps the MMAs themselves in program order.
 }
 
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed

@@ -115,6 +115,16 @@ class HotPath:
         L.check(rc, "infer_host")
         return depth_out, prob_out
 
+    def set_stage_events(self, events) -> None:
+        """events: five torch.cuda.Event(enable_timing=True) (or None) recorded at the stage boundaries of infer()."""
+        if events is None:
+            L.check(self.lib.mvsb200_infer_set_stage_events(None), "set_stage_events")
+            return
+        for e in events:
+            e.record()            # torch creates the underlying cudaEvent lazily on first record
+        arr = (ctypes.c_void_p * 5)(*[e.cuda_event for e in events])
+        L.check(self.lib.mvsb200_infer_set_stage_events(arr), "set_stage_events")
+
     # -- stages (tests, profiling) ---------------------------------------------------------------------
     def regnet(self, cost: torch.Tensor) -> torch.Tensor:
         d, hf, wf, c = cost.shape

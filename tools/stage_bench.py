@@ -34,6 +34,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--regnet", default="", help="comma list of precisions to time the regularizer in")
+    ap.add_argument("--layers", action="store_true", help="time every regularizer layer alone (bf16)")
+    ap.add_argument("--skip-cv", action="store_true", help="skip the cost-volume variant sweep")
     ap.add_argument("--out", default="gpurun_out/stage_bench.json")
     a = ap.parse_args()
     cfg = synthetic.CONFIGS[a.config]
@@ -52,7 +54,7 @@ def main():
     V = D * hf * wf
     for dt, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
         out = torch.empty((D, hf, wf, 32), device="cuda", dtype=dt)
-        for variant in (1, 2, 3, 4, 5):
+        for variant in (() if a.skip_cv else (1, 2, 3, 4, 5)):
             med, mn = timeit(lambda: ops.cost_volume(feats, H, variant=variant, out=out), flush=flush)
             nbytes = n * hf * wf * 32 * 4 + V * 32 * out.element_size()
             res[f"cost_volume_{name}_v{variant}"] = dict(ms=med, min_ms=mn, gbs=nbytes / med / 1e6)
@@ -71,6 +73,28 @@ def main():
         med, mn = timeit(lambda: eng.infer(feats, camsd, ds, di), iters=3, warm=1)
         res[f"infer_{prec}"] = dict(ms=med, min_ms=mn)
         print("infer", prec, med, flush=True)
+    if a.layers:
+        # every RegNetUS0 layer alone at this config's shapes (bf16 / tcgen05)
+        ch = synthetic.regnet_channels(32, 8)
+        lv = {"3dconv1_0": 0, "3dconv2_0": 1, "3dconv3_0": 2, "3dconv0_1": 0, "3dconv1_1": 1, "3dconv2_1": 2,
+              "3dconv3_1": 3, "3dconv4_0": 3, "3dconv5_0": 2, "3dconv6_0": 1, "3dconv6_2": 0}
+        res["layers"] = {}
+        for name, (cin, cout, op, stride) in ch.items():
+            l = lv[name]
+            d, h, wd = D >> l, hf >> l, wf >> l
+            x = torch.randn((d, h, wd, cin), device="cuda").to(torch.bfloat16)
+            kern = torch.from_numpy(w[name + "/kernel"]).cuda()
+            aff = (torch.ones(cin, device="cuda"), torch.zeros(cin, device="cuda")) if name != "3dconv0_1" else None
+            skip = x if name in ("3dconv5_0", "3dconv6_0", "3dconv6_2") else None
+            od = torch.float32 if name == "3dconv6_2" else torch.bfloat16
+            fn = lambda: ops.conv3d_layer(x, kern, stride, op == "deconv", "bf16", x_affine=aff, skip=skip,
+                                          skip_affine=aff if skip is not None else None, out_dtype=od)
+            med, mn = timeit(fn, iters=5, warm=2, flush=flush)
+            vin, vout = d * h * wd, (d * h * wd * 8 if op == "deconv" else d * h * wd // (stride ** 3))
+            flop = 2.0 * 27 * cin * cout * (vin if op == "deconv" else vout)
+            nbytes = vin * cin * 2 * (2 if skip is not None else 1) + vout * cout * (4 if name == "3dconv6_2" else 2)
+            res["layers"][name] = dict(ms=med, min_ms=mn, tflops=flop / med / 1e9, gbs=nbytes / med / 1e6)
+            print(name, "%.3f ms  %.1f TFLOP/s  %.0f GB/s" % (med, flop / med / 1e9, nbytes / med / 1e6), flush=True)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(res, open(a.out, "w"), indent=1)
     print(json.dumps(res))

@@ -50,23 +50,26 @@ __device__ __forceinline__ void store_cost4(void* out, size_t elem, float4 c, bo
 
 // ------------------------------------------------------------------------------------------------
 // Fast path, C = 32: block = 32 reference pixels x 8 channel groups (float4), DC = 8 planes per
-// thread.  The 8 lanes of a pixel each compute the sample position of a different plane and
-// broadcast it with a shuffle, so the coordinate math (2 IEEE divisions) is done once per voxel
-// and view instead of once per channel group.  Taps are 128-bit loads through L1 (features are
-// L2-resident: 5 x 216 x 288 x 32 fp32 = 40 MB at config 2); consecutive planes move the footprint
-// by ~0.35 px, so with REUSE the four taps stay in registers until the 2x2 corner changes.
+// thread.  The 8 lanes of a pixel each build the complete bilinear footprint of a different plane
+// (sample position with 2 IEEE divisions, the four weights, the clamped tap coordinates) and
+// broadcast it with shuffles, so that work is done once per voxel and view instead of once per
+// channel group.  A tap outside the image gets weight 0 and a clamped (always mapped) address,
+// which is arithmetically identical to the reference's zero fill (0 * finite feature) and keeps
+// the loads unpredicated.  Taps are 128-bit loads through L1 (the features are L2-resident:
+// 5 x 216 x 288 x 32 fp32 = 40 MB at config 2); the running sum and squared sum of the 8 planes
+// stay in registers across views.
 // ------------------------------------------------------------------------------------------------
 constexpr int kDC = 8;
 constexpr int kMaxSrcViews = 7;
 
-template <bool BF16OUT, bool REUSE, int TX, int TY>
+template <bool BF16OUT, int TX, int TY>
 __global__ void __launch_bounds__(256, 2)
 cost_volume_c32_kernel(const float* __restrict__ feats, int n_views, int D, int Hf, int Wf, int order,
                        void* __restrict__ out) {
   static_assert(TX * TY == 32, "tile must hold 32 pixels");
   __shared__ float s_coef[kMaxSrcViews * kDC * 8];
   const int tid = threadIdx.x;
-  const int g = tid & 7;            // channel group (4 channels) and plane slot for coordinates
+  const int g = tid & 7;            // channel group (4 channels) and plane slot for the footprint
   const int p = tid >> 3;           // pixel within the tile
   const int x = blockIdx.x * TX + (p % TX);
   const int y = blockIdx.y * TY + (p / TX);
@@ -91,44 +94,54 @@ cost_volume_c32_kernel(const float* __restrict__ feats, int n_views, int D, int 
   const unsigned lane_base = (threadIdx.x & 31) & ~7u;
   for (int v = 0; v < n_src; ++v) {
     const float* img = feats + (size_t)(v + 1) * plane + g * 4;
-    float ix_l, iy_l;
-    transform_coords(&s_coef[(v * kDC + g) * 8], (float)xc, (float)yc, ix_l, iy_l);
-    float4 p00 = make_float4(0.f, 0.f, 0.f, 0.f), p01 = p00, p10 = p00, p11 = p00;
-    int px0 = -0x7fffffff, py0 = -0x7fffffff;
+    // this lane's plane: position, weights (0 where the tap is outside), clamped tap rows / columns
+    float ix, iy;
+    transform_coords(&s_coef[(v * kDC + g) * 8], (float)xc, (float)yc, ix, iy);
+    const Footprint f = make_footprint(ix, iy, Wf, Hf);
+    const float l_wxl = f.vx0 ? f.wxl : 0.0f, l_wxr = f.vx1 ? f.wxr : 0.0f;
+    const float l_wyl = f.vy0 ? f.wyl : 0.0f, l_wyr = f.vy1 ? f.wyr : 0.0f;
+    const int cx0 = min(max(f.x0, 0), Wf - 1), cx1 = min(max(f.x0 + 1, 0), Wf - 1);
+    const int cy0 = min(max(f.y0, 0), Hf - 1), cy1 = min(max(f.y0 + 1, 0), Hf - 1);
+    const int l_col = cx0 | (cx1 << 16), l_row = cy0 | (cy1 << 16);
 #pragma unroll
     for (int dd = 0; dd < kDC; ++dd) {
-      float ix = __shfl_sync(0xffffffffu, ix_l, lane_base | dd);
-      float iy = __shfl_sync(0xffffffffu, iy_l, lane_base | dd);
-      Footprint f = make_footprint(ix, iy, Wf, Hf);
-      if (!REUSE || f.x0 != px0 || f.y0 != py0) {
-        const float* base = img + ((int64_t)f.y0 * Wf + f.x0) * 32;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        p00 = (f.vy0 && f.vx0) ? ldg4(base) : z;
-        p01 = (f.vy0 && f.vx1) ? ldg4(base + 32) : z;
-        p10 = (f.vy1 && f.vx0) ? ldg4(base + (int64_t)Wf * 32) : z;
-        p11 = (f.vy1 && f.vx1) ? ldg4(base + (int64_t)Wf * 32 + 32) : z;
-        px0 = f.x0; py0 = f.y0;
-      }
+      const unsigned src = lane_base | dd;
+      const float wxl = __shfl_sync(0xffffffffu, l_wxl, src), wxr = __shfl_sync(0xffffffffu, l_wxr, src);
+      const float wyl = __shfl_sync(0xffffffffu, l_wyl, src), wyr = __shfl_sync(0xffffffffu, l_wyr, src);
+      const int col = __shfl_sync(0xffffffffu, l_col, src), row = __shfl_sync(0xffffffffu, l_row, src);
+      const int x0 = col & 0xffff, x1 = col >> 16;
+      const int r0 = (row & 0xffff) * Wf, r1 = (row >> 16) * Wf;
+      const float4 p00 = ldg4(img + (size_t)(r0 + x0) * 32), p01 = ldg4(img + (size_t)(r0 + x1) * 32);
+      const float4 p10 = ldg4(img + (size_t)(r1 + x0) * 32), p11 = ldg4(img + (size_t)(r1 + x1) * 32);
       float4 w;
-      w.x = f.wyl * (f.wxl * p00.x + f.wxr * p01.x) + f.wyr * (f.wxl * p10.x + f.wxr * p11.x);
-      w.y = f.wyl * (f.wxl * p00.y + f.wxr * p01.y) + f.wyr * (f.wxl * p10.y + f.wxr * p11.y);
-      w.z = f.wyl * (f.wxl * p00.z + f.wxr * p01.z) + f.wyr * (f.wxl * p10.z + f.wxr * p11.z);
-      w.w = f.wyl * (f.wxl * p00.w + f.wxr * p01.w) + f.wyr * (f.wxl * p10.w + f.wxr * p11.w);
+      w.x = wyl * (wxl * p00.x + wxr * p01.x) + wyr * (wxl * p10.x + wxr * p11.x);
+      w.y = wyl * (wxl * p00.y + wxr * p01.y) + wyr * (wxl * p10.y + wxr * p11.y);
+      w.z = wyl * (wxl * p00.z + wxr * p01.z) + wyr * (wxl * p10.z + wxr * p11.z);
+      w.w = wyl * (wxl * p00.w + wxr * p01.w) + wyr * (wxl * p10.w + wxr * p11.w);
       S[dd].x += w.x; S[dd].y += w.y; S[dd].z += w.z; S[dd].w += w.w;
       Q[dd].x += w.x * w.x; Q[dd].y += w.y * w.y; Q[dd].z += w.z * w.z; Q[dd].w += w.w * w.w;
     }
   }
   if (!active) return;
-  const float n_f = (float)n_views, nn_f = (float)(n_views * n_views);
+  // variance with reciprocal multiplies (<= 1 ulp from the reference's divisions, model.py:458-461 / :330-332)
+  const float inv_n = 1.0f / (float)n_views, inv_nn = 1.0f / (float)(n_views * n_views);
 #pragma unroll
   for (int dd = 0; dd < kDC; ++dd) {
     const int d = d0 + dd;
     if (d < D) {
       float4 c;
-      c.x = variance(S[dd].x, Q[dd].x, n_f, nn_f, order);
-      c.y = variance(S[dd].y, Q[dd].y, n_f, nn_f, order);
-      c.z = variance(S[dd].z, Q[dd].z, n_f, nn_f, order);
-      c.w = variance(S[dd].w, Q[dd].w, n_f, nn_f, order);
+      if (order == MVSB200_ORDER_MEM) {
+        c.x = Q[dd].x * inv_n - (S[dd].x * S[dd].x) * inv_nn;
+        c.y = Q[dd].y * inv_n - (S[dd].y * S[dd].y) * inv_nn;
+        c.z = Q[dd].z * inv_n - (S[dd].z * S[dd].z) * inv_nn;
+        c.w = Q[dd].w * inv_n - (S[dd].w * S[dd].w) * inv_nn;
+      } else {
+        const float mx = S[dd].x * inv_n, my = S[dd].y * inv_n, mz = S[dd].z * inv_n, mw = S[dd].w * inv_n;
+        c.x = Q[dd].x * inv_n - mx * mx;
+        c.y = Q[dd].y * inv_n - my * my;
+        c.z = Q[dd].z * inv_n - mz * mz;
+        c.w = Q[dd].w * inv_n - mw * mw;
+      }
       store_cost4(out, (((size_t)d * Hf + y) * Wf + x) * 32 + g * 4, c, BF16OUT);
     }
   }
@@ -232,10 +245,11 @@ int launch_cost_volume(const float* feats, const float* homographies, int n_view
     prepare_table_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(homographies, rows);
     MVS_LAUNCH_CHECK("prepare_table_kernel");
   }
-  // variant: 0 auto, 1 generic, 2 c32 (always reload taps), 3 c32 with tap reuse, 4/5 = 2/3 with a 16x2 tile
-  bool fast_ok = sampler == MVSB200_SAMPLER_TRANSFORM && channels == 32 && n_views - 1 <= kMaxSrcViews;
+  // variant: 0 auto, 1 generic, 2 fast path with a 32x1 pixel tile, 3 fast path with a 16x2 tile
+  bool fast_ok = sampler == MVSB200_SAMPLER_TRANSFORM && channels == 32 && n_views - 1 <= kMaxSrcViews &&
+                 hf < 65536 && wf < 32768;
   if (variant == 0) variant = fast_ok ? 3 : 1;
-  MVS_CHECK_ARG(variant >= 1 && variant <= 5, "cost_volume: bad variant %d", variant);
+  MVS_CHECK_ARG(variant >= 1 && variant <= 3, "cost_volume: bad variant %d", variant);
   if (variant >= 2 && !fast_ok) {
     set_error("cost_volume: variant %d needs sampler=transform, C=32, n_views<=8", variant);
     return MVSB200_ERR_UNSUPPORTED;
@@ -245,20 +259,14 @@ int launch_cost_volume(const float* feats, const float* homographies, int n_view
     MVS_CUDA(cudaGetSymbolAddress(&g_ptr, g_table));
     MVS_CUDA(cudaMemcpyToSymbolAsync(c_table, g_ptr, (size_t)rows * 8 * sizeof(float), 0,
                                      cudaMemcpyDeviceToDevice, s));
-    const bool wide = variant <= 3;
+    const bool wide = variant == 2;
     const int tx = wide ? 32 : 16, ty = wide ? 1 : 2;
     dim3 grid(ceil_div(wf, tx), ceil_div(hf, ty), ceil_div(depth_num, kDC));
     MVS_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "cost_volume: grid too large");
-#define CV_FAST(BF, RE, TX_, TY_) \
-  cost_volume_c32_kernel<BF, RE, TX_, TY_><<<grid, 256, 0, s>>>(feats, n_views, depth_num, hf, wf, order, out)
-    const bool reuse = (variant == 3 || variant == 5);
-    if (wide) {
-      if (bf16) { if (reuse) CV_FAST(true, true, 32, 1); else CV_FAST(true, false, 32, 1); }
-      else      { if (reuse) CV_FAST(false, true, 32, 1); else CV_FAST(false, false, 32, 1); }
-    } else {
-      if (bf16) { if (reuse) CV_FAST(true, true, 16, 2); else CV_FAST(true, false, 16, 2); }
-      else      { if (reuse) CV_FAST(false, true, 16, 2); else CV_FAST(false, false, 16, 2); }
-    }
+#define CV_FAST(BF, TX_, TY_) \
+  cost_volume_c32_kernel<BF, TX_, TY_><<<grid, 256, 0, s>>>(feats, n_views, depth_num, hf, wf, order, out)
+    if (wide) { if (bf16) CV_FAST(true, 32, 1); else CV_FAST(false, 32, 1); }
+    else      { if (bf16) CV_FAST(true, 16, 2); else CV_FAST(false, 16, 2); }
 #undef CV_FAST
     MVS_LAUNCH_CHECK("cost_volume_c32_kernel");
     return MVSB200_OK;

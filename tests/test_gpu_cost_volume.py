@@ -26,7 +26,7 @@ def _homs(O, p, D=None):
                                         p["depth_interval"])[0] for v in range(1, p["cams"].shape[0])])
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("order", ["mem", "train"])
 def test_cost_volume_variants_vs_oracle(ops, O, small_problem, variant, order):
     p = small_problem
@@ -44,7 +44,7 @@ def test_cost_volume_golden(ops, golden_tiny):
         assert np.abs(out[::2, ::2, ::2, :] - g[key]).max() <= 2e-5
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_ragged_extents(ops, O, small_problem, variant):
     """Wf not a multiple of the tile, Hf odd, D not a multiple of the 8-plane chunk."""
     p = small_problem
@@ -63,7 +63,7 @@ def test_bf16_output_is_rounded_fp32(ops, O, small_problem):
     p = small_problem
     H = to_dev(_homs(O, p))
     f = to_dev(p["feats"])
-    for variant in (1, 3):
+    for variant in (1, 2):
         a = ops.cost_volume(f, H, out_dtype=torch.float32, variant=variant)
         b = ops.cost_volume(f, H, out_dtype=torch.bfloat16, variant=variant)
         assert b.dtype == torch.bfloat16 and torch.equal(b, a.to(torch.bfloat16))
@@ -86,7 +86,7 @@ def test_eight_views_and_iid_features(ops, O):
     feats = synthetic.make_features(cams, 24, 32, 32, iid=True)
     H = np.stack([O.get_homographies(cams[0:1], cams[v:v + 1], 16, 425.0, 20.0)[0] for v in range(1, 8)])
     ref = O.cost_volume(feats, H)
-    for variant in (1, 3):
+    for variant in (1, 2):
         out = ops.cost_volume(to_dev(feats), to_dev(H), variant=variant).cpu().numpy()
         assert np.abs(out - ref).max() <= 5e-5
 
@@ -100,14 +100,14 @@ def test_full_size_properties(ops):
     g = torch.Generator(device="cuda").manual_seed(0)
     feats = torch.randn((5, hf, wf, 32), device="cuda", generator=g)
     H = ops.homographies(to_dev(cams), 192, 425.0, 2.65)
-    a = ops.cost_volume(feats, H, variant=3)
-    b = ops.cost_volume(feats, H, variant=2)
+    a = ops.cost_volume(feats, H, variant=2)
+    b = ops.cost_volume(feats, H, variant=3)
     c = ops.cost_volume(feats, H, variant=1)
     assert (a - b).abs().max().item() <= 1e-5 and (a - c).abs().max().item() <= 1e-5
     assert torch.isfinite(a).all()
     eye = torch.eye(3, device="cuda").expand(4, 192, 3, 3).contiguous()
     same = feats[0:1].expand(5, hf, wf, 32).contiguous()
-    z = ops.cost_volume(same, eye, variant=3)
+    z = ops.cost_volume(same, eye, variant=2)
     assert z.abs().max().item() <= 1e-5
     assert (z >= -1e-5).all()
 

@@ -183,3 +183,26 @@ def test_golden_fixture_matches_oracle(golden_tiny):
     depth, prob, _ = O.depth_regress(g["filtered"], ds, di)
     np.testing.assert_array_equal(depth, g["depth"])
     np.testing.assert_array_equal(prob, g["prob"])
+
+
+def test_c_restatement_matches_numpy_oracle(golden_tiny):
+    """oracle/mvs_oracle.c (independent plain-C restatement) against the NumPy oracle and the golden fixture."""
+    from oracle import c_oracle as C
+    g = golden_tiny
+    D, ds, di = int(g["depth_num"]), float(g["depth_start"]), float(g["depth_interval"])
+    H = C.homographies(g["cams"], D, ds, di)
+    np.testing.assert_array_equal(H, g["homographies"])
+    np.testing.assert_array_equal(C.transform_coefs(H).reshape(2, D, 8), g["transforms"])
+    de = F32(ds) + F32(D - 1) * F32(di)
+    np.testing.assert_array_equal(C.homographies(g["cams"], D, ds, float(de), inverse=True), g["homographies_inv"])
+    w, coords = C.transform_warp(g["feats"][1], g["transforms"][0, 5])
+    np.testing.assert_array_equal(w, g["warped_v0_d5"])
+    _, c0 = C.transform_warp(g["feats"][1], g["transforms"][0, 0])
+    np.testing.assert_array_equal(c0, g["coords"][0])
+    cost = C.cost_volume(g["feats"], H, "mem")
+    np.testing.assert_array_equal(cost[::2, ::2, ::2, :], g["cost_mem_sub"])
+    cost_t = C.cost_volume(g["feats"], H, "train")
+    np.testing.assert_array_equal(cost_t[::2, ::2, ::2, :], g["cost_train_sub"])
+    depth, prob, P = C.depth_regress(g["filtered"], ds, di)
+    np.testing.assert_allclose(depth, g["depth"], rtol=2e-6)               # libm expf vs numpy exp
+    assert np.mean(np.abs(prob - g["prob"]) <= 1e-5) >= 0.999

@@ -61,6 +61,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// 5-D tiled tensor-map load (TMA): box -> shared memory, completion on an mbarrier.  Coordinates are
+// signed; elements outside the tensor are zero-filled by the TMA unit.
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------- TMEM
 // Allocate `cols` (power of two >= 32) TMEM columns; the base address is written to *smem_dst.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {

@@ -1,0 +1,1040 @@
+// Kernel 3: regularizer layers as bf16 implicit GEMM on the 5th-gen tensor cores (tcgen05 + TMEM),
+// fed by the TMA unit.
+//
+// Activation layouts in HBM (bf16, written by the producer's epilogue, read by TMA boxes):
+//   CP8  "chunk planar"   [D][C/8][H][W][8]          input of stride-1 convs and transposed convs
+//   PS8  "parity split"   [D][C/8][4][Hs][Ws][8]     input of stride-2 convs; sub-plane q = (y&1)*2+(x&1)
+//                                                    holds voxel (2*ys+(q>>1), 2*xs+(q&1)), Hs=ceil(H/2)
+// In both a (z, chunk[, parity]) plane is a dense 2-D array of 16-byte cells, so one TMA box of
+// PX x RY cells lands in shared memory exactly as the "cell plane" the MMA descriptors want, halo
+// cells outside the volume zero-filled by the TMA unit (= SAME padding).
+//
+// One persistent CTA owns an (y, x) tile of the GEMM-row space and marches along z.  Input planes
+// live in a shared-memory ring, per 8-channel chunk a dense array of 16-byte cells, one per position
+// of the haloed tile.  In that layout the 128 x 16 A operand of ANY filter tap is a plain no-swizzle
+// K-major UMMA descriptor over the same bytes (start = cell of the tap-shifted first row, SBO = 128 B,
+// LBO = chunk plane stride): im2col is never built, each input voxel is staged once per (tile, z).
+// GEMM rows run over the linearised padded tile (row pitch PX); rows in the halo columns are dropped.
+//
+//   warps 0-3   epilogue: tcgen05.ld accumulators -> bf16/fp32 stores + per-channel batch statistics
+//   warp  4     TMEM allocation; one thread issues every tcgen05.mma and the commits
+//   warp  5     producer: one thread issues the TMA box loads (input planes, skip planes, weights)
+//   warps 6-13  transform (layers whose input needs it): relu(x*scale+shift) [+ relu(skip*..+..)]
+//               applied IN PLACE on the landed plane, halo cells left at zero
+//
+// Layer kinds (all "tap GEMMs" over such planes):
+//   conv s=1 (network.py:210)   taps (kh,kw) of plane dz, cell offset kh*PX+kw
+//   conv s=2 (TF SAME)          PS8 input: the 4 parity sub-arrays make stride-2 rows dense
+//   deconv s=2 (network.py:327) 8 output-parity classes, each with its 1/2/4/8 taps, own TMEM columns
+// z-fold (stride-1 convs): zf consecutive output planes share one step, their channels side by side
+// in the MMA N dimension (N = zf*Cout): an input plane is read from shared memory once for all the
+// output planes it feeds.  Measured on B200: a 128xNx16 MMA from shared memory costs
+// max(32 + N/4, N/2) cycles (operand reads at 128 B/clk), so small-N GEMMs are bound by the A reads
+// and the fold is free.  The B images of the zf+2 input planes are shifted windows of one master
+// image per (kh, kw, 16-channel pair): rows [g*Cout, (g+1)*Cout) hold W[kd = zf+1-g] (zero outside
+// the filter), plane dz starts at g = zf+1-dz.
+#include "common.cuh"
+#include "umma.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+#include <array>
+#include <map>
+#include <mutex>
+
+namespace mvsb200 {
+using namespace umma;
+
+namespace tc {
+
+constexpr int kMaxOps = 108;            // 27 taps x (64 channels / 16)
+constexpr int kEpiWarps = 4, kXfWarps = 8;
+constexpr int kXfThreads = kXfWarps * 32;
+constexpr int kThreads = (kEpiWarps + 2 + kXfWarps) * 32;
+constexpr int kMaxRing = 12, kSkipRing = 3, kMaxSpan = 6, kMaxMB = 4, kMaxK = 12;
+
+enum { MODE_CONV1 = 0, MODE_CONV2 = 1, MODE_DECONV = 2 };
+
+// Descriptor words of one MMA, relative to the slot / B image:
+struct UmmaOp {
+  uint32_t a_lo;   // [0,14) a_off>>4 | [16,30) a_lbo>>4
+  uint32_t b_lo;   // [0,14) b_off>>4 | [16,30) b_lbo>>4
+  uint32_t meta;   // [0,16) tmem column offset in the block | [16] first (overwrite) | [20,24) dz
+  uint32_t pad;
+};
+
+struct Params {
+  alignas(64) CUtensorMap tmap_x;   // input planes
+  alignas(64) CUtensorMap tmap_s;   // skip planes (has_skip)
+  const float *xs, *xb, *ss, *sb;
+  const uint4* wpacked;
+  __nv_bfloat16* y_cp8; __nv_bfloat16* y_ps8; float* y_f32; double* stats;
+  int mode, has_skip, transform;
+  int D, H, W, Cin;              // input volume
+  int Do, Ho, Wo, Cout;          // output volume (all channels)
+  int Hso, Wso;                  // PS8 output sub-plane extents
+  int cout_base, cout_n;         // channel slice handled by this launch
+  int Mz, My, Mx;                // GEMM-row space (output voxels; input voxels for deconv)
+  int TX, TY, tiles_x, tiles_y, zsplit;
+  int PX, RY, nsub, SUBP;        // slot geometry: nsub sub-arrays of RY x PX cells, SUBP cells apart
+  int vstep, cx_off, cy_off;     // cell (sub, r, c) = voxel (vstep*(y0+r+cy_off)+(sub>>1), vstep*(x0+c+cx_off)+(sub&1))
+  int zmul, zoff, zstep, span;   // plane seq of a segment = input z (zmul*zb + zoff + seq); zstep planes per step
+  int NCH, PS, slot_bytes, R;
+  int MB, NB, CP;                // row blocks per step, TMEM columns per block, MMA N
+  int nops, b_bytes, tmem_cols;
+  int zf, cn_shift;              // output planes per step; log2(cout_n) when zf > 1
+  int xf_k;                      // cells per transform thread and plane
+  int dz_begin[kMaxSpan + 1];    // ops [dz_begin[d], dz_begin[d+1]) read input plane d of the step
+  int dbg;                       // development switches (env MVSB200_TC_DBG): 1 no loads, 2 no MMA, 4 no stores
+  long long* prof;               // development: per-role cycle counters of CTA 0 (env MVSB200_TC_PROF)
+  UmmaOp ops[kMaxOps];
+};
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: TF fp32 kernel -> bf16 B images
+// ---------------------------------------------------------------------------------------------
+struct PackOp { int16_t tap[2]; int16_t cbase[2]; };
+struct PackParams {
+  const float* kernel_tf; uint16_t* out;
+  int Cin, Cout, cout_base, cout_n, CP, transposed, nops, zf, master;
+  PackOp ops[kMaxOps];   // per-op images: tap = kd*9+kh*3+kw per K half (-1 = zero half);
+                         // master images: tap = kh*3+kw (kd comes from the row group), one per (kh,kw,pair)
+};
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
+  if (!p.master) {
+    const int total = p.nops * 2 * p.CP * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int k8 = i & 7, n = (i >> 3) % p.CP, half = (i / (8 * p.CP)) & 1, op = i / (16 * p.CP);
+      // column group j = output plane j of the step (z-fold): its filter plane is kd = dz - j
+      const int j = n / p.cout_n, cn = n - j * p.cout_n;
+      int tap = p.ops[op].tap[half];
+      const int ci = p.ops[op].cbase[half] + k8;
+      if (tap >= 0) tap -= 9 * j;
+      float w = 0.0f;
+      if (tap >= 0 && tap < 27 && j < p.zf && ci < p.Cin) {
+        const int co = p.cout_base + cn;
+        w = p.transposed ? p.kernel_tf[((size_t)tap * p.Cout + co) * p.Cin + ci]
+                         : p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + co];
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+  } else {
+    // image m = [2 halves][(2*zf+1) groups][cout_n rows][8]; group g holds W[kd = zf+1-g]
+    const int groups = 2 * p.zf + 1, rows = groups * p.cout_n;
+    const int total = p.nops * 2 * rows * 8;      // nops = number of master images here
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int k8 = i & 7, row = (i >> 3) % rows, half = (i / (8 * rows)) & 1, m = i / (16 * rows);
+      const int g = row / p.cout_n, cn = row - g * p.cout_n, kd = p.zf + 1 - g;
+      const int ci = p.ops[m].cbase[half] + k8;
+      float w = 0.0f;
+      if (kd >= 0 && kd < 3 && ci < p.Cin) {
+        const int tap = kd * 9 + p.ops[m].tap[0];
+        w = p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + p.cout_base + cn];
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(h);
+}
+
+// Issue the MMAs of ops [ob, oe) of one input plane: one 16-byte shared-memory record per op (the unrolled loop
+// prefetches them), the MB row blocks of an op reuse its descriptors (A start + 2 KB, next TMEM column group).
+template <int MB>
+__device__ __forceinline__ void issue_ops(const uint4* s_ops, int ob, int oe, uint32_t sl, uint32_t d_base, uint32_t nb,
+                                          uint64_t desc_hi, uint32_t idesc) {
+#pragma unroll(MB == 1 ? 6 : (MB == 2 ? 3 : 2))
+  for (int o = ob; o < oe; ++o) {
+    const uint4 e = s_ops[o];
+    const uint32_t a_lo = e.x + sl, d_col = d_base + e.z;
+    const uint64_t db = desc_hi | (uint64_t)e.y;
+#pragma unroll
+    for (int b = 0; b < MB; ++b)
+      mma_bf16(d_col + (uint32_t)b * nb, desc_hi | (uint64_t)(a_lo + (uint32_t)b * (2048u >> 4)), db, idesc, e.w);
+  }
+}
+
+template <int CP>
+__global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [B image][R slots][skip slots][op table][plane op ranges][barriers][tmem ptr]
+  unsigned char* s_b = smem;
+  unsigned char* s_slots = smem + p.b_bytes;
+  unsigned char* s_skip = s_slots + (size_t)p.R * p.slot_bytes;
+  uint4* s_ops = reinterpret_cast<uint4*>(s_skip + (p.has_skip ? (size_t)kSkipRing * p.slot_bytes : 0));
+  int* s_dzb = reinterpret_cast<int*>(s_ops + kMaxOps);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dzb + 8);
+  uint64_t* bar_land = bars;                        // [R]  TMA -> transform / MMA
+  uint64_t* bar_ready = bars + kMaxRing;            // [R]  transform -> MMA
+  uint64_t* bar_empty = bars + 2 * kMaxRing;        // [R]  MMA (commit) -> producer
+  uint64_t* bar_sland = bars + 3 * kMaxRing;        // [kSkipRing] TMA -> transform
+  uint64_t* bar_sempty = bar_sland + kSkipRing;     // [kSkipRing] transform -> producer
+  uint64_t* bar_acc_full = bar_sempty + kSkipRing;  // [2]  MMA (commit) -> epilogue
+  uint64_t* bar_acc_empty = bar_acc_full + 2;       // [2]  epilogue -> MMA
+  uint64_t* bar_b = bar_acc_empty + 2;              // [1]  weights landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_b + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bid = blockIdx.x;
+  const int tx = bid % p.tiles_x; bid /= p.tiles_x;
+  const int ty = bid % p.tiles_y; bid /= p.tiles_y;
+  const int zs = bid;
+  const int x0 = tx * p.TX, y0 = ty * p.TY;
+  // z segments in units of steps so that only the last segment can end on a partial step
+  const int steps_all = (p.Mz + p.zf - 1) / p.zf;
+  const int sseg = (steps_all + p.zsplit - 1) / p.zsplit;
+  const int zb = zs * sseg * p.zf, ze = min(p.Mz, zb + sseg * p.zf);
+  const int nsteps = ze > zb ? (ze - zb + p.zf - 1) / p.zf : 0;
+  const int TXe = min(p.TX, p.Mx - x0), TYe = min(p.TY, p.My - y0);
+  const int nplanes = nsteps > 0 ? p.zstep * (nsteps - 1) + p.span : 0;
+
+  {
+    const uint32_t b16 = smem_u32(s_b) >> 4;
+    for (int i = threadIdx.x; i < p.nops; i += blockDim.x) {
+      const UmmaOp e = p.ops[i];
+      s_ops[i] = make_uint4(e.a_lo, e.b_lo + b16, e.meta & 0xFFFFu, ((e.meta >> 16) & 1u) ^ 1u);
+    }
+    if (threadIdx.x <= kMaxSpan) s_dzb[threadIdx.x] = p.dz_begin[threadIdx.x];
+  }
+  // Every cell of the ring starts finite: halo rows of the GEMM read a few cells past the landed boxes
+  // (their results are dropped, but 0 * NaN from stale shared memory must not reach a zero-weighted
+  // K half of a valid row).
+  for (int i = threadIdx.x; i < p.R * p.slot_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.R; ++i) { mbar_init(&bar_land[i], 1); mbar_init(&bar_ready[i], kXfThreads); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < kSkipRing; ++i) { mbar_init(&bar_sland[i], 1); mbar_init(&bar_sempty[i], kXfThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kEpiWarps); }
+    mbar_init(bar_b, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (nsteps > 0) {
+    if (warp == 5) {
+      // ===================================== producer =====================================
+      if (elect_one()) {
+        // weights: bulk async copies in <= 32 KB pieces
+        mbar_arrive_expect_tx(bar_b, (uint32_t)p.b_bytes);
+        for (int off = 0; off < p.b_bytes; off += 32768)
+          bulk_g2s(s_b + off, reinterpret_cast<const unsigned char*>(p.wpacked) + off,
+                   (uint32_t)min(32768, p.b_bytes - off), bar_b);
+        const uint32_t plane_bytes = (uint32_t)(p.nsub * p.NCH * p.RY * p.PX * 16);
+        const int cx = (x0 + p.cx_off) * 8, cy = y0 + p.cy_off;
+        for (int seq = 0; seq < nplanes; ++seq) {
+          const int slot = seq % p.R;
+          if (seq >= p.R) mbar_wait(&bar_empty[slot], (uint32_t)((seq / p.R) - 1) & 1u);
+          const int iz = p.zmul * zb + p.zoff + seq;
+          unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
+          if (!(p.dbg & 1)) {
+            mbar_arrive_expect_tx(&bar_land[slot], plane_bytes);
+            for (int sub = 0; sub < p.nsub; ++sub)
+              for (int ch = 0; ch < p.NCH; ++ch)
+                tma_load_5d(sl + (size_t)ch * p.PS + (size_t)sub * p.SUBP * 16, &p.tmap_x, cx, cy, sub, ch, iz,
+                            &bar_land[slot]);
+          } else {
+            mbar_arrive(&bar_land[slot]);
+          }
+          if (p.has_skip) {
+            const int ss = seq % kSkipRing;
+            if (seq >= kSkipRing) mbar_wait(&bar_sempty[ss], (uint32_t)((seq / kSkipRing) - 1) & 1u);
+            unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
+            if (!(p.dbg & 1)) {
+              mbar_arrive_expect_tx(&bar_sland[ss], plane_bytes);
+              for (int ch = 0; ch < p.NCH; ++ch)
+                tma_load_5d(sk + (size_t)ch * p.PS, &p.tmap_s, cx, cy, 0, ch, iz, &bar_sland[ss]);
+            } else {
+              mbar_arrive(&bar_sland[ss]);
+            }
+          }
+        }
+      }
+    } else if (warp >= 6) {
+      // ===================================== transform =====================================
+      if (p.transform) {
+        const int xt = threadIdx.x - 6 * 32;
+        const int tpc = kXfThreads / p.NCH;           // threads per channel chunk (chunk is warp-uniform)
+        const int ch = xt / tpc, ti = xt - ch * tpc;
+        const int npos = p.nsub * p.RY * p.PX;
+        // loop-invariant cell list of this thread: byte offset in the slot, -1 = outside the volume / none
+        int off[kMaxK];
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) {
+          const int q = ti + k * tpc;
+          off[k] = -1;
+          if (k < p.xf_k && q < npos) {
+            const int c = q % p.PX;
+            const int rest = q / p.PX;
+            const int r = rest % p.RY, sub = rest / p.RY;
+            const int ix = p.vstep * (x0 + c + p.cx_off) + (sub & 1);
+            const int iy = p.vstep * (y0 + r + p.cy_off) + (sub >> 1);
+            if (ix >= 0 && ix < p.W && iy >= 0 && iy < p.H) off[k] = ch * p.PS + (sub * p.SUBP + r * p.PX + c) * 16;
+          }
+        }
+        float xsc[8], xsh[8], ssc[8], ssh[8];
+        const bool x_act = p.xs != nullptr, s_act = p.ss != nullptr;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          xsc[k] = x_act ? p.xs[ch * 8 + k] : 1.0f; xsh[k] = x_act ? p.xb[ch * 8 + k] : 0.0f;
+          ssc[k] = s_act ? p.ss[ch * 8 + k] : 1.0f; ssh[k] = s_act ? p.sb[ch * 8 + k] : 0.0f;
+        }
+        for (int seq = 0; seq < nplanes; ++seq) {
+          const int slot = seq % p.R, ss = seq % kSkipRing;
+          mbar_wait(&bar_land[slot], (uint32_t)(seq / p.R) & 1u);
+          if (p.has_skip) mbar_wait(&bar_sland[ss], (uint32_t)(seq / kSkipRing) & 1u);
+          const int iz = p.zmul * zb + p.zoff + seq;
+          if (iz >= 0 && iz < p.D) {
+            unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
+            const unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) {
+              if (off[k] < 0) continue;
+              uint4 v = *reinterpret_cast<const uint4*>(sl + off[k]);
+              uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+              if (p.has_skip) {
+                const uint4 s4 = *reinterpret_cast<const uint4*>(sk + off[k]);
+                const uint32_t* sw = reinterpret_cast<const uint32_t*>(&s4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 f = unpack_bf16x2(vw[j]), g = unpack_bf16x2(sw[j]);
+                  if (x_act) {
+                    f.x = fmaxf(fmaf(f.x, xsc[2 * j], xsh[2 * j]), 0.0f);
+                    f.y = fmaxf(fmaf(f.y, xsc[2 * j + 1], xsh[2 * j + 1]), 0.0f);
+                  }
+                  if (s_act) {
+                    g.x = fmaxf(fmaf(g.x, ssc[2 * j], ssh[2 * j]), 0.0f);
+                    g.y = fmaxf(fmaf(g.y, ssc[2 * j + 1], ssh[2 * j + 1]), 0.0f);
+                  }
+                  vw[j] = pack_bf16x2(f.x + g.x, f.y + g.y);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 f = unpack_bf16x2(vw[j]);
+                  f.x = fmaxf(fmaf(f.x, xsc[2 * j], xsh[2 * j]), 0.0f);
+                  f.y = fmaxf(fmaf(f.y, xsc[2 * j + 1], xsh[2 * j + 1]), 0.0f);
+                  vw[j] = pack_bf16x2(f.x, f.y);
+                }
+              }
+              *reinterpret_cast<uint4*>(sl + off[k]) = v;
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&bar_ready[slot]);
+          if (p.has_skip) mbar_arrive(&bar_sempty[ss]);
+        }
+      }
+    } else if (warp == 4) {
+      // ===================================== MMA issuer =====================================
+      mbar_wait(bar_b, 0);
+      const uint32_t idesc = make_idesc_bf16_f32(128, CP);
+      const uint32_t slots16 = smem_u32(s_slots) >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
+      const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;   // version 1, SBO = 128 B
+      uint64_t* bar_in = p.transform ? bar_ready : bar_land;
+      int waited = 0, wslot = 0;
+      uint32_t wphase = 0;
+      int slot_lo = 0;                                  // ring slot of the first plane of the step
+      long long pr_t0 = 0, pr_in = 0, pr_acc = 0, pr_issue = 0, pr_g0 = 0;
+      if (p.prof) { pr_t0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_g0)); }
+      for (int t = 0; t < nsteps; ++t) {
+        const int seq_lo = p.zstep * t, seq_hi = seq_lo + p.span - 1;
+        long long pr_a = 0;
+        if (p.prof) pr_a = clock64();
+        while (waited <= seq_hi) {
+          mbar_wait(&bar_in[wslot], wphase);
+          ++waited;
+          if (++wslot == p.R) { wslot = 0; wphase ^= 1u; }
+        }
+        const int stage = t & 1;
+        long long pr_b = 0;
+        if (p.prof) pr_b = clock64();
+        mbar_wait(&bar_acc_empty[stage], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        long long pr_c = 0;
+        if (p.prof) { pr_c = clock64(); pr_in += pr_b - pr_a; pr_acc += pr_c - pr_b; }
+        if (elect_one()) {
+          if (!(p.dbg & 2)) {
+            // plane-major, op-major order.  One 16-byte shared-memory record per op (prefetched by the
+            // unrolled loop); the MB row blocks of an op reuse its descriptors (A start + 2 KB, next
+            // TMEM column group).
+            const uint32_t d_base = tmem_base + (uint32_t)(stage * p.MB * p.NB);
+            int sl_idx = slot_lo;
+            for (int dz = 0; dz < p.span; ++dz) {
+              const uint32_t sl = slots16 + (uint32_t)sl_idx * slot16;
+              if (++sl_idx == p.R) sl_idx = 0;
+              const int ob = s_dzb[dz], oe = s_dzb[dz + 1];
+              switch (p.MB) {
+                case 1: issue_ops<1>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi, idesc); break;
+                case 2: issue_ops<2>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi, idesc); break;
+                case 3: issue_ops<3>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi, idesc); break;
+                default: issue_ops<4>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi, idesc); break;
+              }
+            }
+          }
+          mma_commit(&bar_acc_full[stage]);
+          // planes no later step needs go back to the producer
+          int rs = slot_lo;
+          for (int s = seq_lo; s < min(p.zstep * (t + 1), nplanes); ++s) {
+            mma_commit(&bar_empty[rs]);
+            if (++rs == p.R) rs = 0;
+          }
+        }
+        __syncwarp();
+        if (p.prof) pr_issue += clock64() - pr_c;
+        slot_lo += p.zstep;
+        if (slot_lo >= p.R) slot_lo -= p.R;
+      }
+      if (p.prof && blockIdx.x == 0 && lane == 0) {
+        long long g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        p.prof[0] = clock64() - pr_t0; p.prof[1] = g1 - pr_g0; p.prof[2] = pr_in; p.prof[3] = pr_acc; p.prof[4] = pr_issue;
+        p.prof[5] = (long long)nsteps * p.nops * p.MB;
+      }
+    } else {
+      // ===================================== epilogue =====================================
+      float sum[CP], sq[CP];
+#pragma unroll
+      for (int k = 0; k < CP; ++k) { sum[k] = 0.0f; sq[k] = 0.0f; }
+      const bool deconv = p.mode == MODE_DECONV;
+      const int ncls = deconv ? 8 : 1;
+      const int ncol = p.zf * p.cout_n;
+      const size_t zpitch = (size_t)p.Ho * p.Wo;          // voxels per output plane
+      const int ncho = p.Cout >> 3, chunk0 = p.cout_base >> 3;
+      for (int t = 0; t < nsteps; ++t) {
+        const int stage = t & 1;
+        mbar_wait(&bar_acc_full[stage], (uint32_t)(t >> 1) & 1u);
+        tc_fence_after();
+        const int mz = zb + t * p.zf;
+        const int nlive = min(p.zf, ze - mz);          // output planes of this step inside the volume
+        for (int b = 0; b < p.MB; ++b) {
+          const int m = b * 128 + warp * 32 + lane;
+          const int yy = m / p.PX, xx = m - yy * p.PX;
+          const bool valid = xx < TXe && yy < TYe && !(p.dbg & 4);
+          for (int cls = 0; cls < ncls; ++cls) {
+            uint32_t r[CP];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                                   (uint32_t)((stage * p.MB + b) * p.NB + cls * CP);
+#pragma unroll
+            for (int c0 = 0; c0 < CP; c0 += 16) tmem_ld16(taddr + c0, r + c0);
+            tmem_ld_wait();
+            if (!valid) continue;
+            // columns [j*cout_n, (j+1)*cout_n) belong to output plane mz + j (z-fold); planes past the
+            // end of the volume are computed but neither stored nor counted.  Unused columns are exact zeros.
+            if (nlive == p.zf) {
+#pragma unroll
+              for (int k = 0; k < CP; ++k) {
+                const float v = __uint_as_float(r[k]);
+                sum[k] += v; sq[k] = fmaf(v, v, sq[k]);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < CP; ++k) {
+                const float v = (k >> p.cn_shift) < nlive ? __uint_as_float(r[k]) : 0.0f;
+                sum[k] += v; sq[k] = fmaf(v, v, sq[k]);
+              }
+            }
+            int oz, oy, ox;
+            if (deconv) { oz = 2 * mz + (cls >> 2); oy = 2 * (y0 + yy) + ((cls >> 1) & 1); ox = 2 * (x0 + xx) + (cls & 1); }
+            else { oz = mz; oy = y0 + yy; ox = x0 + xx; }
+            if (p.y_f32) {
+              float* yo = p.y_f32 + (((size_t)oz * p.Ho + oy) * p.Wo + ox) * p.Cout + p.cout_base;
+#pragma unroll
+              for (int k = 0; k < CP; ++k) {
+                const int j = p.zf == 1 ? 0 : (k >> p.cn_shift), cn = k - (p.zf == 1 ? 0 : (j << p.cn_shift));
+                if (k < ncol && j < nlive) yo[(size_t)j * zpitch * p.Cout + cn] = __uint_as_float(r[k]);
+              }
+            } else {
+              // CP8 (and optionally PS8) bf16: one 16-byte cell per 8 channels
+              const size_t cell = ((size_t)oy * p.Wo + ox);
+              const size_t pcell = ((size_t)((oy & 1) * 2 + (ox & 1)) * p.Hso + (oy >> 1)) * p.Wso + (ox >> 1);
+#pragma unroll
+              for (int k = 0; k < CP; k += 8) {
+                const int j = p.zf == 1 ? 0 : (k >> p.cn_shift), cn = k - (p.zf == 1 ? 0 : (j << p.cn_shift));
+                if (k < ncol && j < nlive) {
+                  uint4 pk;
+                  pk.x = pack_bf16x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+                  pk.y = pack_bf16x2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
+                  pk.z = pack_bf16x2(__uint_as_float(r[k + 4]), __uint_as_float(r[k + 5]));
+                  pk.w = pack_bf16x2(__uint_as_float(r[k + 6]), __uint_as_float(r[k + 7]));
+                  const size_t zc = (size_t)(oz + j) * ncho + chunk0 + (cn >> 3);
+                  if (p.y_cp8) *reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8) = pk;
+                  if (p.y_ps8)
+                    *reinterpret_cast<uint4*>(p.y_ps8 + (zc * 4 * (size_t)p.Hso * p.Wso + pcell) * 8) = pk;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_acc_empty[stage]);
+      }
+      // batch statistics: per-thread partials -> warp reduce -> one double atomic per channel and warp
+      if (p.stats) {
+#pragma unroll
+        for (int k = 0; k < CP; ++k) {
+          float s = sum[k], q = sq[k];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+          }
+          if (lane == 0 && k < ncol) {
+            const int cn = p.zf == 1 ? k : (k & (p.cout_n - 1));
+            atomicAdd(p.stats + p.cout_base + cn, (double)s);
+            atomicAdd(p.stats + p.Cout + p.cout_base + cn, (double)q);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion (stand-alone entry points; the fused path writes CP8 / PS8 directly)
+// ---------------------------------------------------------------------------------------------
+__global__ void ndhwc_to_planar_kernel(const __nv_bfloat16* __restrict__ x, int D, int H, int W, int C,
+                                       __nv_bfloat16* __restrict__ cp8, __nv_bfloat16* __restrict__ ps8) {
+  const int nch = C >> 3, Hs = (H + 1) >> 1, Ws = (W + 1) >> 1;
+  const size_t total = (size_t)D * H * W * nch;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % nch);
+    size_t v = i / nch;
+    const int xx = (int)(v % W); v /= W;
+    const int yy = (int)(v % H);
+    const int z = (int)(v / H);
+    const uint4 cell = *reinterpret_cast<const uint4*>(x + i * 8);
+    const size_t zc = (size_t)z * nch + ch;
+    if (cp8) *reinterpret_cast<uint4*>(cp8 + ((zc * H + yy) * W + xx) * 8) = cell;
+    if (ps8)
+      *reinterpret_cast<uint4*>(ps8 + (((zc * 4 + (yy & 1) * 2 + (xx & 1)) * Hs + (yy >> 1)) * Ws + (xx >> 1)) * 8) = cell;
+  }
+}
+
+__global__ void planar_to_ndhwc_kernel(const __nv_bfloat16* __restrict__ cp8, int D, int H, int W, int C,
+                                       __nv_bfloat16* __restrict__ y) {
+  const int nch = C >> 3;
+  const size_t total = (size_t)D * H * W * nch;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % nch);
+    size_t v = i / nch;
+    const int xx = (int)(v % W); v /= W;
+    const int yy = (int)(v % H);
+    const int z = (int)(v / H);
+    *reinterpret_cast<uint4*>(y + i * 8) =
+        *reinterpret_cast<const uint4*>(cp8 + ((((size_t)z * nch + ch) * H + yy) * W + xx) * 8);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side planning
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr size_t kSmemBudget = 225 * 1024;
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Plan {
+  Params cp;
+  PackParams pp;
+  size_t smem;
+  double est_clk;
+};
+
+int pow2_at_least(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+double mma_clk(int n) { const double a = 32.0 + n / 4.0, b = n / 2.0; return (a > b ? a : b) + 2.0; }
+
+// Build the op table for one (mode, Cin, cout slice) and the slot geometry for tile (TX, TY), z-fold zf.
+bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base, int cout_n, int TX, int TY, int zf,
+                bool has_skip, bool transform, Plan* pl) {
+  Params& c = pl->cp;
+  PackParams& pk = pl->pp;
+  if (mode != MODE_CONV1) zf = 1;
+  if (zf > 1 && ((cout_n & (cout_n - 1)) != 0)) return false;     // the epilogue splits folded columns by shift
+  if (zf * cout_n > 32 || zf + 2 > kMaxSpan) return false;
+  const int CP = zf * cout_n <= 16 ? 16 : 32;
+  const bool master = zf > 1 && zf * cout_n == CP && cin >= 16;
+  c.CP = CP;
+  c.zf = zf;
+  c.cn_shift = 0;
+  while ((1 << c.cn_shift) < cout_n) ++c.cn_shift;
+  c.mode = mode; c.D = D; c.H = H; c.W = W; c.Cin = cin; c.Cout = cout; c.cout_base = cout_base; c.cout_n = cout_n;
+  c.has_skip = has_skip ? 1 : 0; c.transform = transform ? 1 : 0;
+  int pbd = 0, pbh = 0, pbw = 0;
+  if (mode == MODE_CONV1) {
+    c.Do = D; c.Ho = H; c.Wo = W; c.Mz = D; c.My = H; c.Mx = W;
+    c.PX = TX + 2; c.RY = TY + 2; c.nsub = 1; c.vstep = 1; c.cx_off = -1; c.cy_off = -1;
+    c.zmul = 1; c.zoff = -1; c.zstep = zf; c.span = zf + 2; c.NB = CP;
+  } else if (mode == MODE_CONV2) {
+    c.Do = ceil_div(D, 2); c.Ho = ceil_div(H, 2); c.Wo = ceil_div(W, 2); c.Mz = c.Do; c.My = c.Ho; c.Mx = c.Wo;
+    pbd = tf_same_pad_before(D, 3, 2); pbh = tf_same_pad_before(H, 3, 2); pbw = tf_same_pad_before(W, 3, 2);
+    c.PX = TX + 1 + pbw; c.RY = TY + 1 + pbh; c.nsub = 4; c.vstep = 2; c.cx_off = -pbw; c.cy_off = -pbh;
+    c.zmul = 2; c.zoff = -pbd; c.zstep = 2; c.span = 3; c.NB = CP;
+  } else {
+    c.Do = 2 * D; c.Ho = 2 * H; c.Wo = 2 * W; c.Mz = D; c.My = H; c.Mx = W;
+    c.PX = TX + 1; c.RY = TY + 1; c.nsub = 1; c.vstep = 1; c.cx_off = -1; c.cy_off = -1;
+    c.zmul = 1; c.zoff = -1; c.zstep = 1; c.span = 2; c.NB = 8 * CP;
+  }
+  c.Hso = (c.Ho + 1) / 2; c.Wso = (c.Wo + 1) / 2;
+  if (c.PX * 8 > 256 || c.RY > 256) return false;     // TMA box limits
+  c.TX = TX; c.TY = TY;
+  c.tiles_x = ceil_div(c.Mx, TX); c.tiles_y = ceil_div(c.My, TY);
+  c.SUBP = (c.RY * c.PX + 7) / 8 * 8;          // sub-arrays start 128-byte aligned (TMA destination)
+  c.NCH = cin / 8;
+  c.MB = ceil_div(TY * c.PX, 128);
+  if (2 * c.MB * c.NB > 512 || c.MB > kMaxMB) return false;
+  c.tmem_cols = pow2_at_least(2 * c.MB * c.NB);
+  c.xf_k = ceil_div(c.nsub * c.RY * c.PX, kXfThreads / c.NCH);
+  if (transform && c.xf_k > kMaxK) return false;
+
+  // ---- taps ---------------------------------------------------------------------------------------
+  struct Tap { int dz, pos, widx, cls; };
+  Tap taps[9 * kMaxSpan];
+  int ntaps = 0;
+  if (mode == MODE_DECONV) {
+    for (int cls = 0; cls < 8; ++cls) {
+      const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+      for (int sz = 0; sz >= (pz ? 0 : -1); --sz)
+        for (int sy = 0; sy >= (py ? 0 : -1); --sy)
+          for (int sx = 0; sx >= (px ? 0 : -1); --sx) {
+            const int kd = pz - 2 * sz, kh = py - 2 * sy, kw = px - 2 * sx;
+            taps[ntaps++] = {1 + sz, (1 + sy) * c.PX + (1 + sx), (kd * 3 + kh) * 3 + kw, cls};
+          }
+    }
+  } else {
+    // CONV1: one tap per input plane dz of the step and (kh, kw) (widx = kh*3+kw when the B images are
+    // windows of a master image, else dz = kd).  CONV2: dz = kd.
+    const int ndz = mode == MODE_CONV1 ? zf + 2 : 3;
+    for (int kd = 0; kd < ndz; ++kd)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          int pos;
+          if (mode == MODE_CONV1) pos = kh * c.PX + kw;
+          else {
+            const int ey = kh - pbh, ex = kw - pbw;
+            const int qy = ey & 1, qx = ex & 1;
+            const int fy = (ey - qy) / 2, fx = (ex - qx) / 2;
+            pos = ((qy << 1) | qx) * c.SUBP + (fy + pbh) * c.PX + (fx + pbw);
+          }
+          taps[ntaps++] = {kd, pos, (kd * 3 + kh) * 3 + kw, 0};
+        }
+  }
+  // plane-major order (the issue loop walks the input planes of a step and their op ranges)
+  for (int i = 1; i < ntaps; ++i)
+    for (int j = i; j > 0 && taps[j].dz < taps[j - 1].dz; --j) { Tap t = taps[j]; taps[j] = taps[j - 1]; taps[j - 1] = t; }
+  int max_pos = 0;
+  for (int i = 0; i < ntaps; ++i) max_pos = taps[i].pos > max_pos ? taps[i].pos : max_pos;
+  const int sp_cells = max_pos + c.MB * 128 + 8;
+  c.PS = (sp_cells * 16 + 127) / 128 * 128;          // chunk planes start 128-byte aligned (TMA destination)
+  if (c.nsub * c.SUBP * 16 > c.PS) c.PS = c.nsub * c.SUBP * 16;
+  c.slot_bytes = c.NCH * c.PS;
+
+  // ---- ops ----------------------------------------------------------------------------------------
+  int nops = 0, nimg = 0;
+  const int b_op_bytes = 2 * CP * 16;
+  const int m_rows = (2 * zf + 1) * cout_n, m_bytes = 2 * m_rows * 16;      // master image
+  auto add_op = [&](int dz, uint32_t a_off, uint32_t a_lbo, uint32_t b_off, uint32_t b_lbo, int col, bool first) {
+    UmmaOp& o = c.ops[nops++];
+    o.a_lo = (a_off >> 4) | ((a_lbo >> 4) << 16);
+    o.b_lo = (b_off >> 4) | ((b_lbo >> 4) << 16);
+    o.meta = (uint32_t)col | ((first ? 1u : 0u) << 16) | ((uint32_t)dz << 20);
+    o.pad = 0;
+  };
+  auto add_img = [&](int tap0, int cb0, int tap1, int cb1) {
+    pk.ops[nimg].tap[0] = (int16_t)tap0; pk.ops[nimg].cbase[0] = (int16_t)cb0;
+    pk.ops[nimg].tap[1] = (int16_t)tap1; pk.ops[nimg].cbase[1] = (int16_t)cb1;
+    return nimg++;
+  };
+  bool seen_cls[8] = {false, false, false, false, false, false, false, false};
+  if (ntaps * (cin >= 16 ? cin / 16 : 1) > kMaxOps) return false;
+  if (master) {
+    // images: one per (kh, kw, channel pair); op of plane dz = window starting at row group zf+1-dz
+    for (int t = 0; t < 9; ++t)
+      for (int j = 0; j < cin / 16; ++j) add_img(t, 16 * j, t, 16 * j + 8);
+    for (int i = 0; i < ntaps; ++i)
+      for (int j = 0; j < cin / 16; ++j) {
+        const bool first = !seen_cls[0];
+        seen_cls[0] = true;
+        const int img = (taps[i].widx % 9) * (cin / 16) + j;
+        add_op(taps[i].dz, (uint32_t)(2 * j * c.PS + taps[i].pos * 16), (uint32_t)c.PS,
+               (uint32_t)(img * m_bytes + (zf + 1 - taps[i].dz) * cout_n * 16), (uint32_t)(m_rows * 16), 0, first);
+      }
+    c.b_bytes = nimg * m_bytes;
+  } else if (cin >= 16) {
+    for (int i = 0; i < ntaps; ++i)
+      for (int j = 0; j < cin / 16; ++j) {
+        const bool first = !seen_cls[taps[i].cls];
+        seen_cls[taps[i].cls] = true;
+        const int img = add_img(taps[i].widx, 16 * j, taps[i].widx, 16 * j + 8);
+        add_op(taps[i].dz, (uint32_t)(2 * j * c.PS + taps[i].pos * 16), (uint32_t)c.PS, (uint32_t)(img * b_op_bytes),
+               (uint32_t)(CP * 16), taps[i].cls * CP, first);
+      }
+    c.b_bytes = nimg * b_op_bytes;
+  } else {
+    // Cin == 8: K = 16 pairs two taps of the same plane and class (second half = first shifted by LBO)
+    bool used[9 * kMaxSpan] = {false};
+    for (int i = 0; i < ntaps; ++i) {
+      if (used[i]) continue;
+      used[i] = true;
+      int mate = -1;
+      for (int j = i + 1; j < ntaps; ++j)
+        if (!used[j] && taps[j].dz == taps[i].dz && taps[j].cls == taps[i].cls && taps[j].pos > taps[i].pos) {
+          mate = j; break;
+        }
+      const bool first = !seen_cls[taps[i].cls];
+      seen_cls[taps[i].cls] = true;
+      if (mate >= 0) {
+        used[mate] = true;
+        const int img = add_img(taps[i].widx, 0, taps[mate].widx, 0);
+        add_op(taps[i].dz, (uint32_t)(taps[i].pos * 16), (uint32_t)((taps[mate].pos - taps[i].pos) * 16),
+               (uint32_t)(img * b_op_bytes), (uint32_t)(CP * 16), taps[i].cls * CP, first);
+      } else {
+        const int img = add_img(taps[i].widx, 0, -1, 0);
+        add_op(taps[i].dz, (uint32_t)(taps[i].pos * 16), 16u, (uint32_t)(img * b_op_bytes), (uint32_t)(CP * 16),
+               taps[i].cls * CP, first);
+      }
+    }
+    c.b_bytes = nimg * b_op_bytes;
+  }
+  if (c.b_bytes >= (1 << 18)) return false;
+  c.nops = nops;
+  // op ranges per input plane of the step (ops are in plane-major order)
+  for (int d = 0; d <= kMaxSpan; ++d) c.dz_begin[d] = nops;
+  for (int o = nops - 1; o >= 0; --o) c.dz_begin[(c.ops[o].meta >> 20) & 15] = o;
+  for (int d = kMaxSpan - 1; d >= 0; --d) if (c.dz_begin[d] > c.dz_begin[d + 1]) c.dz_begin[d] = c.dz_begin[d + 1];
+  pk.zf = zf; pk.master = master ? 1 : 0;
+  pk.nops = nimg; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
+  pk.transposed = mode == MODE_DECONV;
+  const size_t fixed = (size_t)c.b_bytes + (size_t)kMaxOps * 16 + 32 + (3 * kMaxRing + 2 * kSkipRing + 5) * sizeof(uint64_t) + 16;
+  const size_t skip_bytes = has_skip ? (size_t)kSkipRing * c.slot_bytes : 0;
+  c.R = c.span + c.zstep;                         // the planes of the next step land while this one computes
+  if (fixed + skip_bytes + (size_t)c.R * c.slot_bytes > kSmemBudget) {
+    c.R = c.span + 1;
+    if (fixed + skip_bytes + (size_t)c.R * c.slot_bytes > kSmemBudget) return false;
+  }
+  // deepen the ring while shared memory allows: more planes in flight hide the L2 / HBM latency
+  while (c.R < kMaxRing && c.R < c.span + 3 * c.zstep &&
+         fixed + skip_bytes + (size_t)(c.R + 1) * c.slot_bytes <= kSmemBudget) ++c.R;
+  pl->smem = fixed + skip_bytes + (size_t)c.R * c.slot_bytes;
+  return c.slot_bytes < (1 << 18) && (size_t)c.PS < (1u << 18);
+}
+
+// Cycle model of one launch (per SM): the roles run concurrently, a step costs the slowest of them.
+double estimate_clk(const Params& c, int sm_count) {
+  const double mma = (double)c.nops * c.MB * mma_clk(c.CP);
+  const double plane_bytes = (double)c.nsub * c.NCH * c.RY * c.PX * 16.0 * (c.has_skip ? 2.0 : 1.0);
+  const double load = plane_bytes * c.zstep / 18.0;                       // ~HBM share of one SM, B/clk
+  const int ncls = c.mode == MODE_DECONV ? 8 : 1;
+  const double epi = (double)c.MB * ncls * (c.CP * 4.0 * 128.0 / 110.0 + 12.0 * c.CP + 80.0);
+  const double xf = c.transform ? (double)c.xf_k * c.zstep * (c.has_skip ? 70.0 : 45.0) : 0.0;
+  double step = mma;
+  if (load > step) step = load;
+  if (epi > step) step = epi;
+  if (xf > step) step = xf;
+  step += 120.0;
+  const int steps_all = ceil_div(c.Mz, c.zf);
+  const int sseg = ceil_div(steps_all, c.zsplit);
+  const double fill = plane_bytes * c.span / 18.0 + 1500.0;
+  const double cta = sseg * step + fill + 3000.0 + c.b_bytes / 32.0;
+  const int ctas = c.tiles_x * c.tiles_y * c.zsplit;
+  const int waves = ceil_div(ctas, sm_count);
+  return waves * cta;
+}
+
+std::map<std::array<int, 14>, Plan> g_plan_cache;
+std::mutex g_plan_mutex;
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)f;
+  }
+  return fn;
+}
+
+// 5-D map over a CP8 (subs = 1) or PS8 (subs = 4) tensor: (8*Wp, Hp, subs, NCH, D), box (8*PX, RY, 1, 1, 1)
+bool make_tmap(CUtensorMap* tm, const void* base, int Wp, int Hp, int subs, int nch, int D, int PX, int RY) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[5] = {(cuuint64_t)Wp * 8, (cuuint64_t)Hp, (cuuint64_t)subs, (cuuint64_t)nch, (cuuint64_t)D};
+  cuuint64_t gstr[4] = {(cuuint64_t)Wp * 16, (cuuint64_t)Hp * Wp * 16, (cuuint64_t)subs * Hp * Wp * 16,
+                        (cuuint64_t)nch * subs * Hp * Wp * 16};
+  cuuint32_t box[5] = {(cuuint32_t)PX * 8, (cuuint32_t)RY, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+}  // namespace tc
+
+using namespace tc;
+
+size_t conv3d_tc_scratch_bytes() { return align_up((size_t)kMaxOps * 2 * 32 * 16, 256) * 2; }
+
+// x: CP8 for stride-1 convs and transposed convs, PS8 for stride-2 convs.  skip: CP8.
+// Outputs: y_cp8 and / or y_ps8 (bf16, Cout % 8 == 0), or y_f32 (NDHWC fp32, any Cout).
+int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
+                     const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
+                     int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
+                     cudaStream_t s) {
+  if (cin != 8 && cin != 16 && cin != 32 && cin != 64) {
+    set_error("conv3d(bf16/tcgen05): Cin=%d unsupported (need 8, 16, 32 or 64)", cin);
+    return MVSB200_ERR_UNSUPPORTED;
+  }
+  if (!y_f32 && (cout % 8 != 0 || (!y_cp8 && !y_ps8))) {
+    set_error("conv3d(bf16/tcgen05): bf16 output needs Cout %% 8 == 0 (got %d)", cout);
+    return MVSB200_ERR_UNSUPPORTED;
+  }
+  const int mode = transposed ? MODE_DECONV : (stride == 2 ? MODE_CONV2 : MODE_CONV1);
+  if (skip && mode == MODE_CONV2) {
+    set_error("conv3d(bf16/tcgen05): skip input on a stride-2 conv is not supported");
+    return MVSB200_ERR_UNSUPPORTED;
+  }
+  if (!get_encode()) {
+    set_error("conv3d(bf16/tcgen05): cuTensorMapEncodeTiled is not available from the driver");
+    return MVSB200_ERR_CUDA;
+  }
+  int sm_count = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    attr_done = true;
+  }
+  const bool has_skip = skip != nullptr, transform = xs != nullptr || has_skip;
+  // tuning / debugging switches; MVSB200_TC_LAYER="cin,cout,mode" restricts them to one layer shape
+  const char* zf_env = getenv("MVSB200_TC_ZF");
+  const char* tile_env = getenv("MVSB200_TC_TILE");     // "TXxTY" forces the tile
+  const char* dbg_env = getenv("MVSB200_TC_DBG");
+  const char* zs_env = getenv("MVSB200_TC_ZSPLIT");
+  if (const char* only = getenv("MVSB200_TC_LAYER")) {
+    int a = 0, b = 0, m = 0;
+    sscanf(only, "%d,%d,%d", &a, &b, &m);
+    if (a != cin || b != cout || m != mode) zf_env = tile_env = dbg_env = zs_env = nullptr;
+  }
+  int force_tx = 0, force_ty = 0;
+  if (tile_env) sscanf(tile_env, "%dx%d", &force_tx, &force_ty);
+  const int force_zs = zs_env ? atoi(zs_env) : 0;
+  int launch_idx = 0;
+  for (int cb = 0; cb < cout; cb += 32, ++launch_idx) {
+    const int cn = cout - cb < 32 ? cout - cb : 32;
+    const int Mx = mode == MODE_CONV2 ? ceil_div(W, 2) : W, My = mode == MODE_CONV2 ? ceil_div(H, 2) : H,
+              Mz = mode == MODE_CONV2 ? ceil_div(D, 2) : D;
+    const std::array<int, 14> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_env ? atoi(zf_env) : 0,
+                                     force_tx, force_ty, sm_count, force_zs};
+    Plan best;
+    bool found = false;
+    {
+      std::lock_guard<std::mutex> lock(g_plan_mutex);
+      auto it = g_plan_cache.find(key);
+      if (it != g_plan_cache.end()) { best = it->second; found = true; }
+    }
+    if (!found) {
+      const int zf_cands[] = {4, 2, 1};
+      for (int zi = 0; zi < 3; ++zi) {
+        const int zf = zf_cands[zi];
+        if (mode != MODE_CONV1 && zf != 1) continue;
+        if (zf_env && atoi(zf_env) != zf && mode == MODE_CONV1) continue;
+        if (zf > 1 && !zf_env && Mz < 2 * zf) continue;
+        for (int TX = 4; TX <= 30; ++TX) {
+          if (TX > Mx && TX != 4 && TX - 1 >= Mx) break;        // one clipped candidate is enough
+          const int tx_eff = TX < Mx ? TX : Mx;
+          if (force_tx && tx_eff != (force_tx < Mx ? force_tx : Mx)) continue;
+          for (int TY = 1; TY <= 40 && TY <= My; ++TY) {
+            if (force_ty && TY != (force_ty < My ? force_ty : My)) continue;
+            Plan pl;
+            if (!build_plan(mode, D, H, W, cin, cout, cb, cn, tx_eff, TY, zf, has_skip, transform, &pl)) continue;
+            if (pl.smem > kSmemBudget) continue;
+            Params& c = pl.cp;
+            const int tiles = c.tiles_x * c.tiles_y;
+            const int steps_all = ceil_div(Mz, zf);
+            // z split: candidates that fill whole waves of SMs
+            int zcands[6] = {1, 0, 0, 0, 0, 0};
+            int nz = 1;
+            for (int waves = 1; waves <= 4 && nz < 6; ++waves) {
+              int z = (waves * sm_count) / tiles;
+              if (z < 1) z = 1;
+              if (z > steps_all) z = steps_all;
+              zcands[nz++] = z;
+            }
+            if (force_zs) { zcands[0] = force_zs < steps_all ? force_zs : steps_all; nz = 1; }
+            for (int zi2 = 0; zi2 < nz; ++zi2) {
+              const int sseg = ceil_div(steps_all, zcands[zi2]);
+              c.zsplit = ceil_div(steps_all, sseg);           // drops empty trailing segments
+              pl.est_clk = estimate_clk(c, sm_count);
+              if (!found || pl.est_clk < best.est_clk) { best = pl; found = true; }
+            }
+          }
+        }
+      }
+      if (found) {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        g_plan_cache[key] = best;
+      }
+    }
+    if (!found) {
+      set_error("conv3d(bf16/tcgen05): no tile fits (Cin=%d Cout=%d mode=%d)", cin, cout, mode);
+      return MVSB200_ERR_UNSUPPORTED;
+    }
+    Params& c = best.cp;
+    c.xs = xs; c.xb = xb; c.ss = ss; c.sb = sb;
+    c.y_cp8 = (__nv_bfloat16*)y_cp8; c.y_ps8 = (__nv_bfloat16*)y_ps8; c.y_f32 = y_f32; c.stats = stats;
+    const bool ok_x = mode == MODE_CONV2
+                          ? make_tmap(&c.tmap_x, x, (W + 1) / 2, (H + 1) / 2, 4, c.NCH, D, c.PX, c.RY)
+                          : make_tmap(&c.tmap_x, x, W, H, 1, c.NCH, D, c.PX, c.RY);
+    const bool ok_s = !has_skip || make_tmap(&c.tmap_s, skip, W, H, 1, c.NCH, D, c.PX, c.RY);
+    if (!ok_x || !ok_s) {
+      set_error("conv3d(bf16/tcgen05): cuTensorMapEncodeTiled failed (PX=%d RY=%d W=%d H=%d)", c.PX, c.RY, W, H);
+      return MVSB200_ERR_CUDA;
+    }
+    {
+      c.dbg = dbg_env ? atoi(dbg_env) : 0;
+      if (getenv("MVSB200_TC_VERBOSE"))
+        fprintf(stderr, "[tc] mode=%d Cin=%d Cout=%d(+%d) tile %dx%d PX=%d RY=%d MB=%d N=%d R=%d zf=%d zsplit=%d grid=%d smem=%zu "
+                "nops=%d b=%dB xf=%d/%d est=%.0f clk\n",
+                mode, cin, cn, cb, c.TX, c.TY, c.PX, c.RY, c.MB, c.CP, c.R, c.zf, c.zsplit, c.tiles_x * c.tiles_y * c.zsplit,
+                best.smem, c.nops, c.b_bytes, c.transform, c.xf_k, best.est_clk);
+    }
+    unsigned char* wp = (unsigned char*)scratch + (size_t)(launch_idx & 1) * align_up((size_t)kMaxOps * 2 * 32 * 16, 256);
+    c.wpacked = (const uint4*)wp;
+    best.pp.kernel_tf = kernel_tf;
+    best.pp.out = (uint16_t*)wp;
+    pack_weights_kernel<<<ceil_div(c.b_bytes / 2, 256), 256, 0, s>>>(best.pp);
+    MVS_LAUNCH_CHECK("pack_weights_kernel");
+    const int grid = c.tiles_x * c.tiles_y * c.zsplit;
+    static long long* prof_buf = nullptr;
+    c.prof = nullptr;
+    if (getenv("MVSB200_TC_PROF")) {
+      if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 64));
+      c.prof = prof_buf;
+    }
+    if (c.CP == 16) conv3d_tc_kernel<16><<<grid, kThreads, best.smem, s>>>(c);
+    else conv3d_tc_kernel<32><<<grid, kThreads, best.smem, s>>>(c);
+    MVS_LAUNCH_CHECK("conv3d_tc_kernel");
+    if (c.prof) {
+      long long h[6];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[tc-prof] mode=%d Cin=%d Cout=%d: MMA warp of CTA 0: %lld clk in %lld ns (%.0f MHz); wait input %lld, "
+              "wait acc %lld, issue %lld clk; %lld MMAs -> %.1f clk/MMA issued, %.1f clk/MMA overall\n", mode, cin, cn,
+              h[0], h[1], h[1] ? 1e3 * h[0] / h[1] : 0.0, h[2], h[3], h[4], h[5], h[5] ? (double)h[4] / h[5] : 0.0,
+              h[5] ? (double)h[0] / h[5] : 0.0);
+    }
+  }
+  return MVSB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout helpers for callers
+// ---------------------------------------------------------------------------------------------
+size_t planar_bytes(int D, int H, int W, int C, int parity_split) {
+  if (!parity_split) return (size_t)D * H * W * C * 2;
+  return (size_t)D * (C / 8) * 4 * ((H + 1) / 2) * ((W + 1) / 2) * 16;
+}
+
+int launch_ndhwc_to_planar(const void* x_ndhwc, int D, int H, int W, int C, void* cp8, void* ps8, cudaStream_t s) {
+  MVS_CHECK_ARG(C % 8 == 0, "layout: C must be a multiple of 8 (got %d)", C);
+  if (ps8 && ((H | W) & 1)) MVS_CUDA(cudaMemsetAsync(ps8, 0, planar_bytes(D, H, W, C, 1), s));
+  const size_t total = (size_t)D * H * W * (C / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148u * 32u ? (total + 255) / 256 : 148u * 32u);
+  ndhwc_to_planar_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x_ndhwc, D, H, W, C, (__nv_bfloat16*)cp8,
+                                                (__nv_bfloat16*)ps8);
+  MVS_LAUNCH_CHECK("ndhwc_to_planar_kernel");
+  return MVSB200_OK;
+}
+
+int launch_planar_to_ndhwc(const void* cp8, int D, int H, int W, int C, void* y_ndhwc, cudaStream_t s) {
+  MVS_CHECK_ARG(C % 8 == 0, "layout: C must be a multiple of 8 (got %d)", C);
+  const size_t total = (size_t)D * H * W * (C / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148u * 32u ? (total + 255) / 256 : 148u * 32u);
+  planar_to_ndhwc_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)cp8, D, H, W, C, (__nv_bfloat16*)y_ndhwc);
+  MVS_LAUNCH_CHECK("planar_to_ndhwc_kernel");
+  return MVSB200_OK;
+}
+
+int launch_f32_to_bf16(const float* x, size_t n, void* y, cudaStream_t s) {
+  const unsigned blocks = (unsigned)((n + 255) / 256 < 148u * 32u ? (n + 255) / 256 : 148u * 32u);
+  f32_to_bf16_kernel<<<blocks, 256, 0, s>>>(x, n, (__nv_bfloat16*)y);
+  MVS_LAUNCH_CHECK("f32_to_bf16_kernel");
+  return MVSB200_OK;
+}
+
+// Stand-alone layer on NDHWC tensors (mvsb200_conv3d_layer, tests): converts to the planar layouts in
+// stream-ordered temporaries, runs the layer, converts back.  The fused path never comes through here.
+int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
+                           const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout,
+                           int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s) {
+  const bool s2 = !transposed && stride == 2;
+  const int Do = transposed ? 2 * D : ceil_div(D, stride), Ho = transposed ? 2 * H : ceil_div(H, stride),
+            Wo = transposed ? 2 * W : ceil_div(W, stride);
+  void *xp = nullptr, *kp = nullptr, *yp = nullptr, *scratch = nullptr;
+  float* yf = nullptr;
+  MVS_CHECK_ARG(cin % 8 == 0, "conv3d(bf16/tcgen05): Cin must be a multiple of 8 (got %d)", cin);
+  MVS_CUDA(cudaMallocAsync(&xp, planar_bytes(D, H, W, cin, s2), s));
+  MVS_CUDA(cudaMallocAsync(&scratch, conv3d_tc_scratch_bytes(), s));
+  int rc = launch_ndhwc_to_planar(x, D, H, W, cin, s2 ? nullptr : xp, s2 ? xp : nullptr, s);
+  if (!rc && skip) {
+    MVS_CUDA(cudaMallocAsync(&kp, planar_bytes(D, H, W, cin, 0), s));
+    rc = launch_ndhwc_to_planar(skip, D, H, W, cin, kp, nullptr, s);
+  }
+  const bool direct_f32 = y_dtype == MVSB200_F32;
+  const bool via_f32 = !direct_f32 && cout % 8 != 0;
+  if (!rc) {
+    if (direct_f32) yf = (float*)y;
+    else if (via_f32) MVS_CUDA(cudaMallocAsync((void**)&yf, (size_t)Do * Ho * Wo * cout * sizeof(float), s));
+    else MVS_CUDA(cudaMallocAsync(&yp, planar_bytes(Do, Ho, Wo, cout, 0), s));
+    rc = launch_conv3d_tc(xp, xs, xb, kp, ss, sb, kernel_tf, D, H, W, cin, cout, stride, transposed, yp, nullptr, yf,
+                          stats, scratch, s);
+  }
+  if (!rc && yp) rc = launch_planar_to_ndhwc(yp, Do, Ho, Wo, cout, y, s);
+  if (!rc && via_f32) rc = launch_f32_to_bf16(yf, (size_t)Do * Ho * Wo * cout, y, s);
+  if (xp) cudaFreeAsync(xp, s);
+  if (kp) cudaFreeAsync(kp, s);
+  if (yp) cudaFreeAsync(yp, s);
+  if (via_f32 && yf) cudaFreeAsync(yf, s);
+  if (scratch) cudaFreeAsync(scratch, s);
+  return rc;
+}
+
+}  // namespace mvsb200

@@ -62,10 +62,12 @@ __device__ __forceinline__ void store_cost4(void* out, size_t elem, float4 c, bo
 constexpr int kDC = 8;
 constexpr int kMaxSrcViews = 7;
 
-template <bool BF16OUT, int TX, int TY>
+// OUT: 0 = fp32 [D,Hf,Wf,32], 1 = bf16 [D,Hf,Wf,32], 2 = bf16 in the regularizer's planar layouts (conv3d_tc.cu):
+// out = CP8 [D][4][Hf][Wf][8] and out2 = PS8 [D][4][4][Hs][Ws][8] (either may be NULL)
+template <int OUT, int TX, int TY>
 __global__ void __launch_bounds__(256, 2)
 cost_volume_c32_kernel(const float* __restrict__ feats, int n_views, int D, int Hf, int Wf, int order,
-                       void* __restrict__ out) {
+                       void* __restrict__ out, void* __restrict__ out2) {
   static_assert(TX * TY == 32, "tile must hold 32 pixels");
   __shared__ float s_coef[kMaxSrcViews * kDC * 8];
   const int tid = threadIdx.x;
@@ -142,7 +144,17 @@ cost_volume_c32_kernel(const float* __restrict__ feats, int n_views, int D, int 
         c.z = Q[dd].z * inv_n - mz * mz;
         c.w = Q[dd].w * inv_n - mw * mw;
       }
-      store_cost4(out, (((size_t)d * Hf + y) * Wf + x) * 32 + g * 4, c, BF16OUT);
+      if (OUT < 2) {
+        store_cost4(out, (((size_t)d * Hf + y) * Wf + x) * 32 + g * 4, c, OUT == 1);
+      } else {
+        // 8-byte half of the 16-byte cell (chunk g>>1) of this voxel
+        const size_t zc = (size_t)d * 4 + (g >> 1);
+        if (out) store_cost4(out, ((zc * Hf + y) * Wf + x) * 8 + (g & 1) * 4, c, true);
+        if (out2) {
+          const int Hs = (Hf + 1) >> 1, Ws = (Wf + 1) >> 1;
+          store_cost4(out2, (((zc * 4 + (y & 1) * 2 + (x & 1)) * Hs + (y >> 1)) * Ws + (x >> 1)) * 8 + (g & 1) * 4, c, true);
+        }
+      }
     }
   }
 }
@@ -224,10 +236,11 @@ cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restr
   }
 }
 
-int launch_cost_volume(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
-                       int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
-                       cudaStream_t s) {
-  MVS_CHECK_ARG(feats && homographies && out, "cost_volume: NULL pointer");
+// planar_ps8 != NULL or planar != 0: write the bf16 planar layouts (out = CP8, planar_ps8 = PS8); fast path only
+static int launch_cost_volume_any(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
+                                  int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
+                                  int planar, void* planar_ps8, cudaStream_t s) {
+  MVS_CHECK_ARG(feats && homographies && (out || planar_ps8), "cost_volume: NULL pointer");
   MVS_CHECK_ARG(n_views >= 2 && depth_num >= 1 && hf >= 1 && wf >= 1 && channels >= 1,
                 "cost_volume: bad shape N=%d D=%d %dx%dx%d", n_views, depth_num, hf, wf, channels);
   MVS_CHECK_ARG(order == MVSB200_ORDER_MEM || order == MVSB200_ORDER_TRAIN, "cost_volume: bad order %d", order);
@@ -249,6 +262,10 @@ int launch_cost_volume(const float* feats, const float* homographies, int n_view
   bool fast_ok = sampler == MVSB200_SAMPLER_TRANSFORM && channels == 32 && n_views - 1 <= kMaxSrcViews &&
                  hf < 65536 && wf < 32768;
   if (variant == 0) variant = fast_ok ? 3 : 1;
+  if (planar && (!fast_ok || variant < 2)) {
+    set_error("cost_volume: the planar output needs sampler=transform, C=32, n_views<=8");
+    return MVSB200_ERR_UNSUPPORTED;
+  }
   MVS_CHECK_ARG(variant >= 1 && variant <= 3, "cost_volume: bad variant %d", variant);
   if (variant >= 2 && !fast_ok) {
     set_error("cost_volume: variant %d needs sampler=transform, C=32, n_views<=8", variant);
@@ -263,10 +280,13 @@ int launch_cost_volume(const float* feats, const float* homographies, int n_view
     const int tx = wide ? 32 : 16, ty = wide ? 1 : 2;
     dim3 grid(ceil_div(wf, tx), ceil_div(hf, ty), ceil_div(depth_num, kDC));
     MVS_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "cost_volume: grid too large");
-#define CV_FAST(BF, TX_, TY_) \
-  cost_volume_c32_kernel<BF, TX_, TY_><<<grid, 256, 0, s>>>(feats, n_views, depth_num, hf, wf, order, out)
-    if (wide) { if (bf16) CV_FAST(true, 32, 1); else CV_FAST(false, 32, 1); }
-    else      { if (bf16) CV_FAST(true, 16, 2); else CV_FAST(false, 16, 2); }
+#define CV_FAST(O, TX_, TY_) \
+  cost_volume_c32_kernel<O, TX_, TY_><<<grid, 256, 0, s>>>(feats, n_views, depth_num, hf, wf, order, out, planar_ps8)
+    if (planar && ((hf | wf) & 1) && planar_ps8)
+      MVS_CUDA(cudaMemsetAsync(planar_ps8, 0, (size_t)depth_num * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) * 16, s));
+    if (planar) { if (wide) CV_FAST(2, 32, 1); else CV_FAST(2, 16, 2); }
+    else if (wide) { if (bf16) CV_FAST(1, 32, 1); else CV_FAST(0, 32, 1); }
+    else           { if (bf16) CV_FAST(1, 16, 2); else CV_FAST(0, 16, 2); }
 #undef CV_FAST
     MVS_LAUNCH_CHECK("cost_volume_c32_kernel");
     return MVSB200_OK;
@@ -288,6 +308,24 @@ int launch_cost_volume(const float* feats, const float* homographies, int n_view
 #undef CV_GEN
   MVS_LAUNCH_CHECK("cost_volume_generic_kernel");
   return MVSB200_OK;
+}
+
+int launch_cost_volume(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
+                       int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
+                       cudaStream_t s) {
+  return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler, out_dtype,
+                                out, variant, 0, nullptr, s);
+}
+
+bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sampler) {
+  return sampler == MVSB200_SAMPLER_TRANSFORM && channels == 32 && n_views - 1 <= kMaxSrcViews && hf < 65536 &&
+         wf < 32768;
+}
+
+int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
+                              int wf, int channels, int order, int sampler, void* cp8, void* ps8, cudaStream_t s) {
+  return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler,
+                                MVSB200_BF16, cp8, 0, 1, ps8, s);
 }
 
 }  // namespace mvsb200

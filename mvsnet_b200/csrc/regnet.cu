@@ -6,17 +6,24 @@
 // ever written back to HBM.  BN uses batch statistics, as the reference does at inference
 // (network.py:54,64; model.py:337-338; SURVEY.md "facts").
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mvsb200 {
 
 int launch_conv3d_direct(const void* x, int x_dtype, const float* xs, const float* xb, const void* skip,
                          const float* ss, const float* sb, const float* kernel_tf, int D, int H, int W, int cin,
                          int cout, int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);
-int launch_conv3d_umma(const void* x, int x_dtype, const float* xs, const float* xb, const void* skip,
-                       const float* ss, const float* sb, const float* kernel_tf, int D, int H, int W, int cin,
-                       int cout, int stride, int transposed, void* y, int y_dtype, double* stats, void* scratch,
-                       cudaStream_t s);
-size_t conv3d_umma_scratch_bytes(int cin, int cout, int transposed);
+// conv3d_tc.cu: bf16 tcgen05 layers on the planar activation layouts (CP8 / PS8, see that file)
+int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
+                     const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
+                     int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
+                     cudaStream_t s);
+int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
+                           const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout,
+                           int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);
+size_t conv3d_tc_scratch_bytes();
+size_t planar_bytes(int D, int H, int W, int C, int parity_split);
+int launch_ndhwc_to_planar(const void* x_ndhwc, int D, int H, int W, int C, void* cp8, void* ps8, cudaStream_t s);
 
 int launch_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const float* x_shift, const void* skip,
                         const float* skip_scale, const float* skip_shift, const float* kernel_tf, int depth,
@@ -34,9 +41,14 @@ int launch_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const 
   if (precision == MVSB200_PRECISION_FP32)
     return launch_conv3d_direct(x, x_dtype, x_scale, x_shift, skip, skip_scale, skip_shift, kernel_tf, depth, height,
                                 width, cin, cout, stride, transposed, y_raw, y_dtype, stats, s);
-  if (precision == MVSB200_PRECISION_BF16)
-    return launch_conv3d_umma(x, x_dtype, x_scale, x_shift, skip, skip_scale, skip_shift, kernel_tf, depth, height,
-                              width, cin, cout, stride, transposed, y_raw, y_dtype, stats, nullptr, s);
+  if (precision == MVSB200_PRECISION_BF16) {
+    if (x_dtype != MVSB200_BF16) {
+      set_error("conv3d(bf16/tcgen05): input must be bf16");
+      return MVSB200_ERR_UNSUPPORTED;
+    }
+    return launch_conv3d_tc_ndhwc(x, x_scale, x_shift, skip, skip_scale, skip_shift, kernel_tf, depth, height, width,
+                                  cin, cout, stride, transposed, y_raw, y_dtype, stats, s);
+  }
   set_error("conv3d_layer: bad precision %d", precision);
   return MVSB200_ERR_INVALID;
 }
@@ -53,7 +65,11 @@ struct LayerDesc {
 
 struct RegnetPlan {
   LayerDesc layer[MVSB200_REGNET_LAYERS];
-  size_t raw_off[MVSB200_REGNET_LAYERS];     // raw output of each layer (layer 10 writes `filtered` instead)
+  size_t raw_off[MVSB200_REGNET_LAYERS];     // raw output of each layer (layer 10 writes `filtered` instead);
+                                             // fp32 mode: NDHWC, bf16 mode: CP8 chunk-planar (conv3d_tc.cu)
+  size_t ps8_off[MVSB200_REGNET_LAYERS];     // bf16 mode: parity-split copy for layers feeding a stride-2 conv
+  bool has_ps8[MVSB200_REGNET_LAYERS];
+  size_t cost_cp8_off, cost_ps8_off;         // bf16 mode: the cost volume in both planar layouts
   size_t stats_off, scale_off, shift_off, scratch_off;
   size_t stats_bytes, total;
   int elem;                                  // bytes per activation element
@@ -88,6 +104,22 @@ static void make_plan(int D, int H, int W, int cin, int b, int precision, Regnet
     p->raw_off[i] = off;
     if (i != MVSB200_L_3DCONV6_2) off += align_up(p->vox[L[i].out_level] * L[i].cout * p->elem, 256);
     if (L[i].cout > max_c) max_c = L[i].cout;
+    p->has_ps8[i] = false;
+    p->ps8_off[i] = 0;
+  }
+  p->cost_cp8_off = p->cost_ps8_off = 0;
+  if (precision == MVSB200_PRECISION_BF16) {
+    // outputs that feed a stride-2 conv are also written parity-split
+    for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i)
+      if (L[i].stride == 2 && !L[i].transposed && L[i].src >= 0) p->has_ps8[L[i].src] = true;
+    for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i)
+      if (p->has_ps8[i]) {
+        const int* d = p->dims[L[i].out_level];
+        p->ps8_off[i] = off;
+        off += align_up(planar_bytes(d[0], d[1], d[2], L[i].cout, 1), 256);
+      }
+    p->cost_cp8_off = off; off += align_up(planar_bytes(D, H, W, cin, 0), 256);
+    p->cost_ps8_off = off; off += align_up(planar_bytes(D, H, W, cin, 1), 256);
   }
   const int cpad = (max_c + 63) / 64 * 64;
   p->stats_off = off;  p->stats_bytes = (size_t)MVSB200_REGNET_LAYERS * 2 * cpad * sizeof(double); off += align_up(p->stats_bytes, 256);
@@ -95,11 +127,7 @@ static void make_plan(int D, int H, int W, int cin, int b, int precision, Regnet
   p->shift_off = off;  off += align_up((size_t)MVSB200_REGNET_LAYERS * cpad * sizeof(float), 256);
   p->scratch_off = off;
   size_t scratch = 0;
-  if (precision == MVSB200_PRECISION_BF16)
-    for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
-      size_t s = conv3d_umma_scratch_bytes(L[i].cin, L[i].cout, L[i].transposed);
-      if (s > scratch) scratch = s;
-    }
+  if (precision == MVSB200_PRECISION_BF16) scratch = conv3d_tc_scratch_bytes();
   off += align_up(scratch, 256);
   p->total = off;
 }
@@ -118,14 +146,19 @@ static int check_regnet_shape(int D, int H, int W, int cin, int b) {
   return MVSB200_OK;
 }
 
-int regnet_forward_impl(const void* cost, int cost_dtype, const mvsb200_regnet_params* params, int D, int H, int W,
-                        int cin, int b, float eps, int precision, float* filtered, void* workspace,
+// cost_planar != 0 (bf16 mode only): the caller has already written the cost volume in both planar
+// layouts at regnet_cost_planar() inside the workspace and `cost` is ignored.
+int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const mvsb200_regnet_params* params, int D,
+                        int H, int W, int cin, int b, float eps, int precision, float* filtered, void* workspace,
                         size_t workspace_bytes, cudaStream_t s) {
-  MVS_CHECK_ARG(cost && params && filtered && workspace, "regnet_forward: NULL pointer");
+  MVS_CHECK_ARG((cost || cost_planar) && params && filtered && workspace, "regnet_forward: NULL pointer");
   int rc = check_regnet_shape(D, H, W, cin, b);
   if (rc) return rc;
   MVS_CHECK_ARG(precision == MVSB200_PRECISION_FP32 || precision == MVSB200_PRECISION_BF16,
                 "regnet_forward: bad precision %d", precision);
+  const bool bf16 = precision == MVSB200_PRECISION_BF16;
+  if (bf16) MVS_CHECK_ARG(cin % 8 == 0 && b % 8 == 0, "regnet_forward(bf16): channel counts must be multiples of 8 "
+                          "(in_channels=%d base_filter=%d)", cin, b);
   RegnetPlan p;
   make_plan(D, H, W, cin, b, precision, &p);
   if (workspace_bytes < p.total) {
@@ -137,32 +170,52 @@ int regnet_forward_impl(const void* cost, int cost_dtype, const mvsb200_regnet_p
   double* stats = (double*)(ws + p.stats_off);
   float* scale = (float*)(ws + p.scale_off);
   float* shift = (float*)(ws + p.shift_off);
-  const int act_dtype = precision == MVSB200_PRECISION_BF16 ? MVSB200_BF16 : MVSB200_F32;
+  const int act_dtype = bf16 ? MVSB200_BF16 : MVSB200_F32;
   MVS_CUDA(cudaMemsetAsync(stats, 0, p.stats_bytes, s));
+  if (bf16 && !cost_planar) {
+    MVS_CHECK_ARG(cost_dtype == MVSB200_BF16, "regnet_forward: precision bf16 needs a bf16 cost volume");
+    rc = launch_ndhwc_to_planar(cost, D, H, W, cin, ws + p.cost_cp8_off, ws + p.cost_ps8_off, s);
+    if (rc) return rc;
+  }
+  // development aid: MVSB200_REGNET_PROFILE=1 prints per-layer device times (synchronises; not for timed runs)
+  static const bool profile = getenv("MVSB200_REGNET_PROFILE") != nullptr;
+  cudaEvent_t pev[MVSB200_REGNET_LAYERS + 1];
+  if (profile) {
+    for (int i = 0; i <= MVSB200_REGNET_LAYERS; ++i) cudaEventCreate(&pev[i]);
+    cudaEventRecord(pev[0], s);
+  }
   for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
     const LayerDesc& L = p.layer[i];
     MVS_CHECK_ARG(params->kernel[i] != nullptr, "regnet_forward: kernel[%d] is NULL", i);
     const bool last = i == MVSB200_L_3DCONV6_2;
     if (!last) MVS_CHECK_ARG(params->gamma[i] && params->beta[i], "regnet_forward: gamma/beta[%d] is NULL", i);
-    const void* x = L.src < 0 ? cost : (const void*)(ws + p.raw_off[L.src]);
-    const int x_dtype = L.src < 0 ? cost_dtype : act_dtype;
     const float* xs = L.src < 0 ? nullptr : scale + (size_t)L.src * cpad;
     const float* xb = L.src < 0 ? nullptr : shift + (size_t)L.src * cpad;
     const void* sk = L.skip < 0 ? nullptr : (const void*)(ws + p.raw_off[L.skip]);
     const float* ss = L.skip < 0 ? nullptr : scale + (size_t)L.skip * cpad;
     const float* sb = L.skip < 0 ? nullptr : shift + (size_t)L.skip * cpad;
-    if (L.src < 0 && precision == MVSB200_PRECISION_BF16)
-      MVS_CHECK_ARG(cost_dtype == MVSB200_BF16, "regnet_forward: precision bf16 needs a bf16 cost volume");
-    void* y = last ? (void*)filtered : (void*)(ws + p.raw_off[i]);
-    const int y_dtype = last ? MVSB200_F32 : act_dtype;
     double* st = last ? nullptr : stats + (size_t)i * 2 * cpad;
     const int* d = p.dims[L.in_level];
-    if (precision == MVSB200_PRECISION_FP32)
+    if (!bf16) {
+      const void* x = L.src < 0 ? cost : (const void*)(ws + p.raw_off[L.src]);
+      const int x_dtype = L.src < 0 ? cost_dtype : act_dtype;
+      void* y = last ? (void*)filtered : (void*)(ws + p.raw_off[i]);
       rc = launch_conv3d_direct(x, x_dtype, xs, xb, sk, ss, sb, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout,
-                                L.stride, L.transposed, y, y_dtype, st ? st : nullptr, s);
-    else
-      rc = launch_conv3d_umma(x, x_dtype, xs, xb, sk, ss, sb, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout,
-                              L.stride, L.transposed, y, y_dtype, st, ws + p.scratch_off, s);
+                                L.stride, L.transposed, y, MVSB200_F32, st, s);
+    } else {
+      // stride-2 convs read the parity-split copy of their input, everything else the chunk-planar one
+      const bool s2 = L.stride == 2 && !L.transposed;
+      const void* x = L.src < 0 ? (const void*)(ws + (s2 ? p.cost_ps8_off : p.cost_cp8_off))
+                                : (const void*)(ws + (s2 ? p.ps8_off[L.src] : p.raw_off[L.src]));
+      if (!last && p.has_ps8[i] && ((p.dims[L.out_level][1] | p.dims[L.out_level][2]) & 1)) {
+        const int* o = p.dims[L.out_level];
+        MVS_CUDA(cudaMemsetAsync(ws + p.ps8_off[i], 0, planar_bytes(o[0], o[1], o[2], L.cout, 1), s));
+      }
+      rc = launch_conv3d_tc(x, xs, xb, sk, ss, sb, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout, L.stride,
+                            L.transposed, last ? nullptr : ws + p.raw_off[i],
+                            (!last && p.has_ps8[i]) ? ws + p.ps8_off[i] : nullptr, last ? filtered : nullptr, st,
+                            ws + p.scratch_off, s);
+    }
     if (rc) return rc;
     if (!last) {
       // stats hold sum over L.cout channels laid out [sum(cout) | sumsq(cout)]
@@ -170,8 +223,32 @@ int regnet_forward_impl(const void* cost, int cost_dtype, const mvsb200_regnet_p
                               scale + (size_t)i * cpad, shift + (size_t)i * cpad, s);
       if (rc) return rc;
     }
+    if (profile) cudaEventRecord(pev[i + 1], s);
+  }
+  if (profile) {
+    static const char* names[MVSB200_REGNET_LAYERS] = {"3dconv1_0", "3dconv2_0", "3dconv3_0", "3dconv0_1", "3dconv1_1",
+                                                       "3dconv2_1", "3dconv3_1", "3dconv4_0", "3dconv5_0", "3dconv6_0",
+                                                       "3dconv6_2"};
+    cudaStreamSynchronize(s);
+    float total = 0.f;
+    for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pev[i], pev[i + 1]);
+      total += ms;
+      fprintf(stderr, "[regnet] %s %.3f ms\n", names[i], ms);
+    }
+    fprintf(stderr, "[regnet] total %.3f ms\n", total);
+    for (int i = 0; i <= MVSB200_REGNET_LAYERS; ++i) cudaEventDestroy(pev[i]);
   }
   return MVSB200_OK;
+}
+
+// bf16 mode: where the fused path writes the cost volume (chunk-planar and parity-split copies)
+void regnet_cost_planar(void* workspace, int D, int H, int W, int cin, int b, void** cp8, void** ps8) {
+  RegnetPlan p;
+  make_plan(D, H, W, cin, b, MVSB200_PRECISION_BF16, &p);
+  *cp8 = (char*)workspace + p.cost_cp8_off;
+  *ps8 = (char*)workspace + p.cost_ps8_off;
 }
 
 }  // namespace mvsb200
@@ -205,7 +282,7 @@ extern "C" int mvsb200_regnet_forward(const void* cost, int cost_dtype, const mv
                                       int depth, int hf, int wf, int in_channels, int base_filter, float bn_eps,
                                       int precision, float* filtered, void* workspace, size_t workspace_bytes,
                                       void* stream) {
-  return regnet_forward_impl(cost, cost_dtype, params, depth, hf, wf, in_channels, base_filter, bn_eps, precision,
+  return regnet_forward_impl(cost, cost_dtype, 0, params, depth, hf, wf, in_channels, base_filter, bn_eps, precision,
                              filtered, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -226,6 +303,11 @@ extern "C" const void* mvsb200_regnet_layer_raw(const void* workspace, int depth
 // ---------------------------------------------------------------------------------------------
 // whole path
 // ---------------------------------------------------------------------------------------------
+namespace mvsb200 {
+bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sampler);
+int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
+                              int wf, int channels, int order, int sampler, void* cp8, void* ps8, cudaStream_t s);
+}
 namespace {
 struct InferPlan {
   size_t hom_off, cost_off, filtered_off, regnet_off, total;
@@ -234,6 +316,8 @@ struct InferPlan {
 void make_infer_plan(int n_views, int D, int hf, int wf, int C, int b, int precision, InferPlan* ip) {
   size_t off = 0;
   ip->hom_off = off;      off += align_up((size_t)(n_views - 1) * D * 9 * sizeof(float), 256);
+  // (bf16 mode with the fast cost-volume kernel writes the volume straight into the regularizer's planar buffers
+  // inside its workspace; the NDHWC buffer is then unused but stays reserved: the sampler is a per-call choice)
   ip->cost_off = off;     off += align_up((size_t)D * hf * wf * C * (precision == MVSB200_PRECISION_BF16 ? 2 : 4), 256);
   ip->filtered_off = off; off += align_up((size_t)D * hf * wf * sizeof(float), 256);
   ip->regnet_off = off;
@@ -296,11 +380,19 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   if (rc) return rc;
   MVS_STAGE_EVENT(1);
   const int cost_dtype = precision == MVSB200_PRECISION_BF16 ? MVSB200_BF16 : MVSB200_F32;
-  rc = launch_cost_volume(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cost_dtype, cost, 0, s);
+  const bool planar = precision == MVSB200_PRECISION_BF16 && sampler == MVSB200_SAMPLER_TRANSFORM &&
+                      cost_volume_planar_ok(n_views, hf, wf, channels, sampler);
+  if (planar) {
+    void *cp8 = nullptr, *ps8 = nullptr;
+    regnet_cost_planar(ws + ip.regnet_off, depth_num, hf, wf, channels, base_filter, &cp8, &ps8);
+    rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8, s);
+  } else {
+    rc = launch_cost_volume(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cost_dtype, cost, 0, s);
+  }
   if (rc) return rc;
   MVS_STAGE_EVENT(2);
-  rc = regnet_forward_impl(cost, cost_dtype, params, depth_num, hf, wf, channels, base_filter, bn_eps, precision,
-                           filtered, ws + ip.regnet_off, ip.regnet_bytes, s);
+  rc = regnet_forward_impl(cost, cost_dtype, planar ? 1 : 0, params, depth_num, hf, wf, channels, base_filter, bn_eps,
+                           precision, filtered, ws + ip.regnet_off, ip.regnet_bytes, s);
   if (rc) return rc;
   MVS_STAGE_EVENT(3);
   rc = launch_depth_regress(filtered, depth_num, hf, wf, depth_start, depth_interval, inverse_depth, 4, depth_map,

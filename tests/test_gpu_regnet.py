@@ -167,20 +167,17 @@ def test_regnet_bf16_vs_oracle(O, small_problem):
 
 
 @pytest.mark.parametrize("zf", [1, 2, 4])
-@pytest.mark.parametrize("tma", [0, 1])
 @pytest.mark.parametrize("case", [(8, 16, 24, 32, 8, 1, False), (7, 9, 11, 16, 16, 1, False), (10, 16, 24, 8, 1, 1, False),
                                   (18, 20, 40, 32, 8, 1, False), (8, 16, 24, 32, 16, 2, False),
                                   (7, 9, 11, 32, 16, 2, False)])
-def test_bf16_zfold_and_tma_variants(ops, O, monkeypatch, case, zf, tma):
-    """z-fold (several output planes per MMA N) and the TMA tensor-map loader against the oracle, incl. ragged D."""
+def test_bf16_zfold_variants(ops, O, monkeypatch, case, zf):
+    """z-fold (several output planes per MMA N, master B images) against the oracle, incl. ragged D."""
     D, H, W, cin, cout, stride, tr = case
     if stride == 2 and zf != 1:
         pytest.skip("z-fold applies to stride-1 convs only")
     if zf * cout > 32:
         pytest.skip("fold does not fit N <= 32")
-    monkeypatch.setenv("MVSB200_UMMA_ZF", str(zf))
-    if not tma:
-        monkeypatch.setenv("MVSB200_UMMA_NO_TMA", "1")
+    monkeypatch.setenv("MVSB200_TC_ZF", str(zf))
     rng = np.random.RandomState(41)
     x = bf16_round(rng.randn(D, H, W, cin))
     w = (rng.randn(3, 3, 3, cin, cout) * 0.1).astype(np.float32)
@@ -188,8 +185,23 @@ def test_bf16_zfold_and_tma_variants(ops, O, monkeypatch, case, zf, tma):
     ref = _layer_ref(O, x, bf16_round(w), stride, tr)
     assert tuple(y.shape) == ref.shape
     err = np.abs(y.cpu().numpy() - ref).max()
-    assert err <= 1e-3 * max(1.0, np.abs(ref).max()), f"{case} zf={zf} tma={tma}: max abs err {err}"
+    assert err <= 1e-3 * max(1.0, np.abs(ref).max()), f"{case} zf={zf}: max abs err {err}"
     st = stats.cpu().numpy()
     r64 = ref.reshape(-1, cout).astype(np.float64)
     np.testing.assert_allclose(st[:cout], r64.sum(0), rtol=1e-3, atol=0.5)
     np.testing.assert_allclose(st[cout:], (r64 ** 2).sum(0), rtol=1e-3, atol=0.5)
+
+
+@pytest.mark.parametrize("case", [(8, 16, 24, 32, 8, 1, False), (7, 9, 11, 16, 16, 2, False), (6, 10, 12, 32, 16, 2, True)])
+def test_bf16_layer_bf16_output_layouts(ops, O, case):
+    """bf16 output goes through the chunk-planar layout and back to NDHWC (stand-alone entry)."""
+    D, H, W, cin, cout, stride, tr = case
+    rng = np.random.RandomState(52)
+    x = bf16_round(rng.randn(D, H, W, cin))
+    w = (rng.randn(*((3, 3, 3, cout, cin) if tr else (3, 3, 3, cin, cout))) * 0.1).astype(np.float32)
+    y, _ = ops.conv3d_layer(to_dev(x).to(torch.bfloat16), to_dev(w), stride, tr, "bf16")
+    assert y.dtype == torch.bfloat16
+    ref = _layer_ref(O, x, bf16_round(w), stride, tr)
+    assert tuple(y.shape) == ref.shape
+    err = np.abs(y.float().cpu().numpy() - ref).max()
+    assert err <= 1e-2 * max(1.0, np.abs(ref).max()), f"{case}: max abs err {err}"

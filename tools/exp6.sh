@@ -1,0 +1,2 @@
+export MVSB200_TC_VERBOSE=1 MVSB200_REGNET_PROFILE=1 MVSB200_TC_PROF=1
+timeout 300 python tools/stage_bench.py --skip-cv --regnet bf16 --out gpurun_out/tmp.json 2>&1 | grep "tc-prof\|\[regnet\]" | tail -26

@@ -39,7 +39,7 @@ def main():
         e.record()
         torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
-    print(a.layer, "dbg=%s" % os.environ.get("MVSB200_UMMA_DBG", "0"), "ms:", " ".join("%.3f" % t for t in ts), flush=True)
+    print(a.layer, "dbg=%s" % os.environ.get("MVSB200_TC_DBG", "0"), "ms:", " ".join("%.3f" % t for t in ts), flush=True)
 
 
 if __name__ == "__main__":

@@ -7,6 +7,8 @@
 // Transform coefficients live in __constant__ memory (one 8-float row per (view, plane),
 // written once per call by prepare_table_kernel + a device-to-device symbol copy).
 #include "geometry.cuh"
+#include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace mvsb200 {
 
@@ -26,6 +28,25 @@ __global__ void prepare_table_kernel(const float* __restrict__ homographies, int
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of fp32 math)
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
+}
 
 __device__ __forceinline__ float variance(float S, float Q, float n_f, float nn_f, int order) {
   if (order == MVSB200_ORDER_MEM) {
@@ -48,111 +69,214 @@ __device__ __forceinline__ void store_cost4(void* out, size_t elem, float4 c, bo
   }
 }
 
+// x-paired fp16 copy of the source-view features (see TAPS16 below): out [N][Hf][Wf+1][8][2][4]
+__global__ void pair_features_kernel(const float* __restrict__ feats, int n_views, int Hf, int Wf,
+                                     __half* __restrict__ out) {
+  const size_t total = (size_t)n_views * Hf * (Wf + 1) * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    size_t t = i >> 3;
+    const int j = (int)(t % (Wf + 1)); t /= (Wf + 1);     // pair j = pixels (j-1, j)
+    const size_t row = t;                                  // view * Hf + y
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (j >= 1) a = ldg4(feats + (row * Wf + (j - 1)) * 32 + g * 4);
+    if (j < Wf) b = ldg4(feats + (row * Wf + j) * 32 + g * 4);
+    __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y),
+                    __floats2half2_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// Fast path, C = 32: block = 32 reference pixels x 8 channel groups (float4), DC = 8 planes per
-// thread.  The 8 lanes of a pixel each build the complete bilinear footprint of a different plane
-// (sample position with 2 IEEE divisions, the four weights, the clamped tap coordinates) and
-// broadcast it with shuffles, so that work is done once per voxel and view instead of once per
-// channel group.  A tap outside the image gets weight 0 and a clamped (always mapped) address,
-// which is arithmetically identical to the reference's zero fill (0 * finite feature) and keeps
-// the loads unpredicated.  Taps are 128-bit loads through L1 (the features are L2-resident:
-// 5 x 216 x 288 x 32 fp32 = 40 MB at config 2); the running sum and squared sum of the 8 planes
-// stay in registers across views.
+// Fast path, C = 32: block = 32 reference pixels x 8 channel groups (float4), KDC planes per thread and
+// group, a block walks kPlaneChunk consecutive planes (consecutive planes of a pixel sample neighbouring
+// source pixels, so their taps hit in L1).  The KDC x (N-1) bilinear footprints of a pixel and plane group
+// (sample position with 2 IEEE divisions, the four weights, the clamped tap coordinates) are built once,
+// 8 at a time by the 8 lanes of the pixel, and handed to the other lanes through shared memory (one
+// 16-byte and one 8-byte broadcast load per footprint; shuffles would cost as many L1 data-pipe wavefronts
+// as the taps).  KDC is the smallest of 2 / 4 / 8 for which KDC*(N-1) fills whole rounds of 8: few
+// accumulators per thread (KDC = 2 at N = 5) leave registers for 4 resident blocks per SM.  A tap outside
+// the image gets weight 0 and a clamped (always mapped) address, which is arithmetically identical to the
+// reference's zero fill (0 * finite feature) and keeps the loads unpredicated.  Taps are 128-bit loads
+// through L1 (the features are L2-resident: 5 x 216 x 288 x 32 fp32 = 40 MB at config 2); the running sum
+// and squared sum stay in registers across views, accumulated in view order.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDC = 8;
 constexpr int kMaxSrcViews = 7;
+constexpr int kPlaneChunk = 48;
 
 // OUT: 0 = fp32 [D,Hf,Wf,32], 1 = bf16 [D,Hf,Wf,32], 2 = bf16 in the regularizer's planar layouts (conv3d_tc.cu):
 // out = CP8 [D][4][Hf][Wf][8] and out2 = PS8 [D][4][4][Hs][Ws][8] (either may be NULL)
-template <int OUT, int TX, int TY>
-__global__ void __launch_bounds__(256, 2)
-cost_volume_c32_kernel(const float* __restrict__ feats, int n_views, int D, int Hf, int Wf, int order,
-                       void* __restrict__ out, void* __restrict__ out2) {
+// TAPS16: the source views are read from the x-paired fp16 copy built by pair_features_kernel (product mode):
+// feats16 [N][Hf][Wf+1][8 groups][2 pixels][4 ch], pair j = pixels (j-1, j) with zeros outside the image, so the
+// two horizontal taps of a footprint row arrive in ONE 16-byte load per lane and one 128-byte line per pixel
+// (half the L1 wavefronts and load instructions of the fp32 path).  The reference view stays fp32.
+template <int OUT, int TX, int TY, int KDC, bool TAPS16>
+__global__ void __launch_bounds__(256, KDC == 2 ? 4 : (KDC == 4 ? 3 : 2))
+cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict__ feats16, int n_views, int D, int Hf,
+                       int Wf, int order, void* __restrict__ out, void* __restrict__ out2) {
   static_assert(TX * TY == 32, "tile must hold 32 pixels");
-  __shared__ float s_coef[kMaxSrcViews * kDC * 8];
+  static_assert(KDC == 2 || KDC == 4 || KDC == 8, "planes per thread");
+  constexpr int VPR = 8 / KDC;            // source views per footprint round
+  __shared__ float s_coef[kMaxSrcViews * kPlaneChunk * 8];
+  __shared__ float4 s_fw[32][9];          // per pixel: bilinear weights of one round (+1: bank spread)
+  __shared__ int2 s_fi[32][9];            // per pixel: packed clamped tap columns / rows
+  __shared__ uint4 s_cells[OUT == 2 ? KDC * 4 * 32 + 16 : 1];   // one group of output cells (planar layouts)
   const int tid = threadIdx.x;
-  const int g = tid & 7;            // channel group (4 channels) and plane slot for the footprint
+  const int g = tid & 7;            // channel group (4 channels) and footprint slot of the round
   const int p = tid >> 3;           // pixel within the tile
   const int x = blockIdx.x * TX + (p % TX);
   const int y = blockIdx.y * TY + (p / TX);
-  const int d0 = blockIdx.z * kDC;
+  const int dbeg = blockIdx.z * kPlaneChunk;
   const int n_src = n_views - 1;
-  for (int i = tid; i < n_src * kDC * 8; i += 256) {
-    int v = i / (kDC * 8), r = i - v * (kDC * 8);
-    int d = min(d0 + (r >> 3), D - 1);
+  for (int i = tid; i < n_src * kPlaneChunk * 8; i += 256) {
+    int v = i / (kPlaneChunk * 8), r = i - v * (kPlaneChunk * 8);
+    int d = min(dbeg + (r >> 3), D - 1);
     s_coef[i] = c_table[(v * D + d) * 8 + (r & 7)];
   }
   __syncthreads();
   const bool active = (x < Wf) && (y < Hf);
   const int xc = min(x, Wf - 1), yc = min(y, Hf - 1);
-  const size_t plane = (size_t)Hf * Wf * 32;
+  const size_t plane = (size_t)Hf * Wf * 32, plane16 = (size_t)Hf * (Wf + 1) * 64;
   const float4 r = ldg4(feats + ((size_t)yc * Wf + xc) * 32 + g * 4);
-  float4 S[kDC], Q[kDC];
-#pragma unroll
-  for (int dd = 0; dd < kDC; ++dd) {
-    S[dd] = r;
-    Q[dd] = make_float4(r.x * r.x, r.y * r.y, r.z * r.z, r.w * r.w);
-  }
-  const unsigned lane_base = (threadIdx.x & 31) & ~7u;
-  for (int v = 0; v < n_src; ++v) {
-    const float* img = feats + (size_t)(v + 1) * plane + g * 4;
-    // this lane's plane: position, weights (0 where the tap is outside), clamped tap rows / columns
-    float ix, iy;
-    transform_coords(&s_coef[(v * kDC + g) * 8], (float)xc, (float)yc, ix, iy);
-    const Footprint f = make_footprint(ix, iy, Wf, Hf);
-    const float l_wxl = f.vx0 ? f.wxl : 0.0f, l_wxr = f.vx1 ? f.wxr : 0.0f;
-    const float l_wyl = f.vy0 ? f.wyl : 0.0f, l_wyr = f.vy1 ? f.wyr : 0.0f;
-    const int cx0 = min(max(f.x0, 0), Wf - 1), cx1 = min(max(f.x0 + 1, 0), Wf - 1);
-    const int cy0 = min(max(f.y0, 0), Hf - 1), cy1 = min(max(f.y0 + 1, 0), Hf - 1);
-    const int l_col = cx0 | (cx1 << 16), l_row = cy0 | (cy1 << 16);
-#pragma unroll
-    for (int dd = 0; dd < kDC; ++dd) {
-      const unsigned src = lane_base | dd;
-      const float wxl = __shfl_sync(0xffffffffu, l_wxl, src), wxr = __shfl_sync(0xffffffffu, l_wxr, src);
-      const float wyl = __shfl_sync(0xffffffffu, l_wyl, src), wyr = __shfl_sync(0xffffffffu, l_wyr, src);
-      const int col = __shfl_sync(0xffffffffu, l_col, src), row = __shfl_sync(0xffffffffu, l_row, src);
-      const int x0 = col & 0xffff, x1 = col >> 16;
-      const int r0 = (row & 0xffff) * Wf, r1 = (row >> 16) * Wf;
-      const float4 p00 = ldg4(img + (size_t)(r0 + x0) * 32), p01 = ldg4(img + (size_t)(r0 + x1) * 32);
-      const float4 p10 = ldg4(img + (size_t)(r1 + x0) * 32), p11 = ldg4(img + (size_t)(r1 + x1) * 32);
-      float4 w;
-      w.x = wyl * (wxl * p00.x + wxr * p01.x) + wyr * (wxl * p10.x + wxr * p11.x);
-      w.y = wyl * (wxl * p00.y + wxr * p01.y) + wyr * (wxl * p10.y + wxr * p11.y);
-      w.z = wyl * (wxl * p00.z + wxr * p01.z) + wyr * (wxl * p10.z + wxr * p11.z);
-      w.w = wyl * (wxl * p00.w + wxr * p01.w) + wyr * (wxl * p10.w + wxr * p11.w);
-      S[dd].x += w.x; S[dd].y += w.y; S[dd].z += w.z; S[dd].w += w.w;
-      Q[dd].x += w.x * w.x; Q[dd].y += w.y * w.y; Q[dd].z += w.z * w.z; Q[dd].w += w.w * w.w;
-    }
-  }
-  if (!active) return;
-  // variance with reciprocal multiplies (<= 1 ulp from the reference's divisions, model.py:458-461 / :330-332)
+  const float4 rq = make_float4(r.x * r.x, r.y * r.y, r.z * r.z, r.w * r.w);
   const float inv_n = 1.0f / (float)n_views, inv_nn = 1.0f / (float)(n_views * n_views);
+  const int dend = min(D, dbeg + kPlaneChunk);
+  const int rounds = (KDC * n_src) / 8;       // the launcher picks KDC so that this is exact
+  const char* base16 = reinterpret_cast<const char*>(feats16) + g * 16;
+  // footprint slot g of a round: view (round*VPR + g / KDC), plane g % KDC of the group
+  const int my_dd = g % KDC, my_dv = g / KDC;
+  for (int d0 = dbeg; d0 < dend; d0 += KDC) {
+    float4 S[KDC], Q[KDC];
 #pragma unroll
-  for (int dd = 0; dd < kDC; ++dd) {
-    const int d = d0 + dd;
-    if (d < D) {
-      float4 c;
+    for (int dd = 0; dd < KDC; ++dd) { S[dd] = r; Q[dd] = rq; }
+    for (int rd = 0; rd < rounds; ++rd) {
+      {
+        const int v = rd * VPR + my_dv;
+        float ix, iy;
+        transform_coords(&s_coef[(v * kPlaneChunk + (d0 - dbeg) + my_dd) * 8], (float)xc, (float)yc, ix, iy);
+        const Footprint f = make_footprint(ix, iy, Wf, Hf);
+        const float l_wxl = f.vx0 ? f.wxl : 0.0f, l_wxr = f.vx1 ? f.wxr : 0.0f;
+        const float l_wyl = f.vy0 ? f.wyl : 0.0f, l_wyr = f.vy1 ? f.wyr : 0.0f;
+        const int cx0 = min(max(f.x0, 0), Wf - 1), cx1 = min(max(f.x0 + 1, 0), Wf - 1);
+        const int cy0 = min(max(f.y0, 0), Hf - 1), cy1 = min(max(f.y0 + 1, 0), Hf - 1);
+        __syncwarp();
+        if (TAPS16) {
+          // the four tap weights as products, and the byte offsets of the two row pairs inside feats16: pair index
+          // of (x0, x0+1) in [0, Wf] (either pixel may be the zero guard; its weight is 0 there)
+          const int xp = min(max(f.x0 + 1, 0), Wf);
+          const unsigned vbase = (unsigned)(v + 1) * (unsigned)(Hf * (Wf + 1));
+          s_fw[p][g] = make_float4(l_wyl * l_wxl, l_wyl * l_wxr, l_wyr * l_wxl, l_wyr * l_wxr);
+          s_fi[p][g] = make_int2((int)((vbase + (unsigned)(cy0 * (Wf + 1) + xp)) * 128u),
+                                 (int)((vbase + (unsigned)(cy1 * (Wf + 1) + xp)) * 128u));
+        } else {
+          s_fw[p][g] = make_float4(l_wxl, l_wxr, l_wyl, l_wyr);
+          s_fi[p][g] = make_int2(cx0 | (cx1 << 16), cy0 | (cy1 << 16));
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        constexpr int kdc = KDC;
+        const int dd = j % kdc;                       // compile-time after unrolling
+        const float4 fw = s_fw[p][j];
+        const int2 fi = s_fi[p][j];
+        float4 w;
+        if (TAPS16) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.x));
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.y));
+          const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+          const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&a.z)), a3 = __half22float2(*reinterpret_cast<const __half2*>(&a.w));
+          const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+          const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&b.z)), b3 = __half22float2(*reinterpret_cast<const __half2*>(&b.w));
+          // fw = (w00, w01, w10, w11): 4 multiply-adds per channel instead of 6, two channels per packed
+          // instruction (rounding differs from the reference op order by an ulp or two; this variant feeds a
+          // bf16 volume)
+          const float2 w00 = make_float2(fw.x, fw.x), w01 = make_float2(fw.y, fw.y), w10 = make_float2(fw.z, fw.z),
+                       w11 = make_float2(fw.w, fw.w);
+          const float2 lo = ffma2(w11, b2, ffma2(w10, b0, ffma2(w01, a2, fmul2(w00, a0))));
+          const float2 hi = ffma2(w11, b3, ffma2(w10, b1, ffma2(w01, a3, fmul2(w00, a1))));
+          float2* S2 = reinterpret_cast<float2*>(&S[dd]);
+          float2* Q2 = reinterpret_cast<float2*>(&Q[dd]);
+          S2[0] = fadd2(S2[0], lo); S2[1] = fadd2(S2[1], hi);
+          Q2[0] = ffma2(lo, lo, Q2[0]); Q2[1] = ffma2(hi, hi, Q2[1]);
+          continue;
+        } else {
+          const float wxl = fw.x, wxr = fw.y, wyl = fw.z, wyr = fw.w;
+          const float* img = feats + (size_t)(rd * VPR + j / kdc + 1) * plane + g * 4;
+          const int x0 = fi.x & 0xffff, x1 = fi.x >> 16;
+          const int r0 = (fi.y & 0xffff) * Wf, r1 = (fi.y >> 16) * Wf;
+          const float4 p00 = ldg4(img + (size_t)(r0 + x0) * 32), p01 = ldg4(img + (size_t)(r0 + x1) * 32);
+          const float4 p10 = ldg4(img + (size_t)(r1 + x0) * 32), p11 = ldg4(img + (size_t)(r1 + x1) * 32);
+          w.x = wyl * (wxl * p00.x + wxr * p01.x) + wyr * (wxl * p10.x + wxr * p11.x);
+          w.y = wyl * (wxl * p00.y + wxr * p01.y) + wyr * (wxl * p10.y + wxr * p11.y);
+          w.z = wyl * (wxl * p00.z + wxr * p01.z) + wyr * (wxl * p10.z + wxr * p11.z);
+          w.w = wyl * (wxl * p00.w + wxr * p01.w) + wyr * (wxl * p10.w + wxr * p11.w);
+        }
+        S[dd].x += w.x; S[dd].y += w.y; S[dd].z += w.z; S[dd].w += w.w;
+        Q[dd].x += w.x * w.x; Q[dd].y += w.y * w.y; Q[dd].z += w.z * w.z; Q[dd].w += w.w * w.w;
+      }
+    }
+    // variance with reciprocal multiplies (<= 1 ulp from the reference's divisions, model.py:458-461 / :330-332)
+    float4 c[KDC];
+#pragma unroll
+    for (int dd = 0; dd < KDC; ++dd) {
       if (order == MVSB200_ORDER_MEM) {
-        c.x = Q[dd].x * inv_n - (S[dd].x * S[dd].x) * inv_nn;
-        c.y = Q[dd].y * inv_n - (S[dd].y * S[dd].y) * inv_nn;
-        c.z = Q[dd].z * inv_n - (S[dd].z * S[dd].z) * inv_nn;
-        c.w = Q[dd].w * inv_n - (S[dd].w * S[dd].w) * inv_nn;
+        c[dd].x = Q[dd].x * inv_n - (S[dd].x * S[dd].x) * inv_nn;
+        c[dd].y = Q[dd].y * inv_n - (S[dd].y * S[dd].y) * inv_nn;
+        c[dd].z = Q[dd].z * inv_n - (S[dd].z * S[dd].z) * inv_nn;
+        c[dd].w = Q[dd].w * inv_n - (S[dd].w * S[dd].w) * inv_nn;
       } else {
         const float mx = S[dd].x * inv_n, my = S[dd].y * inv_n, mz = S[dd].z * inv_n, mw = S[dd].w * inv_n;
-        c.x = Q[dd].x * inv_n - mx * mx;
-        c.y = Q[dd].y * inv_n - my * my;
-        c.z = Q[dd].z * inv_n - mz * mz;
-        c.w = Q[dd].w * inv_n - mw * mw;
+        c[dd].x = Q[dd].x * inv_n - mx * mx;
+        c[dd].y = Q[dd].y * inv_n - my * my;
+        c[dd].z = Q[dd].z * inv_n - mz * mz;
+        c[dd].w = Q[dd].w * inv_n - mw * mw;
       }
-      if (OUT < 2) {
-        store_cost4(out, (((size_t)d * Hf + y) * Wf + x) * 32 + g * 4, c, OUT == 1);
-      } else {
-        // 8-byte half of the 16-byte cell (chunk g>>1) of this voxel
-        const size_t zc = (size_t)d * 4 + (g >> 1);
-        if (out) store_cost4(out, ((zc * Hf + y) * Wf + x) * 8 + (g & 1) * 4, c, true);
-        if (out2) {
-          const int Hs = (Hf + 1) >> 1, Ws = (Wf + 1) >> 1;
-          store_cost4(out2, (((zc * 4 + (y & 1) * 2 + (x & 1)) * Hs + (y >> 1)) * Ws + (x >> 1)) * 8 + (g & 1) * 4, c, true);
+    }
+    if (OUT < 2) {
+      if (active) {
+#pragma unroll
+        for (int dd = 0; dd < KDC; ++dd)
+          if (d0 + dd < D) store_cost4(out, (((size_t)(d0 + dd) * Hf + y) * Wf + x) * 32 + g * 4, c[dd], OUT == 1);
+      }
+    } else {
+      // planar layouts: lanes g and g^1 hold the two halves of a 16-byte cell (chunk g>>1).  They swap halves of
+      // neighbouring planes so that the even lane owns the whole cell of plane 2k and the odd lane that of 2k+1;
+      // the cells go through shared memory so that the global stores run along x (whole 32-byte sectors in both
+      // the chunk-planar and the parity-split copy).
+      const bool odd = g & 1;
+      __syncthreads();                       // the previous group's cells have been read
+#pragma unroll
+      for (int k = 0; k < KDC / 2; ++k) {
+        const float4 mine = odd ? c[2 * k + 1] : c[2 * k], give = odd ? c[2 * k] : c[2 * k + 1];
+        __nv_bfloat162 g0 = __floats2bfloat162_rn(give.x, give.y), g1 = __floats2bfloat162_rn(give.z, give.w);
+        const uint32_t t0 = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&g0), 1);
+        const uint32_t t1 = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&g1), 1);
+        __nv_bfloat162 m0 = __floats2bfloat162_rn(mine.x, mine.y), m1 = __floats2bfloat162_rn(mine.z, mine.w);
+        const uint32_t u0 = *reinterpret_cast<uint32_t*>(&m0), u1 = *reinterpret_cast<uint32_t*>(&m1);
+        // channel order inside the cell: even lane's 4 channels first
+        const int pc = (2 * k + (odd ? 1 : 0)) * 4 + (g >> 1);
+        s_cells[pc * 32 + p + (pc >> 1)] = odd ? make_uint4(t0, t1, u0, u1) : make_uint4(u0, u1, t0, t1);
+      }
+      __syncthreads();
+      const int Hs = (Hf + 1) >> 1, Ws = (Wf + 1) >> 1;
+      // cell i of the group: (plane, chunk) = i / 32, pixel slot = i % 32 visited parity-major along x
+#pragma unroll
+      for (int k = 0; k < KDC / 2; ++k) {
+        const int i = k * 256 + tid;
+        const int pc = i >> 5, l = i & 31;
+        int px;                                           // pixel index inside the TX x TY tile
+        if (TX == 16) px = (l >> 4) * 16 + 2 * (l & 7) + ((l >> 3) & 1);
+        else px = 2 * (l & 15) + (l >> 4);
+        const int xx = blockIdx.x * TX + (px % TX), yy = blockIdx.y * TY + (px / TX);
+        const int d = d0 + (pc >> 2);
+        if (xx < Wf && yy < Hf && d < D) {
+          const uint4 cell = s_cells[pc * 32 + px + (pc >> 1)];
+          const size_t zc = (size_t)d * 4 + (pc & 3);
+          if (out) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + ((zc * Hf + yy) * Wf + xx) * 8) = cell;
+          if (out2)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out2) +
+                                      (((zc * 4 + (yy & 1) * 2 + (xx & 1)) * Hs + (yy >> 1)) * Ws + (xx >> 1)) * 8) = cell;
         }
       }
     }
@@ -239,7 +363,7 @@ cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restr
 // planar_ps8 != NULL or planar != 0: write the bf16 planar layouts (out = CP8, planar_ps8 = PS8); fast path only
 static int launch_cost_volume_any(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                                   int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
-                                  int planar, void* planar_ps8, cudaStream_t s) {
+                                  int planar, void* planar_ps8, void* feats16, cudaStream_t s) {
   MVS_CHECK_ARG(feats && homographies && (out || planar_ps8), "cost_volume: NULL pointer");
   MVS_CHECK_ARG(n_views >= 2 && depth_num >= 1 && hf >= 1 && wf >= 1 && channels >= 1,
                 "cost_volume: bad shape N=%d D=%d %dx%dx%d", n_views, depth_num, hf, wf, channels);
@@ -278,15 +402,40 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
                                      cudaMemcpyDeviceToDevice, s));
     const bool wide = variant == 2;
     const int tx = wide ? 32 : 16, ty = wide ? 1 : 2;
-    dim3 grid(ceil_div(wf, tx), ceil_div(hf, ty), ceil_div(depth_num, kDC));
+    dim3 grid(ceil_div(wf, tx), ceil_div(hf, ty), ceil_div(depth_num, kPlaneChunk));
     MVS_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "cost_volume: grid too large");
-#define CV_FAST(O, TX_, TY_) \
-  cost_volume_c32_kernel<O, TX_, TY_><<<grid, 256, 0, s>>>(feats, n_views, depth_num, hf, wf, order, out, planar_ps8)
+#define CV_FAST(O, TX_, TY_, K_)                                                                                  \
+  do {                                                                                                            \
+    if (O == 2 && feats16)                                                                                        \
+      cost_volume_c32_kernel<O, TX_, TY_, K_, true><<<grid, 256, 0, s>>>(feats, (const __half*)feats16, n_views,  \
+                                                                         depth_num, hf, wf, order, out, planar_ps8); \
+    else                                                                                                          \
+      cost_volume_c32_kernel<O, TX_, TY_, K_, false><<<grid, 256, 0, s>>>(feats, nullptr, n_views, depth_num, hf, \
+                                                                          wf, order, out, planar_ps8);            \
+  } while (0)
+#define CV_FAST_K(O, TX_, TY_)                                  \
+  do {                                                          \
+    if (kdc == 2) CV_FAST(O, TX_, TY_, 2);                      \
+    else if (kdc == 4) CV_FAST(O, TX_, TY_, 4);                 \
+    else CV_FAST(O, TX_, TY_, 8);                               \
+  } while (0)
     if (planar && ((hf | wf) & 1) && planar_ps8)
       MVS_CUDA(cudaMemsetAsync(planar_ps8, 0, (size_t)depth_num * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) * 16, s));
-    if (planar) { if (wide) CV_FAST(2, 32, 1); else CV_FAST(2, 16, 2); }
-    else if (wide) { if (bf16) CV_FAST(1, 32, 1); else CV_FAST(0, 32, 1); }
-    else           { if (bf16) CV_FAST(1, 16, 2); else CV_FAST(0, 16, 2); }
+    if (planar && feats16) {
+      pair_features_kernel<<<148 * 8, 256, 0, s>>>(feats, n_views, hf, wf, (__half*)feats16);
+      MVS_LAUNCH_CHECK("pair_features_kernel");
+    }
+    // planes per thread: the smallest of 2 / 4 / 8 whose footprints fill whole rounds of 8 lanes
+    const int n_src = n_views - 1;
+    int kdc = (2 * n_src) % 8 == 0 ? 2 : ((4 * n_src) % 8 == 0 ? 4 : 8);
+    if (const char* e = getenv("MVSB200_CV_KDC")) {           // tuning: 2 / 4 / 8 when it still fills whole rounds
+      const int k = atoi(e);
+      if ((k == 2 || k == 4 || k == 8) && (k * n_src) % 8 == 0) kdc = k;
+    }
+    if (planar) { if (wide) CV_FAST_K(2, 32, 1); else CV_FAST_K(2, 16, 2); }
+    else if (wide) { if (bf16) CV_FAST_K(1, 32, 1); else CV_FAST_K(0, 32, 1); }
+    else           { if (bf16) CV_FAST_K(1, 16, 2); else CV_FAST_K(0, 16, 2); }
+#undef CV_FAST_K
 #undef CV_FAST
     MVS_LAUNCH_CHECK("cost_volume_c32_kernel");
     return MVSB200_OK;
@@ -314,7 +463,7 @@ int launch_cost_volume(const float* feats, const float* homographies, int n_view
                        int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
                        cudaStream_t s) {
   return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler, out_dtype,
-                                out, variant, 0, nullptr, s);
+                                out, variant, 0, nullptr, nullptr, s);
 }
 
 bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sampler) {
@@ -322,10 +471,14 @@ bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sample
          wf < 32768;
 }
 
+// feats16: scratch of cost_volume_pair_bytes() for the x-paired fp16 copy of the features (NULL: fp32 taps)
+size_t cost_volume_pair_bytes(int n_views, int hf, int wf) { return (size_t)n_views * hf * (wf + 1) * 128; }
+
 int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
-                              int wf, int channels, int order, int sampler, void* cp8, void* ps8, cudaStream_t s) {
+                              int wf, int channels, int order, int sampler, void* cp8, void* ps8, void* feats16,
+                              cudaStream_t s) {
   return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler,
-                                MVSB200_BF16, cp8, 0, 1, ps8, s);
+                                MVSB200_BF16, cp8, 0, 1, ps8, feats16, s);
 }
 
 }  // namespace mvsb200

@@ -306,11 +306,13 @@ extern "C" const void* mvsb200_regnet_layer_raw(const void* workspace, int depth
 namespace mvsb200 {
 bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sampler);
 int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
-                              int wf, int channels, int order, int sampler, void* cp8, void* ps8, cudaStream_t s);
+                              int wf, int channels, int order, int sampler, void* cp8, void* ps8, void* feats16,
+                              cudaStream_t s);
+size_t cost_volume_pair_bytes(int n_views, int hf, int wf);
 }
 namespace {
 struct InferPlan {
-  size_t hom_off, cost_off, filtered_off, regnet_off, total;
+  size_t hom_off, cost_off, filtered_off, pair_off, regnet_off, total;
   size_t regnet_bytes;
 };
 void make_infer_plan(int n_views, int D, int hf, int wf, int C, int b, int precision, InferPlan* ip) {
@@ -320,6 +322,7 @@ void make_infer_plan(int n_views, int D, int hf, int wf, int C, int b, int preci
   // inside its workspace; the NDHWC buffer is then unused but stays reserved: the sampler is a per-call choice)
   ip->cost_off = off;     off += align_up((size_t)D * hf * wf * C * (precision == MVSB200_PRECISION_BF16 ? 2 : 4), 256);
   ip->filtered_off = off; off += align_up((size_t)D * hf * wf * sizeof(float), 256);
+  ip->pair_off = off;     off += align_up(cost_volume_pair_bytes(n_views, hf, wf), 256);
   ip->regnet_off = off;
   ip->regnet_bytes = mvsb200_regnet_workspace_bytes(D, hf, wf, C, b, precision);
   off += ip->regnet_bytes;
@@ -385,7 +388,9 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   if (planar) {
     void *cp8 = nullptr, *ps8 = nullptr;
     regnet_cost_planar(ws + ip.regnet_off, depth_num, hf, wf, channels, base_filter, &cp8, &ps8);
-    rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8, s);
+    static const bool fp32_taps = getenv("MVSB200_CV_FP32_TAPS") != nullptr;
+    rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8,
+                                   fp32_taps ? nullptr : ws + ip.pair_off, s);
   } else {
     rc = launch_cost_volume(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cost_dtype, cost, 0, s);
   }

@@ -17,10 +17,11 @@
 // GEMM rows run over the linearised padded tile (row pitch PX); rows in the halo columns are dropped.
 //
 //   warps 0-3   epilogue: tcgen05.ld accumulators -> bf16/fp32 stores + per-channel batch statistics
-//   warp  4     TMEM allocation; one thread issues every tcgen05.mma and the commits
-//   warp  5     producer: one thread issues the TMA box loads (input planes, skip planes, weights)
-//   warps 6-13  transform (layers whose input needs it): relu(x*scale+shift) [+ relu(skip*..+..)]
+//   warps 4-11  transform (layers whose input needs it): relu(x*scale+shift) [+ relu(skip*..+..)]
 //               applied IN PLACE on the landed plane, halo cells left at zero
+//   warp  12    producer: one thread issues the TMA box loads (input planes, skip planes, weights)
+//   warp  13    TMEM allocation; one thread issues every tcgen05.mma and the commits (the highest warp id:
+//               the issue arbiter favours it over the busy transform warps)
 //
 // Layer kinds (all "tap GEMMs" over such planes):
 //   conv s=1 (network.py:210)   taps (kh,kw) of plane dz, cell offset kh*PX+kw
@@ -50,7 +51,8 @@ constexpr int kMaxOps = 108;            // 27 taps x (64 channels / 16)
 constexpr int kEpiWarps = 4, kXfWarps = 8;
 constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kThreads = (kEpiWarps + 2 + kXfWarps) * 32;
-constexpr int kMaxRing = 12, kSkipRing = 3, kMaxSpan = 6, kMaxMB = 4, kMaxK = 12;
+constexpr int kXfWarp0 = kEpiWarps, kProdWarp = kEpiWarps + kXfWarps, kMmaWarp = kProdWarp + 1;
+constexpr int kMaxRing = 12, kMaxSkipRing = 8, kMinSkipRing = 2, kMaxSpan = 6, kMaxMB = 4, kMaxK = 12;
 
 enum { MODE_CONV1 = 0, MODE_CONV2 = 1, MODE_DECONV = 2 };
 
@@ -78,7 +80,7 @@ struct Params {
   int PX, RY, nsub, SUBP;        // slot geometry: nsub sub-arrays of RY x PX cells, SUBP cells apart
   int vstep, cx_off, cy_off;     // cell (sub, r, c) = voxel (vstep*(y0+r+cy_off)+(sub>>1), vstep*(x0+c+cx_off)+(sub&1))
   int zmul, zoff, zstep, span;   // plane seq of a segment = input z (zmul*zb + zoff + seq); zstep planes per step
-  int NCH, PS, slot_bytes, R;
+  int NCH, PS, slot_bytes, R, RS;    // RS = skip ring depth (has_skip)
   int MB, NB, CP;                // row blocks per step, TMEM columns per block, MMA N
   int nops, b_bytes, tmem_cols;
   int zf, cn_shift;              // output planes per step; log2(cout_n) when zf > 1
@@ -173,20 +175,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   unsigned char* s_b = smem;
   unsigned char* s_slots = smem + p.b_bytes;
   unsigned char* s_skip = s_slots + (size_t)p.R * p.slot_bytes;
-  uint4* s_ops = reinterpret_cast<uint4*>(s_skip + (p.has_skip ? (size_t)kSkipRing * p.slot_bytes : 0));
+  uint4* s_ops = reinterpret_cast<uint4*>(s_skip + (p.has_skip ? (size_t)p.RS * p.slot_bytes : 0));
   int* s_dzb = reinterpret_cast<int*>(s_ops + kMaxOps);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dzb + 8);
   uint64_t* bar_land = bars;                        // [R]  TMA -> transform / MMA
   uint64_t* bar_ready = bars + kMaxRing;            // [R]  transform -> MMA
   uint64_t* bar_empty = bars + 2 * kMaxRing;        // [R]  MMA (commit) -> producer
-  uint64_t* bar_sland = bars + 3 * kMaxRing;        // [kSkipRing] TMA -> transform
-  uint64_t* bar_sempty = bar_sland + kSkipRing;     // [kSkipRing] transform -> producer
-  uint64_t* bar_acc_full = bar_sempty + kSkipRing;  // [2]  MMA (commit) -> epilogue
+  uint64_t* bar_sland = bars + 3 * kMaxRing;        // [RS] TMA -> transform
+  uint64_t* bar_sempty = bar_sland + kMaxSkipRing;  // [RS] transform -> producer
+  uint64_t* bar_acc_full = bar_sempty + kMaxSkipRing;  // [2]  MMA (commit) -> epilogue
   uint64_t* bar_acc_empty = bar_acc_full + 2;       // [2]  epilogue -> MMA
   uint64_t* bar_b = bar_acc_empty + 2;              // [1]  weights landed
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_b + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long pr_entry = 0;
+  if (p.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_entry));
   int bid = blockIdx.x;
   const int tx = bid % p.tiles_x; bid /= p.tiles_x;
   const int ty = bid % p.tiles_y; bid /= p.tiles_y;
@@ -215,13 +219,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.R; ++i) { mbar_init(&bar_land[i], 1); mbar_init(&bar_ready[i], kXfThreads); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < kSkipRing; ++i) { mbar_init(&bar_sland[i], 1); mbar_init(&bar_sempty[i], kXfThreads); }
+    for (int i = 0; i < p.R; ++i) { mbar_init(&bar_land[i], 1); mbar_init(&bar_ready[i], kXfWarps); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < kMaxSkipRing; ++i) { mbar_init(&bar_sland[i], 1); mbar_init(&bar_sempty[i], kXfWarps); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kEpiWarps); }
     mbar_init(bar_b, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
@@ -231,48 +235,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   const uint32_t tmem_base = *s_tmem;
 
   if (nsteps > 0) {
-    if (warp == 5) {
+    if (warp == kProdWarp) {
       // ===================================== producer =====================================
-      if (elect_one()) {
+      // The whole warp walks the planes; lane 0 arms the barriers, then the lanes issue the plane's TMA boxes
+      // (chunks x parity sub-arrays, skip chunks) in parallel.
+      if (lane == 0) {
         // weights: bulk async copies in <= 32 KB pieces
         mbar_arrive_expect_tx(bar_b, (uint32_t)p.b_bytes);
         for (int off = 0; off < p.b_bytes; off += 32768)
           bulk_g2s(s_b + off, reinterpret_cast<const unsigned char*>(p.wpacked) + off,
                    (uint32_t)min(32768, p.b_bytes - off), bar_b);
-        const uint32_t plane_bytes = (uint32_t)(p.nsub * p.NCH * p.RY * p.PX * 16);
-        const int cx = (x0 + p.cx_off) * 8, cy = y0 + p.cy_off;
-        for (int seq = 0; seq < nplanes; ++seq) {
-          const int slot = seq % p.R;
-          if (seq >= p.R) mbar_wait(&bar_empty[slot], (uint32_t)((seq / p.R) - 1) & 1u);
-          const int iz = p.zmul * zb + p.zoff + seq;
-          unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
-          if (!(p.dbg & 1)) {
-            mbar_arrive_expect_tx(&bar_land[slot], plane_bytes);
-            for (int sub = 0; sub < p.nsub; ++sub)
-              for (int ch = 0; ch < p.NCH; ++ch)
-                tma_load_5d(sl + (size_t)ch * p.PS + (size_t)sub * p.SUBP * 16, &p.tmap_x, cx, cy, sub, ch, iz,
-                            &bar_land[slot]);
-          } else {
-            mbar_arrive(&bar_land[slot]);
+      }
+      const uint32_t plane_bytes = (uint32_t)(p.nsub * p.NCH * p.RY * p.PX * 16);
+      const int cx = (x0 + p.cx_off) * 8, cy = y0 + p.cy_off;
+      const int nbox = p.nsub * p.NCH;
+      long long pw_empty = 0, pw_sempty = 0, pw_t0 = 0;
+      if (p.prof) pw_t0 = clock64();
+      for (int seq = 0; seq < nplanes; ++seq) {
+        const int slot = seq % p.R;
+        long long pa = 0;
+        if (p.prof) pa = clock64();
+        if (seq >= p.R) mbar_wait(&bar_empty[slot], (uint32_t)((seq / p.R) - 1) & 1u);
+        if (p.prof) pw_empty += clock64() - pa;
+        const int iz = p.zmul * zb + p.zoff + seq;
+        unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
+        if (!(p.dbg & 1)) {
+          if (lane == 0) mbar_arrive_expect_tx(&bar_land[slot], plane_bytes);
+          __syncwarp();
+          for (int i = lane; i < nbox; i += 32) {
+            const int sub = i / p.NCH, ch = i - sub * p.NCH;
+            tma_load_5d(sl + (size_t)ch * p.PS + (size_t)sub * p.SUBP * 16, &p.tmap_x, cx, cy, sub, ch, iz, &bar_land[slot]);
           }
-          if (p.has_skip) {
-            const int ss = seq % kSkipRing;
-            if (seq >= kSkipRing) mbar_wait(&bar_sempty[ss], (uint32_t)((seq / kSkipRing) - 1) & 1u);
-            unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
-            if (!(p.dbg & 1)) {
-              mbar_arrive_expect_tx(&bar_sland[ss], plane_bytes);
-              for (int ch = 0; ch < p.NCH; ++ch)
-                tma_load_5d(sk + (size_t)ch * p.PS, &p.tmap_s, cx, cy, 0, ch, iz, &bar_sland[ss]);
-            } else {
-              mbar_arrive(&bar_sland[ss]);
-            }
+        } else if (lane == 0) {
+          mbar_arrive(&bar_land[slot]);
+        }
+        if (p.has_skip) {
+          const int ss = seq % p.RS;
+          long long pb = 0;
+          if (p.prof) pb = clock64();
+          if (seq >= p.RS) mbar_wait(&bar_sempty[ss], (uint32_t)((seq / p.RS) - 1) & 1u);
+          if (p.prof) pw_sempty += clock64() - pb;
+          unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
+          if (!(p.dbg & 1)) {
+            if (lane == 0) mbar_arrive_expect_tx(&bar_sland[ss], plane_bytes);
+            __syncwarp();
+            if (lane < p.NCH) tma_load_5d(sk + (size_t)lane * p.PS, &p.tmap_s, cx, cy, 0, lane, iz, &bar_sland[ss]);
+          } else if (lane == 0) {
+            mbar_arrive(&bar_sland[ss]);
           }
         }
       }
-    } else if (warp >= 6) {
+      if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[9] = clock64() - pw_t0; p.prof[10] = pw_empty; p.prof[11] = pw_sempty; }
+    } else if (warp >= kXfWarp0 && warp < kProdWarp) {
       // ===================================== transform =====================================
       if (p.transform) {
-        const int xt = threadIdx.x - 6 * 32;
+        const int xt = threadIdx.x - kXfWarp0 * 32;
         const int tpc = kXfThreads / p.NCH;           // threads per channel chunk (chunk is warp-uniform)
         const int ch = xt / tpc, ti = xt - ch * tpc;
         const int npos = p.nsub * p.RY * p.PX;
@@ -298,53 +315,77 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           xsc[k] = x_act ? p.xs[ch * 8 + k] : 1.0f; xsh[k] = x_act ? p.xb[ch * 8 + k] : 0.0f;
           ssc[k] = s_act ? p.ss[ch * 8 + k] : 1.0f; ssh[k] = s_act ? p.sb[ch * 8 + k] : 0.0f;
         }
+        long long xw = 0, xt0 = 0;
+        if (p.prof) xt0 = clock64();
         for (int seq = 0; seq < nplanes; ++seq) {
-          const int slot = seq % p.R, ss = seq % kSkipRing;
+          const int slot = seq % p.R, ss = seq % p.RS;
+          long long xa = 0;
+          if (p.prof) xa = clock64();
           mbar_wait(&bar_land[slot], (uint32_t)(seq / p.R) & 1u);
-          if (p.has_skip) mbar_wait(&bar_sland[ss], (uint32_t)(seq / kSkipRing) & 1u);
+          if (p.has_skip) mbar_wait(&bar_sland[ss], (uint32_t)(seq / p.RS) & 1u);
+          if (p.prof) xw += clock64() - xa;
           const int iz = p.zmul * zb + p.zoff + seq;
           if (iz >= 0 && iz < p.D) {
             unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
             const unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
+            // groups of 4 cells: all loads of a group are issued before its first store (the in-place stores would
+            // otherwise serialise every load behind the previous cell's store)
 #pragma unroll
-            for (int k = 0; k < kMaxK; ++k) {
-              if (off[k] < 0) continue;
-              uint4 v = *reinterpret_cast<const uint4*>(sl + off[k]);
-              uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
-              if (p.has_skip) {
-                const uint4 s4 = *reinterpret_cast<const uint4*>(sk + off[k]);
-                const uint32_t* sw = reinterpret_cast<const uint32_t*>(&s4);
+            for (int k0 = 0; k0 < kMaxK; k0 += 4) {
+              if (k0 >= p.xf_k) break;
+              uint4 v[4], s4[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 f = unpack_bf16x2(vw[j]), g = unpack_bf16x2(sw[j]);
-                  if (x_act) {
-                    f.x = fmaxf(fmaf(f.x, xsc[2 * j], xsh[2 * j]), 0.0f);
-                    f.y = fmaxf(fmaf(f.y, xsc[2 * j + 1], xsh[2 * j + 1]), 0.0f);
-                  }
-                  if (s_act) {
-                    g.x = fmaxf(fmaf(g.x, ssc[2 * j], ssh[2 * j]), 0.0f);
-                    g.y = fmaxf(fmaf(g.y, ssc[2 * j + 1], ssh[2 * j + 1]), 0.0f);
-                  }
-                  vw[j] = pack_bf16x2(f.x + g.x, f.y + g.y);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 f = unpack_bf16x2(vw[j]);
-                  f.x = fmaxf(fmaf(f.x, xsc[2 * j], xsh[2 * j]), 0.0f);
-                  f.y = fmaxf(fmaf(f.y, xsc[2 * j + 1], xsh[2 * j + 1]), 0.0f);
-                  vw[j] = pack_bf16x2(f.x, f.y);
+              for (int u = 0; u < 4; ++u) {
+                v[u] = make_uint4(0u, 0u, 0u, 0u); s4[u] = v[u];
+                if (off[k0 + u] >= 0) {
+                  v[u] = *reinterpret_cast<const uint4*>(sl + off[k0 + u]);
+                  if (p.has_skip) s4[u] = *reinterpret_cast<const uint4*>(sk + off[k0 + u]);
                 }
               }
-              *reinterpret_cast<uint4*>(sl + off[k]) = v;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (off[k0 + u] < 0) continue;
+                uint32_t* vw = reinterpret_cast<uint32_t*>(&v[u]);
+                const uint32_t* sw = reinterpret_cast<const uint32_t*>(&s4[u]);
+                if (p.has_skip) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float2 f = unpack_bf16x2(vw[j]), g = unpack_bf16x2(sw[j]);
+                    if (x_act) {
+                      f.x = fmaxf(fmaf(f.x, xsc[2 * j], xsh[2 * j]), 0.0f);
+                      f.y = fmaxf(fmaf(f.y, xsc[2 * j + 1], xsh[2 * j + 1]), 0.0f);
+                    }
+                    if (s_act) {
+                      g.x = fmaxf(fmaf(g.x, ssc[2 * j], ssh[2 * j]), 0.0f);
+                      g.y = fmaxf(fmaf(g.y, ssc[2 * j + 1], ssh[2 * j + 1]), 0.0f);
+                    }
+                    vw[j] = pack_bf16x2(f.x + g.x, f.y + g.y);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float2 f = unpack_bf16x2(vw[j]);
+                    f.x = fmaxf(fmaf(f.x, xsc[2 * j], xsh[2 * j]), 0.0f);
+                    f.y = fmaxf(fmaf(f.y, xsc[2 * j + 1], xsh[2 * j + 1]), 0.0f);
+                    vw[j] = pack_bf16x2(f.x, f.y);
+                  }
+                }
+                *reinterpret_cast<uint4*>(sl + off[k0 + u]) = v[u];
+              }
             }
           }
+          // every writer fences its generic-proxy stores, then ONE lane per warp arrives (256 arrivals on one
+          // mbarrier word serialise for ~1 us per plane)
           fence_proxy_async_smem();
-          mbar_arrive(&bar_ready[slot]);
-          if (p.has_skip) mbar_arrive(&bar_sempty[ss]);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bar_ready[slot]);
+            if (p.has_skip) mbar_arrive(&bar_sempty[ss]);
+          }
         }
+        if (p.prof && blockIdx.x == 0 && xt == 0) { p.prof[12] = clock64() - xt0; p.prof[13] = xw; }
       }
-    } else if (warp == 4) {
+    } else if (warp == kMmaWarp) {
       // ===================================== MMA issuer =====================================
       mbar_wait(bar_b, 0);
       const uint32_t idesc = make_idesc_bf16_f32(128, CP);
@@ -409,6 +450,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
         p.prof[0] = clock64() - pr_t0; p.prof[1] = g1 - pr_g0; p.prof[2] = pr_in; p.prof[3] = pr_acc; p.prof[4] = pr_issue;
         p.prof[5] = (long long)nsteps * p.nops * p.MB;
+        p.prof[6] = pr_g0 - pr_entry;      // prologue: kernel entry -> MMA warp past the weights barrier
+        p.prof[7] = g1 - pr_entry;         // kernel entry -> MMA warp done issuing
       }
     } else {
       // ===================================== epilogue =====================================
@@ -420,12 +463,68 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       const int ncol = p.zf * p.cout_n;
       const size_t zpitch = (size_t)p.Ho * p.Wo;          // voxels per output plane
       const int ncho = p.Cout >> 3, chunk0 = p.cout_base >> 3;
+      long long ew = 0, et0 = 0;
+      if (p.prof) et0 = clock64();
       for (int t = 0; t < nsteps; ++t) {
         const int stage = t & 1;
+        long long ea = 0;
+        if (p.prof) ea = clock64();
         mbar_wait(&bar_acc_full[stage], (uint32_t)(t >> 1) & 1u);
         tc_fence_after();
+        if (p.prof) ew += clock64() - ea;
         const int mz = zb + t * p.zf;
         const int nlive = min(p.zf, ze - mz);          // output planes of this step inside the volume
+        if (CP == 16 && deconv && !p.y_f32) {
+          // transposed conv, bf16 out: the two x-parity classes of a row are adjacent cells of the output, so they
+          // are drained together (32 columns per wait, 32 contiguous bytes per thread and channel chunk); the
+          // TMEM load of the next pair is in flight while this one is reduced and stored.
+          const int npair = p.MB * 4;
+          const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(stage * p.MB * p.NB);
+          uint32_t ra[32], rb[32];
+          tmem_ld16(tbase, ra); tmem_ld16(tbase + 16, ra + 16);
+          for (int i = 0; i < npair; i += 2) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int ii = i + half;
+              uint32_t* r = half ? rb : ra;
+              uint32_t* rn = half ? ra : rb;
+              tmem_ld_wait();
+              if (ii + 1 < npair) {
+                const int bn = (ii + 1) >> 2, pn = (ii + 1) & 3;
+                const uint32_t ta = tbase + (uint32_t)(bn * p.NB + pn * 32);
+                tmem_ld16(ta, rn); tmem_ld16(ta + 16, rn + 16);
+              }
+              const int b = ii >> 2, pr = ii & 3;               // pair pr = classes 2*pr, 2*pr+1 (pz, py fixed)
+              const int m = b * 128 + warp * 32 + lane;
+              const int yy = m / p.PX, xx = m - yy * p.PX;
+              if (!(xx < TXe && yy < TYe) || (p.dbg & 4)) continue;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float v0 = __uint_as_float(r[k]), v1 = __uint_as_float(r[16 + k]);
+                sum[k] += v0 + v1; sq[k] = fmaf(v1, v1, fmaf(v0, v0, sq[k]));
+              }
+              const int oz = 2 * mz + (pr >> 1), oy = 2 * (y0 + yy) + (pr & 1), ox = 2 * (x0 + xx);
+              const size_t cell = ((size_t)oy * p.Wo + ox);
+#pragma unroll
+              for (int k = 0; k < 16; k += 8) {
+                if (k < p.cout_n) {
+                  uint4 c0, c1;
+                  c0.x = pack_bf16x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+                  c0.y = pack_bf16x2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
+                  c0.z = pack_bf16x2(__uint_as_float(r[k + 4]), __uint_as_float(r[k + 5]));
+                  c0.w = pack_bf16x2(__uint_as_float(r[k + 6]), __uint_as_float(r[k + 7]));
+                  c1.x = pack_bf16x2(__uint_as_float(r[16 + k]), __uint_as_float(r[16 + k + 1]));
+                  c1.y = pack_bf16x2(__uint_as_float(r[16 + k + 2]), __uint_as_float(r[16 + k + 3]));
+                  c1.z = pack_bf16x2(__uint_as_float(r[16 + k + 4]), __uint_as_float(r[16 + k + 5]));
+                  c1.w = pack_bf16x2(__uint_as_float(r[16 + k + 6]), __uint_as_float(r[16 + k + 7]));
+                  const size_t zc = (size_t)oz * ncho + chunk0 + (k >> 3);
+                  uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
+                  dst[0] = c0; dst[1] = c1;
+                }
+              }
+            }
+          }
+        } else
         for (int b = 0; b < p.MB; ++b) {
           const int m = b * 128 + warp * 32 + lane;
           const int yy = m / p.PX, xx = m - yy * p.PX;
@@ -489,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_acc_empty[stage]);
       }
+      if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
       // batch statistics: per-thread partials -> warp reduce -> one double atomic per channel and warp
       if (p.stats) {
 #pragma unroll
@@ -510,7 +610,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (p.prof && threadIdx.x == 0) {
+    long long g2;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g2));
+    if (blockIdx.x == 0) p.prof[8] = g2 - pr_entry;             // whole CTA
+    p.prof[16 + 2 * blockIdx.x] = pr_entry;
+    p.prof[17 + 2 * blockIdx.x] = g2;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -735,16 +842,27 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   pk.zf = zf; pk.master = master ? 1 : 0;
   pk.nops = nimg; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
   pk.transposed = mode == MODE_DECONV;
-  const size_t fixed = (size_t)c.b_bytes + (size_t)kMaxOps * 16 + 32 + (3 * kMaxRing + 2 * kSkipRing + 5) * sizeof(uint64_t) + 16;
-  const size_t skip_bytes = has_skip ? (size_t)kSkipRing * c.slot_bytes : 0;
+  const size_t fixed = (size_t)c.b_bytes + (size_t)kMaxOps * 16 + 32 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
+  c.RS = has_skip ? kMinSkipRing : 0;
+  size_t skip_bytes = (size_t)c.RS * c.slot_bytes;
   c.R = c.span + c.zstep;                         // the planes of the next step land while this one computes
   if (fixed + skip_bytes + (size_t)c.R * c.slot_bytes > kSmemBudget) {
     c.R = c.span + 1;
     if (fixed + skip_bytes + (size_t)c.R * c.slot_bytes > kSmemBudget) return false;
   }
-  // deepen the ring while shared memory allows: more planes in flight hide the L2 / HBM latency
-  while (c.R < kMaxRing && c.R < c.span + 3 * c.zstep &&
-         fixed + skip_bytes + (size_t)(c.R + 1) * c.slot_bytes <= kSmemBudget) ++c.R;
+  // deepen the rings while shared memory allows: more planes in flight hide the L2 / HBM latency.  A skip plane
+  // is held until its input plane is transformed, so the skip ring bounds the producer's lead.
+  for (;;) {
+    const bool grow_skip = has_skip && c.RS < kMaxSkipRing && c.RS < c.R - c.span + c.zstep + 1;
+    const bool grow_ring = c.R < kMaxRing && c.R < c.span + 3 * c.zstep;
+    if (grow_skip && fixed + skip_bytes + c.slot_bytes + (size_t)c.R * c.slot_bytes <= kSmemBudget) {
+      ++c.RS; skip_bytes += c.slot_bytes;
+    } else if (grow_ring && fixed + skip_bytes + (size_t)(c.R + 1) * c.slot_bytes <= kSmemBudget) {
+      ++c.R;
+    } else {
+      break;
+    }
+  }
   pl->smem = fixed + skip_bytes + (size_t)c.R * c.slot_bytes;
   return c.slot_bytes < (1 << 18) && (size_t)c.PS < (1u << 18);
 }
@@ -932,9 +1050,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       c.dbg = dbg_env ? atoi(dbg_env) : 0;
       if (getenv("MVSB200_TC_VERBOSE"))
         fprintf(stderr, "[tc] mode=%d Cin=%d Cout=%d(+%d) tile %dx%d PX=%d RY=%d MB=%d N=%d R=%d zf=%d zsplit=%d grid=%d smem=%zu "
-                "nops=%d b=%dB xf=%d/%d est=%.0f clk\n",
+                "RS=%d nops=%d b=%dB xf=%d/%d est=%.0f clk\n",
                 mode, cin, cn, cb, c.TX, c.TY, c.PX, c.RY, c.MB, c.CP, c.R, c.zf, c.zsplit, c.tiles_x * c.tiles_y * c.zsplit,
-                best.smem, c.nops, c.b_bytes, c.transform, c.xf_k, best.est_clk);
+                best.smem, c.RS, c.nops, c.b_bytes, c.transform, c.xf_k, best.est_clk);
     }
     unsigned char* wp = (unsigned char*)scratch + (size_t)(launch_idx & 1) * align_up((size_t)kMaxOps * 2 * 32 * 16, 256);
     c.wpacked = (const uint4*)wp;
@@ -946,16 +1064,46 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     static long long* prof_buf = nullptr;
     c.prof = nullptr;
     if (getenv("MVSB200_TC_PROF")) {
-      if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 64));
+      if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 128 + 16 * 4096));
       c.prof = prof_buf;
     }
     if (c.CP == 16) conv3d_tc_kernel<16><<<grid, kThreads, best.smem, s>>>(c);
     else conv3d_tc_kernel<32><<<grid, kThreads, best.smem, s>>>(c);
     MVS_LAUNCH_CHECK("conv3d_tc_kernel");
     if (c.prof) {
-      long long h[6];
+      long long h[16];
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaStreamSynchronize(s);
+      // second, timed launch of the same kernel (the first one may have overlapped the pack kernel's tail)
+      cudaEventRecord(e0, s);
+      if (c.CP == 16) conv3d_tc_kernel<16><<<grid, kThreads, best.smem, s>>>(c);
+      else conv3d_tc_kernel<32><<<grid, kThreads, best.smem, s>>>(c);
+      cudaEventRecord(e1, s);
+      cudaStreamSynchronize(s);
+      float kms = 0.f;
+      cudaEventElapsedTime(&kms, e0, e1);
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      fprintf(stderr, "[tc-prof] kernel alone %.1f us (grid %d); ", kms * 1e3, grid);
       cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "CTA 0: prologue %.1f us, MMA warp done at %.1f us, CTA end %.1f us\n", h[6] * 1e-3, h[7] * 1e-3, h[8] * 1e-3);
+      fprintf(stderr, "[tc-prof] producer %lld clk (wait empty %lld, wait skip-empty %lld); transform %lld clk (wait landed %lld); "
+              "epilogue %lld clk (wait acc %lld)\n", h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
+      if (grid <= 4096) {
+        static long long hh[2 * 4096];
+        cudaMemcpy(hh, prof_buf + 16, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
+        long long t0 = hh[0], t1 = hh[1], smax = hh[0], emin = hh[1];
+        double avg = 0;
+        for (int i = 0; i < grid; ++i) {
+          if (hh[2 * i] < t0) t0 = hh[2 * i];
+          if (hh[2 * i] > smax) smax = hh[2 * i];
+          if (hh[2 * i + 1] > t1) t1 = hh[2 * i + 1];
+          if (hh[2 * i + 1] < emin) emin = hh[2 * i + 1];
+          avg += (double)(hh[2 * i + 1] - hh[2 * i]);
+        }
+        fprintf(stderr, "[tc-prof] CTAs: first start 0, last start %.1f us, first end %.1f us, last end %.1f us, mean life %.1f us\n",
+                (smax - t0) * 1e-3, (emin - t0) * 1e-3, (t1 - t0) * 1e-3, avg / grid * 1e-3);
+      }
       fprintf(stderr, "[tc-prof] mode=%d Cin=%d Cout=%d: MMA warp of CTA 0: %lld clk in %lld ns (%.0f MHz); wait input %lld, "
               "wait acc %lld, issue %lld clk; %lld MMAs -> %.1f clk/MMA issued, %.1f clk/MMA overall\n", mode, cin, cn,
               h[0], h[1], h[1] ? 1e3 * h[0] / h[1] : 0.0, h[2], h[3], h[4], h[5], h[5] ? (double)h[4] / h[5] : 0.0,

@@ -27,6 +27,12 @@
 //   conv s=1 (network.py:210)   taps (kh,kw) of plane dz, cell offset kh*PX+kw
 //   conv s=2 (TF SAME)          PS8 input: the 4 parity sub-arrays make stride-2 rows dense
 //   deconv s=2 (network.py:327) 8 output-parity classes, each with its 1/2/4/8 taps, own TMEM columns
+// x-fold (stride-1 convs): the three kw taps of a filter row are folded into the MMA N dimension as well.  The
+// padded tile is exactly 8 / 16 / 32 cells wide, GEMM row (yy, xx) = input column x0 + xx - 1, and column
+// group kw of that row holds the partial sum that belongs to output column xx - (kw - 1); the epilogue adds
+// the three partials with two intra-warp shuffles (a warp's 32 TMEM lanes are whole tile rows, so the
+// neighbours are always in the warp).  One MMA per (plane, kh, 16 channels) instead of three: the A operand is
+// read from shared memory a third as often, which is what bounds these skinny GEMMs.
 // z-fold (stride-1 convs): zf consecutive output planes share one step, their channels side by side
 // in the MMA N dimension (N = zf*Cout): an input plane is read from shared memory once for all the
 // output planes it feeds.  Measured on B200: a 128xNx16 MMA from shared memory costs
@@ -84,6 +90,7 @@ struct Params {
   int MB, NB, CP;                // row blocks per step, TMEM columns per block, MMA N
   int nops, b_bytes, tmem_cols;
   int zf, cn_shift;              // output planes per step; log2(cout_n) when zf > 1
+  int xfold;                     // kw taps folded into N: columns [j][kw][co], see the epilogue
   int xf_k;                      // cells per transform thread and plane
   int dz_begin[kMaxSpan + 1];    // ops [dz_begin[d], dz_begin[d+1]) read input plane d of the step
   int dbg;                       // development switches (env MVSB200_TC_DBG): 1 no loads, 2 no MMA, 4 no stores
@@ -97,21 +104,23 @@ struct Params {
 struct PackOp { int16_t tap[2]; int16_t cbase[2]; };
 struct PackParams {
   const float* kernel_tf; uint16_t* out;
-  int Cin, Cout, cout_base, cout_n, CP, transposed, nops, zf, master;
+  int Cin, Cout, cout_base, cout_n, CP, transposed, nops, zf, master, xfold;
   PackOp ops[kMaxOps];   // per-op images: tap = kd*9+kh*3+kw per K half (-1 = zero half);
                          // master images: tap = kh*3+kw (kd comes from the row group), one per (kh,kw,pair)
 };
 
 __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
+  // column n of a B image: [output plane j of the step][kw when the x-fold is on][output channel]
+  const int kwn = p.xfold ? 3 : 1, grp = kwn * p.cout_n;
   if (!p.master) {
     const int total = p.nops * 2 * p.CP * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
       const int k8 = i & 7, n = (i >> 3) % p.CP, half = (i / (8 * p.CP)) & 1, op = i / (16 * p.CP);
       // column group j = output plane j of the step (z-fold): its filter plane is kd = dz - j
-      const int j = n / p.cout_n, cn = n - j * p.cout_n;
+      const int j = n / grp, rem = n - j * grp, kw = rem / p.cout_n, cn = rem - kw * p.cout_n;
       int tap = p.ops[op].tap[half];
       const int ci = p.ops[op].cbase[half] + k8;
-      if (tap >= 0) tap -= 9 * j;
+      if (tap >= 0) tap += (p.xfold ? kw : 0) - 9 * j;       // x-fold: the op's tap code has kw = 0
       float w = 0.0f;
       if (tap >= 0 && tap < 27 && j < p.zf && ci < p.Cin) {
         const int co = p.cout_base + cn;
@@ -122,16 +131,16 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
       p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
     }
   } else {
-    // image m = [2 halves][(2*zf+1) groups][cout_n rows][8]; group g holds W[kd = zf+1-g]
-    const int groups = 2 * p.zf + 1, rows = groups * p.cout_n;
+    // image m = [2 halves][(2*zf+1) groups][grp rows][8]; group g holds W[kd = zf+1-g]
+    const int groups = 2 * p.zf + 1, rows = groups * grp;
     const int total = p.nops * 2 * rows * 8;      // nops = number of master images here
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
       const int k8 = i & 7, row = (i >> 3) % rows, half = (i / (8 * rows)) & 1, m = i / (16 * rows);
-      const int g = row / p.cout_n, cn = row - g * p.cout_n, kd = p.zf + 1 - g;
+      const int g = row / grp, rem = row - g * grp, kw = rem / p.cout_n, cn = rem - kw * p.cout_n, kd = p.zf + 1 - g;
       const int ci = p.ops[m].cbase[half] + k8;
       float w = 0.0f;
       if (kd >= 0 && kd < 3 && ci < p.Cin) {
-        const int tap = kd * 9 + p.ops[m].tap[0];
+        const int tap = kd * 9 + p.ops[m].tap[0] + (p.xfold ? kw : 0);
         w = p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + p.cout_base + cn];
       }
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
@@ -168,7 +177,7 @@ __device__ __forceinline__ void issue_ops(const uint4* s_ops, int ob, int oe, ui
   }
 }
 
-template <int CP>
+template <int CP, bool XF>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [B image][R slots][skip slots][op table][plane op ranges][barriers][tmem ptr]
@@ -388,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     } else if (warp == kMmaWarp) {
       // ===================================== MMA issuer =====================================
       mbar_wait(bar_b, 0);
-      const uint32_t idesc = make_idesc_bf16_f32(128, CP);
+      const uint32_t idesc = make_idesc_bf16_f32(128, XF ? p.CP : CP);
       const uint32_t slots16 = smem_u32(s_slots) >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
       const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;   // version 1, SBO = 128 B
       uint64_t* bar_in = p.transform ? bar_ready : bar_land;
@@ -455,6 +464,116 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       }
     } else {
       // ===================================== epilogue =====================================
+      if (XF) {
+        // x-fold: columns [j][kw][co]; output (yy, xx-1) = P[kw=0] of lane-1 + P[kw=1] + P[kw=2] of lane+1.
+        // A warp's 32 TMEM lanes are 32 / PX whole tile rows, so the shuffles (width PX) never leave a row; the
+        // halo columns xx = 0 and PX-1 only supply partial sums.
+        float sum[32], sq[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { sum[k] = 0.0f; sq[k] = 0.0f; }
+        const int grp = 3 * p.cout_n, nchunk = p.cout_n >> 3;
+        const size_t zpitch = (size_t)p.Ho * p.Wo;
+        const int ncho = p.Cout >> 3, chunk0 = p.cout_base >> 3;
+        const int px_shift = 31 - __clz(p.PX);
+        long long ew = 0, et0 = 0;
+        if (p.prof) et0 = clock64();
+        for (int t = 0; t < nsteps; ++t) {
+          const int stage = t & 1;
+          long long ea = 0;
+          if (p.prof) ea = clock64();
+          mbar_wait(&bar_acc_full[stage], (uint32_t)(t >> 1) & 1u);
+          tc_fence_after();
+          if (p.prof) ew += clock64() - ea;
+          const int mz = zb + t * p.zf;
+          const int nlive = min(p.zf, ze - mz);
+          for (int b = 0; b < p.MB; ++b) {
+            const int m = b * 128 + warp * 32 + lane;
+            const int yy = m >> px_shift, xx = m & (p.PX - 1);
+            const bool valid = xx >= 1 && xx <= TXe && yy < TYe && !(p.dbg & 4);
+            const int oy = y0 + yy, ox = x0 + xx - 1;
+            const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((stage * p.MB + b) * p.NB);
+            if (p.cout_n == 1) {
+              // Cout = 1 (3dconv6_2): N = 3*zf <= 12 columns, fp32 [D,H,W] output
+              uint32_t r[16];
+              tmem_ld16(tb, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j < p.zf) {
+                  const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(r[3 * j]), 1, p.PX);
+                  const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(r[3 * j + 2]), 1, p.PX);
+                  const float v = lft + __uint_as_float(r[3 * j + 1]) + rgt;
+                  if (valid && j < nlive) {
+                    sum[0] += v; sq[0] = fmaf(v, v, sq[0]);
+                    if (p.y_f32) p.y_f32[((size_t)(mz + j) * p.Ho + oy) * p.Wo + ox] = v;
+                  }
+                }
+              }
+            } else {
+              for (int j = 0; j < p.zf; ++j) {
+#pragma unroll
+                for (int ck = 0; ck < 4; ++ck) {
+                  if (ck < nchunk) {
+                    uint32_t ra[8], rb[8], rc[8];
+                    const uint32_t col = (uint32_t)(j * grp + ck * 8);
+                    tmem_ld8(tb + col, ra);
+                    tmem_ld8(tb + col + (uint32_t)p.cout_n, rb);
+                    tmem_ld8(tb + col + 2u * (uint32_t)p.cout_n, rc);
+                    tmem_ld_wait();
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(ra[k]), 1, p.PX);
+                      const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(rc[k]), 1, p.PX);
+                      v[k] = lft + __uint_as_float(rb[k]) + rgt;
+                    }
+                    if (valid && j < nlive) {
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) { sum[ck * 8 + k] += v[k]; sq[ck * 8 + k] = fmaf(v[k], v[k], sq[ck * 8 + k]); }
+                      const int oz = mz + j;
+                      if (p.y_f32) {
+                        float4* yo = reinterpret_cast<float4*>(p.y_f32 + (((size_t)oz * p.Ho + oy) * p.Wo + ox) * p.Cout +
+                                                               p.cout_base + ck * 8);
+                        yo[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        yo[1] = make_float4(v[4], v[5], v[6], v[7]);
+                      } else {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+                        pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+                        const size_t zc = (size_t)oz * ncho + chunk0 + ck;
+                        if (p.y_cp8) *reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + (size_t)oy * p.Wo + ox) * 8) = pk;
+                        if (p.y_ps8) {
+                          const size_t pcell = ((size_t)((oy & 1) * 2 + (ox & 1)) * p.Hso + (oy >> 1)) * p.Wso + (ox >> 1);
+                          *reinterpret_cast<uint4*>(p.y_ps8 + (zc * 4 * (size_t)p.Hso * p.Wso + pcell) * 8) = pk;
+                        }
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[stage]);
+        }
+        if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
+        if (p.stats) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            float s_ = sum[k], q_ = sq[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s_ += __shfl_xor_sync(0xffffffffu, s_, o);
+              q_ += __shfl_xor_sync(0xffffffffu, q_, o);
+            }
+            if (lane == 0 && k < p.cout_n) {
+              atomicAdd(p.stats + p.cout_base + k, (double)s_);
+              atomicAdd(p.stats + p.Cout + p.cout_base + k, (double)q_);
+            }
+          }
+        }
+      } else {
       float sum[CP], sq[CP];
 #pragma unroll
       for (int k = 0; k < CP; ++k) { sum[k] = 0.0f; sq[k] = 0.0f; }
@@ -606,6 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           }
         }
       }
+      }
     }
   }
   tc_fence_before();
@@ -683,16 +803,24 @@ double mma_clk(int n) { const double a = 32.0 + n / 4.0, b = n / 2.0; return (a 
 
 // Build the op table for one (mode, Cin, cout slice) and the slot geometry for tile (TX, TY), z-fold zf.
 bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base, int cout_n, int TX, int TY, int zf,
-                bool has_skip, bool transform, Plan* pl) {
+                bool xfold, bool has_skip, bool transform, Plan* pl) {
   Params& c = pl->cp;
   PackParams& pk = pl->pp;
   if (mode != MODE_CONV1) zf = 1;
-  if (zf > 1 && ((cout_n & (cout_n - 1)) != 0)) return false;     // the epilogue splits folded columns by shift
-  if (zf * cout_n > 32 || zf + 2 > kMaxSpan) return false;
-  const int CP = zf * cout_n <= 16 ? 16 : 32;
-  const bool master = zf > 1 && zf * cout_n == CP && cin >= 16;
+  if (xfold) {
+    // x-fold: the padded tile is 8 / 16 / 32 cells wide and fills whole 128-row blocks
+    if (mode != MODE_CONV1 || !(cout_n == 1 || cout_n % 8 == 0)) return false;
+    const int px = TX + 2;
+    if ((px != 8 && px != 16 && px != 32) || (TY * px) % 128 != 0) return false;
+  }
+  if (zf > 1 && !xfold && ((cout_n & (cout_n - 1)) != 0)) return false;     // the epilogue splits folded columns by shift
+  const int kwn = xfold ? 3 : 1, grp = kwn * cout_n, ncols = zf * grp;
+  if (ncols > (xfold ? 128 : 32) || zf + 2 > kMaxSpan) return false;
+  const int CP = xfold ? (ncols + 15) / 16 * 16 : (ncols <= 16 ? 16 : 32);
+  const bool master = zf > 1 && ncols == CP && cin >= 16;
   c.CP = CP;
   c.zf = zf;
+  c.xfold = xfold ? 1 : 0;
   c.cn_shift = 0;
   while ((1 << c.cn_shift) < cout_n) ++c.cn_shift;
   c.mode = mode; c.D = D; c.H = H; c.W = W; c.Cin = cin; c.Cout = cout; c.cout_base = cout_base; c.cout_n = cout_n;
@@ -744,7 +872,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
     const int ndz = mode == MODE_CONV1 ? zf + 2 : 3;
     for (int kd = 0; kd < ndz; ++kd)
       for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw) {
+        for (int kw = 0; kw < (xfold ? 1 : 3); ++kw) {      // x-fold: one tap per filter row, kw lives in N
           int pos;
           if (mode == MODE_CONV1) pos = kh * c.PX + kw;
           else {
@@ -769,7 +897,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   // ---- ops ----------------------------------------------------------------------------------------
   int nops = 0, nimg = 0;
   const int b_op_bytes = 2 * CP * 16;
-  const int m_rows = (2 * zf + 1) * cout_n, m_bytes = 2 * m_rows * 16;      // master image
+  const int m_rows = (2 * zf + 1) * grp, m_bytes = 2 * m_rows * 16;      // master image
   auto add_op = [&](int dz, uint32_t a_off, uint32_t a_lbo, uint32_t b_off, uint32_t b_lbo, int col, bool first) {
     UmmaOp& o = c.ops[nops++];
     o.a_lo = (a_off >> 4) | ((a_lbo >> 4) << 16);
@@ -786,15 +914,15 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   if (ntaps * (cin >= 16 ? cin / 16 : 1) > kMaxOps) return false;
   if (master) {
     // images: one per (kh, kw, channel pair); op of plane dz = window starting at row group zf+1-dz
-    for (int t = 0; t < 9; ++t)
+    for (int t = 0; t < 9; t += kwn)
       for (int j = 0; j < cin / 16; ++j) add_img(t, 16 * j, t, 16 * j + 8);
     for (int i = 0; i < ntaps; ++i)
       for (int j = 0; j < cin / 16; ++j) {
         const bool first = !seen_cls[0];
         seen_cls[0] = true;
-        const int img = (taps[i].widx % 9) * (cin / 16) + j;
+        const int img = ((taps[i].widx % 9) / kwn) * (cin / 16) + j;
         add_op(taps[i].dz, (uint32_t)(2 * j * c.PS + taps[i].pos * 16), (uint32_t)c.PS,
-               (uint32_t)(img * m_bytes + (zf + 1 - taps[i].dz) * cout_n * 16), (uint32_t)(m_rows * 16), 0, first);
+               (uint32_t)(img * m_bytes + (zf + 1 - taps[i].dz) * grp * 16), (uint32_t)(m_rows * 16), 0, first);
       }
     c.b_bytes = nimg * m_bytes;
   } else if (cin >= 16) {
@@ -839,7 +967,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   for (int d = 0; d <= kMaxSpan; ++d) c.dz_begin[d] = nops;
   for (int o = nops - 1; o >= 0; --o) c.dz_begin[(c.ops[o].meta >> 20) & 15] = o;
   for (int d = kMaxSpan - 1; d >= 0; --d) if (c.dz_begin[d] > c.dz_begin[d + 1]) c.dz_begin[d] = c.dz_begin[d + 1];
-  pk.zf = zf; pk.master = master ? 1 : 0;
+  pk.zf = zf; pk.master = master ? 1 : 0; pk.xfold = xfold ? 1 : 0;
   pk.nops = nimg; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
   pk.transposed = mode == MODE_DECONV;
   const size_t fixed = (size_t)c.b_bytes + (size_t)kMaxOps * 16 + 32 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
@@ -873,7 +1001,8 @@ double estimate_clk(const Params& c, int sm_count) {
   const double plane_bytes = (double)c.nsub * c.NCH * c.RY * c.PX * 16.0 * (c.has_skip ? 2.0 : 1.0);
   const double load = plane_bytes * c.zstep / 18.0;                       // ~HBM share of one SM, B/clk
   const int ncls = c.mode == MODE_DECONV ? 8 : 1;
-  const double epi = (double)c.MB * ncls * (c.CP * 4.0 * 128.0 / 110.0 + 12.0 * c.CP + 80.0);
+  const double epi = c.xfold ? (double)c.MB * c.zf * (c.cout_n >= 8 ? c.cout_n / 8 : 1) * 420.0
+                             : (double)c.MB * ncls * (c.CP * 4.0 * 128.0 / 110.0 + 12.0 * c.CP + 80.0);
   const double xf = c.transform ? (double)c.xf_k * c.zstep * (c.has_skip ? 70.0 : 45.0) : 0.0;
   double step = mma;
   if (load > step) step = load;
@@ -956,8 +1085,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
   }
   static bool attr_done = false;
   if (!attr_done) {
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     attr_done = true;
   }
   const bool has_skip = skip != nullptr, transform = xs != nullptr || has_skip;
@@ -966,21 +1096,23 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
   const char* tile_env = getenv("MVSB200_TC_TILE");     // "TXxTY" forces the tile
   const char* dbg_env = getenv("MVSB200_TC_DBG");
   const char* zs_env = getenv("MVSB200_TC_ZSPLIT");
+  const char* xf_env = getenv("MVSB200_TC_XFOLD");     // 0 switches the x-fold off
   if (const char* only = getenv("MVSB200_TC_LAYER")) {
     int a = 0, b = 0, m = 0;
     sscanf(only, "%d,%d,%d", &a, &b, &m);
-    if (a != cin || b != cout || m != mode) zf_env = tile_env = dbg_env = zs_env = nullptr;
+    if (a != cin || b != cout || m != mode) zf_env = tile_env = dbg_env = zs_env = xf_env = nullptr;
   }
   int force_tx = 0, force_ty = 0;
   if (tile_env) sscanf(tile_env, "%dx%d", &force_tx, &force_ty);
   const int force_zs = zs_env ? atoi(zs_env) : 0;
+  const bool no_xfold = xf_env && atoi(xf_env) == 0;
   int launch_idx = 0;
   for (int cb = 0; cb < cout; cb += 32, ++launch_idx) {
     const int cn = cout - cb < 32 ? cout - cb : 32;
     const int Mx = mode == MODE_CONV2 ? ceil_div(W, 2) : W, My = mode == MODE_CONV2 ? ceil_div(H, 2) : H,
               Mz = mode == MODE_CONV2 ? ceil_div(D, 2) : D;
     const std::array<int, 14> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_env ? atoi(zf_env) : 0,
-                                     force_tx, force_ty, sm_count, force_zs};
+                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0)};
     Plan best;
     bool found = false;
     {
@@ -995,14 +1127,16 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
         if (mode != MODE_CONV1 && zf != 1) continue;
         if (zf_env && atoi(zf_env) != zf && mode == MODE_CONV1) continue;
         if (zf > 1 && !zf_env && Mz < 2 * zf) continue;
+        for (int xf = (mode == MODE_CONV1 && !no_xfold) ? 1 : 0; xf >= 0; --xf)
         for (int TX = 4; TX <= 30; ++TX) {
-          if (TX > Mx && TX != 4 && TX - 1 >= Mx) break;        // one clipped candidate is enough
-          const int tx_eff = TX < Mx ? TX : Mx;
-          if (force_tx && tx_eff != (force_tx < Mx ? force_tx : Mx)) continue;
-          for (int TY = 1; TY <= 40 && TY <= My; ++TY) {
-            if (force_ty && TY != (force_ty < My ? force_ty : My)) continue;
+          if (xf && TX != 6 && TX != 14 && TX != 30) continue;
+          if (!xf && TX > Mx && TX != 4 && TX - 1 >= Mx) break;        // one clipped candidate is enough
+          const int tx_eff = xf ? TX : (TX < Mx ? TX : Mx);
+          if (force_tx && tx_eff != (xf ? force_tx : (force_tx < Mx ? force_tx : Mx))) continue;
+          for (int TY = 1; TY <= 64 && (TY <= My || xf); ++TY) {
+            if (force_ty && TY != (force_ty < My || xf ? force_ty : My)) continue;
             Plan pl;
-            if (!build_plan(mode, D, H, W, cin, cout, cb, cn, tx_eff, TY, zf, has_skip, transform, &pl)) continue;
+            if (!build_plan(mode, D, H, W, cin, cout, cb, cn, tx_eff, TY, zf, xf != 0, has_skip, transform, &pl)) continue;
             if (pl.smem > kSmemBudget) continue;
             Params& c = pl.cp;
             const int tiles = c.tiles_x * c.tiles_y;
@@ -1049,9 +1183,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     {
       c.dbg = dbg_env ? atoi(dbg_env) : 0;
       if (getenv("MVSB200_TC_VERBOSE"))
-        fprintf(stderr, "[tc] mode=%d Cin=%d Cout=%d(+%d) tile %dx%d PX=%d RY=%d MB=%d N=%d R=%d zf=%d zsplit=%d grid=%d smem=%zu "
+        fprintf(stderr, "[tc] mode=%d Cin=%d Cout=%d(+%d) tile %dx%d PX=%d RY=%d MB=%d N=%d R=%d zf=%d xf=%d zsplit=%d grid=%d smem=%zu "
                 "RS=%d nops=%d b=%dB xf=%d/%d est=%.0f clk\n",
-                mode, cin, cn, cb, c.TX, c.TY, c.PX, c.RY, c.MB, c.CP, c.R, c.zf, c.zsplit, c.tiles_x * c.tiles_y * c.zsplit,
+                mode, cin, cn, cb, c.TX, c.TY, c.PX, c.RY, c.MB, c.CP, c.R, c.zf, c.xfold, c.zsplit, c.tiles_x * c.tiles_y * c.zsplit,
                 best.smem, c.RS, c.nops, c.b_bytes, c.transform, c.xf_k, best.est_clk);
     }
     unsigned char* wp = (unsigned char*)scratch + (size_t)(launch_idx & 1) * align_up((size_t)kMaxOps * 2 * 32 * 16, 256);
@@ -1067,8 +1201,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 128 + 16 * 4096));
       c.prof = prof_buf;
     }
-    if (c.CP == 16) conv3d_tc_kernel<16><<<grid, kThreads, best.smem, s>>>(c);
-    else conv3d_tc_kernel<32><<<grid, kThreads, best.smem, s>>>(c);
+    if (c.xfold) conv3d_tc_kernel<32, true><<<grid, kThreads, best.smem, s>>>(c);
+    else if (c.CP == 16) conv3d_tc_kernel<16, false><<<grid, kThreads, best.smem, s>>>(c);
+    else conv3d_tc_kernel<32, false><<<grid, kThreads, best.smem, s>>>(c);
     MVS_LAUNCH_CHECK("conv3d_tc_kernel");
     if (c.prof) {
       long long h[16];
@@ -1077,8 +1212,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       cudaStreamSynchronize(s);
       // second, timed launch of the same kernel (the first one may have overlapped the pack kernel's tail)
       cudaEventRecord(e0, s);
-      if (c.CP == 16) conv3d_tc_kernel<16><<<grid, kThreads, best.smem, s>>>(c);
-      else conv3d_tc_kernel<32><<<grid, kThreads, best.smem, s>>>(c);
+      if (c.xfold) conv3d_tc_kernel<32, true><<<grid, kThreads, best.smem, s>>>(c);
+      else if (c.CP == 16) conv3d_tc_kernel<16, false><<<grid, kThreads, best.smem, s>>>(c);
+      else conv3d_tc_kernel<32, false><<<grid, kThreads, best.smem, s>>>(c);
       cudaEventRecord(e1, s);
       cudaStreamSynchronize(s);
       float kms = 0.f;

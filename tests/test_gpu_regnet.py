@@ -166,18 +166,21 @@ def test_regnet_bf16_vs_oracle(O, small_problem):
     assert np.corrcoef(out.ravel(), ref.ravel())[0, 1] >= 0.999
 
 
+@pytest.mark.parametrize("xfold", [0, 1])
 @pytest.mark.parametrize("zf", [1, 2, 4])
 @pytest.mark.parametrize("case", [(8, 16, 24, 32, 8, 1, False), (7, 9, 11, 16, 16, 1, False), (10, 16, 24, 8, 1, 1, False),
                                   (18, 20, 40, 32, 8, 1, False), (8, 16, 24, 32, 16, 2, False),
                                   (7, 9, 11, 32, 16, 2, False)])
-def test_bf16_zfold_variants(ops, O, monkeypatch, case, zf):
-    """z-fold (several output planes per MMA N, master B images) against the oracle, incl. ragged D."""
+def test_bf16_zfold_variants(ops, O, monkeypatch, case, zf, xfold):
+    """z-fold (several output planes per MMA N, master B images) and x-fold (kw taps in N, shuffled epilogue)
+    against the oracle, incl. ragged D and tiles wider than the volume."""
     D, H, W, cin, cout, stride, tr = case
     if stride == 2 and zf != 1:
         pytest.skip("z-fold applies to stride-1 convs only")
-    if zf * cout > 32:
-        pytest.skip("fold does not fit N <= 32")
+    if zf * cout > 32 or (xfold and stride != 1):
+        pytest.skip("fold does not apply")
     monkeypatch.setenv("MVSB200_TC_ZF", str(zf))
+    monkeypatch.setenv("MVSB200_TC_XFOLD", str(xfold))
     rng = np.random.RandomState(41)
     x = bf16_round(rng.randn(D, H, W, cin))
     w = (rng.randn(3, 3, 3, cin, cout) * 0.1).astype(np.float32)
@@ -185,7 +188,7 @@ def test_bf16_zfold_variants(ops, O, monkeypatch, case, zf):
     ref = _layer_ref(O, x, bf16_round(w), stride, tr)
     assert tuple(y.shape) == ref.shape
     err = np.abs(y.cpu().numpy() - ref).max()
-    assert err <= 1e-3 * max(1.0, np.abs(ref).max()), f"{case} zf={zf}: max abs err {err}"
+    assert err <= 1e-3 * max(1.0, np.abs(ref).max()), f"{case} zf={zf} xfold={xfold}: max abs err {err}"
     st = stats.cpu().numpy()
     r64 = ref.reshape(-1, cout).astype(np.float64)
     np.testing.assert_allclose(st[:cout], r64.sum(0), rtol=1e-3, atol=0.5)

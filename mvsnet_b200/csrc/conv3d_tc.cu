@@ -91,6 +91,7 @@ struct Params {
   int nops, b_bytes, tmem_cols;
   int zf, cn_shift;              // output planes per step; log2(cout_n) when zf > 1
   int xfold;                     // kw taps folded into N: columns [j][kw][co], see the epilogue
+  int one_box;                   // chunk planes are dense in the slot: one TMA box loads all chunks of a plane
   int xf_k;                      // cells per transform thread and plane
   int dz_begin[kMaxSpan + 1];    // ops [dz_begin[d], dz_begin[d+1]) read input plane d of the step
   int dbg;                       // development switches (env MVSB200_TC_DBG): 1 no loads, 2 no MMA, 4 no stores
@@ -258,26 +259,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       const uint32_t plane_bytes = (uint32_t)(p.nsub * p.NCH * p.RY * p.PX * 16);
       const int cx = (x0 + p.cx_off) * 8, cy = y0 + p.cy_off;
       const int nbox = p.nsub * p.NCH;
-      long long pw_empty = 0, pw_sempty = 0, pw_t0 = 0;
+      long long pw_empty = 0, pw_sempty = 0, pw_t0 = 0, pw_issue = 0;
       if (p.prof) pw_t0 = clock64();
       for (int seq = 0; seq < nplanes; ++seq) {
         const int slot = seq % p.R;
         long long pa = 0;
         if (p.prof) pa = clock64();
         if (seq >= p.R) mbar_wait(&bar_empty[slot], (uint32_t)((seq / p.R) - 1) & 1u);
-        if (p.prof) pw_empty += clock64() - pa;
+        long long pc0 = 0;
+        if (p.prof) { pc0 = clock64(); pw_empty += pc0 - pa; }
         const int iz = p.zmul * zb + p.zoff + seq;
         unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
         if (!(p.dbg & 1)) {
           if (lane == 0) mbar_arrive_expect_tx(&bar_land[slot], plane_bytes);
           __syncwarp();
-          for (int i = lane; i < nbox; i += 32) {
-            const int sub = i / p.NCH, ch = i - sub * p.NCH;
-            tma_load_5d(sl + (size_t)ch * p.PS + (size_t)sub * p.SUBP * 16, &p.tmap_x, cx, cy, sub, ch, iz, &bar_land[slot]);
+          if (p.one_box) {
+            // dense chunk planes (x-fold): one box covers every channel chunk of the plane
+            if (lane == 0) tma_load_5d(sl, &p.tmap_x, cx, cy, 0, 0, iz, &bar_land[slot]);
+          } else {
+            for (int i = lane; i < nbox; i += 32) {
+              const int sub = i / p.NCH, ch = i - sub * p.NCH;
+              tma_load_5d(sl + (size_t)ch * p.PS + (size_t)sub * p.SUBP * 16, &p.tmap_x, cx, cy, sub, ch, iz, &bar_land[slot]);
+            }
           }
         } else if (lane == 0) {
           mbar_arrive(&bar_land[slot]);
         }
+        if (p.prof) pw_issue += clock64() - pc0;
         if (p.has_skip) {
           const int ss = seq % p.RS;
           long long pb = 0;
@@ -288,13 +296,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           if (!(p.dbg & 1)) {
             if (lane == 0) mbar_arrive_expect_tx(&bar_sland[ss], plane_bytes);
             __syncwarp();
-            if (lane < p.NCH) tma_load_5d(sk + (size_t)lane * p.PS, &p.tmap_s, cx, cy, 0, lane, iz, &bar_sland[ss]);
+            if (p.one_box) {
+              if (lane == 0) tma_load_5d(sk, &p.tmap_s, cx, cy, 0, 0, iz, &bar_sland[ss]);
+            } else if (lane < p.NCH) {
+              tma_load_5d(sk + (size_t)lane * p.PS, &p.tmap_s, cx, cy, 0, lane, iz, &bar_sland[ss]);
+            }
           } else if (lane == 0) {
             mbar_arrive(&bar_sland[ss]);
           }
         }
       }
-      if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[9] = clock64() - pw_t0; p.prof[10] = pw_empty; p.prof[11] = pw_sempty; }
+      if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[9] = clock64() - pw_t0; p.prof[10] = pw_empty; p.prof[11] = pw_sempty; p.prof[5 + 11] = pw_issue; }
     } else if (warp >= kXfWarp0 && warp < kProdWarp) {
       // ===================================== transform =====================================
       if (p.transform) {
@@ -735,8 +747,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     long long g2;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g2));
     if (blockIdx.x == 0) p.prof[8] = g2 - pr_entry;             // whole CTA
-    p.prof[16 + 2 * blockIdx.x] = pr_entry;
-    p.prof[17 + 2 * blockIdx.x] = g2;
+    p.prof[32 + 2 * blockIdx.x] = pr_entry;
+    p.prof[33 + 2 * blockIdx.x] = g2;
   }
 }
 
@@ -892,6 +904,10 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   const int sp_cells = max_pos + c.MB * 128 + 8;
   c.PS = (sp_cells * 16 + 127) / 128 * 128;          // chunk planes start 128-byte aligned (TMA destination)
   if (c.nsub * c.SUBP * 16 > c.PS) c.PS = c.nsub * c.SUBP * 16;
+  // x-fold: the 128-row blocks cover the padded tile exactly, no row reads past the plane, so the chunk planes
+  // can sit back to back and one TMA box (PX x RY x all chunks) loads a whole plane
+  c.one_box = 0;
+  if (xfold && cin >= 16) { c.PS = c.RY * c.PX * 16; c.one_box = 1; }
   c.slot_bytes = c.NCH * c.PS;
 
   // ---- ops ----------------------------------------------------------------------------------------
@@ -1001,7 +1017,7 @@ double estimate_clk(const Params& c, int sm_count) {
   const double plane_bytes = (double)c.nsub * c.NCH * c.RY * c.PX * 16.0 * (c.has_skip ? 2.0 : 1.0);
   const double load = plane_bytes * c.zstep / 18.0;                       // ~HBM share of one SM, B/clk
   const int ncls = c.mode == MODE_DECONV ? 8 : 1;
-  const double epi = c.xfold ? (double)c.MB * c.zf * (c.cout_n >= 8 ? c.cout_n / 8 : 1) * 420.0
+  const double epi = c.xfold ? (c.cout_n == 1 ? (double)c.MB * 300.0 : (double)c.MB * c.zf * (c.cout_n / 8) * 420.0)
                              : (double)c.MB * ncls * (c.CP * 4.0 * 128.0 / 110.0 + 12.0 * c.CP + 80.0);
   const double xf = c.transform ? (double)c.xf_k * c.zstep * (c.has_skip ? 70.0 : 45.0) : 0.0;
   double step = mma;
@@ -1034,13 +1050,14 @@ PFN_encodeTiled get_encode() {
 }
 
 // 5-D map over a CP8 (subs = 1) or PS8 (subs = 4) tensor: (8*Wp, Hp, subs, NCH, D), box (8*PX, RY, 1, 1, 1)
-bool make_tmap(CUtensorMap* tm, const void* base, int Wp, int Hp, int subs, int nch, int D, int PX, int RY) {
+bool make_tmap(CUtensorMap* tm, const void* base, int Wp, int Hp, int subs, int nch, int D, int PX, int RY,
+               int box_ch = 1) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[5] = {(cuuint64_t)Wp * 8, (cuuint64_t)Hp, (cuuint64_t)subs, (cuuint64_t)nch, (cuuint64_t)D};
   cuuint64_t gstr[4] = {(cuuint64_t)Wp * 16, (cuuint64_t)Hp * Wp * 16, (cuuint64_t)subs * Hp * Wp * 16,
                         (cuuint64_t)nch * subs * Hp * Wp * 16};
-  cuuint32_t box[5] = {(cuuint32_t)PX * 8, (cuuint32_t)RY, 1, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)PX * 8, (cuuint32_t)RY, 1, (cuuint32_t)box_ch, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1174,8 +1191,8 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     c.y_cp8 = (__nv_bfloat16*)y_cp8; c.y_ps8 = (__nv_bfloat16*)y_ps8; c.y_f32 = y_f32; c.stats = stats;
     const bool ok_x = mode == MODE_CONV2
                           ? make_tmap(&c.tmap_x, x, (W + 1) / 2, (H + 1) / 2, 4, c.NCH, D, c.PX, c.RY)
-                          : make_tmap(&c.tmap_x, x, W, H, 1, c.NCH, D, c.PX, c.RY);
-    const bool ok_s = !has_skip || make_tmap(&c.tmap_s, skip, W, H, 1, c.NCH, D, c.PX, c.RY);
+                          : make_tmap(&c.tmap_x, x, W, H, 1, c.NCH, D, c.PX, c.RY, c.one_box ? c.NCH : 1);
+    const bool ok_s = !has_skip || make_tmap(&c.tmap_s, skip, W, H, 1, c.NCH, D, c.PX, c.RY, c.one_box ? c.NCH : 1);
     if (!ok_x || !ok_s) {
       set_error("conv3d(bf16/tcgen05): cuTensorMapEncodeTiled failed (PX=%d RY=%d W=%d H=%d)", c.PX, c.RY, W, H);
       return MVSB200_ERR_CUDA;
@@ -1198,7 +1215,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     static long long* prof_buf = nullptr;
     c.prof = nullptr;
     if (getenv("MVSB200_TC_PROF")) {
-      if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 128 + 16 * 4096));
+      if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 256 + 16 * 4096));
       c.prof = prof_buf;
     }
     if (c.xfold) conv3d_tc_kernel<32, true><<<grid, kThreads, best.smem, s>>>(c);
@@ -1206,7 +1223,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     else conv3d_tc_kernel<32, false><<<grid, kThreads, best.smem, s>>>(c);
     MVS_LAUNCH_CHECK("conv3d_tc_kernel");
     if (c.prof) {
-      long long h[16];
+      long long h[17];
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaStreamSynchronize(s);
@@ -1225,9 +1242,10 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       fprintf(stderr, "CTA 0: prologue %.1f us, MMA warp done at %.1f us, CTA end %.1f us\n", h[6] * 1e-3, h[7] * 1e-3, h[8] * 1e-3);
       fprintf(stderr, "[tc-prof] producer %lld clk (wait empty %lld, wait skip-empty %lld); transform %lld clk (wait landed %lld); "
               "epilogue %lld clk (wait acc %lld)\n", h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
+      fprintf(stderr, "[tc-prof] producer: %lld clk in expect_tx + TMA issue\n", h[16]);
       if (grid <= 4096) {
         static long long hh[2 * 4096];
-        cudaMemcpy(hh, prof_buf + 16, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hh, prof_buf + 32, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
         long long t0 = hh[0], t1 = hh[1], smax = hh[0], emin = hh[1];
         double avg = 0;
         for (int i = 0; i < grid; ++i) {

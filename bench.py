@@ -10,7 +10,7 @@ data-path collective ("weak" scaling).  Prints ONE JSON line on ra
 
   value     depth maps/s, inputs resident in HBM, device-timed (CUDA events, max over ranks)
   e2e       the same through the host-buffer C-ABI call (pinned host -> device copy of feats+cams and
-            device -> host read of depth+prob inside the timed region)
+            device -> host read of depth+prob inside the timed region; two views in flight on two streams)
   roofline  the dominant kernel (fused warp+variance) against the measured HBM copy bandwidth
   cpu_baseline / --impl reference   the CPU restatement of the reference (oracle/) on the host cores
 """
@@ -207,17 +207,32 @@ def run_ours(args, rank, world, local_rank):
     stage_ms = np.array([[evs[j].elapsed_time(evs[j + 1]) for j in range(4)] for evs in stage_events]).mean(axis=0)
 
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
-    for i in range(min(args.warmup, 3)):
-        eng.infer_host(feats_h[i % N_CLUSTERS], cams_h[i % N_CLUSTERS], ds, di, depth_h, prob_h)
+    # Two reference views in flight on two streams (own staging + workspace each): the pinned-host -> device feed
+    # of one view overlaps the kernels of the other, as a prefetching input pipeline would feed sess.run.  Every
+    # step still copies its own inputs in and its own depth + probability maps out inside the timed region.
+    engs = [eng, HotPath(n, D, hf, wf, eng.weights, precision="bf16", device=dev)]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    outs = [(depth_h, prob_h), (torch.empty((hf, wf)).pin_memory(), torch.empty((hf, wf)).pin_memory())]
+
+    def e2e_pass(count):
+        for i in range(count):
+            k = i % 2
+            with torch.cuda.stream(streams[k]):
+                engs[k].infer_host_async(feats_h[i % N_CLUSTERS], cams_h[i % N_CLUSTERS], ds, di, outs[k][0], outs[k][1])
+
+    e2e_pass(min(args.warmup, 4))
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
     e0.record()
-    for i in range(args.steps):
-        eng.infer_host(feats_h[i % N_CLUSTERS], cams_h[i % N_CLUSTERS], ds, di, depth_h, prob_h)
-    e1.record()
+    for st in streams:
+        st.wait_event(e0)
+    e2e_pass(args.steps)
+    for k, st in enumerate(streams):
+        e1[k].record(st)
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    checksum = float(depth_h.sum())
+    ms_e2e = max(e0.elapsed_time(e1[0]), e0.elapsed_time(e1[1]))
+    checksum = float(outs[(args.steps - 1) % 2][0].sum())
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)

@@ -187,6 +187,18 @@ int mvsb200_infer_host(const float* feats_host, const float* cams_host, int n_vi
                        float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* The same without the final synchronisation: the copies and kernels are enqueued on `stream` and the
+ * host outputs are valid once the caller has synchronised that stream.  Host buffers must be pinned
+ * for the copies to overlap.  Two reference views in flight on two streams (each with its own staging
+ * and workspace) hide the host->device feed of one behind the kernels of the other, the way a
+ * prefetching input pipeline feeds sess.run (inference.py:105-112). */
+int mvsb200_infer_host_async(const float* feats_host, const float* cams_host, int n_views, int depth_num,
+                             int hf, int wf, int channels, float depth_start, float depth_interval,
+                             int inverse_depth, int order, int sampler, const mvsb200_regnet_params* params,
+                             int base_filter, float bn_eps, int precision, float* depth_map_host,
+                             float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* Diagnostic (not on the product path): one 128 x n x (16*kblocks) tcgen05.mma tile computed from
  * caller-built shared-memory images of the A and B operands (no-swizzle K-major core-matrix
  * layout).  Pins the descriptor semantics conv3d_umma.cu relies on.  d_out [128*n] fp32. */

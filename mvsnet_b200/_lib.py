@@ -60,6 +60,8 @@ SIGNATURES = {
     "mvsb200_infer_host_staging_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mvsb200_infer_host": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
                                    POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "mvsb200_infer_host_async": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
+                                   POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "mvsb200_umma_probe": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, _P, _P]),
     "mvsb200_launch_count": (c_uint64, []),

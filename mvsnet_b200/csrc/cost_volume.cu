@@ -4,8 +4,10 @@
 // warped volume is never written: each thread keeps the running sum and squared sum of its
 // voxels in registers across views and stores only the variance.
 //
-// Transform coefficients live in __constant__ memory (one 8-float row per (view, plane),
-// written once per call by prepare_table_kernel + a device-to-device symbol copy).
+// Transform coefficients: one 8-float row per (view, plane) in global memory, staged per block in
+// shared memory.  The whole-path entry points pass the table the homography kernel wrote into the
+// caller's workspace (so calls on different streams do not share state); the stand-alone entry point
+// derives it from the homographies into a library-owned table (one call in flight at a time).
 #include "geometry.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -13,8 +15,7 @@
 namespace mvsb200 {
 
 constexpr int kTableFloats = 14336;  // 56 KB: (N-1)*D*8 for N=8, D=256 (inference.py:29-31 defaults)
-__constant__ float c_table[kTableFloats];
-__device__ float g_table[kTableFloats];  // staging copy in global memory (generic kernel reads this one)
+__device__ float g_table[kTableFloats];  // table of the stand-alone entry point
 
 __global__ void prepare_table_kernel(const float* __restrict__ homographies, int count) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,8 +113,9 @@ constexpr int kPlaneChunk = 48;
 // (half the L1 wavefronts and load instructions of the fp32 path).  The reference view stays fp32.
 template <int OUT, int TX, int TY, int KDC, bool TAPS16>
 __global__ void __launch_bounds__(256, KDC == 2 ? 4 : (KDC == 4 ? 3 : 2))
-cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict__ feats16, int n_views, int D, int Hf,
-                       int Wf, int order, void* __restrict__ out, void* __restrict__ out2) {
+cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict__ feats16,
+                       const float* __restrict__ coef, int n_views, int D, int Hf, int Wf, int order,
+                       void* __restrict__ out, void* __restrict__ out2) {
   static_assert(TX * TY == 32, "tile must hold 32 pixels");
   static_assert(KDC == 2 || KDC == 4 || KDC == 8, "planes per thread");
   constexpr int VPR = 8 / KDC;            // source views per footprint round
@@ -131,7 +133,7 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
   for (int i = tid; i < n_src * kPlaneChunk * 8; i += 256) {
     int v = i / (kPlaneChunk * 8), r = i - v * (kPlaneChunk * 8);
     int d = min(dbeg + (r >> 3), D - 1);
-    s_coef[i] = c_table[(v * D + d) * 8 + (r & 7)];
+    s_coef[i] = __ldg(coef + (v * D + d) * 8 + (r & 7));
   }
   __syncthreads();
   const bool active = (x < Wf) && (y < Hf);
@@ -288,8 +290,9 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
 // ------------------------------------------------------------------------------------------------
 template <int VEC, int SAMPLER, bool BF16OUT>
 __global__ void __launch_bounds__(256)
-cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restrict__ homographies, int n_views,
-                           int D, int Hf, int Wf, int C, int order, void* __restrict__ out) {
+cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restrict__ homographies,
+                           const float* __restrict__ coef, int n_views, int D, int Hf, int Wf, int C, int order,
+                           void* __restrict__ out) {
   const int groups = C / VEC;
   const size_t total = (size_t)D * Hf * Wf * groups;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,7 +313,7 @@ cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restr
     float w[VEC];
     if (SAMPLER == MVSB200_SAMPLER_TRANSFORM) {
       float ix, iy;
-      transform_coords(&g_table[(v * D + d) * 8], (float)x, (float)y, ix, iy);
+      transform_coords(coef + (v * D + d) * 8, (float)x, (float)y, ix, iy);
       Footprint f = make_footprint(ix, iy, Wf, Hf);
       const float* base = img + ((int64_t)f.y0 * Wf + f.x0) * C + c0;
       const int64_t row = (int64_t)Wf * C;
@@ -363,7 +366,8 @@ cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restr
 // planar_ps8 != NULL or planar != 0: write the bf16 planar layouts (out = CP8, planar_ps8 = PS8); fast path only
 static int launch_cost_volume_any(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                                   int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
-                                  int planar, void* planar_ps8, void* feats16, cudaStream_t s) {
+                                  int planar, void* planar_ps8, void* feats16, const float* coef_table,
+                                  cudaStream_t s) {
   MVS_CHECK_ARG(feats && homographies && (out || planar_ps8), "cost_volume: NULL pointer");
   MVS_CHECK_ARG(n_views >= 2 && depth_num >= 1 && hf >= 1 && wf >= 1 && channels >= 1,
                 "cost_volume: bad shape N=%d D=%d %dx%dx%d", n_views, depth_num, hf, wf, channels);
@@ -373,7 +377,8 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
   MVS_CHECK_ARG(out_dtype == MVSB200_F32 || out_dtype == MVSB200_BF16, "cost_volume: bad out_dtype %d", out_dtype);
   const int rows = (n_views - 1) * depth_num;
   const bool bf16 = out_dtype == MVSB200_BF16;
-  if (sampler == MVSB200_SAMPLER_TRANSFORM) {
+  const float* coef = coef_table;
+  if (sampler == MVSB200_SAMPLER_TRANSFORM && !coef) {
     if (rows * 8 > kTableFloats) {
       set_error("cost_volume: (n_views-1)*depth_num = %d exceeds the %d-row coefficient table", rows,
                 kTableFloats / 8);
@@ -381,6 +386,9 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
     }
     prepare_table_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(homographies, rows);
     MVS_LAUNCH_CHECK("prepare_table_kernel");
+    void* g_ptr = nullptr;
+    MVS_CUDA(cudaGetSymbolAddress(&g_ptr, g_table));
+    coef = (const float*)g_ptr;
   }
   // variant: 0 auto, 1 generic, 2 fast path with a 32x1 pixel tile, 3 fast path with a 16x2 tile
   bool fast_ok = sampler == MVSB200_SAMPLER_TRANSFORM && channels == 32 && n_views - 1 <= kMaxSrcViews &&
@@ -396,10 +404,6 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
     return MVSB200_ERR_UNSUPPORTED;
   }
   if (variant >= 2) {
-    void* g_ptr = nullptr;
-    MVS_CUDA(cudaGetSymbolAddress(&g_ptr, g_table));
-    MVS_CUDA(cudaMemcpyToSymbolAsync(c_table, g_ptr, (size_t)rows * 8 * sizeof(float), 0,
-                                     cudaMemcpyDeviceToDevice, s));
     const bool wide = variant == 2;
     const int tx = wide ? 32 : 16, ty = wide ? 1 : 2;
     dim3 grid(ceil_div(wf, tx), ceil_div(hf, ty), ceil_div(depth_num, kPlaneChunk));
@@ -407,11 +411,13 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
 #define CV_FAST(O, TX_, TY_, K_)                                                                                  \
   do {                                                                                                            \
     if (O == 2 && feats16)                                                                                        \
-      cost_volume_c32_kernel<O, TX_, TY_, K_, true><<<grid, 256, 0, s>>>(feats, (const __half*)feats16, n_views,  \
-                                                                         depth_num, hf, wf, order, out, planar_ps8); \
+      cost_volume_c32_kernel<O, TX_, TY_, K_, true><<<grid, 256, 0, s>>>(feats, (const __half*)feats16, coef,     \
+                                                                         n_views, depth_num, hf, wf, order, out,  \
+                                                                         planar_ps8);                             \
     else                                                                                                          \
-      cost_volume_c32_kernel<O, TX_, TY_, K_, false><<<grid, 256, 0, s>>>(feats, nullptr, n_views, depth_num, hf, \
-                                                                          wf, order, out, planar_ps8);            \
+      cost_volume_c32_kernel<O, TX_, TY_, K_, false><<<grid, 256, 0, s>>>(feats, nullptr, coef, n_views,          \
+                                                                          depth_num, hf, wf, order, out,          \
+                                                                          planar_ps8);                            \
   } while (0)
 #define CV_FAST_K(O, TX_, TY_)                                  \
   do {                                                          \
@@ -445,8 +451,8 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
   MVS_CHECK_ARG((total + 255) / 256 <= 0x7fffffffu, "cost_volume: problem too large for one launch");
   unsigned blocks = (unsigned)((total + 255) / 256);
 #define CV_GEN(V, SM, BF)                                                                                  \
-  cost_volume_generic_kernel<V, SM, BF><<<blocks, 256, 0, s>>>(feats, homographies, n_views, depth_num, hf, \
-                                                               wf, channels, order, out)
+  cost_volume_generic_kernel<V, SM, BF><<<blocks, 256, 0, s>>>(feats, homographies, coef, n_views, depth_num, \
+                                                               hf, wf, channels, order, out)
   if (sampler == MVSB200_SAMPLER_TRANSFORM) {
     if (vec == 4) { if (bf16) CV_GEN(4, MVSB200_SAMPLER_TRANSFORM, true); else CV_GEN(4, MVSB200_SAMPLER_TRANSFORM, false); }
     else          { if (bf16) CV_GEN(1, MVSB200_SAMPLER_TRANSFORM, true); else CV_GEN(1, MVSB200_SAMPLER_TRANSFORM, false); }
@@ -463,7 +469,15 @@ int launch_cost_volume(const float* feats, const float* homographies, int n_view
                        int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
                        cudaStream_t s) {
   return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler, out_dtype,
-                                out, variant, 0, nullptr, nullptr, s);
+                                out, variant, 0, nullptr, nullptr, nullptr, s);
+}
+
+// whole-path variant: `coef_table` [(n_views-1), depth_num, 8] written by launch_homographies into caller memory
+int launch_cost_volume_coef(const float* feats, const float* homographies, const float* coef_table, int n_views,
+                            int depth_num, int hf, int wf, int channels, int order, int sampler, int out_dtype,
+                            void* out, cudaStream_t s) {
+  return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler, out_dtype,
+                                out, 0, 0, nullptr, nullptr, coef_table, s);
 }
 
 bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sampler) {
@@ -476,9 +490,9 @@ size_t cost_volume_pair_bytes(int n_views, int hf, int wf) { return (size_t)n_vi
 
 int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                               int wf, int channels, int order, int sampler, void* cp8, void* ps8, void* feats16,
-                              cudaStream_t s) {
+                              const float* coef_table, cudaStream_t s) {
   return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler,
-                                MVSB200_BF16, cp8, 0, 1, ps8, feats16, s);
+                                MVSB200_BF16, cp8, 0, 1, ps8, feats16, coef_table, s);
 }
 
 }  // namespace mvsb200

@@ -307,17 +307,21 @@ namespace mvsb200 {
 bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sampler);
 int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                               int wf, int channels, int order, int sampler, void* cp8, void* ps8, void* feats16,
-                              cudaStream_t s);
+                              const float* coef_table, cudaStream_t s);
+int launch_cost_volume_coef(const float* feats, const float* homographies, const float* coef_table, int n_views,
+                            int depth_num, int hf, int wf, int channels, int order, int sampler, int out_dtype,
+                            void* out, cudaStream_t s);
 size_t cost_volume_pair_bytes(int n_views, int hf, int wf);
 }
 namespace {
 struct InferPlan {
-  size_t hom_off, cost_off, filtered_off, pair_off, regnet_off, total;
+  size_t hom_off, coef_off, cost_off, filtered_off, pair_off, regnet_off, total;
   size_t regnet_bytes;
 };
 void make_infer_plan(int n_views, int D, int hf, int wf, int C, int b, int precision, InferPlan* ip) {
   size_t off = 0;
   ip->hom_off = off;      off += align_up((size_t)(n_views - 1) * D * 9 * sizeof(float), 256);
+  ip->coef_off = off;     off += align_up((size_t)(n_views - 1) * D * 8 * sizeof(float), 256);
   // (bf16 mode with the fast cost-volume kernel writes the volume straight into the regularizer's planar buffers
   // inside its workspace; the NDHWC buffer is then unused but stays reserved: the sampler is a per-call choice)
   ip->cost_off = off;     off += align_up((size_t)D * hf * wf * C * (precision == MVSB200_PRECISION_BF16 ? 2 : 4), 256);
@@ -378,8 +382,9 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   volatile float prod = dm1 * depth_interval;
   volatile float depth_end = depth_start + prod;
   MVS_STAGE_EVENT(0);
+  float* coefs = (float*)(ws + ip.coef_off);      // pixel-coordinate transform rows, private to this call's workspace
   rc = launch_homographies(cams, n_views, depth_num, depth_start, inverse_depth ? (float)depth_end : depth_interval,
-                           inverse_depth, homs, nullptr, s);
+                           inverse_depth, homs, coefs, s);
   if (rc) return rc;
   MVS_STAGE_EVENT(1);
   const int cost_dtype = precision == MVSB200_PRECISION_BF16 ? MVSB200_BF16 : MVSB200_F32;
@@ -390,9 +395,10 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
     regnet_cost_planar(ws + ip.regnet_off, depth_num, hf, wf, channels, base_filter, &cp8, &ps8);
     static const bool fp32_taps = getenv("MVSB200_CV_FP32_TAPS") != nullptr;
     rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8,
-                                   fp32_taps ? nullptr : ws + ip.pair_off, s);
+                                   fp32_taps ? nullptr : ws + ip.pair_off, coefs, s);
   } else {
-    rc = launch_cost_volume(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cost_dtype, cost, 0, s);
+    rc = launch_cost_volume_coef(feats, homs, coefs, n_views, depth_num, hf, wf, channels, order, sampler, cost_dtype,
+                                 cost, s);
   }
   if (rc) return rc;
   MVS_STAGE_EVENT(2);
@@ -413,12 +419,11 @@ extern "C" size_t mvsb200_infer_host_staging_bytes(int n_views, int hf, int wf, 
          align_up((size_t)n_views * 32 * sizeof(float), 256) + 2 * align_up((size_t)hf * wf * sizeof(float), 256);
 }
 
-extern "C" int mvsb200_infer_host(const float* feats_host, const float* cams_host, int n_views, int depth_num,
-                                  int hf, int wf, int channels, float depth_start, float depth_interval,
-                                  int inverse_depth, int order, int sampler, const mvsb200_regnet_params* params,
-                                  int base_filter, float bn_eps, int precision, float* depth_map_host,
-                                  float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+static int infer_host_enqueue(const float* feats_host, const float* cams_host, int n_views, int depth_num, int hf,
+                              int wf, int channels, float depth_start, float depth_interval, int inverse_depth, int order,
+                              int sampler, const mvsb200_regnet_params* params, int base_filter, float bn_eps,
+                              int precision, float* depth_map_host, float* prob_map_host, void* staging_dev,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   MVS_CHECK_ARG(feats_host && cams_host && depth_map_host && prob_map_host && staging_dev, "infer_host: NULL pointer");
   MVS_CHECK_ARG(n_views >= 2 && hf > 0 && wf > 0 && channels > 0, "infer_host: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
@@ -438,6 +443,30 @@ extern "C" int mvsb200_infer_host(const float* feats_host, const float* cams_hos
   if (rc) return rc;
   MVS_CUDA(cudaMemcpyAsync(depth_map_host, d_depth, map_bytes, cudaMemcpyDeviceToHost, s));
   MVS_CUDA(cudaMemcpyAsync(prob_map_host, d_prob, map_bytes, cudaMemcpyDeviceToHost, s));
-  MVS_CUDA(cudaStreamSynchronize(s));
   return MVSB200_OK;
+}
+
+extern "C" int mvsb200_infer_host(const float* feats_host, const float* cams_host, int n_views, int depth_num,
+                                  int hf, int wf, int channels, float depth_start, float depth_interval,
+                                  int inverse_depth, int order, int sampler, const mvsb200_regnet_params* params,
+                                  int base_filter, float bn_eps, int precision, float* depth_map_host,
+                                  float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  int rc = infer_host_enqueue(feats_host, cams_host, n_views, depth_num, hf, wf, channels, depth_start, depth_interval,
+                              inverse_depth, order, sampler, params, base_filter, bn_eps, precision, depth_map_host,
+                              prob_map_host, staging_dev, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  MVS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return MVSB200_OK;
+}
+
+extern "C" int mvsb200_infer_host_async(const float* feats_host, const float* cams_host, int n_views, int depth_num,
+                                        int hf, int wf, int channels, float depth_start, float depth_interval,
+                                        int inverse_depth, int order, int sampler,
+                                        const mvsb200_regnet_params* params, int base_filter, float bn_eps,
+                                        int precision, float* depth_map_host, float* prob_map_host, void* staging_dev,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  return infer_host_enqueue(feats_host, cams_host, n_views, depth_num, hf, wf, channels, depth_start, depth_interval,
+                            inverse_depth, order, sampler, params, base_filter, bn_eps, precision, depth_map_host,
+                            prob_map_host, staging_dev, workspace, workspace_bytes, stream);
 }

@@ -115,6 +115,22 @@ class HotPath:
         L.check(rc, "infer_host")
         return depth_out, prob_out
 
+    def infer_host_async(self, feats_host: torch.Tensor, cams_host: torch.Tensor, depth_start: float,
+                         depth_interval: float, depth_out: torch.Tensor, prob_out: torch.Tensor):
+        """infer_host without the final synchronisation: everything is enqueued on the current stream and the
+        (pinned) host outputs are valid after that stream has been synchronised.  Two engines on two streams
+        overlap the feed of one reference view with the kernels of the other."""
+        for t in (feats_host, cams_host, depth_out, prob_out):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_pinned():
+                raise ValueError("infer_host_async takes contiguous fp32 PINNED host tensors")
+        rc = self.lib.mvsb200_infer_host_async(
+            L.ptr(feats_host), L.ptr(cams_host), self.n_views, self.depth_num, self.hf, self.wf, self.channels,
+            float(depth_start), float(depth_interval), self.inverse_depth, self.order, self.sampler,
+            ctypes.byref(self.weights.params), self.base_filter, self.bn_eps, self.precision, L.ptr(depth_out),
+            L.ptr(prob_out), L.ptr(self.staging), L.ptr(self.workspace), self.workspace.numel(), L.stream_ptr())
+        L.check(rc, "infer_host_async")
+        return depth_out, prob_out
+
     def set_stage_events(self, events) -> None:
         """events: five torch.cuda.Event(enable_timing=True) (or None) recorded at the stage boundaries of infer()."""
         if events is None:

@@ -91,3 +91,33 @@ def test_reference_named_inference(small_problem, oracle_small):
     assert np.abs(out[0, ..., 0].cpu().numpy() - allr["filtered"]).max() <= 2e-3 * np.abs(allr["filtered"]).max()
     mvsnetworks.RegNetUS0.precision = "bf16"
     model.FLAGS.precision = "bf16"
+
+
+def test_infer_host_async_two_streams(tiny_problem):
+    """Two engines on two streams (own staging + workspace) fed from pinned host buffers: both results match
+    the synchronous call bit for bit (no state is shared between calls in flight)."""
+    from mvsnet_b200.engine import HotPath
+    p = tiny_problem
+    fh = torch.from_numpy(p["feats"]).pin_memory()
+    ch = torch.from_numpy(p["cams"]).pin_memory()
+    # a second, different problem: permute the source views
+    perm = [0] + list(range(p["n_views"] - 1, 0, -1))
+    fh2 = fh[perm].contiguous().pin_memory()
+    ch2 = ch[perm].contiguous().pin_memory()
+    engs = [HotPath(p["n_views"], p["depth_num"], p["hf"], p["wf"], p["weights"], precision="bf16") for _ in range(2)]
+    ref = []
+    for f, c in ((fh, ch), (fh2, ch2)):
+        d = torch.empty((p["hf"], p["wf"])).pin_memory()
+        q = torch.empty((p["hf"], p["wf"])).pin_memory()
+        engs[0].infer_host(f, c, p["depth_start"], p["depth_interval"], d, q)
+        ref.append((d.clone(), q.clone()))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [(torch.empty((p["hf"], p["wf"])).pin_memory(), torch.empty((p["hf"], p["wf"])).pin_memory()) for _ in range(2)]
+    for rep in range(3):
+        for k, (f, c) in enumerate(((fh, ch), (fh2, ch2))):
+            with torch.cuda.stream(streams[k]):
+                engs[k].infer_host_async(f, c, p["depth_start"], p["depth_interval"], outs[k][0], outs[k][1])
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert torch.equal(outs[k][0], ref[k][0])
+        assert torch.equal(outs[k][1], ref[k][1])

@@ -201,7 +201,7 @@ int mvsb200_infer_host_async(const float* feats_host, const float* cams_host, in
 
 /* Diagnostic (not on the product path): one 128 x n x (16*kblocks) tcgen05.mma tile computed from
  * caller-built shared-memory images of the A and B operands (no-swizzle K-major core-matrix
- * layout).  Pins the descriptor semantics conv3d_umma.cu relies on.  d_out [128*n] fp32. */
+ * layout).  Pins the descriptor semantics conv3d_tc.cu relies on.  d_out [128*n] fp32. */
 int mvsb200_umma_probe(const void* a_image, int a_bytes, const void* b_image, int b_bytes, int n,
                        int kblocks, int a_kblock_stride, int a_start, int a_lbo, int a_sbo,
                        int b_kblock_stride, int b_lbo, int b_sbo, float* d_out, void* stream);

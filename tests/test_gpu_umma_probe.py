@@ -1,4 +1,4 @@
-"""Pins the tcgen05 shared-memory descriptor semantics conv3d_umma.cu relies on (no-swizzle K-major
+"""Pins the tcgen05 shared-memory descriptor semantics conv3d_tc.cu relies on (no-swizzle K-major
 core matrices, arbitrary 16-byte-aligned start / leading / stride byte offsets) against numpy."""
 import numpy as np
 import pytest

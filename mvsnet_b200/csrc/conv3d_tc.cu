@@ -51,6 +51,11 @@
 namespace mvsb200 {
 using namespace umma;
 
+// Batch-norm source of an input tensor: the producer's channel statistics (sum | sum of squares over `count`
+// voxels) and its gamma / beta.  The consumer derives scale / shift itself (no bn_finalize launch in between).
+struct TcBnSrc { const double* stats; const float* gamma; const float* beta; double count; float eps; int channels;
+                 int reps; int rep_stride; };   // statistics are the sum of `reps` partial copies, rep_stride doubles apart
+
 namespace tc {
 
 constexpr int kMaxOps = 108;            // 27 taps x (64 channels / 16)
@@ -74,8 +79,10 @@ struct Params {
   alignas(64) CUtensorMap tmap_x;   // input planes
   alignas(64) CUtensorMap tmap_s;   // skip planes (has_skip)
   const float *xs, *xb, *ss, *sb;
+  TcBnSrc xbn, sbn;                 // used instead of xs/xb, ss/sb when .stats is set
   const uint4* wpacked;
   __nv_bfloat16* y_cp8; __nv_bfloat16* y_ps8; float* y_f32; double* stats;
+  int stats_reps, stats_rep_stride;   // CTAs spread their atomics over `stats_reps` partial copies of the statistics
   int mode, has_skip, transform;
   int D, H, W, Cin;              // input volume
   int Do, Ho, Wo, Cout;          // output volume (all channels)
@@ -162,6 +169,56 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   return __bfloat1622float2(h);
 }
 
+// scale / shift of channel c from batch statistics: the arithmetic of bn_finalize_kernel (conv3d_direct.cu), i.e.
+// fp64 moments rounded once, then tf.nn.batch_normalization in fp32 (network.py:496-506, Appendix A.6)
+__device__ __forceinline__ void bn_scale_shift(const TcBnSrc& b, int c, float& scale, float& shift) {
+  double sm = 0.0, sq = 0.0;
+  for (int r = 0; r < b.reps; ++r) {
+    sm += b.stats[(size_t)r * b.rep_stride + c];
+    sq += b.stats[(size_t)r * b.rep_stride + b.channels + c];
+  }
+  const double mean = sm / b.count;
+  double var = sq / b.count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float meanf = (float)mean, varf = (float)var;
+  const float inv = __fmul_rn(__fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(varf, b.eps))), b.gamma[c]);
+  scale = inv;
+  shift = __fsub_rn(b.beta[c], __fmul_rn(meanf, inv));
+}
+
+// Batch statistics of a CTA: per-thread partials -> warp reduce -> the 4 epilogue warps combine in shared memory ->
+// one double atomic per channel and CTA, spread over partial copies (thousands of atomics on the same 2*C
+// addresses serialise in L2 and used to cost more than the small layers themselves).
+template <int NV>
+__device__ __forceinline__ void flush_stats(const Params& p, float (&sum)[NV], float (&sq)[NV], int ncol, bool fold,
+                                            float* s_red, int warp, int lane) {
+  if (lane < 32) { s_red[(warp * 2 + 0) * 32 + lane] = 0.0f; s_red[(warp * 2 + 1) * 32 + lane] = 0.0f; }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float s = sum[k], q = sq[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0 && k < ncol) {
+      const int cn = fold ? (k & (p.cout_n - 1)) : k;       // z-folded columns of the same channel
+      s_red[(warp * 2 + 0) * 32 + cn] += s;
+      s_red[(warp * 2 + 1) * 32 + cn] += q;
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
+  if (warp == 0 && lane < p.cout_n) {
+    float s = 0.0f, q = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { s += s_red[(w * 2 + 0) * 32 + lane]; q += s_red[(w * 2 + 1) * 32 + lane]; }
+    double* st = p.stats + (size_t)(blockIdx.x % p.stats_reps) * p.stats_rep_stride;
+    atomicAdd(st + p.cout_base + lane, (double)s);
+    atomicAdd(st + p.Cout + p.cout_base + lane, (double)q);
+  }
+}
+
 // Issue the MMAs of ops [ob, oe) of one input plane: one 16-byte shared-memory record per op (the unrolled loop
 // prefetches them), the MB row blocks of an op reuse its descriptors (A start + 2 KB, next TMEM column group).
 template <int MB>
@@ -187,7 +244,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   unsigned char* s_skip = s_slots + (size_t)p.R * p.slot_bytes;
   uint4* s_ops = reinterpret_cast<uint4*>(s_skip + (p.has_skip ? (size_t)p.RS * p.slot_bytes : 0));
   int* s_dzb = reinterpret_cast<int*>(s_ops + kMaxOps);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dzb + 8);
+  float* s_red = reinterpret_cast<float*>(s_dzb + 8);      // [4 warps][sum | sumsq][32 channels]
+  float* s_aff = s_red + 256;                              // [x scale | x shift | skip scale | skip shift][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_aff + 256);
   uint64_t* bar_land = bars;                        // [R]  TMA -> transform / MMA
   uint64_t* bar_ready = bars + kMaxRing;            // [R]  transform -> MMA
   uint64_t* bar_empty = bars + 2 * kMaxRing;        // [R]  MMA (commit) -> producer
@@ -221,6 +280,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       s_ops[i] = make_uint4(e.a_lo, e.b_lo + b16, e.meta & 0xFFFFu, ((e.meta >> 16) & 1u) ^ 1u);
     }
     if (threadIdx.x <= kMaxSpan) s_dzb[threadIdx.x] = p.dz_begin[threadIdx.x];
+    // BN scale / shift of the input (and skip) channels, one thread per channel (fp64 moments are slow: not per
+    // transform thread)
+    if (threadIdx.x < 2 * p.Cin) {
+      const int c = threadIdx.x % p.Cin, which = threadIdx.x / p.Cin;
+      float sc = 1.0f, sh = 0.0f;
+      if (which == 0) {
+        if (p.xbn.stats) bn_scale_shift(p.xbn, c, sc, sh);
+        else if (p.xs) { sc = p.xs[c]; sh = p.xb[c]; }
+      } else {
+        if (p.sbn.stats) bn_scale_shift(p.sbn, c, sc, sh);
+        else if (p.ss) { sc = p.ss[c]; sh = p.sb[c]; }
+      }
+      s_aff[which * 128 + c] = sc;
+      s_aff[which * 128 + 64 + c] = sh;
+    }
   }
   // Every cell of the ring starts finite: halo rows of the GEMM read a few cells past the landed boxes
   // (their results are dropped, but 0 * NaN from stale shared memory must not reach a zero-weighted
@@ -330,11 +404,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           }
         }
         float xsc[8], xsh[8], ssc[8], ssh[8];
-        const bool x_act = p.xs != nullptr, s_act = p.ss != nullptr;
+        const bool x_act = p.xs != nullptr || p.xbn.stats != nullptr, s_act = p.ss != nullptr || p.sbn.stats != nullptr;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          xsc[k] = x_act ? p.xs[ch * 8 + k] : 1.0f; xsh[k] = x_act ? p.xb[ch * 8 + k] : 0.0f;
-          ssc[k] = s_act ? p.ss[ch * 8 + k] : 1.0f; ssh[k] = s_act ? p.sb[ch * 8 + k] : 0.0f;
+          xsc[k] = s_aff[ch * 8 + k]; xsh[k] = s_aff[64 + ch * 8 + k];
+          ssc[k] = s_aff[128 + ch * 8 + k]; ssh[k] = s_aff[192 + ch * 8 + k];
         }
         long long xw = 0, xt0 = 0;
         if (p.prof) xt0 = clock64();
@@ -570,21 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           if (lane == 0) mbar_arrive(&bar_acc_empty[stage]);
         }
         if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
-        if (p.stats) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            float s_ = sum[k], q_ = sq[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s_ += __shfl_xor_sync(0xffffffffu, s_, o);
-              q_ += __shfl_xor_sync(0xffffffffu, q_, o);
-            }
-            if (lane == 0 && k < p.cout_n) {
-              atomicAdd(p.stats + p.cout_base + k, (double)s_);
-              atomicAdd(p.stats + p.Cout + p.cout_base + k, (double)q_);
-            }
-          }
-        }
+        if (p.stats && !(p.dbg & 8)) flush_stats<32>(p, sum, sq, p.cout_n, false, s_red, warp, lane);
       } else {
       float sum[CP], sq[CP];
 #pragma unroll
@@ -720,23 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         if (lane == 0) mbar_arrive(&bar_acc_empty[stage]);
       }
       if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
-      // batch statistics: per-thread partials -> warp reduce -> one double atomic per channel and warp
-      if (p.stats) {
-#pragma unroll
-        for (int k = 0; k < CP; ++k) {
-          float s = sum[k], q = sq[k];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
-          }
-          if (lane == 0 && k < ncol) {
-            const int cn = p.zf == 1 ? k : (k & (p.cout_n - 1));
-            atomicAdd(p.stats + p.cout_base + cn, (double)s);
-            atomicAdd(p.stats + p.Cout + p.cout_base + cn, (double)q);
-          }
-        }
-      }
+      if (p.stats && !(p.dbg & 8)) flush_stats<CP>(p, sum, sq, ncol, p.zf != 1, s_red, warp, lane);
       }
     }
   }
@@ -986,7 +1030,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   pk.zf = zf; pk.master = master ? 1 : 0; pk.xfold = xfold ? 1 : 0;
   pk.nops = nimg; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
   pk.transposed = mode == MODE_DECONV;
-  const size_t fixed = (size_t)c.b_bytes + (size_t)kMaxOps * 16 + 32 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
+  const size_t fixed = (size_t)c.b_bytes + (size_t)kMaxOps * 16 + 32 + 2048 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
   c.RS = has_skip ? kMinSkipRing : 0;
   size_t skip_bytes = (size_t)c.RS * c.slot_bytes;
   c.R = c.span + c.zstep;                         // the planes of the next step land while this one computes
@@ -1069,45 +1113,9 @@ bool make_tmap(CUtensorMap* tm, const void* base, int Wp, int Hp, int subs, int 
 
 using namespace tc;
 
-size_t conv3d_tc_scratch_bytes() { return align_up((size_t)kMaxOps * 2 * 32 * 16, 256) * 2; }
-
-// x: CP8 for stride-1 convs and transposed convs, PS8 for stride-2 convs.  skip: CP8.
-// Outputs: y_cp8 and / or y_ps8 (bf16, Cout % 8 == 0), or y_f32 (NDHWC fp32, any Cout).
-int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
-                     const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
-                     int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
-                     cudaStream_t s) {
-  if (cin != 8 && cin != 16 && cin != 32 && cin != 64) {
-    set_error("conv3d(bf16/tcgen05): Cin=%d unsupported (need 8, 16, 32 or 64)", cin);
-    return MVSB200_ERR_UNSUPPORTED;
-  }
-  if (!y_f32 && (cout % 8 != 0 || (!y_cp8 && !y_ps8))) {
-    set_error("conv3d(bf16/tcgen05): bf16 output needs Cout %% 8 == 0 (got %d)", cout);
-    return MVSB200_ERR_UNSUPPORTED;
-  }
-  const int mode = transposed ? MODE_DECONV : (stride == 2 ? MODE_CONV2 : MODE_CONV1);
-  if (skip && mode == MODE_CONV2) {
-    set_error("conv3d(bf16/tcgen05): skip input on a stride-2 conv is not supported");
-    return MVSB200_ERR_UNSUPPORTED;
-  }
-  if (!get_encode()) {
-    set_error("conv3d(bf16/tcgen05): cuTensorMapEncodeTiled is not available from the driver");
-    return MVSB200_ERR_CUDA;
-  }
-  int sm_count = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    attr_done = true;
-  }
-  const bool has_skip = skip != nullptr, transform = xs != nullptr || has_skip;
+// Plan (tile, folds, z split, op table) of one launch: output channels [cb, cb+cn) of a layer.  Cached per shape.
+static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, int cn, bool has_skip, bool transform,
+                      int sm_count, Plan* out, int* dbg_out) {
   // tuning / debugging switches; MVSB200_TC_LAYER="cin,cout,mode" restricts them to one layer shape
   const char* zf_env = getenv("MVSB200_TC_ZF");
   const char* tile_env = getenv("MVSB200_TC_TILE");     // "TXxTY" forces the tile
@@ -1123,9 +1131,6 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
   if (tile_env) sscanf(tile_env, "%dx%d", &force_tx, &force_ty);
   const int force_zs = zs_env ? atoi(zs_env) : 0;
   const bool no_xfold = xf_env && atoi(xf_env) == 0;
-  int launch_idx = 0;
-  for (int cb = 0; cb < cout; cb += 32, ++launch_idx) {
-    const int cn = cout - cb < 32 ? cout - cb : 32;
     const int Mx = mode == MODE_CONV2 ? ceil_div(W, 2) : W, My = mode == MODE_CONV2 ? ceil_div(H, 2) : H,
               Mz = mode == MODE_CONV2 ? ceil_div(D, 2) : D;
     const std::array<int, 14> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_env ? atoi(zf_env) : 0,
@@ -1182,12 +1187,148 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
         g_plan_cache[key] = best;
       }
     }
-    if (!found) {
+    if (found) *out = best;
+    if (dbg_out) *dbg_out = dbg_env ? atoi(dbg_env) : 0;
+    return found;
+}
+
+size_t conv3d_tc_pack_slot_bytes() { return align_up((size_t)kMaxOps * 2 * 32 * 16, 256); }
+size_t conv3d_tc_scratch_bytes() { return conv3d_tc_pack_slot_bytes() * 2; }
+
+// ---------------------------------------------------------------------------------------------
+// all weights of a network in one launch
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPackJobs = 24;
+struct PackAll { int n; PackParams job[kMaxPackJobs]; };
+
+__global__ void pack_all_kernel(const __grid_constant__ PackAll a) {
+  const PackParams& p = a.job[blockIdx.y];
+  const int kwn = p.xfold ? 3 : 1, grp = kwn * p.cout_n;
+  if (!p.master) {
+    const int total = p.nops * 2 * p.CP * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int k8 = i & 7, n = (i >> 3) % p.CP, half = (i / (8 * p.CP)) & 1, op = i / (16 * p.CP);
+      const int j = n / grp, rem = n - j * grp, kw = rem / p.cout_n, cn = rem - kw * p.cout_n;
+      int tap = p.ops[op].tap[half];
+      const int ci = p.ops[op].cbase[half] + k8;
+      if (tap >= 0) tap += (p.xfold ? kw : 0) - 9 * j;
+      float w = 0.0f;
+      if (tap >= 0 && tap < 27 && j < p.zf && ci < p.Cin) {
+        const int co = p.cout_base + cn;
+        w = p.transposed ? p.kernel_tf[((size_t)tap * p.Cout + co) * p.Cin + ci]
+                         : p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + co];
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+  } else {
+    const int groups = 2 * p.zf + 1, rows = groups * grp;
+    const int total = p.nops * 2 * rows * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int k8 = i & 7, row = (i >> 3) % rows, half = (i / (8 * rows)) & 1, m = i / (16 * rows);
+      const int g = row / grp, rem = row - g * grp, kw = rem / p.cout_n, cn = rem - kw * p.cout_n, kd = p.zf + 1 - g;
+      const int ci = p.ops[m].cbase[half] + k8;
+      float w = 0.0f;
+      if (kd >= 0 && kd < 3 && ci < p.Cin) {
+        const int tap = kd * 9 + p.ops[m].tap[0] + (p.xfold ? kw : 0);
+        w = p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + p.cout_base + cn];
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+  }
+}
+
+// One job per layer; its launches (output-channel slices of 32) take consecutive slots starting at slot0.
+struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0; };
+
+int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStream_t s) {
+  static PackAll a;      // too large for the stack of some callers; filled and consumed under the launch below
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int sm_count = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  a.n = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const TcPackJob& jb = jobs[j];
+    const int mode = jb.transposed ? MODE_DECONV : (jb.stride == 2 ? MODE_CONV2 : MODE_CONV1);
+    int slot = jb.slot0;
+    for (int cb = 0; cb < jb.cout; cb += 32, ++slot) {
+      const int cn = jb.cout - cb < 32 ? jb.cout - cb : 32;
+      Plan pl;
+      if (!find_plan(mode, jb.D, jb.H, jb.W, jb.cin, jb.cout, cb, cn, jb.has_skip != 0, jb.transform != 0, sm_count, &pl,
+                     nullptr)) {
+        set_error("conv3d(bf16/tcgen05): no tile fits (Cin=%d Cout=%d mode=%d)", jb.cin, jb.cout, mode);
+        return MVSB200_ERR_UNSUPPORTED;
+      }
+      MVS_CHECK_ARG(a.n < kMaxPackJobs, "conv3d_tc_pack_all: too many launches");
+      a.job[a.n] = pl.pp;
+      a.job[a.n].kernel_tf = jb.kernel_tf;
+      a.job[a.n].out = (uint16_t*)((unsigned char*)dst_base + (size_t)slot * conv3d_tc_pack_slot_bytes());
+      ++a.n;
+    }
+  }
+  pack_all_kernel<<<dim3(16, a.n), 256, 0, s>>>(a);
+  MVS_LAUNCH_CHECK("pack_all_kernel");
+  return MVSB200_OK;
+}
+
+// x: CP8 for stride-1 convs and transposed convs, PS8 for stride-2 convs.  skip: CP8.
+// Outputs: y_cp8 and / or y_ps8 (bf16, Cout % 8 == 0), or y_f32 (NDHWC fp32, any Cout).
+int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
+                     const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
+                     int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
+                     const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
+                     int stats_rep_stride, cudaStream_t s) {
+  if (cin != 8 && cin != 16 && cin != 32 && cin != 64) {
+    set_error("conv3d(bf16/tcgen05): Cin=%d unsupported (need 8, 16, 32 or 64)", cin);
+    return MVSB200_ERR_UNSUPPORTED;
+  }
+  if (!y_f32 && (cout % 8 != 0 || (!y_cp8 && !y_ps8))) {
+    set_error("conv3d(bf16/tcgen05): bf16 output needs Cout %% 8 == 0 (got %d)", cout);
+    return MVSB200_ERR_UNSUPPORTED;
+  }
+  const int mode = transposed ? MODE_DECONV : (stride == 2 ? MODE_CONV2 : MODE_CONV1);
+  if (skip && mode == MODE_CONV2) {
+    set_error("conv3d(bf16/tcgen05): skip input on a stride-2 conv is not supported");
+    return MVSB200_ERR_UNSUPPORTED;
+  }
+  if (!get_encode()) {
+    set_error("conv3d(bf16/tcgen05): cuTensorMapEncodeTiled is not available from the driver");
+    return MVSB200_ERR_CUDA;
+  }
+  int sm_count = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    attr_done = true;
+  }
+  const bool has_skip = skip != nullptr, transform = xs != nullptr || has_skip || (x_bn && x_bn->stats);
+  int launch_idx = 0;
+  for (int cb = 0; cb < cout; cb += 32, ++launch_idx) {
+    const int cn = cout - cb < 32 ? cout - cb : 32;
+    Plan best;
+    int dbg_flags = 0;
+    if (!find_plan(mode, D, H, W, cin, cout, cb, cn, has_skip, transform, sm_count, &best, &dbg_flags)) {
       set_error("conv3d(bf16/tcgen05): no tile fits (Cin=%d Cout=%d mode=%d)", cin, cout, mode);
       return MVSB200_ERR_UNSUPPORTED;
     }
     Params& c = best.cp;
     c.xs = xs; c.xb = xb; c.ss = ss; c.sb = sb;
+    c.xbn = x_bn ? *x_bn : TcBnSrc{nullptr, nullptr, nullptr, 1.0, 0.f, 0, 1, 0};
+    c.sbn = s_bn ? *s_bn : TcBnSrc{nullptr, nullptr, nullptr, 1.0, 0.f, 0, 1, 0};
+    c.stats_reps = stats_reps > 0 ? stats_reps : 1; c.stats_rep_stride = stats_rep_stride;
     c.y_cp8 = (__nv_bfloat16*)y_cp8; c.y_ps8 = (__nv_bfloat16*)y_ps8; c.y_f32 = y_f32; c.stats = stats;
     const bool ok_x = mode == MODE_CONV2
                           ? make_tmap(&c.tmap_x, x, (W + 1) / 2, (H + 1) / 2, 4, c.NCH, D, c.PX, c.RY)
@@ -1198,19 +1339,24 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       return MVSB200_ERR_CUDA;
     }
     {
-      c.dbg = dbg_env ? atoi(dbg_env) : 0;
+      c.dbg = dbg_flags;
       if (getenv("MVSB200_TC_VERBOSE"))
         fprintf(stderr, "[tc] mode=%d Cin=%d Cout=%d(+%d) tile %dx%d PX=%d RY=%d MB=%d N=%d R=%d zf=%d xf=%d zsplit=%d grid=%d smem=%zu "
                 "RS=%d nops=%d b=%dB xf=%d/%d est=%.0f clk\n",
                 mode, cin, cn, cb, c.TX, c.TY, c.PX, c.RY, c.MB, c.CP, c.R, c.zf, c.xfold, c.zsplit, c.tiles_x * c.tiles_y * c.zsplit,
                 best.smem, c.RS, c.nops, c.b_bytes, c.transform, c.xf_k, best.est_clk);
     }
-    unsigned char* wp = (unsigned char*)scratch + (size_t)(launch_idx & 1) * align_up((size_t)kMaxOps * 2 * 32 * 16, 256);
-    c.wpacked = (const uint4*)wp;
-    best.pp.kernel_tf = kernel_tf;
-    best.pp.out = (uint16_t*)wp;
-    pack_weights_kernel<<<ceil_div(c.b_bytes / 2, 256), 256, 0, s>>>(best.pp);
-    MVS_LAUNCH_CHECK("pack_weights_kernel");
+    if (prepacked) {
+      // weights were packed for the whole network in one launch (conv3d_tc_pack_all), one slot per launch
+      c.wpacked = (const uint4*)((const unsigned char*)prepacked + (size_t)launch_idx * conv3d_tc_pack_slot_bytes());
+    } else {
+      unsigned char* wp = (unsigned char*)scratch + (size_t)(launch_idx & 1) * conv3d_tc_pack_slot_bytes();
+      c.wpacked = (const uint4*)wp;
+      best.pp.kernel_tf = kernel_tf;
+      best.pp.out = (uint16_t*)wp;
+      pack_weights_kernel<<<ceil_div(c.b_bytes / 2, 256), 256, 0, s>>>(best.pp);
+      MVS_LAUNCH_CHECK("pack_weights_kernel");
+    }
     const int grid = c.tiles_x * c.tiles_y * c.zsplit;
     static long long* prof_buf = nullptr;
     c.prof = nullptr;
@@ -1218,9 +1364,13 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 256 + 16 * 4096));
       c.prof = prof_buf;
     }
-    if (c.xfold) conv3d_tc_kernel<32, true><<<grid, kThreads, best.smem, s>>>(c);
-    else if (c.CP == 16) conv3d_tc_kernel<16, false><<<grid, kThreads, best.smem, s>>>(c);
-    else conv3d_tc_kernel<32, false><<<grid, kThreads, best.smem, s>>>(c);
+    // every launch asks for the same (maximum) dynamic shared memory: a different carve-out per layer makes the
+    // SMs re-partition L1 / shared memory between launches
+    static const bool exact_smem = getenv("MVSB200_TC_EXACT_SMEM") != nullptr;
+    const size_t smem_launch = exact_smem ? best.smem : kSmemBudget;
+    if (c.xfold) conv3d_tc_kernel<32, true><<<grid, kThreads, smem_launch, s>>>(c);
+    else if (c.CP == 16) conv3d_tc_kernel<16, false><<<grid, kThreads, smem_launch, s>>>(c);
+    else conv3d_tc_kernel<32, false><<<grid, kThreads, smem_launch, s>>>(c);
     MVS_LAUNCH_CHECK("conv3d_tc_kernel");
     if (c.prof) {
       long long h[17];
@@ -1327,7 +1477,7 @@ int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, cons
     else if (via_f32) MVS_CUDA(cudaMallocAsync((void**)&yf, (size_t)Do * Ho * Wo * cout * sizeof(float), s));
     else MVS_CUDA(cudaMallocAsync(&yp, planar_bytes(Do, Ho, Wo, cout, 0), s));
     rc = launch_conv3d_tc(xp, xs, xb, kp, ss, sb, kernel_tf, D, H, W, cin, cout, stride, transposed, yp, nullptr, yf,
-                          stats, scratch, s);
+                          stats, scratch, nullptr, nullptr, nullptr, 1, 0, s);
   }
   if (!rc && yp) rc = launch_planar_to_ndhwc(yp, Do, Ho, Wo, cout, y, s);
   if (!rc && via_f32) rc = launch_f32_to_bf16(yf, (size_t)Do * Ho * Wo * cout, y, s);

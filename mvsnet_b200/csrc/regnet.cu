@@ -14,10 +14,20 @@ int launch_conv3d_direct(const void* x, int x_dtype, const float* xs, const floa
                          const float* ss, const float* sb, const float* kernel_tf, int D, int H, int W, int cin,
                          int cout, int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);
 // conv3d_tc.cu: bf16 tcgen05 layers on the planar activation layouts (CP8 / PS8, see that file)
+struct TcBnSrc { const double* stats; const float* gamma; const float* beta; double count; float eps; int channels;
+                 int reps; int rep_stride; };
+struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0; };
 int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
                      const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
-                     cudaStream_t s);
+                     const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
+                     int stats_rep_stride, cudaStream_t s);
+int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStream_t s);
+size_t conv3d_tc_pack_slot_bytes();
+int launch_bn_finalize_all(const double* stats, const float* const* gamma, const float* const* beta, const int* channels,
+                           const double* counts, int layers, int cpad, int reps, float eps, float* scale, float* shift,
+                           cudaStream_t s);
+constexpr int kStatsReps = 16;      // partial copies of every layer's statistics (bf16 mode), summed by the consumers
 int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
                            const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout,
                            int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);
@@ -122,18 +132,20 @@ static void make_plan(int D, int H, int W, int cin, int b, int precision, Regnet
     p->cost_ps8_off = off; off += align_up(planar_bytes(D, H, W, cin, 1), 256);
   }
   const int cpad = (max_c + 63) / 64 * 64;
-  p->stats_off = off;  p->stats_bytes = (size_t)MVSB200_REGNET_LAYERS * 2 * cpad * sizeof(double); off += align_up(p->stats_bytes, 256);
+  p->stats_off = off;
+  p->stats_bytes = (size_t)(precision == MVSB200_PRECISION_BF16 ? kStatsReps : 1) * MVSB200_REGNET_LAYERS * 2 * cpad * sizeof(double);
+  off += align_up(p->stats_bytes, 256);
   p->scale_off = off;  off += align_up((size_t)MVSB200_REGNET_LAYERS * cpad * sizeof(float), 256);
   p->shift_off = off;  off += align_up((size_t)MVSB200_REGNET_LAYERS * cpad * sizeof(float), 256);
   p->scratch_off = off;
   size_t scratch = 0;
-  if (precision == MVSB200_PRECISION_BF16) scratch = conv3d_tc_scratch_bytes();
+  if (precision == MVSB200_PRECISION_BF16) scratch = conv3d_tc_pack_slot_bytes() * 2 * MVSB200_REGNET_LAYERS;   // 2 launch slots per layer
   off += align_up(scratch, 256);
   p->total = off;
 }
 
 static inline int plan_cpad(const RegnetPlan& p) {
-  return (int)(p.stats_bytes / (MVSB200_REGNET_LAYERS * 2 * sizeof(double)));
+  return (int)(p.stats_bytes / ((p.elem == 2 ? kStatsReps : 1) * MVSB200_REGNET_LAYERS * 2 * sizeof(double)));
 }
 
 static int check_regnet_shape(int D, int H, int W, int cin, int b) {
@@ -185,10 +197,25 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
     cudaEventRecord(pev[0], s);
   }
   for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
-    const LayerDesc& L = p.layer[i];
     MVS_CHECK_ARG(params->kernel[i] != nullptr, "regnet_forward: kernel[%d] is NULL", i);
+    if (i != MVSB200_L_3DCONV6_2)
+      MVS_CHECK_ARG(params->gamma[i] && params->beta[i], "regnet_forward: gamma/beta[%d] is NULL", i);
+  }
+  if (bf16) {
+    // every layer's weights -> bf16 B images, one launch (slot 2*i, 2*i+1 = the <=2 output-channel slices of layer i)
+    TcPackJob jobs[MVSB200_REGNET_LAYERS];
+    for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+      const LayerDesc& L = p.layer[i];
+      const int* d = p.dims[L.in_level];
+      jobs[i] = {params->kernel[i], d[0], d[1], d[2], L.cin, L.cout, L.stride, L.transposed, L.skip >= 0 ? 1 : 0,
+                 (L.src >= 0 || L.skip >= 0) ? 1 : 0, 2 * i};
+    }
+    rc = conv3d_tc_pack_all(jobs, MVSB200_REGNET_LAYERS, ws + p.scratch_off, s);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+    const LayerDesc& L = p.layer[i];
     const bool last = i == MVSB200_L_3DCONV6_2;
-    if (!last) MVS_CHECK_ARG(params->gamma[i] && params->beta[i], "regnet_forward: gamma/beta[%d] is NULL", i);
     const float* xs = L.src < 0 ? nullptr : scale + (size_t)L.src * cpad;
     const float* xb = L.src < 0 ? nullptr : shift + (size_t)L.src * cpad;
     const void* sk = L.skip < 0 ? nullptr : (const void*)(ws + p.raw_off[L.skip]);
@@ -202,8 +229,16 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
       void* y = last ? (void*)filtered : (void*)(ws + p.raw_off[i]);
       rc = launch_conv3d_direct(x, x_dtype, xs, xb, sk, ss, sb, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout,
                                 L.stride, L.transposed, y, MVSB200_F32, st, s);
+      if (rc) return rc;
+      if (!last) {
+        // stats hold sum over L.cout channels laid out [sum(cout) | sumsq(cout)]
+        rc = launch_bn_finalize(st, params->gamma[i], params->beta[i], L.cout, (double)p.vox[L.out_level], eps,
+                                scale + (size_t)i * cpad, shift + (size_t)i * cpad, s);
+        if (rc) return rc;
+      }
     } else {
-      // stride-2 convs read the parity-split copy of their input, everything else the chunk-planar one
+      // stride-2 convs read the parity-split copy of their input, everything else the chunk-planar one; the BN of
+      // the producer(s) is derived from their statistics inside the consumer (no launch in between)
       const bool s2 = L.stride == 2 && !L.transposed;
       const void* x = L.src < 0 ? (const void*)(ws + (s2 ? p.cost_ps8_off : p.cost_cp8_off))
                                 : (const void*)(ws + (s2 ? p.ps8_off[L.src] : p.raw_off[L.src]));
@@ -211,19 +246,37 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
         const int* o = p.dims[L.out_level];
         MVS_CUDA(cudaMemsetAsync(ws + p.ps8_off[i], 0, planar_bytes(o[0], o[1], o[2], L.cout, 1), s));
       }
-      rc = launch_conv3d_tc(x, xs, xb, sk, ss, sb, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout, L.stride,
-                            L.transposed, last ? nullptr : ws + p.raw_off[i],
+      // statistics: kStatsReps partial copies [rep][layer][2*cpad]; CTAs pick a copy, consumers add them up
+      const int rep_stride = MVSB200_REGNET_LAYERS * 2 * cpad;
+      TcBnSrc xbn = {nullptr, nullptr, nullptr, 1.0, eps, 0, 1, 0}, sbn = xbn;
+      if (L.src >= 0)
+        xbn = {stats + (size_t)L.src * 2 * cpad, params->gamma[L.src], params->beta[L.src],
+               (double)p.vox[p.layer[L.src].out_level], eps, p.layer[L.src].cout, kStatsReps, rep_stride};
+      if (L.skip >= 0)
+        sbn = {stats + (size_t)L.skip * 2 * cpad, params->gamma[L.skip], params->beta[L.skip],
+               (double)p.vox[p.layer[L.skip].out_level], eps, p.layer[L.skip].cout, kStatsReps, rep_stride};
+      rc = launch_conv3d_tc(x, nullptr, nullptr, sk, nullptr, nullptr, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout,
+                            L.stride, L.transposed, last ? nullptr : ws + p.raw_off[i],
                             (!last && p.has_ps8[i]) ? ws + p.ps8_off[i] : nullptr, last ? filtered : nullptr, st,
-                            ws + p.scratch_off, s);
-    }
-    if (rc) return rc;
-    if (!last) {
-      // stats hold sum over L.cout channels laid out [sum(cout) | sumsq(cout)]
-      rc = launch_bn_finalize(st, params->gamma[i], params->beta[i], L.cout, (double)p.vox[L.out_level], eps,
-                              scale + (size_t)i * cpad, shift + (size_t)i * cpad, s);
+                            nullptr, L.src >= 0 ? &xbn : nullptr, L.skip >= 0 ? &sbn : nullptr,
+                            ws + p.scratch_off + (size_t)2 * i * conv3d_tc_pack_slot_bytes(), kStatsReps, rep_stride, s);
       if (rc) return rc;
     }
     if (profile) cudaEventRecord(pev[i + 1], s);
+  }
+  if (bf16) {
+    // scale / shift of every layer for mvsb200_regnet_layer_raw (inspection only; the layers above do not read them)
+    const float* gam[MVSB200_REGNET_LAYERS];
+    const float* bet[MVSB200_REGNET_LAYERS];
+    int chans[MVSB200_REGNET_LAYERS];
+    double counts[MVSB200_REGNET_LAYERS];
+    for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+      gam[i] = params->gamma[i]; bet[i] = params->beta[i];
+      chans[i] = i == MVSB200_L_3DCONV6_2 ? 0 : p.layer[i].cout;
+      counts[i] = (double)p.vox[p.layer[i].out_level];
+    }
+    rc = launch_bn_finalize_all(stats, gam, bet, chans, counts, MVSB200_REGNET_LAYERS, cpad, kStatsReps, eps, scale, shift, s);
+    if (rc) return rc;
   }
   if (profile) {
     static const char* names[MVSB200_REGNET_LAYERS] = {"3dconv1_0", "3dconv2_0", "3dconv3_0", "3dconv0_1", "3dconv1_1",
@@ -394,6 +447,7 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
     void *cp8 = nullptr, *ps8 = nullptr;
     regnet_cost_planar(ws + ip.regnet_off, depth_num, hf, wf, channels, base_filter, &cp8, &ps8);
     static const bool fp32_taps = getenv("MVSB200_CV_FP32_TAPS") != nullptr;
+    if (getenv("MVSB200_CV_NO_PS8")) ps8 = nullptr;      // timing experiment only (3dconv1_0 then reads stale data)
     rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8,
                                    fp32_taps ? nullptr : ws + ip.pair_off, coefs, s);
   } else {

@@ -99,6 +99,7 @@ struct Params {
   int zf, cn_shift;              // output planes per step; log2(cout_n) when zf > 1
   int xfold;                     // kw taps folded into N: columns [j][kw][co], see the epilogue
   int one_box;                   // chunk planes are dense in the slot: one TMA box loads all chunks of a plane
+  int ring_pad;                  // zeroed bytes after the last slot (rows of the last block may read past their plane)
   int xf_k;                      // cells per transform thread and plane
   int dz_begin[kMaxSpan + 1];    // ops [dz_begin[d], dz_begin[d+1]) read input plane d of the step
   int dbg;                       // development switches (env MVSB200_TC_DBG): 1 no loads, 2 no MMA, 4 no stores
@@ -235,13 +236,16 @@ __device__ __forceinline__ void issue_ops(const uint4* s_ops, int ob, int oe, ui
   }
 }
 
-template <int CP, bool XF>
+// XFC = 0: classic epilogue (CP accumulator columns per row block); XFC = 1 / 2 / 4: x-fold epilogue for launches of
+// 8 * XFC output channels (Cout = 1 uses XFC = 1)
+template <int CP, int XFC>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_constant__ Params p) {
+  constexpr bool XF = XFC != 0;
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [B image][R slots][skip slots][op table][plane op ranges][barriers][tmem ptr]
   unsigned char* s_b = smem;
   unsigned char* s_slots = smem + p.b_bytes;
-  unsigned char* s_skip = s_slots + (size_t)p.R * p.slot_bytes;
+  unsigned char* s_skip = s_slots + (size_t)p.R * p.slot_bytes + p.ring_pad;
   uint4* s_ops = reinterpret_cast<uint4*>(s_skip + (p.has_skip ? (size_t)p.RS * p.slot_bytes : 0));
   int* s_dzb = reinterpret_cast<int*>(s_ops + kMaxOps);
   float* s_red = reinterpret_cast<float*>(s_dzb + 8);      // [4 warps][sum | sumsq][32 channels]
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   // Every cell of the ring starts finite: halo rows of the GEMM read a few cells past the landed boxes
   // (their results are dropped, but 0 * NaN from stale shared memory must not reach a zero-weighted
   // K half of a valid row).
-  for (int i = threadIdx.x; i < p.R * p.slot_bytes / 16; i += blockDim.x)
+  for (int i = threadIdx.x; i < (p.R * p.slot_bytes + p.ring_pad) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           __syncwarp();
           if (p.one_box) {
             // dense chunk planes (x-fold): one box covers every channel chunk of the plane
-            if (lane == 0) tma_load_5d(sl, &p.tmap_x, cx, cy, 0, 0, iz, &bar_land[slot]);
+            if (lane == 0) tma_load_5d(sl, &p.tmap_x, cx, cy, 0, 0, iz, &bar_land[slot]);      // box spans parities and chunks
           } else {
             for (int i = lane; i < nbox; i += 32) {
               const int sub = i / p.NCH, ch = i - sub * p.NCH;
@@ -554,9 +558,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         // x-fold: columns [j][kw][co]; output (yy, xx-1) = P[kw=0] of lane-1 + P[kw=1] + P[kw=2] of lane+1.
         // A warp's 32 TMEM lanes are 32 / PX whole tile rows, so the shuffles (width PX) never leave a row; the
         // halo columns xx = 0 and PX-1 only supply partial sums.
-        float sum[32], sq[32];
+        constexpr int NST = XF ? XFC * 8 : 8;
+        float sum[NST], sq[NST];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) { sum[k] = 0.0f; sq[k] = 0.0f; }
+        for (int k = 0; k < NST; ++k) { sum[k] = 0.0f; sq[k] = 0.0f; }
         const int grp = 3 * p.cout_n, nchunk = p.cout_n >> 3;
         const size_t zpitch = (size_t)p.Ho * p.Wo;
         const int ncho = p.Cout >> 3, chunk0 = p.cout_base >> 3;
@@ -595,47 +600,74 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   }
                 }
               }
-            } else {
-              for (int j = 0; j < p.zf; ++j) {
+            }
+          }
+          if (p.cout_n != 1) {
+            // items (row block, output plane j, 8-channel chunk): the three TMEM loads of the next item are in flight
+            // while this one is shuffled, reduced and stored
+            const int nitems = p.MB * p.zf * nchunk;
+            uint32_t r0[24], r1[24];
+            const uint32_t tstage = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(stage * p.MB * p.NB);
+            auto issue = [&](int b, int j, int ck, uint32_t* r) {
+              const uint32_t col = tstage + (uint32_t)(b * p.NB + j * grp + ck * 8);
+              tmem_ld8(col, r);
+              tmem_ld8(col + (uint32_t)p.cout_n, r + 8);
+              tmem_ld8(col + 2u * (uint32_t)p.cout_n, r + 16);
+            };
+            // (with 32 channels of statistics the registers do not allow a load in flight: the asynchronous TMEM load
+            // must not be caught by a spill, so that variant loads, waits, then works)
+            constexpr bool kPrefetch = XFC < 4;
+            int b = 0, j = 0, ck = 0;                 // current item; (nb, nj, nck) = the next one
+            if (kPrefetch) issue(0, 0, 0, r0);
+            for (int it0 = 0; it0 < nitems; it0 += 2) {
 #pragma unroll
-                for (int ck = 0; ck < 4; ++ck) {
-                  if (ck < nchunk) {
-                    uint32_t ra[8], rb[8], rc[8];
-                    const uint32_t col = (uint32_t)(j * grp + ck * 8);
-                    tmem_ld8(tb + col, ra);
-                    tmem_ld8(tb + col + (uint32_t)p.cout_n, rb);
-                    tmem_ld8(tb + col + 2u * (uint32_t)p.cout_n, rc);
-                    tmem_ld_wait();
-                    float v[8];
+              for (int half = 0; half < 2; ++half) {
+                const int it = it0 + half;
+                if (it >= nitems) break;
+                uint32_t* r = half ? r1 : r0;
+                int nck = ck + 1, nj = j, nb = b;
+                if (nck == nchunk) { nck = 0; if (++nj == p.zf) { nj = 0; ++nb; } }
+                if (!kPrefetch) issue(b, j, ck, r);
+                tmem_ld_wait();
+                if (kPrefetch && it + 1 < nitems) issue(nb, nj, nck, half ? r0 : r1);
+                const int m = b * 128 + warp * 32 + lane;
+                const int yy = m >> px_shift, xx = m & (p.PX - 1);
+                const bool valid = xx >= 1 && xx <= TXe && yy < TYe && !(p.dbg & 4);
+                const int oy = y0 + yy, ox = x0 + xx - 1;
+                float v[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                      const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(ra[k]), 1, p.PX);
-                      const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(rc[k]), 1, p.PX);
-                      v[k] = lft + __uint_as_float(rb[k]) + rgt;
+                for (int k = 0; k < 8; ++k) {
+                  const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(r[k]), 1, p.PX);
+                  const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(r[16 + k]), 1, p.PX);
+                  v[k] = lft + __uint_as_float(r[8 + k]) + rgt;
+                }
+                if (valid && j < nlive) {
+                  // channel chunk ck of this launch: statistics registers are indexed at compile time
+#pragma unroll
+                  for (int c4 = 0; c4 < (XF ? XFC : 1); ++c4)
+                    if (c4 == ck) {
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) { sum[c4 * 8 + k] += v[k]; sq[c4 * 8 + k] = fmaf(v[k], v[k], sq[c4 * 8 + k]); }
                     }
-                    if (valid && j < nlive) {
-#pragma unroll
-                      for (int k = 0; k < 8; ++k) { sum[ck * 8 + k] += v[k]; sq[ck * 8 + k] = fmaf(v[k], v[k], sq[ck * 8 + k]); }
-                      const int oz = mz + j;
-                      if (p.y_f32) {
-                        float4* yo = reinterpret_cast<float4*>(p.y_f32 + (((size_t)oz * p.Ho + oy) * p.Wo + ox) * p.Cout +
-                                                               p.cout_base + ck * 8);
-                        yo[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        yo[1] = make_float4(v[4], v[5], v[6], v[7]);
-                      } else {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-                        pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-                        const size_t zc = (size_t)oz * ncho + chunk0 + ck;
-                        if (p.y_cp8) *reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + (size_t)oy * p.Wo + ox) * 8) = pk;
-                        if (p.y_ps8) {
-                          const size_t pcell = ((size_t)((oy & 1) * 2 + (ox & 1)) * p.Hso + (oy >> 1)) * p.Wso + (ox >> 1);
-                          *reinterpret_cast<uint4*>(p.y_ps8 + (zc * 4 * (size_t)p.Hso * p.Wso + pcell) * 8) = pk;
-                        }
-                      }
+                  const int oz = mz + j;
+                  if (p.y_f32) {
+                    float4* yo = reinterpret_cast<float4*>(p.y_f32 + (((size_t)oz * p.Ho + oy) * p.Wo + ox) * p.Cout +
+                                                           p.cout_base + ck * 8);
+                    yo[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    yo[1] = make_float4(v[4], v[5], v[6], v[7]);
+                  } else {
+                    uint4 pk;
+                    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+                    pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+                    const size_t zc = (size_t)oz * ncho + chunk0 + ck;
+                    if (p.y_cp8) *reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + (size_t)oy * p.Wo + ox) * 8) = pk;
+                    if (p.y_ps8) {
+                      const size_t pcell = ((size_t)((oy & 1) * 2 + (ox & 1)) * p.Hso + (oy >> 1)) * p.Wso + (ox >> 1);
+                      *reinterpret_cast<uint4*>(p.y_ps8 + (zc * 4 * (size_t)p.Hso * p.Wso + pcell) * 8) = pk;
                     }
                   }
                 }
+                b = nb; j = nj; ck = nck;
               }
             }
           }
@@ -644,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           if (lane == 0) mbar_arrive(&bar_acc_empty[stage]);
         }
         if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
-        if (p.stats && !(p.dbg & 8)) flush_stats<32>(p, sum, sq, p.cout_n, false, s_red, warp, lane);
+        if (p.stats && !(p.dbg & 8)) flush_stats<NST>(p, sum, sq, p.cout_n, false, s_red, warp, lane);
       } else {
       float sum[CP], sq[CP];
 #pragma unroll
@@ -901,6 +933,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   c.TX = TX; c.TY = TY;
   c.tiles_x = ceil_div(c.Mx, TX); c.tiles_y = ceil_div(c.My, TY);
   c.SUBP = (c.RY * c.PX + 7) / 8 * 8;          // sub-arrays start 128-byte aligned (TMA destination)
+  const bool dense = (c.RY * c.PX) % 8 == 0;   // sub-arrays and chunk planes back to back: one TMA box per plane
   c.NCH = cin / 8;
   c.MB = ceil_div(TY * c.PX, 128);
   if (2 * c.MB * c.NB > 512 || c.MB > kMaxMB) return false;
@@ -945,13 +978,19 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
     for (int j = i; j > 0 && taps[j].dz < taps[j - 1].dz; --j) { Tap t = taps[j]; taps[j] = taps[j - 1]; taps[j - 1] = t; }
   int max_pos = 0;
   for (int i = 0; i < ntaps; ++i) max_pos = taps[i].pos > max_pos ? taps[i].pos : max_pos;
-  const int sp_cells = max_pos + c.MB * 128 + 8;
-  c.PS = (sp_cells * 16 + 127) / 128 * 128;          // chunk planes start 128-byte aligned (TMA destination)
-  if (c.nsub * c.SUBP * 16 > c.PS) c.PS = c.nsub * c.SUBP * 16;
-  // x-fold: the 128-row blocks cover the padded tile exactly, no row reads past the plane, so the chunk planes
-  // can sit back to back and one TMA box (PX x RY x all chunks) loads a whole plane
+  const int sp_cells = max_pos + c.MB * 128 + 8;            // cells an A descriptor may touch from the plane start
   c.one_box = 0;
-  if (xfold && cin >= 16) { c.PS = c.RY * c.PX * 16; c.one_box = 1; }
+  c.ring_pad = 0;
+  if (dense) {
+    // rows of the last 128-row block read past their chunk plane into the next one, the next slot or the zeroed
+    // pad behind the ring: finite data, and those rows are dropped
+    c.PS = c.nsub * c.SUBP * 16;
+    c.one_box = 1;
+    if (sp_cells * 16 > c.PS) c.ring_pad = (sp_cells * 16 - c.PS + 127) / 128 * 128;
+  } else {
+    c.PS = (sp_cells * 16 + 127) / 128 * 128;          // chunk planes start 128-byte aligned (TMA destination)
+    if (c.nsub * c.SUBP * 16 > c.PS) c.PS = c.nsub * c.SUBP * 16;
+  }
   c.slot_bytes = c.NCH * c.PS;
 
   // ---- ops ----------------------------------------------------------------------------------------
@@ -1030,7 +1069,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   pk.zf = zf; pk.master = master ? 1 : 0; pk.xfold = xfold ? 1 : 0;
   pk.nops = nimg; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
   pk.transposed = mode == MODE_DECONV;
-  const size_t fixed = (size_t)c.b_bytes + (size_t)kMaxOps * 16 + 32 + 2048 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
+  const size_t fixed = (size_t)c.b_bytes + (size_t)c.ring_pad + (size_t)kMaxOps * 16 + 32 + 2048 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
   c.RS = has_skip ? kMinSkipRing : 0;
   size_t skip_bytes = (size_t)c.RS * c.slot_bytes;
   c.R = c.span + c.zstep;                         // the planes of the next step land while this one computes
@@ -1063,11 +1102,13 @@ double estimate_clk(const Params& c, int sm_count) {
   const int ncls = c.mode == MODE_DECONV ? 8 : 1;
   const double epi = c.xfold ? (c.cout_n == 1 ? (double)c.MB * 300.0 : (double)c.MB * c.zf * (c.cout_n / 8) * 420.0)
                              : (double)c.MB * ncls * (c.CP * 4.0 * 128.0 / 110.0 + 12.0 * c.CP + 80.0);
+  const double tma_issue = (c.one_box ? 1.0 : (double)c.nsub * c.NCH) * (c.has_skip ? 2.0 : 1.0) * 250.0 * c.zstep;
   const double xf = c.transform ? (double)c.xf_k * c.zstep * (c.has_skip ? 70.0 : 45.0) : 0.0;
   double step = mma;
   if (load > step) step = load;
   if (epi > step) step = epi;
   if (xf > step) step = xf;
+  if (tma_issue > step) step = tma_issue;
   step += 120.0;
   const int steps_all = ceil_div(c.Mz, c.zf);
   const int sseg = ceil_div(steps_all, c.zsplit);
@@ -1095,13 +1136,13 @@ PFN_encodeTiled get_encode() {
 
 // 5-D map over a CP8 (subs = 1) or PS8 (subs = 4) tensor: (8*Wp, Hp, subs, NCH, D), box (8*PX, RY, 1, 1, 1)
 bool make_tmap(CUtensorMap* tm, const void* base, int Wp, int Hp, int subs, int nch, int D, int PX, int RY,
-               int box_ch = 1) {
+               int box_ch = 1, int box_sub = 1) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[5] = {(cuuint64_t)Wp * 8, (cuuint64_t)Hp, (cuuint64_t)subs, (cuuint64_t)nch, (cuuint64_t)D};
   cuuint64_t gstr[4] = {(cuuint64_t)Wp * 16, (cuuint64_t)Hp * Wp * 16, (cuuint64_t)subs * Hp * Wp * 16,
                         (cuuint64_t)nch * subs * Hp * Wp * 16};
-  cuuint32_t box[5] = {(cuuint32_t)PX * 8, (cuuint32_t)RY, 1, (cuuint32_t)box_ch, 1};
+  cuuint32_t box[5] = {(cuuint32_t)PX * 8, (cuuint32_t)RY, (cuuint32_t)box_sub, (cuuint32_t)box_ch, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1309,9 +1350,11 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
   }
   static bool attr_done = false;
   if (!attr_done) {
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     attr_done = true;
   }
   const bool has_skip = skip != nullptr, transform = xs != nullptr || has_skip || (x_bn && x_bn->stats);
@@ -1331,7 +1374,8 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     c.stats_reps = stats_reps > 0 ? stats_reps : 1; c.stats_rep_stride = stats_rep_stride;
     c.y_cp8 = (__nv_bfloat16*)y_cp8; c.y_ps8 = (__nv_bfloat16*)y_ps8; c.y_f32 = y_f32; c.stats = stats;
     const bool ok_x = mode == MODE_CONV2
-                          ? make_tmap(&c.tmap_x, x, (W + 1) / 2, (H + 1) / 2, 4, c.NCH, D, c.PX, c.RY)
+                          ? make_tmap(&c.tmap_x, x, (W + 1) / 2, (H + 1) / 2, 4, c.NCH, D, c.PX, c.RY, c.one_box ? c.NCH : 1,
+                                      c.one_box ? 4 : 1)
                           : make_tmap(&c.tmap_x, x, W, H, 1, c.NCH, D, c.PX, c.RY, c.one_box ? c.NCH : 1);
     const bool ok_s = !has_skip || make_tmap(&c.tmap_s, skip, W, H, 1, c.NCH, D, c.PX, c.RY, c.one_box ? c.NCH : 1);
     if (!ok_x || !ok_s) {
@@ -1368,9 +1412,18 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     // SMs re-partition L1 / shared memory between launches
     static const bool exact_smem = getenv("MVSB200_TC_EXACT_SMEM") != nullptr;
     const size_t smem_launch = exact_smem ? best.smem : kSmemBudget;
-    if (c.xfold) conv3d_tc_kernel<32, true><<<grid, kThreads, smem_launch, s>>>(c);
-    else if (c.CP == 16) conv3d_tc_kernel<16, false><<<grid, kThreads, smem_launch, s>>>(c);
-    else conv3d_tc_kernel<32, false><<<grid, kThreads, smem_launch, s>>>(c);
+    auto launch = [&]() {
+      if (c.xfold) {
+        if (c.cout_n <= 8) conv3d_tc_kernel<32, 1><<<grid, kThreads, smem_launch, s>>>(c);
+        else if (c.cout_n <= 16) conv3d_tc_kernel<32, 2><<<grid, kThreads, smem_launch, s>>>(c);
+        else conv3d_tc_kernel<32, 4><<<grid, kThreads, smem_launch, s>>>(c);
+      } else if (c.CP == 16) {
+        conv3d_tc_kernel<16, 0><<<grid, kThreads, smem_launch, s>>>(c);
+      } else {
+        conv3d_tc_kernel<32, 0><<<grid, kThreads, smem_launch, s>>>(c);
+      }
+    };
+    launch();
     MVS_LAUNCH_CHECK("conv3d_tc_kernel");
     if (c.prof) {
       long long h[17];
@@ -1379,9 +1432,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       cudaStreamSynchronize(s);
       // second, timed launch of the same kernel (the first one may have overlapped the pack kernel's tail)
       cudaEventRecord(e0, s);
-      if (c.xfold) conv3d_tc_kernel<32, true><<<grid, kThreads, best.smem, s>>>(c);
-      else if (c.CP == 16) conv3d_tc_kernel<16, false><<<grid, kThreads, best.smem, s>>>(c);
-      else conv3d_tc_kernel<32, false><<<grid, kThreads, best.smem, s>>>(c);
+      launch();
       cudaEventRecord(e1, s);
       cudaStreamSynchronize(s);
       float kms = 0.f;

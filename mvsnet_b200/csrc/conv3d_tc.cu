@@ -98,6 +98,8 @@ struct Params {
   int nops, b_bytes, tmem_cols;
   int zf, cn_shift;              // output planes per step; log2(cout_n) when zf > 1
   int xfold;                     // kw taps folded into N: columns [j][kw][co], see the epilogue
+  int mma_n;                     // N of every MMA of this launch
+  int cw, dmerge;                // transposed conv: TMEM columns per output-parity class; classes merged into one N
   int one_box;                   // chunk planes are dense in the slot: one TMA box loads all chunks of a plane
   int ring_pad;                  // zeroed bytes after the last slot (rows of the last block may read past their plane)
   int xf_k;                      // cells per transform thread and plane
@@ -113,12 +115,33 @@ struct Params {
 struct PackOp { int16_t tap[2]; int16_t cbase[2]; };
 struct PackParams {
   const float* kernel_tf; uint16_t* out;
-  int Cin, Cout, cout_base, cout_n, CP, transposed, nops, zf, master, xfold;
+  int Cin, Cout, cout_base, cout_n, CP, transposed, nops, zf, master, xfold, dmerge, cw;
   PackOp ops[kMaxOps];   // per-op images: tap = kd*9+kh*3+kw per K half (-1 = zero half);
                          // master images: tap = kh*3+kw (kd comes from the row group), one per (kh,kw,pair)
 };
 
 __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
+  if (p.dmerge) {
+    // transposed conv, classes merged: image = [2 halves][8 classes x cw rows][8]; the op's tap code is its input
+    // shift (bit 2: z-1, bit 1: y-1, bit 0: x-1); class (pz,py,px) takes filter tap k = parity + 2 on a shifted axis
+    const int rows = 8 * p.cw;
+    const int total = p.nops * 2 * rows * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int k8 = i & 7, n = (i >> 3) % rows, half = (i / (8 * rows)) & 1, op = i / (16 * rows);
+      const int cls = n / p.cw, cn = n - cls * p.cw;
+      const int sh = p.ops[op].tap[half], ci = p.ops[op].cbase[half] + k8;
+      const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+      const int sz = (sh >> 2) & 1, sy = (sh >> 1) & 1, sx = sh & 1;
+      float w = 0.0f;
+      if ((!sz || !pz) && (!sy || !py) && (!sx || !px) && cn < p.cout_n && ci < p.Cin) {
+        const int tap = ((pz + 2 * sz) * 3 + (py + 2 * sy)) * 3 + (px + 2 * sx);
+        w = p.kernel_tf[((size_t)tap * p.Cout + p.cout_base + cn) * p.Cin + ci];
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+    return;
+  }
   // column n of a B image: [output plane j of the step][kw when the x-fold is on][output channel]
   const int kwn = p.xfold ? 3 : 1, grp = kwn * p.cout_n;
   if (!p.master) {
@@ -487,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     } else if (warp == kMmaWarp) {
       // ===================================== MMA issuer =====================================
       mbar_wait(bar_b, 0);
-      const uint32_t idesc = make_idesc_bf16_f32(128, XF ? p.CP : CP);
+      const uint32_t idesc = make_idesc_bf16_f32(128, p.mma_n);
       const uint32_t slots16 = smem_u32(s_slots) >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
       const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;   // version 1, SBO = 128 B
       uint64_t* bar_in = p.transform ? bar_ready : bar_land;
@@ -699,12 +722,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         const int nlive = min(p.zf, ze - mz);          // output planes of this step inside the volume
         if (CP == 16 && deconv && !p.y_f32) {
           // transposed conv, bf16 out: the two x-parity classes of a row are adjacent cells of the output, so they
-          // are drained together (32 columns per wait, 32 contiguous bytes per thread and channel chunk); the
+          // are drained together (2*cw columns per wait, 32 contiguous bytes per thread and channel chunk); the
           // TMEM load of the next pair is in flight while this one is reduced and stored.
           const int npair = p.MB * 4;
           const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(stage * p.MB * p.NB);
+          const bool narrow = p.cw == 8;               // 8 columns per class: one 16-column load holds the pair
           uint32_t ra[32], rb[32];
-          tmem_ld16(tbase, ra); tmem_ld16(tbase + 16, ra + 16);
+          tmem_ld16(tbase, ra);
+          if (!narrow) tmem_ld16(tbase + 16, ra + 16);
           for (int i = 0; i < npair; i += 2) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -714,35 +739,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
               tmem_ld_wait();
               if (ii + 1 < npair) {
                 const int bn = (ii + 1) >> 2, pn = (ii + 1) & 3;
-                const uint32_t ta = tbase + (uint32_t)(bn * p.NB + pn * 32);
-                tmem_ld16(ta, rn); tmem_ld16(ta + 16, rn + 16);
+                const uint32_t ta = tbase + (uint32_t)(bn * p.NB + pn * 2 * p.cw);
+                tmem_ld16(ta, rn);
+                if (!narrow) tmem_ld16(ta + 16, rn + 16);
               }
               const int b = ii >> 2, pr = ii & 3;               // pair pr = classes 2*pr, 2*pr+1 (pz, py fixed)
               const int m = b * 128 + warp * 32 + lane;
               const int yy = m / p.PX, xx = m - yy * p.PX;
               if (!(xx < TXe && yy < TYe) || (p.dbg & 4)) continue;
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const float v0 = __uint_as_float(r[k]), v1 = __uint_as_float(r[16 + k]);
-                sum[k] += v0 + v1; sq[k] = fmaf(v1, v1, fmaf(v0, v0, sq[k]));
-              }
               const int oz = 2 * mz + (pr >> 1), oy = 2 * (y0 + yy) + (pr & 1), ox = 2 * (x0 + xx);
               const size_t cell = ((size_t)oy * p.Wo + ox);
+              if (narrow) {
 #pragma unroll
-              for (int k = 0; k < 16; k += 8) {
-                if (k < p.cout_n) {
-                  uint4 c0, c1;
-                  c0.x = pack_bf16x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
-                  c0.y = pack_bf16x2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
-                  c0.z = pack_bf16x2(__uint_as_float(r[k + 4]), __uint_as_float(r[k + 5]));
-                  c0.w = pack_bf16x2(__uint_as_float(r[k + 6]), __uint_as_float(r[k + 7]));
-                  c1.x = pack_bf16x2(__uint_as_float(r[16 + k]), __uint_as_float(r[16 + k + 1]));
-                  c1.y = pack_bf16x2(__uint_as_float(r[16 + k + 2]), __uint_as_float(r[16 + k + 3]));
-                  c1.z = pack_bf16x2(__uint_as_float(r[16 + k + 4]), __uint_as_float(r[16 + k + 5]));
-                  c1.w = pack_bf16x2(__uint_as_float(r[16 + k + 6]), __uint_as_float(r[16 + k + 7]));
-                  const size_t zc = (size_t)oz * ncho + chunk0 + (k >> 3);
-                  uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
-                  dst[0] = c0; dst[1] = c1;
+                for (int k = 0; k < 8; ++k) {
+                  const float v0 = __uint_as_float(r[k]), v1 = __uint_as_float(r[8 + k]);
+                  sum[k] += v0 + v1; sq[k] = fmaf(v1, v1, fmaf(v0, v0, sq[k]));
+                }
+                uint4 c0, c1;
+                c0.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+                c0.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                c0.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
+                c0.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                c1.x = pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));
+                c1.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+                c1.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
+                c1.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+                const size_t zc = (size_t)oz * ncho + chunk0;
+                uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
+                dst[0] = c0; dst[1] = c1;
+              } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  const float v0 = __uint_as_float(r[k]), v1 = __uint_as_float(r[16 + k]);
+                  sum[k] += v0 + v1; sq[k] = fmaf(v1, v1, fmaf(v0, v0, sq[k]));
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k += 8) {
+                  if (k < p.cout_n) {
+                    uint4 c0, c1;
+                    c0.x = pack_bf16x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+                    c0.y = pack_bf16x2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
+                    c0.z = pack_bf16x2(__uint_as_float(r[k + 4]), __uint_as_float(r[k + 5]));
+                    c0.w = pack_bf16x2(__uint_as_float(r[k + 6]), __uint_as_float(r[k + 7]));
+                    c1.x = pack_bf16x2(__uint_as_float(r[16 + k]), __uint_as_float(r[16 + k + 1]));
+                    c1.y = pack_bf16x2(__uint_as_float(r[16 + k + 2]), __uint_as_float(r[16 + k + 3]));
+                    c1.z = pack_bf16x2(__uint_as_float(r[16 + k + 4]), __uint_as_float(r[16 + k + 5]));
+                    c1.w = pack_bf16x2(__uint_as_float(r[16 + k + 6]), __uint_as_float(r[16 + k + 7]));
+                    const size_t zc = (size_t)oz * ncho + chunk0 + (k >> 3);
+                    uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
+                    dst[0] = c0; dst[1] = c1;
+                  }
                 }
               }
             }
@@ -755,9 +801,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           for (int cls = 0; cls < ncls; ++cls) {
             uint32_t r[CP];
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                                   (uint32_t)((stage * p.MB + b) * p.NB + cls * CP);
+                                   (uint32_t)((stage * p.MB + b) * p.NB + cls * p.cw);
+            if (p.cw == 8) {
+              // merged transposed conv with 8 columns per class: the other CP - 8 registers count as zero columns
+              tmem_ld8(taddr, r);
 #pragma unroll
-            for (int c0 = 0; c0 < CP; c0 += 16) tmem_ld16(taddr + c0, r + c0);
+              for (int k = 8; k < CP; ++k) r[k] = 0u;
+            } else {
+#pragma unroll
+              for (int c0 = 0; c0 < CP; c0 += 16) tmem_ld16(taddr + c0, r + c0);
+            }
             tmem_ld_wait();
             if (!valid) continue;
             // columns [j*cout_n, (j+1)*cout_n) belong to output plane mz + j (z-fold); planes past the
@@ -928,6 +981,13 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
     c.PX = TX + 1; c.RY = TY + 1; c.nsub = 1; c.vstep = 1; c.cx_off = -1; c.cy_off = -1;
     c.zmul = 1; c.zoff = -1; c.zstep = 1; c.span = 2; c.NB = 8 * CP;
   }
+  // transposed conv with <= 16 output channels: the 8 output-parity classes that read the same shifted input
+  // are merged into ONE MMA (N = 8 classes x cw columns, zero rows for the classes that do not use the shift):
+  // 8 MMAs per 16 input channels instead of 27
+  c.cw = CP; c.dmerge = 0; c.mma_n = CP;
+  if (mode == MODE_DECONV && cout_n <= 16 && cin >= 16) {
+    c.dmerge = 1; c.cw = cout_n <= 8 ? 8 : 16; c.NB = 8 * c.cw; c.mma_n = 8 * c.cw;
+  }
   c.Hso = (c.Ho + 1) / 2; c.Wso = (c.Wo + 1) / 2;
   if (c.PX * 8 > 256 || c.RY > 256) return false;     // TMA box limits
   c.TX = TX; c.TY = TY;
@@ -945,7 +1005,12 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   struct Tap { int dz, pos, widx, cls; };
   Tap taps[9 * kMaxSpan];
   int ntaps = 0;
-  if (mode == MODE_DECONV) {
+  if (mode == MODE_DECONV && c.dmerge) {
+    for (int sh = 0; sh < 8; ++sh) {
+      const int sz = -((sh >> 2) & 1), sy = -((sh >> 1) & 1), sx = -(sh & 1);
+      taps[ntaps++] = {1 + sz, (1 + sy) * c.PX + (1 + sx), sh, 0};
+    }
+  } else if (mode == MODE_DECONV) {
     for (int cls = 0; cls < 8; ++cls) {
       const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
       for (int sz = 0; sz >= (pz ? 0 : -1); --sz)
@@ -1024,6 +1089,16 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
                (uint32_t)(img * m_bytes + (zf + 1 - taps[i].dz) * grp * 16), (uint32_t)(m_rows * 16), 0, first);
       }
     c.b_bytes = nimg * m_bytes;
+  } else if (c.dmerge) {
+    const int img_bytes = 2 * c.mma_n * 16;
+    for (int i = 0; i < ntaps; ++i)
+      for (int j = 0; j < cin / 16; ++j) {
+        const bool first = nops == 0;
+        const int img = add_img(taps[i].widx, 16 * j, taps[i].widx, 16 * j + 8);
+        add_op(taps[i].dz, (uint32_t)(2 * j * c.PS + taps[i].pos * 16), (uint32_t)c.PS, (uint32_t)(img * img_bytes),
+               (uint32_t)(c.mma_n * 16), 0, first);
+      }
+    c.b_bytes = nimg * img_bytes;
   } else if (cin >= 16) {
     for (int i = 0; i < ntaps; ++i)
       for (int j = 0; j < cin / 16; ++j) {
@@ -1066,7 +1141,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   for (int d = 0; d <= kMaxSpan; ++d) c.dz_begin[d] = nops;
   for (int o = nops - 1; o >= 0; --o) c.dz_begin[(c.ops[o].meta >> 20) & 15] = o;
   for (int d = kMaxSpan - 1; d >= 0; --d) if (c.dz_begin[d] > c.dz_begin[d + 1]) c.dz_begin[d] = c.dz_begin[d + 1];
-  pk.zf = zf; pk.master = master ? 1 : 0; pk.xfold = xfold ? 1 : 0;
+  pk.zf = zf; pk.master = master ? 1 : 0; pk.xfold = xfold ? 1 : 0; pk.dmerge = c.dmerge; pk.cw = c.cw;
   pk.nops = nimg; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
   pk.transposed = mode == MODE_DECONV;
   const size_t fixed = (size_t)c.b_bytes + (size_t)c.ring_pad + (size_t)kMaxOps * 16 + 32 + 2048 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
@@ -1096,7 +1171,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
 
 // Cycle model of one launch (per SM): the roles run concurrently, a step costs the slowest of them.
 double estimate_clk(const Params& c, int sm_count) {
-  const double mma = (double)c.nops * c.MB * mma_clk(c.CP);
+  const double mma = (double)c.nops * c.MB * mma_clk(c.mma_n);
   const double plane_bytes = (double)c.nsub * c.NCH * c.RY * c.PX * 16.0 * (c.has_skip ? 2.0 : 1.0);
   const double load = plane_bytes * c.zstep / 18.0;                       // ~HBM share of one SM, B/clk
   const int ncls = c.mode == MODE_DECONV ? 8 : 1;
@@ -1244,6 +1319,27 @@ struct PackAll { int n; PackParams job[kMaxPackJobs]; };
 
 __global__ void pack_all_kernel(const __grid_constant__ PackAll a) {
   const PackParams& p = a.job[blockIdx.y];
+  if (p.dmerge) {
+    // transposed conv, classes merged: image = [2 halves][8 classes x cw rows][8]; the op's tap code is its input
+    // shift (bit 2: z-1, bit 1: y-1, bit 0: x-1); class (pz,py,px) takes filter tap k = parity + 2 on a shifted axis
+    const int rows = 8 * p.cw;
+    const int total = p.nops * 2 * rows * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int k8 = i & 7, n = (i >> 3) % rows, half = (i / (8 * rows)) & 1, op = i / (16 * rows);
+      const int cls = n / p.cw, cn = n - cls * p.cw;
+      const int sh = p.ops[op].tap[half], ci = p.ops[op].cbase[half] + k8;
+      const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+      const int sz = (sh >> 2) & 1, sy = (sh >> 1) & 1, sx = sh & 1;
+      float w = 0.0f;
+      if ((!sz || !pz) && (!sy || !py) && (!sx || !px) && cn < p.cout_n && ci < p.Cin) {
+        const int tap = ((pz + 2 * sz) * 3 + (py + 2 * sy)) * 3 + (px + 2 * sx);
+        w = p.kernel_tf[((size_t)tap * p.Cout + p.cout_base + cn) * p.Cin + ci];
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+    return;
+  }
   const int kwn = p.xfold ? 3 : 1, grp = kwn * p.cout_n;
   if (!p.master) {
     const int total = p.nops * 2 * p.CP * 8;

@@ -126,6 +126,13 @@ int mvsb200_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const
                          int stride, int transposed, int precision, void* y_raw, int y_dtype,
                          double* stats, void* stream);
 
+/* Host-only: the launch plan the bf16 / tcgen05 path uses for one layer shape (tile, folds, ring depth, shared and
+ * tensor memory), without touching the device.  numbers[12] = {launches, tile_x, tile_y, cells_x, cells_y, row
+ * blocks, mma_n, z_fold, x_fold, ring, smem_bytes, tmem_columns} of the first launch; text (may be NULL) gets one
+ * line per launch.  sm_count <= 0 means 148. */
+int mvsb200_conv3d_plan(int depth, int height, int width, int cin, int cout, int stride, int transposed,
+                        int has_skip, int transform, int sm_count, int* numbers, char* text, int text_len);
+
 /* Batch-norm finalise: stats[2*C] (sum, sumsq over `count` voxels) -> scale = gamma*rsqrt(var+eps),
  * shift = beta - mean*scale (network.py:496-506, Appendix A.6). */
 int mvsb200_bn_finalize(const double* stats, const float* gamma, const float* beta, int channels,

@@ -1564,6 +1564,40 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
   return MVSB200_OK;
 }
 
+// Host-only view of the planner (no device work): the plan the bf16 path would use for a layer shape, as text, and
+// its invariants as numbers (tests/test_planner.py).  out[0..11] = {launches, TX, TY, PX, RY, MB, mma_n, zf, xfold,
+// ring, smem_bytes, tmem_cols} of the first launch.
+int conv3d_tc_describe(int D, int H, int W, int cin, int cout, int stride, int transposed, int has_skip, int transform,
+                       int sm_count, int* out, char* text, int text_len) {
+  const int mode = transposed ? MODE_DECONV : (stride == 2 ? MODE_CONV2 : MODE_CONV1);
+  if (cin != 8 && cin != 16 && cin != 32 && cin != 64) {
+    set_error("conv3d(bf16/tcgen05): Cin=%d unsupported (need 8, 16, 32 or 64)", cin);
+    return MVSB200_ERR_UNSUPPORTED;
+  }
+  int launches = 0, written = 0;
+  for (int cb = 0; cb < cout; cb += 32, ++launches) {
+    const int cn = cout - cb < 32 ? cout - cb : 32;
+    Plan pl;
+    if (!find_plan(mode, D, H, W, cin, cout, cb, cn, has_skip != 0, transform != 0, sm_count > 0 ? sm_count : 148, &pl,
+                   nullptr)) {
+      set_error("conv3d(bf16/tcgen05): no tile fits (Cin=%d Cout=%d mode=%d)", cin, cout, mode);
+      return MVSB200_ERR_UNSUPPORTED;
+    }
+    const Params& c = pl.cp;
+    if (launches == 0 && out) {
+      const int v[12] = {0, c.TX, c.TY, c.PX, c.RY, c.MB, c.mma_n, c.zf, c.xfold, c.R, (int)pl.smem, c.tmem_cols};
+      for (int i = 0; i < 12; ++i) out[i] = v[i];
+    }
+    if (text && written < text_len)
+      written += snprintf(text + written, (size_t)(text_len - written),
+                          "cout[%d:%d] tile %dx%d cells %dx%d blocks %d N %d zfold %d xfold %d ring %d+%d grid %dx%dx%d ops %d "
+                          "smem %zu tmem %d one_box %d\n", cb, cb + cn, c.TX, c.TY, c.PX, c.RY, c.MB, c.mma_n, c.zf, c.xfold,
+                          c.R, c.RS, c.tiles_x, c.tiles_y, c.zsplit, c.nops, pl.smem, c.tmem_cols, c.one_box);
+  }
+  if (out) out[0] = launches;
+  return MVSB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // layout helpers for callers
 // ---------------------------------------------------------------------------------------------

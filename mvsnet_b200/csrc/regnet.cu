@@ -318,6 +318,16 @@ extern "C" int mvsb200_conv3d_layer(const void* x, int x_dtype, const float* x_s
                              (cudaStream_t)stream);
 }
 
+namespace mvsb200 {
+int conv3d_tc_describe(int D, int H, int W, int cin, int cout, int stride, int transposed, int has_skip, int transform,
+                       int sm_count, int* out, char* text, int text_len);
+}
+extern "C" int mvsb200_conv3d_plan(int depth, int height, int width, int cin, int cout, int stride, int transposed,
+                                   int has_skip, int transform, int sm_count, int* numbers, char* text, int text_len) {
+  return conv3d_tc_describe(depth, height, width, cin, cout, stride, transposed, has_skip, transform, sm_count, numbers,
+                            text, text_len);
+}
+
 extern "C" int mvsb200_bn_finalize(const double* stats, const float* gamma, const float* beta, int channels,
                                    double count, float eps, float* scale, float* shift, void* stream) {
   return launch_bn_finalize(stats, gamma, beta, channels, count, eps, scale, shift, (cudaStream_t)stream);

@@ -111,7 +111,10 @@ constexpr int kPlaneChunk = 48;
 // feats16 [N][Hf][Wf+1][8 groups][2 pixels][4 ch], pair j = pixels (j-1, j) with zeros outside the image, so the
 // two horizontal taps of a footprint row arrive in ONE 16-byte load per lane and one 128-byte line per pixel
 // (half the L1 wavefronts and load instructions of the fp32 path).  The reference view stays fp32.
-template <int OUT, int TX, int TY, int KDC, bool TAPS16>
+// HINT (with TAPS16): the 4-tap blend itself runs in packed fp16 (HFMA2, two channels per instruction, no
+// per-tap conversions); the blended value is widened once and the running sums stay fp32.  The blend error
+// (~1e-3 relative) is below the bf16 rounding of the volume this variant writes.
+template <int OUT, int TX, int TY, int KDC, bool TAPS16, bool HINT>
 __global__ void __launch_bounds__(256, KDC == 2 ? 4 : (KDC == 4 ? 3 : 2))
 cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict__ feats16,
                        const float* __restrict__ coef, int n_views, int D, int Hf, int Wf, int order,
@@ -167,7 +170,18 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
           // of (x0, x0+1) in [0, Wf] (either pixel may be the zero guard; its weight is 0 there)
           const int xp = min(max(f.x0 + 1, 0), Wf);
           const unsigned vbase = (unsigned)(v + 1) * (unsigned)(Hf * (Wf + 1));
-          s_fw[p][g] = make_float4(l_wyl * l_wxl, l_wyl * l_wxr, l_wyr * l_wxl, l_wyr * l_wxr);
+          if (HINT) {
+            const __half2 h00 = __float2half2_rn(l_wyl * l_wxl), h01 = __float2half2_rn(l_wyl * l_wxr);
+            const __half2 h10 = __float2half2_rn(l_wyr * l_wxl), h11 = __float2half2_rn(l_wyr * l_wxr);
+            float4 packed;
+            packed.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h00));
+            packed.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h01));
+            packed.z = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h10));
+            packed.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h11));
+            s_fw[p][g] = packed;
+          } else {
+            s_fw[p][g] = make_float4(l_wyl * l_wxl, l_wyl * l_wxr, l_wyr * l_wxl, l_wyr * l_wxr);
+          }
           s_fi[p][g] = make_int2((int)((vbase + (unsigned)(cy0 * (Wf + 1) + xp)) * 128u),
                                  (int)((vbase + (unsigned)(cy1 * (Wf + 1) + xp)) * 128u));
         } else {
@@ -186,6 +200,24 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
         if (TAPS16) {
           const uint4 a = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.x));
           const uint4 b = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.y));
+          if (HINT) {
+            const __half2 w00 = *reinterpret_cast<const __half2*>(&fw.x), w01 = *reinterpret_cast<const __half2*>(&fw.y);
+            const __half2 w10 = *reinterpret_cast<const __half2*>(&fw.z), w11 = *reinterpret_cast<const __half2*>(&fw.w);
+            const __half2 hlo = __hfma2(w11, *reinterpret_cast<const __half2*>(&b.z),
+                                __hfma2(w10, *reinterpret_cast<const __half2*>(&b.x),
+                                __hfma2(w01, *reinterpret_cast<const __half2*>(&a.z),
+                                __hmul2(w00, *reinterpret_cast<const __half2*>(&a.x)))));
+            const __half2 hhi = __hfma2(w11, *reinterpret_cast<const __half2*>(&b.w),
+                                __hfma2(w10, *reinterpret_cast<const __half2*>(&b.y),
+                                __hfma2(w01, *reinterpret_cast<const __half2*>(&a.w),
+                                __hmul2(w00, *reinterpret_cast<const __half2*>(&a.y)))));
+            const float2 lo = __half22float2(hlo), hi = __half22float2(hhi);
+            float2* S2 = reinterpret_cast<float2*>(&S[dd]);
+            float2* Q2 = reinterpret_cast<float2*>(&Q[dd]);
+            S2[0] = fadd2(S2[0], lo); S2[1] = fadd2(S2[1], hi);
+            Q2[0] = ffma2(lo, lo, Q2[0]); Q2[1] = ffma2(hi, hi, Q2[1]);
+            continue;
+          }
           const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
           const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&a.z)), a3 = __half22float2(*reinterpret_cast<const __half2*>(&a.w));
           const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
@@ -410,14 +442,18 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
     MVS_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "cost_volume: grid too large");
 #define CV_FAST(O, TX_, TY_, K_)                                                                                  \
   do {                                                                                                            \
-    if (O == 2 && feats16)                                                                                        \
-      cost_volume_c32_kernel<O, TX_, TY_, K_, true><<<grid, 256, 0, s>>>(feats, (const __half*)feats16, coef,     \
-                                                                         n_views, depth_num, hf, wf, order, out,  \
-                                                                         planar_ps8);                             \
+    if (O == 2 && feats16 && half_interp)                                                                         \
+      cost_volume_c32_kernel<O, TX_, TY_, K_, true, true><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,     \
+                                                                               coef, n_views, depth_num, hf, wf,  \
+                                                                               order, out, planar_ps8);           \
+    else if (O == 2 && feats16)                                                                                   \
+      cost_volume_c32_kernel<O, TX_, TY_, K_, true, false><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,    \
+                                                                                coef, n_views, depth_num, hf, wf, \
+                                                                                order, out, planar_ps8);          \
     else                                                                                                          \
-      cost_volume_c32_kernel<O, TX_, TY_, K_, false><<<grid, 256, 0, s>>>(feats, nullptr, coef, n_views,          \
-                                                                          depth_num, hf, wf, order, out,          \
-                                                                          planar_ps8);                            \
+      cost_volume_c32_kernel<O, TX_, TY_, K_, false, false><<<grid, 256, 0, s>>>(feats, nullptr, coef, n_views,   \
+                                                                                 depth_num, hf, wf, order, out,   \
+                                                                                 planar_ps8);                     \
   } while (0)
 #define CV_FAST_K(O, TX_, TY_)                                  \
   do {                                                          \
@@ -431,6 +467,7 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
       pair_features_kernel<<<148 * 8, 256, 0, s>>>(feats, n_views, hf, wf, (__half*)feats16);
       MVS_LAUNCH_CHECK("pair_features_kernel");
     }
+    static const bool half_interp = getenv("MVSB200_CV_FP32_BLEND") == nullptr;   // fp16 blend unless asked otherwise
     // planes per thread: the smallest of 2 / 4 / 8 whose footprints fill whole rounds of 8 lanes
     const int n_src = n_views - 1;
     int kdc = (2 * n_src) % 8 == 0 ? 2 : ((4 * n_src) % 8 == 0 ? 4 : 8);

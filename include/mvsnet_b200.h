@@ -206,6 +206,33 @@ int mvsb200_infer_host_async(const float* feats_host, const float* cams_host, in
                              float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ---- D-slab mode (BASELINE config 5): ONE volume split along depth over `slabs` GPUs ------------
+ * Rank `slab` runs the bf16 path on depth_num/slabs consecutive planes (a multiple of 8).  Tensors in the slab
+ * workspace carry one halo plane before and after the local planes.  Between the calls below the HOST exchanges
+ * data between ranks (mvsnet_b200/dslab.py does it with torch.distributed / NCCL over NVLink):
+ *   after mvsb200_slab_layer(l): all-reduce (SUM, fp64) the statistics region of l and swap the boundary planes
+ *   of l's output tensors with both neighbours; after the last layer all-gather the filtered slabs and call
+ *   mvsb200_depth_regress.  Every rank holds all feature maps, so the cost volume needs no exchange. */
+size_t mvsb200_slab_workspace_bytes(int n_views, int depth_num, int slabs, int hf, int wf, int channels,
+                                    int base_filter);
+/* homographies, the slab's cost-volume planes (and its two halo planes), weight packing, cleared statistics */
+int mvsb200_slab_begin(const float* feats, const float* cams, int n_views, int depth_num, int slab, int slabs,
+                       int hf, int wf, int channels, float depth_start, float depth_interval,
+                       int inverse_depth, int order, const mvsb200_regnet_params* params, int base_filter,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* RegNetUS0 layer `layer` (MVSB200_L_*) on the local slab */
+int mvsb200_slab_layer(int layer, int n_views, int depth_num, int slab, int slabs, int hf, int wf, int channels,
+                       const mvsb200_regnet_params* params, int base_filter, float bn_eps, void* workspace,
+                       void* stream);
+/* Host-only: byte offsets into the slab workspace of what is exchanged after `layer`.
+ *   out[0..1]   statistics: offset, bytes
+ *   out[2+5t..6+5t], t = 0 (chunk-planar output) / 1 (parity-split copy): plane bytes (0 = absent), first local
+ *               plane (-> previous rank's AFTER halo), last local plane (-> next rank's BEFORE halo), own BEFORE
+ *               halo, own AFTER halo
+ *   out[12..13] filtered slab [depth_num/slabs, hf, wf] fp32: offset, bytes */
+int mvsb200_slab_regions(int layer, int n_views, int depth_num, int slabs, int hf, int wf, int channels,
+                         int base_filter, unsigned long long* out);
+
 /* Diagnostic (not on the product path): one 128 x n x (16*kblocks) tcgen05.mma tile computed from
  * caller-built shared-memory images of the A and B operands (no-swizzle K-major core-matrix
  * layout).  Pins the descriptor semantics conv3d_tc.cu relies on.  d_out [128*n] fp32. */

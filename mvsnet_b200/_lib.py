@@ -58,6 +58,11 @@ SIGNATURES = {
                               POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
     "mvsb200_infer_set_stage_events": (c_int, [POINTER(c_void_p)]),
     "mvsb200_conv3d_plan": (c_int, [c_int] * 10 + [_P, ctypes.c_char_p, c_int]),
+    "mvsb200_slab_workspace_bytes": (c_size_t, [c_int] * 7),
+    "mvsb200_slab_begin": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int,
+                                   _P, c_int, _P, c_size_t, _P]),
+    "mvsb200_slab_layer": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P]),
+    "mvsb200_slab_regions": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mvsb200_infer_host_staging_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mvsb200_infer_host": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
                                    POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),

@@ -53,6 +53,10 @@ using namespace umma;
 
 // Batch-norm source of an input tensor: the producer's channel statistics (sum | sum of squares over `count`
 // voxels) and its gamma / beta.  The consumer derives scale / shift itself (no bn_finalize launch in between).
+// D-slab mode (one volume split along z over several GPUs): the input (and skip) tensor carries one halo plane
+// before and after the D local planes; planes outside [zv_lo, zv_hi) (extended coordinates) are SAME padding.
+struct TcSlab { int halo; int zv_lo; int zv_hi; };
+
 struct TcBnSrc { const double* stats; const float* gamma; const float* beta; double count; float eps; int channels;
                  int reps; int rep_stride; };   // statistics are the sum of `reps` partial copies, rep_stride doubles apart
 
@@ -92,6 +96,7 @@ struct Params {
   int TX, TY, tiles_x, tiles_y, zsplit;
   int PX, RY, nsub, SUBP;        // slot geometry: nsub sub-arrays of RY x PX cells, SUBP cells apart
   int vstep, cx_off, cy_off;     // cell (sub, r, c) = voxel (vstep*(y0+r+cy_off)+(sub>>1), vstep*(x0+c+cx_off)+(sub&1))
+  int zv_lo, zv_hi;              // input planes outside [zv_lo, zv_hi) are padding: the transform leaves them at zero
   int zmul, zoff, zstep, span;   // plane seq of a segment = input z (zmul*zb + zoff + seq); zstep planes per step
   int NCH, PS, slot_bytes, R, RS;    // RS = skip ring depth (has_skip)
   int MB, NB, CP;                // row blocks per step, TMEM columns per block, MMA N
@@ -447,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           if (p.has_skip) mbar_wait(&bar_sland[ss], (uint32_t)(seq / p.RS) & 1u);
           if (p.prof) xw += clock64() - xa;
           const int iz = p.zmul * zb + p.zoff + seq;
-          if (iz >= 0 && iz < p.D) {
+          if (iz >= p.zv_lo && iz < p.zv_hi) {
             unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
             const unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
             // groups of 4 cells: all loads of a group are issued before its first store (the in-place stores would
@@ -1420,7 +1425,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
                      const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
                      const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
-                     int stats_rep_stride, cudaStream_t s) {
+                     int stats_rep_stride, const TcSlab* slab, cudaStream_t s) {
   if (cin != 8 && cin != 16 && cin != 32 && cin != 64) {
     set_error("conv3d(bf16/tcgen05): Cin=%d unsupported (need 8, 16, 32 or 64)", cin);
     return MVSB200_ERR_UNSUPPORTED;
@@ -1469,11 +1474,15 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     c.sbn = s_bn ? *s_bn : TcBnSrc{nullptr, nullptr, nullptr, 1.0, 0.f, 0, 1, 0};
     c.stats_reps = stats_reps > 0 ? stats_reps : 1; c.stats_rep_stride = stats_rep_stride;
     c.y_cp8 = (__nv_bfloat16*)y_cp8; c.y_ps8 = (__nv_bfloat16*)y_ps8; c.y_f32 = y_f32; c.stats = stats;
+    // D-slab mode: the tensors hold D + 2 planes (halo before / after), local plane l is extended plane l + 1
+    const int Dt = slab && slab->halo ? D + 2 : D;
+    c.zv_lo = 0; c.zv_hi = D;
+    if (slab && slab->halo) { c.zoff += 1; c.zv_lo = slab->zv_lo; c.zv_hi = slab->zv_hi; }
     const bool ok_x = mode == MODE_CONV2
-                          ? make_tmap(&c.tmap_x, x, (W + 1) / 2, (H + 1) / 2, 4, c.NCH, D, c.PX, c.RY, c.one_box ? c.NCH : 1,
+                          ? make_tmap(&c.tmap_x, x, (W + 1) / 2, (H + 1) / 2, 4, c.NCH, Dt, c.PX, c.RY, c.one_box ? c.NCH : 1,
                                       c.one_box ? 4 : 1)
-                          : make_tmap(&c.tmap_x, x, W, H, 1, c.NCH, D, c.PX, c.RY, c.one_box ? c.NCH : 1);
-    const bool ok_s = !has_skip || make_tmap(&c.tmap_s, skip, W, H, 1, c.NCH, D, c.PX, c.RY, c.one_box ? c.NCH : 1);
+                          : make_tmap(&c.tmap_x, x, W, H, 1, c.NCH, Dt, c.PX, c.RY, c.one_box ? c.NCH : 1);
+    const bool ok_s = !has_skip || make_tmap(&c.tmap_s, skip, W, H, 1, c.NCH, Dt, c.PX, c.RY, c.one_box ? c.NCH : 1);
     if (!ok_x || !ok_s) {
       set_error("conv3d(bf16/tcgen05): cuTensorMapEncodeTiled failed (PX=%d RY=%d W=%d H=%d)", c.PX, c.RY, W, H);
       return MVSB200_ERR_CUDA;
@@ -1658,7 +1667,7 @@ int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, cons
     else if (via_f32) MVS_CUDA(cudaMallocAsync((void**)&yf, (size_t)Do * Ho * Wo * cout * sizeof(float), s));
     else MVS_CUDA(cudaMallocAsync(&yp, planar_bytes(Do, Ho, Wo, cout, 0), s));
     rc = launch_conv3d_tc(xp, xs, xb, kp, ss, sb, kernel_tf, D, H, W, cin, cout, stride, transposed, yp, nullptr, yf,
-                          stats, scratch, nullptr, nullptr, nullptr, 1, 0, s);
+                          stats, scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, s);
   }
   if (!rc && yp) rc = launch_planar_to_ndhwc(yp, Do, Ho, Wo, cout, y, s);
   if (!rc && via_f32) rc = launch_f32_to_bf16(yf, (size_t)Do * Ho * Wo * cout, y, s);

@@ -114,11 +114,13 @@ constexpr int kPlaneChunk = 48;
 // HINT (with TAPS16): the 4-tap blend itself runs in packed fp16 (HFMA2, two channels per instruction, no
 // per-tap conversions); the blended value is widened once and the running sums stay fp32.  The blend error
 // (~1e-3 relative) is below the bf16 rounding of the volume this variant writes.
-template <int OUT, int TX, int TY, int KDC, bool TAPS16, bool HINT>
-__global__ void __launch_bounds__(256, KDC == 2 ? 4 : (KDC == 4 ? 3 : 2))
+template <int OUT, int TX, int TY, int KDC, bool TAPS16, bool HINT, int MINB = (KDC == 2 ? 4 : (KDC == 4 ? 3 : 2))>
+__global__ void __launch_bounds__(256, MINB)
 cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict__ feats16,
-                       const float* __restrict__ coef, int n_views, int D, int Hf, int Wf, int order,
-                       void* __restrict__ out, void* __restrict__ out2) {
+                       const float* __restrict__ coef, int n_views, int D, int d0g, int Dloc, int Hf, int Wf,
+                       int order, void* __restrict__ out, void* __restrict__ out2) {
+  // plane window (D-slab mode): local plane l = global plane d0g + l of the D-plane sweep, Dloc local planes are
+  // written (those whose global index falls outside [0, D) are left alone); whole volume: d0g = 0, Dloc = D
   static_assert(TX * TY == 32, "tile must hold 32 pixels");
   static_assert(KDC == 2 || KDC == 4 || KDC == 8, "planes per thread");
   constexpr int VPR = 8 / KDC;            // source views per footprint round
@@ -135,7 +137,7 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
   const int n_src = n_views - 1;
   for (int i = tid; i < n_src * kPlaneChunk * 8; i += 256) {
     int v = i / (kPlaneChunk * 8), r = i - v * (kPlaneChunk * 8);
-    int d = min(dbeg + (r >> 3), D - 1);
+    int d = min(max(d0g + dbeg + (r >> 3), 0), D - 1);
     s_coef[i] = __ldg(coef + (v * D + d) * 8 + (r & 7));
   }
   __syncthreads();
@@ -145,7 +147,7 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
   const float4 r = ldg4(feats + ((size_t)yc * Wf + xc) * 32 + g * 4);
   const float4 rq = make_float4(r.x * r.x, r.y * r.y, r.z * r.z, r.w * r.w);
   const float inv_n = 1.0f / (float)n_views, inv_nn = 1.0f / (float)(n_views * n_views);
-  const int dend = min(D, dbeg + kPlaneChunk);
+  const int dend = min(Dloc, dbeg + kPlaneChunk);
   const int rounds = (KDC * n_src) / 8;       // the launcher picks KDC so that this is exact
   const char* base16 = reinterpret_cast<const char*>(feats16) + g * 16;
   // footprint slot g of a round: view (round*VPR + g / KDC), plane g % KDC of the group
@@ -271,7 +273,8 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
       if (active) {
 #pragma unroll
         for (int dd = 0; dd < KDC; ++dd)
-          if (d0 + dd < D) store_cost4(out, (((size_t)(d0 + dd) * Hf + y) * Wf + x) * 32 + g * 4, c[dd], OUT == 1);
+          if (d0 + dd < Dloc && (unsigned)(d0g + d0 + dd) < (unsigned)D)
+            store_cost4(out, (((size_t)(d0 + dd) * Hf + y) * Wf + x) * 32 + g * 4, c[dd], OUT == 1);
       }
     } else {
       // planar layouts: lanes g and g^1 hold the two halves of a 16-byte cell (chunk g>>1).  They swap halves of
@@ -304,7 +307,7 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
         else px = 2 * (l & 15) + (l >> 4);
         const int xx = blockIdx.x * TX + (px % TX), yy = blockIdx.y * TY + (px / TX);
         const int d = d0 + (pc >> 2);
-        if (xx < Wf && yy < Hf && d < D) {
+        if (xx < Wf && yy < Hf && d < Dloc && (unsigned)(d0g + d) < (unsigned)D) {
           const uint4 cell = s_cells[pc * 32 + px + (pc >> 1)];
           const size_t zc = (size_t)d * 4 + (pc & 3);
           if (out) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + ((zc * Hf + yy) * Wf + xx) * 8) = cell;
@@ -399,7 +402,9 @@ cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restr
 static int launch_cost_volume_any(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                                   int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
                                   int planar, void* planar_ps8, void* feats16, const float* coef_table,
-                                  cudaStream_t s) {
+                                  cudaStream_t s, int d0g = 0, int dloc = -1) {
+  // (d0g, dloc): plane window of the D-slab mode; the coefficient table always covers all depth_num planes
+  if (dloc < 0) dloc = depth_num;
   MVS_CHECK_ARG(feats && homographies && (out || planar_ps8), "cost_volume: NULL pointer");
   MVS_CHECK_ARG(n_views >= 2 && depth_num >= 1 && hf >= 1 && wf >= 1 && channels >= 1,
                 "cost_volume: bad shape N=%d D=%d %dx%dx%d", n_views, depth_num, hf, wf, channels);
@@ -438,21 +443,29 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
   if (variant >= 2) {
     const bool wide = variant == 2;
     const int tx = wide ? 32 : 16, ty = wide ? 1 : 2;
-    dim3 grid(ceil_div(wf, tx), ceil_div(hf, ty), ceil_div(depth_num, kPlaneChunk));
+    dim3 grid(ceil_div(wf, tx), ceil_div(hf, ty), ceil_div(dloc, kPlaneChunk));
     MVS_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "cost_volume: grid too large");
 #define CV_FAST(O, TX_, TY_, K_)                                                                                  \
   do {                                                                                                            \
-    if (O == 2 && feats16 && half_interp)                                                                         \
+    if (O == 2 && feats16 && half_interp && minb_env == 3 && K_ == 2)                                             \
+      cost_volume_c32_kernel<O, TX_, TY_, 2, true, true, 3><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,   \
+                                                                               coef, n_views, depth_num, d0g, dloc, hf, wf, \
+                                                                               order, out, planar_ps8);           \
+    else if (O == 2 && feats16 && half_interp && minb_env == 2 && K_ == 2)                                        \
+      cost_volume_c32_kernel<O, TX_, TY_, 2, true, true, 2><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,   \
+                                                                               coef, n_views, depth_num, d0g, dloc, hf, wf, \
+                                                                               order, out, planar_ps8);           \
+    else if (O == 2 && feats16 && half_interp)                                                                    \
       cost_volume_c32_kernel<O, TX_, TY_, K_, true, true><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,     \
-                                                                               coef, n_views, depth_num, hf, wf,  \
+                                                                               coef, n_views, depth_num, d0g, dloc, hf, wf, \
                                                                                order, out, planar_ps8);           \
     else if (O == 2 && feats16)                                                                                   \
       cost_volume_c32_kernel<O, TX_, TY_, K_, true, false><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,    \
-                                                                                coef, n_views, depth_num, hf, wf, \
+                                                                                coef, n_views, depth_num, d0g, dloc, hf, wf, \
                                                                                 order, out, planar_ps8);          \
     else                                                                                                          \
       cost_volume_c32_kernel<O, TX_, TY_, K_, false, false><<<grid, 256, 0, s>>>(feats, nullptr, coef, n_views,   \
-                                                                                 depth_num, hf, wf, order, out,   \
+                                                                                 depth_num, d0g, dloc, hf, wf, order, out, \
                                                                                  planar_ps8);                     \
   } while (0)
 #define CV_FAST_K(O, TX_, TY_)                                  \
@@ -462,12 +475,13 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
     else CV_FAST(O, TX_, TY_, 8);                               \
   } while (0)
     if (planar && ((hf | wf) & 1) && planar_ps8)
-      MVS_CUDA(cudaMemsetAsync(planar_ps8, 0, (size_t)depth_num * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) * 16, s));
+      MVS_CUDA(cudaMemsetAsync(planar_ps8, 0, (size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) * 16, s));
     if (planar && feats16) {
       pair_features_kernel<<<148 * 8, 256, 0, s>>>(feats, n_views, hf, wf, (__half*)feats16);
       MVS_LAUNCH_CHECK("pair_features_kernel");
     }
-    static const bool half_interp = getenv("MVSB200_CV_FP32_BLEND") == nullptr;   // fp16 blend unless asked otherwise
+    static const bool half_interp = getenv("MVSB200_CV_FP32_BLEND") == nullptr;
+    static const int minb_env = getenv("MVSB200_CV_MINB") ? atoi(getenv("MVSB200_CV_MINB")) : 0;   // tuning   // fp16 blend unless asked otherwise
     // planes per thread: the smallest of 2 / 4 / 8 whose footprints fill whole rounds of 8 lanes
     const int n_src = n_views - 1;
     int kdc = (2 * n_src) % 8 == 0 ? 2 : ((4 * n_src) % 8 == 0 ? 4 : 8);
@@ -530,6 +544,14 @@ int launch_cost_volume_planar(const float* feats, const float* homographies, int
                               const float* coef_table, cudaStream_t s) {
   return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler,
                                 MVSB200_BF16, cp8, 0, 1, ps8, feats16, coef_table, s);
+}
+
+// D-slab mode: local planes [0, dloc) = global planes [d0g, d0g + dloc) of the depth_num-plane sweep
+int launch_cost_volume_slab(const float* feats, const float* homographies, int n_views, int depth_num, int d0g,
+                            int dloc, int hf, int wf, int channels, int order, int sampler, void* cp8, void* ps8,
+                            void* feats16, const float* coef_table, cudaStream_t s) {
+  return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler,
+                                MVSB200_BF16, cp8, 0, 1, ps8, feats16, coef_table, s, d0g, dloc);
 }
 
 }  // namespace mvsb200

@@ -16,12 +16,13 @@ int launch_conv3d_direct(const void* x, int x_dtype, const float* xs, const floa
 // conv3d_tc.cu: bf16 tcgen05 layers on the planar activation layouts (CP8 / PS8, see that file)
 struct TcBnSrc { const double* stats; const float* gamma; const float* beta; double count; float eps; int channels;
                  int reps; int rep_stride; };
+struct TcSlab { int halo; int zv_lo; int zv_hi; };
 struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0; };
 int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
                      const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
                      const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
-                     int stats_rep_stride, cudaStream_t s);
+                     int stats_rep_stride, const TcSlab* slab, cudaStream_t s);
 int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStream_t s);
 size_t conv3d_tc_pack_slot_bytes();
 int launch_bn_finalize_all(const double* stats, const float* const* gamma, const float* const* beta, const int* channels,
@@ -259,7 +260,7 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
                             L.stride, L.transposed, last ? nullptr : ws + p.raw_off[i],
                             (!last && p.has_ps8[i]) ? ws + p.ps8_off[i] : nullptr, last ? filtered : nullptr, st,
                             nullptr, L.src >= 0 ? &xbn : nullptr, L.skip >= 0 ? &sbn : nullptr,
-                            ws + p.scratch_off + (size_t)2 * i * conv3d_tc_pack_slot_bytes(), kStatsReps, rep_stride, s);
+                            ws + p.scratch_off + (size_t)2 * i * conv3d_tc_pack_slot_bytes(), kStatsReps, rep_stride, nullptr, s);
       if (rc) return rc;
     }
     if (profile) cudaEventRecord(pev[i + 1], s);
@@ -361,6 +362,202 @@ extern "C" const void* mvsb200_regnet_layer_raw(const void* workspace, int depth
   if (shift) *shift = (const float*)(ws + p.shift_off) + (size_t)layer * cpad;
   if (layer == MVSB200_L_3DCONV6_2) return nullptr;
   return ws + p.raw_off[layer];
+}
+
+// ---------------------------------------------------------------------------------------------
+// D-slab mode: ONE volume split along depth over `slabs` GPUs (BASELINE config 5).  Every rank runs the
+// bf16 path on D/slabs consecutive planes; between layers the host exchanges (NCCL over NVLink, see
+// mvsnet_b200/dslab.py) one boundary plane per tensor with each neighbour and all-reduces the batch statistics.
+// Tensors carry one halo plane before and after the local planes; the library only exposes where they are.
+// ---------------------------------------------------------------------------------------------
+namespace mvsb200 {
+int launch_cost_volume_slab(const float* feats, const float* homographies, int n_views, int depth_num, int d0g,
+                            int dloc, int hf, int wf, int channels, int order, int sampler, void* cp8, void* ps8,
+                            void* feats16, const float* coef_table, cudaStream_t s);
+size_t cost_volume_pair_bytes(int n_views, int hf, int wf);
+bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sampler);
+
+struct SlabPlan {
+  RegnetPlan net;                       // layer table; dims = LOCAL extents (depth / slabs)
+  size_t raw_off[MVSB200_REGNET_LAYERS], ps8_off[MVSB200_REGNET_LAYERS];      // tensors with halo planes
+  size_t raw_plane[MVSB200_REGNET_LAYERS], ps8_plane[MVSB200_REGNET_LAYERS];  // bytes per plane
+  size_t cost_cp8_off, cost_ps8_off, cost_cp8_plane, cost_ps8_plane;
+  size_t hom_off, coef_off, pair_off, filtered_off, stats_off, stats_bytes, scratch_off, total;
+  int cpad;
+};
+
+static int make_slab_plan(int n_views, int D, int slabs, int H, int W, int cin, int b, SlabPlan* sp) {
+  MVS_CHECK_ARG(slabs >= 1 && D % slabs == 0 && (D / slabs) % 8 == 0,
+                "slab: depth %d must split into %d slabs of a multiple of 8 planes", D, slabs);
+  const int Dl = D / slabs;
+  int rc = check_regnet_shape(Dl, H, W, cin, b);
+  if (rc) return rc;
+  MVS_CHECK_ARG(cin % 8 == 0 && b % 8 == 0, "slab: channel counts must be multiples of 8");
+  make_plan(Dl, H, W, cin, b, MVSB200_PRECISION_BF16, &sp->net);
+  const RegnetPlan& p = sp->net;
+  size_t off = 0;
+  sp->hom_off = off;  off += align_up((size_t)(n_views - 1) * D * 9 * sizeof(float), 256);
+  sp->coef_off = off; off += align_up((size_t)(n_views - 1) * D * 8 * sizeof(float), 256);
+  sp->pair_off = off; off += align_up(cost_volume_pair_bytes(n_views, H, W), 256);
+  sp->cost_cp8_plane = planar_bytes(1, H, W, cin, 0);
+  sp->cost_ps8_plane = planar_bytes(1, H, W, cin, 1);
+  sp->cost_cp8_off = off; off += align_up(sp->cost_cp8_plane * (Dl + 2), 256);
+  sp->cost_ps8_off = off; off += align_up(sp->cost_ps8_plane * (Dl + 2), 256);
+  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+    const LayerDesc& L = p.layer[i];
+    const int* d = p.dims[L.out_level];
+    sp->raw_plane[i] = sp->ps8_plane[i] = 0;
+    sp->raw_off[i] = sp->ps8_off[i] = 0;
+    if (i == MVSB200_L_3DCONV6_2) continue;
+    sp->raw_plane[i] = planar_bytes(1, d[1], d[2], L.cout, 0);
+    sp->raw_off[i] = off; off += align_up(sp->raw_plane[i] * (d[0] + 2), 256);
+    if (p.has_ps8[i]) {
+      sp->ps8_plane[i] = planar_bytes(1, d[1], d[2], L.cout, 1);
+      sp->ps8_off[i] = off; off += align_up(sp->ps8_plane[i] * (d[0] + 2), 256);
+    }
+  }
+  sp->filtered_off = off; off += align_up((size_t)Dl * H * W * sizeof(float), 256);
+  sp->cpad = 64;
+  // statistics [layer][copy][2*cpad]: one contiguous region per layer for the all-reduce
+  sp->stats_bytes = (size_t)MVSB200_REGNET_LAYERS * kStatsReps * 2 * sp->cpad * sizeof(double);
+  sp->stats_off = off; off += align_up(sp->stats_bytes, 256);
+  sp->scratch_off = off; off += align_up(conv3d_tc_pack_slot_bytes() * 2 * MVSB200_REGNET_LAYERS, 256);
+  sp->total = off;
+  return MVSB200_OK;
+}
+}  // namespace mvsb200
+
+extern "C" size_t mvsb200_slab_workspace_bytes(int n_views, int depth_num, int slabs, int hf, int wf, int channels,
+                                               int base_filter) {
+  SlabPlan sp;
+  if (n_views < 2 || make_slab_plan(n_views, depth_num, slabs, hf, wf, channels, base_filter, &sp)) return 0;
+  return sp.total;
+}
+
+// Stage 0 of a slab: homographies of all planes, the slab's cost volume planes (plus its two halo planes, which
+// need no exchange: every rank holds all feature maps), weight packing, cleared statistics.
+extern "C" int mvsb200_slab_begin(const float* feats, const float* cams, int n_views, int depth_num, int slab, int slabs,
+                                  int hf, int wf, int channels, float depth_start, float depth_interval,
+                                  int inverse_depth, int order, const mvsb200_regnet_params* params, int base_filter,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  MVS_CHECK_ARG(feats && cams && params && workspace, "slab_begin: NULL pointer");
+  MVS_CHECK_ARG(slab >= 0 && slab < slabs, "slab_begin: slab %d of %d", slab, slabs);
+  SlabPlan sp;
+  int rc = make_slab_plan(n_views, depth_num, slabs, hf, wf, channels, base_filter, &sp);
+  if (rc) return rc;
+  if (workspace_bytes < sp.total) {
+    set_error("slab_begin: workspace %zu < required %zu bytes", workspace_bytes, sp.total);
+    return MVSB200_ERR_WORKSPACE;
+  }
+  MVS_CHECK_ARG(cost_volume_planar_ok(n_views, hf, wf, channels, MVSB200_SAMPLER_TRANSFORM),
+                "slab_begin: needs 32 feature channels and at most 8 views");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const RegnetPlan& p = sp.net;
+  const int Dl = depth_num / slabs;
+  volatile float dm1 = (float)depth_num - 1.0f;
+  volatile float prod = dm1 * depth_interval;
+  volatile float depth_end = depth_start + prod;
+  float* homs = (float*)(ws + sp.hom_off);
+  float* coefs = (float*)(ws + sp.coef_off);
+  rc = launch_homographies(cams, n_views, depth_num, depth_start, inverse_depth ? (float)depth_end : depth_interval,
+                           inverse_depth, homs, coefs, s);
+  if (rc) return rc;
+  // SAME padding at the ends of the volume: the halo planes nobody writes
+  auto clear_ends = [&](size_t off, size_t plane, int planes) -> int {
+    if (slab == 0) MVS_CUDA(cudaMemsetAsync(ws + off, 0, plane, s));
+    if (slab == slabs - 1) MVS_CUDA(cudaMemsetAsync(ws + off + plane * (size_t)(planes + 1), 0, plane, s));
+    return MVSB200_OK;
+  };
+  if ((rc = clear_ends(sp.cost_cp8_off, sp.cost_cp8_plane, Dl))) return rc;
+  if ((rc = clear_ends(sp.cost_ps8_off, sp.cost_ps8_plane, Dl))) return rc;
+  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+    const int dl = p.dims[p.layer[i].out_level][0];
+    if (sp.raw_plane[i] && (rc = clear_ends(sp.raw_off[i], sp.raw_plane[i], dl))) return rc;
+    if (sp.ps8_plane[i] && (rc = clear_ends(sp.ps8_off[i], sp.ps8_plane[i], dl))) return rc;
+  }
+  rc = launch_cost_volume_slab(feats, homs, n_views, depth_num, slab * Dl - 1, Dl + 2, hf, wf, channels, order,
+                               MVSB200_SAMPLER_TRANSFORM, ws + sp.cost_cp8_off, ws + sp.cost_ps8_off, ws + sp.pair_off,
+                               coefs, s);
+  if (rc) return rc;
+  MVS_CUDA(cudaMemsetAsync(ws + sp.stats_off, 0, sp.stats_bytes, s));
+  TcPackJob jobs[MVSB200_REGNET_LAYERS];
+  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+    const LayerDesc& L = p.layer[i];
+    MVS_CHECK_ARG(params->kernel[i] != nullptr, "slab_begin: kernel[%d] is NULL", i);
+    const int* d = p.dims[L.in_level];
+    jobs[i] = {params->kernel[i], d[0], d[1], d[2], L.cin, L.cout, L.stride, L.transposed, L.skip >= 0 ? 1 : 0,
+               (L.src >= 0 || L.skip >= 0) ? 1 : 0, 2 * i};
+  }
+  return conv3d_tc_pack_all(jobs, MVSB200_REGNET_LAYERS, ws + sp.scratch_off, s);
+}
+
+// Layer `layer` on the local slab.  Its inputs' halo planes and its producers' statistics must have been
+// exchanged (mvsb200_slab_regions says where they live).
+extern "C" int mvsb200_slab_layer(int layer, int n_views, int depth_num, int slab, int slabs, int hf, int wf,
+                                  int channels, const mvsb200_regnet_params* params, int base_filter, float bn_eps,
+                                  void* workspace, void* stream) {
+  MVS_CHECK_ARG(layer >= 0 && layer < MVSB200_REGNET_LAYERS && params && workspace, "slab_layer: bad arguments");
+  SlabPlan sp;
+  int rc = make_slab_plan(n_views, depth_num, slabs, hf, wf, channels, base_filter, &sp);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const RegnetPlan& p = sp.net;
+  const LayerDesc& L = p.layer[layer];
+  const bool last = layer == MVSB200_L_3DCONV6_2;
+  const bool s2 = L.stride == 2 && !L.transposed;
+  const int* d = p.dims[L.in_level];
+  double* stats = (double*)(ws + sp.stats_off);
+  const int lstride = kStatsReps * 2 * sp.cpad;          // doubles per layer
+  const void* x = L.src < 0 ? (const void*)(ws + (s2 ? sp.cost_ps8_off : sp.cost_cp8_off))
+                            : (const void*)(ws + (s2 ? sp.ps8_off[L.src] : sp.raw_off[L.src]));
+  const void* sk = L.skip < 0 ? nullptr : (const void*)(ws + sp.raw_off[L.skip]);
+  TcBnSrc xbn = {nullptr, nullptr, nullptr, 1.0, bn_eps, 0, 1, 0}, sbn = xbn;
+  // batch statistics span the whole volume: counts are global, the sums have been all-reduced by the host
+  if (L.src >= 0)
+    xbn = {stats + (size_t)L.src * lstride, params->gamma[L.src], params->beta[L.src],
+           (double)p.vox[p.layer[L.src].out_level] * slabs, bn_eps, p.layer[L.src].cout, kStatsReps, 2 * sp.cpad};
+  if (L.skip >= 0)
+    sbn = {stats + (size_t)L.skip * lstride, params->gamma[L.skip], params->beta[L.skip],
+           (double)p.vox[p.layer[L.skip].out_level] * slabs, bn_eps, p.layer[L.skip].cout, kStatsReps, 2 * sp.cpad};
+  const TcSlab win = {1, slab == 0 ? 1 : 0, slab == slabs - 1 ? d[0] + 1 : d[0] + 2};
+  // outputs start at extended plane 1
+  void* y_cp8 = last ? nullptr : ws + sp.raw_off[layer] + sp.raw_plane[layer];
+  void* y_ps8 = (!last && sp.ps8_plane[layer]) ? ws + sp.ps8_off[layer] + sp.ps8_plane[layer] : nullptr;
+  return launch_conv3d_tc(x, nullptr, nullptr, sk, nullptr, nullptr, params->kernel[layer], d[0], d[1], d[2], L.cin, L.cout,
+                          L.stride, L.transposed, y_cp8, y_ps8, last ? (float*)(ws + sp.filtered_off) : nullptr,
+                          last ? nullptr : stats + (size_t)layer * lstride, nullptr, L.src >= 0 ? &xbn : nullptr,
+                          L.skip >= 0 ? &sbn : nullptr, ws + sp.scratch_off + (size_t)2 * layer * conv3d_tc_pack_slot_bytes(),
+                          kStatsReps, 2 * sp.cpad, &win, s);
+}
+
+// Regions the host exchanges after layer `layer` (byte offsets into the workspace):
+//   out[0], out[1]   statistics of the layer: offset, bytes (fp64; all-reduce SUM over the slabs)
+//   per tensor t in {0: chunk-planar, 1: parity-split copy}: out[2+5t .. 6+5t] = plane bytes (0 = absent),
+//   first local plane (-> previous rank's AFTER halo), last local plane (-> next rank's BEFORE halo),
+//   own BEFORE halo, own AFTER halo
+//   out[12], out[13] the filtered slab [D/slabs, Hf, Wf] fp32: offset, bytes
+extern "C" int mvsb200_slab_regions(int layer, int n_views, int depth_num, int slabs, int hf, int wf, int channels,
+                                    int base_filter, unsigned long long* out) {
+  MVS_CHECK_ARG(layer >= 0 && layer < MVSB200_REGNET_LAYERS && out, "slab_regions: bad arguments");
+  SlabPlan sp;
+  int rc = make_slab_plan(n_views, depth_num, slabs, hf, wf, channels, base_filter, &sp);
+  if (rc) return rc;
+  const int dl = sp.net.dims[sp.net.layer[layer].out_level][0];
+  out[0] = sp.stats_off + (size_t)layer * kStatsReps * 2 * sp.cpad * sizeof(double);
+  out[1] = layer == MVSB200_L_3DCONV6_2 ? 0 : (size_t)kStatsReps * 2 * sp.cpad * sizeof(double);
+  const size_t offs[2] = {sp.raw_off[layer], sp.ps8_off[layer]}, planes[2] = {sp.raw_plane[layer], sp.ps8_plane[layer]};
+  for (int t = 0; t < 2; ++t) {
+    out[2 + 5 * t] = planes[t];
+    out[3 + 5 * t] = offs[t] + planes[t];                       // first local plane
+    out[4 + 5 * t] = offs[t] + planes[t] * (size_t)dl;          // last local plane
+    out[5 + 5 * t] = offs[t];                                   // before halo
+    out[6 + 5 * t] = offs[t] + planes[t] * (size_t)(dl + 1);    // after halo
+  }
+  out[12] = sp.filtered_off;
+  out[13] = (size_t)(depth_num / slabs) * hf * wf * sizeof(float);
+  return MVSB200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,116 @@
+"""D-slab mode: ONE cost volume split along depth over the GPUs of a box (BASELINE config 5).
+
+Rank r owns planes [r*D/G, (r+1)*D/G) of every tensor of the path.  The kernels are the single-GPU ones, run on a
+depth window (include/mvsnet_b200.h, mvsb200_slab_*); this module is the exchange step between them, over
+`torch.distributed` (NCCL on NVLink / NVSwitch; gloo in the CPU tests):
+
+  * cost volume: no exchange -- every rank holds all feature maps and computes its own two halo planes;
+  * after every layer: all-reduce (SUM) of its batch statistics (BN uses statistics of the WHOLE volume,
+    network.py:496) and a halo exchange of the boundary planes of its output with both neighbours (the 3x3x3
+    receptive field of the consumers, network.py:210,327);
+  * after the last layer: all-gather of the filtered slabs so that the softmax over depth (model.py:474) sees all
+    planes.
+
+`exchange_layer` only touches byte regions of a flat workspace tensor, so it is testable on CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import ops
+
+N_LAYERS = 11
+
+
+def slab_range(depth_num: int, rank: int, world: int):
+    """[begin, end) of the depth planes rank `rank` owns; the regularizer needs multiples of 8 planes per slab."""
+    if depth_num % world or (depth_num // world) % 8:
+        raise ValueError(f"depth {depth_num} does not split into {world} slabs of a multiple of 8 planes")
+    dl = depth_num // world
+    return rank * dl, (rank + 1) * dl
+
+
+def layer_regions(layer: int, n_views: int, depth_num: int, world: int, hf: int, wf: int, channels: int,
+                  base_filter: int) -> dict:
+    """Byte regions of the slab workspace the host exchanges after `layer` (host-only call)."""
+    lib = L.load()
+    out = (ctypes.c_ulonglong * 14)()
+    L.check(lib.mvsb200_slab_regions(layer, n_views, depth_num, world, hf, wf, channels, base_filter, out), "slab_regions")
+    v = [int(x) for x in out]
+    tensors = []
+    for t in range(2):
+        plane, first, last, before, after = v[2 + 5 * t:7 + 5 * t]
+        if plane:
+            tensors.append(dict(plane=plane, first=first, last=last, before=before, after=after))
+    return dict(stats=(v[0], v[1]), tensors=tensors, filtered=(v[12], v[13]))
+
+
+def exchange_layer(ws: torch.Tensor, regions: dict, rank: int, world: int, group=None) -> None:
+    """All-reduce the layer's statistics and swap boundary planes with the neighbours.  `ws` is the flat uint8
+    workspace; everything happens in place."""
+    off, nbytes = regions["stats"]
+    if nbytes:
+        dist.all_reduce(ws[off:off + nbytes].view(torch.float64), op=dist.ReduceOp.SUM, group=group)
+    opsl: List[dist.P2POp] = []
+    for t in regions["tensors"]:
+        n = t["plane"]
+        if rank > 0:          # my first plane is the previous rank's AFTER halo; its last plane is my BEFORE halo
+            opsl.append(dist.P2POp(dist.isend, ws[t["first"]:t["first"] + n], rank - 1, group))
+            opsl.append(dist.P2POp(dist.irecv, ws[t["before"]:t["before"] + n], rank - 1, group))
+        if rank < world - 1:
+            opsl.append(dist.P2POp(dist.isend, ws[t["last"]:t["last"] + n], rank + 1, group))
+            opsl.append(dist.P2POp(dist.irecv, ws[t["after"]:t["after"] + n], rank + 1, group))
+    if opsl:
+        for req in dist.batch_isend_irecv(opsl):
+            req.wait()
+
+
+class DSlabHotPath:
+    """feats [N,Hf,Wf,32] + cams -> depth map + probability map with the volume's depth split over the ranks of
+    `group`.  Every rank calls infer() with the same inputs and gets the same maps."""
+
+    def __init__(self, n_views, depth_num, hf, wf, weights, channels=32, order="mem", inverse_depth=False, bn_eps=1e-5,
+                 device="cuda", group=None):
+        from .engine import RegnetWeights
+        self.lib = L.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.begin, self.end = slab_range(depth_num, self.rank, self.world)
+        self.device = torch.device(device)
+        self.n_views, self.depth_num, self.hf, self.wf, self.channels = n_views, depth_num, hf, wf, channels
+        self.order = ops._ORDER[order]
+        self.inverse_depth = int(bool(inverse_depth))
+        self.bn_eps = float(bn_eps)
+        self.weights = weights if isinstance(weights, RegnetWeights) else RegnetWeights(weights, self.device)
+        self.base_filter = self.weights.base_filter
+        nbytes = self.lib.mvsb200_slab_workspace_bytes(n_views, depth_num, self.world, hf, wf, channels, self.base_filter)
+        if nbytes == 0:
+            raise L.MVSB200Error("slab_workspace_bytes rejected the shape: " + L.last_error())
+        self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        self.regions = [layer_regions(i, n_views, depth_num, self.world, hf, wf, channels, self.base_filter)
+                        for i in range(N_LAYERS)]
+        self.filtered = torch.empty((depth_num, hf, wf), dtype=torch.float32, device=self.device)
+
+    def infer(self, feats: torch.Tensor, cams: torch.Tensor, depth_start: float, depth_interval: float):
+        L.require_cuda(feats, cams)
+        args = (self.n_views, self.depth_num, self.rank, self.world, self.hf, self.wf, self.channels)
+        rc = self.lib.mvsb200_slab_begin(L.ptr(feats.contiguous()), L.ptr(cams.contiguous()), *args,
+                                         float(depth_start), float(depth_interval), self.inverse_depth, self.order,
+                                         ctypes.byref(self.weights.params), self.base_filter, L.ptr(self.ws),
+                                         self.ws.numel(), L.stream_ptr())
+        L.check(rc, "slab_begin")
+        for layer in range(N_LAYERS):
+            rc = self.lib.mvsb200_slab_layer(layer, *args, ctypes.byref(self.weights.params), self.base_filter,
+                                             self.bn_eps, L.ptr(self.ws), L.stream_ptr())
+            L.check(rc, f"slab_layer {layer}")
+            if layer != N_LAYERS - 1:
+                exchange_layer(self.ws, self.regions[layer], self.rank, self.world, self.group)
+        off, nbytes = self.regions[N_LAYERS - 1]["filtered"]
+        mine = self.ws[off:off + nbytes].view(torch.float32)
+        dist.all_gather_into_tensor(self.filtered.view(-1), mine, group=self.group)
+        return ops.depth_regress(self.filtered, depth_start, depth_interval, bool(self.inverse_depth))

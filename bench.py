@@ -43,42 +43,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML polled from a thread every few
+    milliseconds (the timed region of 20 steps is ~60 ms, too short for `nvidia-smi -lms`), nvidia-smi as a fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.thread, self.stop_flag, self.nvml, self.max_mhz = index, [], None, False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+        self.stop_flag = False
+        self.thread = threading.Thread(target=self._poll if self.nvml else self._poll_smi, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(
+                    n, "nvmlDeviceGetCurrentClocksEventReasons") else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
+    def _poll_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.max_mhz = float(out[1])
+                self.rows.append((float(out[0]), int(out[2].strip(), 16)))
+            except Exception:
+                time.sleep(0.05)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no clock samples"], "samples": 0}
+        sm = [r[0] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        reasons = [name for name, mask in self.REASONS if bits & mask]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -123,7 +145,7 @@ def run_reference(args, rank, world):
     value = frac / float(np.mean(ts))          # whole depth maps per second, per-voxel cost is plane-independent
     V = cfg["depth_num"] * (cfg["height"] // 4) * (cfg["width"] // 4)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 0, "steps": len(ts),
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts),
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * float(np.mean(ts)) / frac, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, cfg), "gvox_per_s": value * V / 1e9},
@@ -296,6 +318,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3, help="cap on timed CPU-reference steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.cpu_planes = max(8, (args.cpu_planes + 7) // 8 * 8)      # RegNetUS0 halves the depth three times
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

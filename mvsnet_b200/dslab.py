@@ -50,12 +50,22 @@ def layer_regions(layer: int, n_views: int, depth_num: int, world: int, hf: int,
     return dict(stats=(v[0], v[1]), tensors=tensors, filtered=(v[12], v[13]))
 
 
-def exchange_layer(ws: torch.Tensor, regions: dict, rank: int, world: int, group=None) -> None:
+# RegNetUS0 data flow (mvsnetworks.py:131-158): producers whose exchanged outputs / statistics layer i reads
+LAYER_INPUTS = {0: [], 1: [0], 2: [1], 3: [], 4: [0], 5: [1], 6: [2], 7: [6], 8: [7, 5], 9: [8, 4], 10: [9, 3]}
+# Execution order in slab mode: every layer directly after a layer it does NOT depend on where possible, so that
+# the exchange of one layer's output runs under the next layer's kernels (3dconv1_0 | 3dconv0_1 | 3dconv2_0 | ...)
+SLAB_ORDER = [0, 3, 1, 4, 2, 5, 6, 7, 8, 9, 10]
+
+
+def exchange_layer(ws: torch.Tensor, regions: dict, rank: int, world: int, group=None, wait: bool = True):
     """All-reduce the layer's statistics and swap boundary planes with the neighbours.  `ws` is the flat uint8
-    workspace; everything happens in place."""
+    workspace; everything happens in place.  With wait=False the pending work handles are returned and the caller
+    waits on them before the first consumer of the layer runs."""
+    pending = []
     off, nbytes = regions["stats"]
     if nbytes:
-        dist.all_reduce(ws[off:off + nbytes].view(torch.float64), op=dist.ReduceOp.SUM, group=group)
+        w = dist.all_reduce(ws[off:off + nbytes].view(torch.float64), op=dist.ReduceOp.SUM, group=group, async_op=True)
+        pending.append(w)
     opsl: List[dist.P2POp] = []
     for t in regions["tensors"]:
         n = t["plane"]
@@ -66,8 +76,12 @@ def exchange_layer(ws: torch.Tensor, regions: dict, rank: int, world: int, group
             opsl.append(dist.P2POp(dist.isend, ws[t["last"]:t["last"] + n], rank + 1, group))
             opsl.append(dist.P2POp(dist.irecv, ws[t["after"]:t["after"] + n], rank + 1, group))
     if opsl:
-        for req in dist.batch_isend_irecv(opsl):
-            req.wait()
+        pending.extend(dist.batch_isend_irecv(opsl))
+    if wait:
+        for w in pending:
+            w.wait()
+        return []
+    return pending
 
 
 class DSlabHotPath:
@@ -104,12 +118,20 @@ class DSlabHotPath:
                                          ctypes.byref(self.weights.params), self.base_filter, L.ptr(self.ws),
                                          self.ws.numel(), L.stream_ptr())
         L.check(rc, "slab_begin")
-        for layer in range(N_LAYERS):
+        pending = {}
+        for layer in SLAB_ORDER:
+            for src in LAYER_INPUTS[layer]:                 # the exchanges this layer reads must have landed
+                for w in pending.pop(src, []):
+                    w.wait()
             rc = self.lib.mvsb200_slab_layer(layer, *args, ctypes.byref(self.weights.params), self.base_filter,
                                              self.bn_eps, L.ptr(self.ws), L.stream_ptr())
             L.check(rc, f"slab_layer {layer}")
             if layer != N_LAYERS - 1:
-                exchange_layer(self.ws, self.regions[layer], self.rank, self.world, self.group)
+                pending[layer] = exchange_layer(self.ws, self.regions[layer], self.rank, self.world, self.group,
+                                                wait=False)
+        for works in pending.values():
+            for w in works:
+                w.wait()
         off, nbytes = self.regions[N_LAYERS - 1]["filtered"]
         mine = self.ws[off:off + nbytes].view(torch.float32)
         dist.all_gather_into_tensor(self.filtered.view(-1), mine, group=self.group)

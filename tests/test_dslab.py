@@ -104,3 +104,14 @@ def test_exchange_over_gloo(world):
         assert p.exitcode == 0
     got = sorted(q.get(timeout=10) for _ in range(world))
     assert got == [(r, True) for r in range(world)]
+
+
+def test_slab_schedule_respects_the_data_flow():
+    """Every layer runs after its producers; the schedule covers each layer once."""
+    assert sorted(dslab.SLAB_ORDER) == list(range(dslab.N_LAYERS))
+    done = set()
+    for layer in dslab.SLAB_ORDER:
+        assert all(src in done for src in dslab.LAYER_INPUTS[layer]), layer
+        done.add(layer)
+    # the table mirrors the reference graph: skip adds feed 3dconv5_0 / 6_0 / 6_2 (mvsnetworks.py:148-157)
+    assert dslab.LAYER_INPUTS[8] == [7, 5] and dslab.LAYER_INPUTS[9] == [8, 4] and dslab.LAYER_INPUTS[10] == [9, 3]

@@ -172,20 +172,23 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
           // of (x0, x0+1) in [0, Wf] (either pixel may be the zero guard; its weight is 0 there)
           const int xp = min(max(f.x0 + 1, 0), Wf);
           const unsigned vbase = (unsigned)(v + 1) * (unsigned)(Hf * (Wf + 1));
+          const unsigned off0 = (vbase + (unsigned)(cy0 * (Wf + 1) + xp)) * 128u;
+          const unsigned off1 = (vbase + (unsigned)(cy1 * (Wf + 1) + xp)) * 128u;
           if (HINT) {
-            const __half2 h00 = __float2half2_rn(l_wyl * l_wxl), h01 = __float2half2_rn(l_wyl * l_wxr);
-            const __half2 h10 = __float2half2_rn(l_wyr * l_wxl), h11 = __float2half2_rn(l_wyr * l_wxr);
+            // one 16-byte record per footprint (a 128-bit shared load costs 4 data-pipe wavefronts per warp whatever
+            // it broadcasts, so the weights travel as four halves next to the two offsets)
+            const __half2 hx = __floats2half2_rn(l_wyl * l_wxl, l_wyl * l_wxr);
+            const __half2 hy = __floats2half2_rn(l_wyr * l_wxl, l_wyr * l_wxr);
             float4 packed;
-            packed.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h00));
-            packed.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h01));
-            packed.z = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h10));
-            packed.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h11));
+            packed.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hx));
+            packed.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hy));
+            packed.z = __uint_as_float(off0);
+            packed.w = __uint_as_float(off1);
             s_fw[p][g] = packed;
           } else {
             s_fw[p][g] = make_float4(l_wyl * l_wxl, l_wyl * l_wxr, l_wyr * l_wxl, l_wyr * l_wxr);
+            s_fi[p][g] = make_int2((int)off0, (int)off1);
           }
-          s_fi[p][g] = make_int2((int)((vbase + (unsigned)(cy0 * (Wf + 1) + xp)) * 128u),
-                                 (int)((vbase + (unsigned)(cy1 * (Wf + 1) + xp)) * 128u));
         } else {
           s_fw[p][g] = make_float4(l_wxl, l_wxr, l_wyl, l_wyr);
           s_fi[p][g] = make_int2(cx0 | (cx1 << 16), cy0 | (cy1 << 16));
@@ -197,14 +200,16 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
         constexpr int kdc = KDC;
         const int dd = j % kdc;                       // compile-time after unrolling
         const float4 fw = s_fw[p][j];
-        const int2 fi = s_fi[p][j];
+        int2 fi;
+        if (TAPS16 && HINT) fi = make_int2(__float_as_int(fw.z), __float_as_int(fw.w));
+        else fi = s_fi[p][j];
         float4 w;
         if (TAPS16) {
           const uint4 a = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.x));
           const uint4 b = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.y));
           if (HINT) {
-            const __half2 w00 = *reinterpret_cast<const __half2*>(&fw.x), w01 = *reinterpret_cast<const __half2*>(&fw.y);
-            const __half2 w10 = *reinterpret_cast<const __half2*>(&fw.z), w11 = *reinterpret_cast<const __half2*>(&fw.w);
+            const __half2 hx = *reinterpret_cast<const __half2*>(&fw.x), hy = *reinterpret_cast<const __half2*>(&fw.y);
+            const __half2 w00 = __low2half2(hx), w01 = __high2half2(hx), w10 = __low2half2(hy), w11 = __high2half2(hy);
             const __half2 hlo = __hfma2(w11, *reinterpret_cast<const __half2*>(&b.z),
                                 __hfma2(w10, *reinterpret_cast<const __half2*>(&b.x),
                                 __hfma2(w01, *reinterpret_cast<const __half2*>(&a.z),

@@ -177,6 +177,11 @@ int mvsb200_infer(const float* feats, const float* cams, int n_views, int depth_
                   int precision, float* depth_map, float* prob_map, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Byte offsets, inside the mvsb200_infer workspace, of the cost volume in the regularizer's planar layouts
+ * (bf16 mode): chunk-planar [D][C/8][Hf][Wf][8] and parity-split [D][C/8][4][Hf/2][Wf/2][8] bf16. */
+int mvsb200_infer_cost_offsets(int n_views, int depth_num, int hf, int wf, int channels, int base_filter,
+                               int precision, size_t* cp8_offset, size_t* ps8_offset);
+
 /* Optional instrumentation: five cudaEvent_t handles recorded by mvsb200_infer on its stream at the
  * stage boundaries (start, after homographies, after cost volume, after regularizer, after regression);
  * NULL switches it off.  Per calling thread. */

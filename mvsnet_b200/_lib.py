@@ -63,6 +63,7 @@ SIGNATURES = {
                                    _P, c_int, _P, c_size_t, _P]),
     "mvsb200_slab_layer": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P]),
     "mvsb200_slab_regions": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mvsb200_infer_cost_offsets": (c_int, [c_int] * 7 + [_P, _P]),
     "mvsb200_infer_host_staging_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mvsb200_infer_host": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
                                    POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),

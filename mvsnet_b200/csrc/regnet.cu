@@ -617,6 +617,23 @@ extern "C" size_t mvsb200_infer_workspace_bytes(int n_views, int depth_num, int 
   return ip.total;
 }
 
+// Byte offsets, inside the whole-path workspace, of the cost volume in the regularizer's planar layouts (bf16 mode;
+// tests and inspection)
+extern "C" int mvsb200_infer_cost_offsets(int n_views, int depth_num, int hf, int wf, int channels, int base_filter,
+                                          int precision, size_t* cp8_offset, size_t* ps8_offset) {
+  MVS_CHECK_ARG(cp8_offset && ps8_offset && precision == MVSB200_PRECISION_BF16, "infer_cost_offsets: bf16 mode only");
+  MVS_CHECK_ARG(n_views >= 2, "infer_cost_offsets: n_views must be >= 2");
+  int rc = check_regnet_shape(depth_num, hf, wf, channels, base_filter);
+  if (rc) return rc;
+  InferPlan ip;
+  make_infer_plan(n_views, depth_num, hf, wf, channels, base_filter, precision, &ip);
+  RegnetPlan p;
+  make_plan(depth_num, hf, wf, channels, base_filter, precision, &p);
+  *cp8_offset = ip.regnet_off + p.cost_cp8_off;
+  *ps8_offset = ip.regnet_off + p.cost_ps8_off;
+  return MVSB200_OK;
+}
+
 extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views, int depth_num, int hf, int wf,
                              int channels, float depth_start, float depth_interval, int inverse_depth, int order,
                              int sampler, const mvsb200_regnet_params* params, int base_filter, float bn_eps,

@@ -142,6 +142,19 @@ class HotPath:
         L.check(self.lib.mvsb200_infer_set_stage_events(arr), "set_stage_events")
 
     # -- stages (tests, profiling) ---------------------------------------------------------------------
+    def cost_volume_planar(self, feats: torch.Tensor, cams: torch.Tensor, depth_start: float, depth_interval: float):
+        """Run the whole path once and return views of the cost volume inside the workspace in the regularizer's two
+        layouts: CP8 [D, C/8, Hf, Wf, 8] and PS8 [D, C/8, 4, Hf/2, Wf/2, 8] (bf16 mode, even Hf / Wf)."""
+        self.infer(feats, cams, depth_start, depth_interval)
+        cp8_off, ps8_off = ctypes.c_size_t(), ctypes.c_size_t()
+        L.check(self.lib.mvsb200_infer_cost_offsets(self.n_views, self.depth_num, self.hf, self.wf, self.channels,
+                                                    self.base_filter, self.precision, ctypes.byref(cp8_off),
+                                                    ctypes.byref(ps8_off)), "infer_cost_offsets")
+        n = self.depth_num * self.hf * self.wf * self.channels * 2
+        cp8 = self.workspace[cp8_off.value:cp8_off.value + n].view(torch.bfloat16)
+        ps8 = self.workspace[ps8_off.value:ps8_off.value + n].view(torch.bfloat16)
+        return cp8, ps8
+
     def regnet(self, cost: torch.Tensor) -> torch.Tensor:
         d, hf, wf, c = cost.shape
         nbytes = self.lib.mvsb200_regnet_workspace_bytes(d, hf, wf, c, self.base_filter, self.precision)

@@ -195,6 +195,8 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
         }
         __syncwarp();
       }
+      uint4 ta = make_uint4(0u, 0u, 0u, 0u), tb = ta;
+      int2 prev_fi = make_int2(-1, -1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         constexpr int kdc = KDC;
@@ -205,8 +207,13 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
         else fi = s_fi[p][j];
         float4 w;
         if (TAPS16) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.x));
-          const uint4 b = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.y));
+          // consecutive planes of a pixel often fall into the same source cell (the sample moves a fraction of a
+          // pixel per plane): the second plane of the pair then reuses the taps already in registers (a predicated
+          // load makes no L1 traffic for the lanes that skip it)
+          if (!(HINT && kdc == 2 && (j & 1) && fi.x == prev_fi.x)) ta = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.x));
+          if (!(HINT && kdc == 2 && (j & 1) && fi.y == prev_fi.y)) tb = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.y));
+          prev_fi = fi;
+          const uint4 a = ta, b = tb;
           if (HINT) {
             const __half2 hx = *reinterpret_cast<const __half2*>(&fw.x), hy = *reinterpret_cast<const __half2*>(&fw.y);
             const __half2 w00 = __low2half2(hx), w01 = __high2half2(hx), w10 = __low2half2(hy), w11 = __high2half2(hy);

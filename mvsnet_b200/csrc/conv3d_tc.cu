@@ -42,6 +42,7 @@
 // the filter), plane dz starts at g = zf+1-dz.
 #include "common.cuh"
 #include "umma.cuh"
+#include "conv3d_tc.h"
 #include <cuda.h>
 #include <stdlib.h>
 #include <array>
@@ -53,13 +54,6 @@ using namespace umma;
 
 // Batch-norm source of an input tensor: the producer's channel statistics (sum | sum of squares over `count`
 // voxels) and its gamma / beta.  The consumer derives scale / shift itself (no bn_finalize launch in between).
-// D-slab mode (one volume split along z over several GPUs): the input (and skip) tensor carries one halo plane
-// before and after the D local planes; planes outside [zv_lo, zv_hi) (extended coordinates) are SAME padding.
-struct TcSlab { int halo; int zv_lo; int zv_hi; };
-
-struct TcBnSrc { const double* stats; const float* gamma; const float* beta; double count; float eps; int channels;
-                 int reps; int rep_stride; };   // statistics are the sum of `reps` partial copies, rep_stride doubles apart
-
 namespace tc {
 
 constexpr int kMaxOps = 108;            // 27 taps x (64 channels / 16)
@@ -1381,9 +1375,6 @@ __global__ void pack_all_kernel(const __grid_constant__ PackAll a) {
   }
 }
 
-// One job per layer; its launches (output-channel slices of 32) take consecutive slots starting at slot0.
-struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0; };
-
 int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStream_t s) {
   static PackAll a;      // too large for the stack of some callers; filled and consumed under the launch below
   static std::mutex mu;
@@ -1642,6 +1633,22 @@ int launch_f32_to_bf16(const float* x, size_t n, void* y, cudaStream_t s) {
   return MVSB200_OK;
 }
 
+namespace {
+// stream-ordered temporaries of the stand-alone entry point, released on every exit path
+struct StreamTemps {
+  cudaStream_t s;
+  void* ptr[8];
+  int n = 0;
+  explicit StreamTemps(cudaStream_t stream) : s(stream) {}
+  ~StreamTemps() { for (int i = 0; i < n; ++i) cudaFreeAsync(ptr[i], s); }
+  cudaError_t alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes, s);
+    if (e == cudaSuccess) ptr[n++] = *p;
+    return e;
+  }
+};
+}  // namespace
+
 // Stand-alone layer on NDHWC tensors (mvsb200_conv3d_layer, tests): converts to the planar layouts in
 // stream-ordered temporaries, runs the layer, converts back.  The fused path never comes through here.
 int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
@@ -1650,32 +1657,28 @@ int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, cons
   const bool s2 = !transposed && stride == 2;
   const int Do = transposed ? 2 * D : ceil_div(D, stride), Ho = transposed ? 2 * H : ceil_div(H, stride),
             Wo = transposed ? 2 * W : ceil_div(W, stride);
+  MVS_CHECK_ARG(cin % 8 == 0, "conv3d(bf16/tcgen05): Cin must be a multiple of 8 (got %d)", cin);
+  StreamTemps tmp(s);
   void *xp = nullptr, *kp = nullptr, *yp = nullptr, *scratch = nullptr;
   float* yf = nullptr;
-  MVS_CHECK_ARG(cin % 8 == 0, "conv3d(bf16/tcgen05): Cin must be a multiple of 8 (got %d)", cin);
-  MVS_CUDA(cudaMallocAsync(&xp, planar_bytes(D, H, W, cin, s2), s));
-  MVS_CUDA(cudaMallocAsync(&scratch, conv3d_tc_scratch_bytes(), s));
+  MVS_CUDA(tmp.alloc(&xp, planar_bytes(D, H, W, cin, s2)));
+  MVS_CUDA(tmp.alloc(&scratch, conv3d_tc_scratch_bytes()));
   int rc = launch_ndhwc_to_planar(x, D, H, W, cin, s2 ? nullptr : xp, s2 ? xp : nullptr, s);
-  if (!rc && skip) {
-    MVS_CUDA(cudaMallocAsync(&kp, planar_bytes(D, H, W, cin, 0), s));
-    rc = launch_ndhwc_to_planar(skip, D, H, W, cin, kp, nullptr, s);
+  if (rc) return rc;
+  if (skip) {
+    MVS_CUDA(tmp.alloc(&kp, planar_bytes(D, H, W, cin, 0)));
+    if ((rc = launch_ndhwc_to_planar(skip, D, H, W, cin, kp, nullptr, s))) return rc;
   }
   const bool direct_f32 = y_dtype == MVSB200_F32;
-  const bool via_f32 = !direct_f32 && cout % 8 != 0;
-  if (!rc) {
-    if (direct_f32) yf = (float*)y;
-    else if (via_f32) MVS_CUDA(cudaMallocAsync((void**)&yf, (size_t)Do * Ho * Wo * cout * sizeof(float), s));
-    else MVS_CUDA(cudaMallocAsync(&yp, planar_bytes(Do, Ho, Wo, cout, 0), s));
-    rc = launch_conv3d_tc(xp, xs, xb, kp, ss, sb, kernel_tf, D, H, W, cin, cout, stride, transposed, yp, nullptr, yf,
-                          stats, scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, s);
-  }
-  if (!rc && yp) rc = launch_planar_to_ndhwc(yp, Do, Ho, Wo, cout, y, s);
-  if (!rc && via_f32) rc = launch_f32_to_bf16(yf, (size_t)Do * Ho * Wo * cout, y, s);
-  if (xp) cudaFreeAsync(xp, s);
-  if (kp) cudaFreeAsync(kp, s);
-  if (yp) cudaFreeAsync(yp, s);
-  if (via_f32 && yf) cudaFreeAsync(yf, s);
-  if (scratch) cudaFreeAsync(scratch, s);
+  const bool via_f32 = !direct_f32 && cout % 8 != 0;        // bf16 NDHWC with a ragged channel count: via fp32
+  if (direct_f32) yf = (float*)y;
+  else if (via_f32) MVS_CUDA(tmp.alloc((void**)&yf, (size_t)Do * Ho * Wo * cout * sizeof(float)));
+  else MVS_CUDA(tmp.alloc(&yp, planar_bytes(Do, Ho, Wo, cout, 0)));
+  rc = launch_conv3d_tc(xp, xs, xb, kp, ss, sb, kernel_tf, D, H, W, cin, cout, stride, transposed, yp, nullptr, yf, stats,
+                        scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, s);
+  if (rc) return rc;
+  if (yp) rc = launch_planar_to_ndhwc(yp, Do, Ho, Wo, cout, y, s);
+  else if (via_f32) rc = launch_f32_to_bf16(yf, (size_t)Do * Ho * Wo * cout, y, s);
   return rc;
 }
 

@@ -1,11 +1,12 @@
 // RegNetUS0 forward (mvsnetworks.py:122-158) and the whole-path entry points.
 //
 // Data flow: every conv / deconv layer writes its RAW (pre-BN) output plus per-channel
-// sum / sum-of-squares; bn_finalize turns those into (scale, shift); the consumer applies
-// relu(raw*scale+shift) (and the skip add) while reading its input.  No normalised tensor is
-// ever written back to HBM.  BN uses batch statistics, as the reference does at inference
-// (network.py:54,64; model.py:337-338; SURVEY.md "facts").
+// sum / sum-of-squares; the consumer turns those into (scale, shift) (fp32 mode: a bn_finalize launch;
+// bf16 mode: inside the consumer's prologue) and applies relu(raw*scale+shift) (and the skip add) while
+// reading its input.  No normalised tensor is ever written back to HBM.  BN uses batch statistics, as the
+// reference does at inference (network.py:54,64; model.py:337-338; SURVEY.md "facts").
 #include "common.cuh"
+#include "conv3d_tc.h"
 #include <stdlib.h>
 
 namespace mvsb200 {
@@ -13,28 +14,10 @@ namespace mvsb200 {
 int launch_conv3d_direct(const void* x, int x_dtype, const float* xs, const float* xb, const void* skip,
                          const float* ss, const float* sb, const float* kernel_tf, int D, int H, int W, int cin,
                          int cout, int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);
-// conv3d_tc.cu: bf16 tcgen05 layers on the planar activation layouts (CP8 / PS8, see that file)
-struct TcBnSrc { const double* stats; const float* gamma; const float* beta; double count; float eps; int channels;
-                 int reps; int rep_stride; };
-struct TcSlab { int halo; int zv_lo; int zv_hi; };
-struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0; };
-int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
-                     const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
-                     int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
-                     const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
-                     int stats_rep_stride, const TcSlab* slab, cudaStream_t s);
-int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStream_t s);
-size_t conv3d_tc_pack_slot_bytes();
 int launch_bn_finalize_all(const double* stats, const float* const* gamma, const float* const* beta, const int* channels,
                            const double* counts, int layers, int cpad, int reps, float eps, float* scale, float* shift,
                            cudaStream_t s);
 constexpr int kStatsReps = 16;      // partial copies of every layer's statistics (bf16 mode), summed by the consumers
-int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
-                           const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout,
-                           int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);
-size_t conv3d_tc_scratch_bytes();
-size_t planar_bytes(int D, int H, int W, int C, int parity_split);
-int launch_ndhwc_to_planar(const void* x_ndhwc, int D, int H, int W, int C, void* cp8, void* ps8, cudaStream_t s);
 
 int launch_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const float* x_shift, const void* skip,
                         const float* skip_scale, const float* skip_shift, const float* kernel_tf, int depth,
@@ -319,10 +302,6 @@ extern "C" int mvsb200_conv3d_layer(const void* x, int x_dtype, const float* x_s
                              (cudaStream_t)stream);
 }
 
-namespace mvsb200 {
-int conv3d_tc_describe(int D, int H, int W, int cin, int cout, int stride, int transposed, int has_skip, int transform,
-                       int sm_count, int* out, char* text, int text_len);
-}
 extern "C" int mvsb200_conv3d_plan(int depth, int height, int width, int cin, int cout, int stride, int transposed,
                                    int has_skip, int transform, int sm_count, int* numbers, char* text, int text_len) {
   return conv3d_tc_describe(depth, height, width, cin, cout, stride, transposed, has_skip, transform, sm_count, numbers,
@@ -671,7 +650,6 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
     void *cp8 = nullptr, *ps8 = nullptr;
     regnet_cost_planar(ws + ip.regnet_off, depth_num, hf, wf, channels, base_filter, &cp8, &ps8);
     static const bool fp32_taps = getenv("MVSB200_CV_FP32_TAPS") != nullptr;
-    if (getenv("MVSB200_CV_NO_PS8")) ps8 = nullptr;      // timing experiment only (3dconv1_0 then reads stale data)
     rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8,
                                    fp32_taps ? nullptr : ws + ip.pair_off, coefs, s);
   } else {

@@ -103,6 +103,7 @@ struct Params {
   int ring_pad;                  // zeroed bytes after the last slot (rows of the last block may read past their plane)
   int xf_k;                      // cells per transform thread and plane
   int dz_begin[kMaxSpan + 1];    // ops [dz_begin[d], dz_begin[d+1]) read input plane d of the step
+  int pdl;                       // programmatic dependent launch: 1 = let the next layer start at CTA start, 2 = at CTA end
   int dbg;                       // development switches (env MVSB200_TC_DBG): 1 no loads, 2 no MMA, 4 no stores
   long long* prof;               // development: per-role cycle counters of CTA 0 (env MVSB200_TC_PROF)
   UmmaOp ops[kMaxOps];
@@ -306,21 +307,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       s_ops[i] = make_uint4(e.a_lo, e.b_lo + b16, e.meta & 0xFFFFu, ((e.meta >> 16) & 1u) ^ 1u);
     }
     if (threadIdx.x <= kMaxSpan) s_dzb[threadIdx.x] = p.dz_begin[threadIdx.x];
-    // BN scale / shift of the input (and skip) channels, one thread per channel (fp64 moments are slow: not per
-    // transform thread)
-    if (threadIdx.x < 2 * p.Cin) {
-      const int c = threadIdx.x % p.Cin, which = threadIdx.x / p.Cin;
-      float sc = 1.0f, sh = 0.0f;
-      if (which == 0) {
-        if (p.xbn.stats) bn_scale_shift(p.xbn, c, sc, sh);
-        else if (p.xs) { sc = p.xs[c]; sh = p.xb[c]; }
-      } else {
-        if (p.sbn.stats) bn_scale_shift(p.sbn, c, sc, sh);
-        else if (p.ss) { sc = p.ss[c]; sh = p.sb[c]; }
-      }
-      s_aff[which * 128 + c] = sc;
-      s_aff[which * 128 + 64 + c] = sh;
-    }
   }
   // Every cell of the ring starts finite: halo rows of the GEMM read a few cells past the landed boxes
   // (their results are dropped, but 0 * NaN from stale shared memory must not reach a zero-weighted
@@ -338,6 +324,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   if (warp == kMmaWarp) {
     tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
     tmem_relinquish();
+  }
+  // Programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; from
+  // here on its outputs (statistics, activations) are read.  A single-wave grid lets the next kernel's CTAs take
+  // over SMs as they free up; a multi-wave grid only triggers at CTA end (its own waiting CTAs must get the SMs).
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  {
+    // BN scale / shift of the input (and skip) channels, one thread per channel (fp64 moments are slow: not per
+    // transform thread)
+    if (threadIdx.x < 2 * p.Cin) {
+      const int c = threadIdx.x % p.Cin, which = threadIdx.x / p.Cin;
+      float sc = 1.0f, sh = 0.0f;
+      if (which == 0) {
+        if (p.xbn.stats) bn_scale_shift(p.xbn, c, sc, sh);
+        else if (p.xs) { sc = p.xs[c]; sh = p.xb[c]; }
+      } else {
+        if (p.sbn.stats) bn_scale_shift(p.sbn, c, sc, sh);
+        else if (p.ss) { sc = p.ss[c]; sh = p.sb[c]; }
+      }
+      s_aff[which * 128 + c] = sc;
+      s_aff[which * 128 + 64 + c] = sh;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -870,6 +880,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.pdl == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (p.prof && threadIdx.x == 0) {
     long long g2;
@@ -1508,18 +1519,32 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     // SMs re-partition L1 / shared memory between launches
     static const bool exact_smem = getenv("MVSB200_TC_EXACT_SMEM") != nullptr;
     const size_t smem_launch = exact_smem ? best.smem : kSmemBudget;
+    // programmatic dependent launch (prologue of this layer under the tail of the previous kernel)
+    static const bool no_pdl = getenv("MVSB200_TC_NO_PDL") != nullptr;
+    c.pdl = no_pdl ? 0 : (grid <= sm_count ? 1 : 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_launch; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = c.pdl ? 1 : 0;
+    cudaError_t lerr = cudaSuccess;
     auto launch = [&]() {
       if (c.xfold) {
-        if (c.cout_n <= 8) conv3d_tc_kernel<32, 1><<<grid, kThreads, smem_launch, s>>>(c);
-        else if (c.cout_n <= 16) conv3d_tc_kernel<32, 2><<<grid, kThreads, smem_launch, s>>>(c);
-        else conv3d_tc_kernel<32, 4><<<grid, kThreads, smem_launch, s>>>(c);
+        if (c.cout_n <= 8) lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<32, 1>, c);
+        else if (c.cout_n <= 16) lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<32, 2>, c);
+        else lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<32, 4>, c);
       } else if (c.CP == 16) {
-        conv3d_tc_kernel<16, 0><<<grid, kThreads, smem_launch, s>>>(c);
+        lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<16, 0>, c);
       } else {
-        conv3d_tc_kernel<32, 0><<<grid, kThreads, smem_launch, s>>>(c);
+        lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<32, 0>, c);
       }
     };
     launch();
+    if (lerr != cudaSuccess) {
+      set_error("launch of conv3d_tc_kernel failed: %s", cudaGetErrorString(lerr));
+      return MVSB200_ERR_CUDA;
+    }
     MVS_LAUNCH_CHECK("conv3d_tc_kernel");
     if (c.prof) {
       long long h[17];

@@ -238,6 +238,26 @@ int mvsb200_slab_layer(int layer, int n_views, int depth_num, int slab, int slab
 int mvsb200_slab_regions(int layer, int n_views, int depth_num, int slabs, int hf, int wf, int channels,
                          int base_filter, unsigned long long* out);
 
+/* D-slab mode with the exchange fused into the kernels (peer memory over NVLink, no collective between layers).
+ * The slab workspaces live in IPC-exportable memory (mvsb200_ipc_*) and every rank maps all of them:
+ * peers_dev / peers_host = the same `slabs` base addresses as a device array and a host array (own workspace at
+ * index `slab`).  The layer's epilogue also stores its boundary planes into the neighbours' halo planes, a one-block
+ * kernel publishes its statistics into every rank's per-source table and raises flag (layer, slab) = seq on every
+ * rank, and a consuming kernel first waits (bounded spin) until all ranks have published the layers it reads.
+ * seq = 1, 2, 3, ... per inference; the caller puts a cross-rank barrier (e.g. the final all-gather) between
+ * inferences.  mvsb200_slab_p2p_error returns 1 (and clears it) if a wait timed out. */
+int mvsb200_slab_layer_p2p(int layer, int n_views, int depth_num, int slab, int slabs, int hf, int wf, int channels,
+                           const mvsb200_regnet_params* params, int base_filter, float bn_eps, void* workspace,
+                           void* const* peers_dev, void* const* peers_host, unsigned seq, void* stream);
+int mvsb200_slab_p2p_error(int n_views, int depth_num, int slabs, int hf, int wf, int channels, int base_filter,
+                           void* workspace, void* stream);
+/* cudaMalloc'ed, zeroed device memory and its CUDA-IPC handle (64 bytes) / mapping in another process */
+int mvsb200_ipc_alloc(size_t bytes, void** ptr);
+int mvsb200_ipc_free(void* ptr);
+int mvsb200_ipc_export(void* ptr, unsigned char* handle64);
+int mvsb200_ipc_open(const unsigned char* handle64, void** ptr);
+int mvsb200_ipc_close(void* ptr);
+
 /* Diagnostic (not on the product path): one 128 x n x (16*kblocks) tcgen05.mma tile computed from
  * caller-built shared-memory images of the A and B operands (no-swizzle K-major core-matrix
  * layout).  Pins the descriptor semantics conv3d_tc.cu relies on.  d_out [128*n] fp32. */

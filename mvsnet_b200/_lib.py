@@ -62,6 +62,14 @@ SIGNATURES = {
     "mvsb200_slab_begin": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int,
                                    _P, c_int, _P, c_size_t, _P]),
     "mvsb200_slab_layer": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P]),
+    "mvsb200_slab_layer_p2p": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P, _P,
+                                       ctypes.c_uint, _P]),
+    "mvsb200_slab_p2p_error": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "mvsb200_ipc_alloc": (c_int, [c_size_t, _P]),
+    "mvsb200_ipc_free": (c_int, [_P]),
+    "mvsb200_ipc_export": (c_int, [_P, _P]),
+    "mvsb200_ipc_open": (c_int, [_P, _P]),
+    "mvsb200_ipc_close": (c_int, [_P]),
     "mvsb200_slab_regions": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mvsb200_infer_cost_offsets": (c_int, [c_int] * 7 + [_P, _P]),
     "mvsb200_infer_host_staging_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -81,6 +81,13 @@ struct Params {
   const uint4* wpacked;
   __nv_bfloat16* y_cp8; __nv_bfloat16* y_ps8; float* y_f32; double* stats;
   int stats_reps, stats_rep_stride;   // CTAs spread their atomics over `stats_reps` partial copies of the statistics
+  // D-slab mode with peer memory (NVLink): boundary planes of the output are ALSO stored into the neighbours'
+  // halo planes, [0] = chunk-planar, [1] = parity-split copy (NULL: no neighbour / not in that mode)
+  __nv_bfloat16* mir_prev[2];       // previous rank's AFTER-halo plane of this output tensor
+  __nv_bfloat16* mir_next[2];       // next rank's BEFORE-halo plane
+  // ... and the kernel waits, before it reads anything, until every rank has published the layers it consumes
+  const unsigned* wait_flags[2];    // per producer layer: `wait_n` words, one per rank (NULL: nothing to wait for)
+  int wait_n; unsigned wait_seq; unsigned* err_flag;
   int mode, has_skip, transform;
   int D, H, W, Cin;              // input volume
   int Do, Ho, Wo, Cout;          // output volume (all channels)
@@ -243,6 +250,19 @@ __device__ __forceinline__ void flush_stats(const Params& p, float (&sum)[NV], f
   }
 }
 
+// One 16-byte cell of the chunk-planar (cell index inside the plane, which = 0) or parity-split (which = 1) output;
+// boundary planes go to the neighbouring slabs' halo planes as well (peer memory over NVLink).
+__device__ __forceinline__ void store_cell(const Params& p, int which, int oz, int chunk, size_t plane_cells, size_t cell,
+                                           const uint4& pk) {
+  __nv_bfloat16* y = which ? p.y_ps8 : p.y_cp8;
+  const int ncho = p.Cout >> 3;
+  *reinterpret_cast<uint4*>(y + (((size_t)oz * ncho + chunk) * plane_cells + cell) * 8) = pk;
+  if (oz == 0 && p.mir_prev[which])
+    *reinterpret_cast<uint4*>(p.mir_prev[which] + ((size_t)chunk * plane_cells + cell) * 8) = pk;
+  if (oz == p.Do - 1 && p.mir_next[which])
+    *reinterpret_cast<uint4*>(p.mir_next[which] + ((size_t)chunk * plane_cells + cell) * 8) = pk;
+}
+
 // Issue the MMAs of ops [ob, oe) of one input plane: one 16-byte shared-memory record per op (the unrolled loop
 // prefetches them), the MB row blocks of an op reuse its descriptors (A start + 2 KB, next TMEM column group).
 template <int MB>
@@ -332,6 +352,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
+  // D-slab mode over peer memory: the layers this one consumes must have been published by EVERY rank (their
+  // statistics) -- which covers the two neighbours whose boundary planes landed in our halo planes.  One flag word
+  // per (layer, rank) holds the sequence number of the last published inference.  The spin is bounded.
+  if (p.wait_n > 0 && threadIdx.x < 2 * p.wait_n) {
+    const unsigned* f = p.wait_flags[threadIdx.x / p.wait_n];
+    if (f) {
+      f += threadIdx.x % p.wait_n;
+      const long long t0 = clock64();
+      for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int)(v - p.wait_seq) >= 0) break;
+        if (clock64() - t0 > 4000000000LL) { if (p.err_flag) atomicExch(p.err_flag, 1u); break; }
+        __nanosleep(200);
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");      // the halo planes are read by the TMA unit (async proxy)
+    }
+  }
+  __syncthreads();
   {
     // BN scale / shift of the input (and skip) channels, one thread per channel (fp64 moments are slow: not per
     // transform thread)
@@ -691,11 +730,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                     uint4 pk;
                     pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
                     pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-                    const size_t zc = (size_t)oz * ncho + chunk0 + ck;
-                    if (p.y_cp8) *reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + (size_t)oy * p.Wo + ox) * 8) = pk;
+                    if (p.y_cp8) store_cell(p, 0, oz, chunk0 + ck, zpitch, (size_t)oy * p.Wo + ox, pk);
                     if (p.y_ps8) {
                       const size_t pcell = ((size_t)((oy & 1) * 2 + (ox & 1)) * p.Hso + (oy >> 1)) * p.Wso + (ox >> 1);
-                      *reinterpret_cast<uint4*>(p.y_ps8 + (zc * 4 * (size_t)p.Hso * p.Wso + pcell) * 8) = pk;
+                      store_cell(p, 1, oz, chunk0 + ck, 4 * (size_t)p.Hso * p.Wso, pcell, pk);
                     }
                   }
                 }
@@ -773,9 +811,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                 c1.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
                 c1.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
                 c1.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
-                const size_t zc = (size_t)oz * ncho + chunk0;
-                uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
-                dst[0] = c0; dst[1] = c1;
+                store_cell(p, 0, oz, chunk0, zpitch, cell, c0);
+                store_cell(p, 0, oz, chunk0, zpitch, cell + 1, c1);
               } else {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -794,9 +831,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                     c1.y = pack_bf16x2(__uint_as_float(r[16 + k + 2]), __uint_as_float(r[16 + k + 3]));
                     c1.z = pack_bf16x2(__uint_as_float(r[16 + k + 4]), __uint_as_float(r[16 + k + 5]));
                     c1.w = pack_bf16x2(__uint_as_float(r[16 + k + 6]), __uint_as_float(r[16 + k + 7]));
-                    const size_t zc = (size_t)oz * ncho + chunk0 + (k >> 3);
-                    uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
-                    dst[0] = c0; dst[1] = c1;
+                    store_cell(p, 0, oz, chunk0 + (k >> 3), zpitch, cell, c0);
+                    store_cell(p, 0, oz, chunk0 + (k >> 3), zpitch, cell + 1, c1);
                   }
                 }
               }
@@ -860,10 +896,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   pk.y = pack_bf16x2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
                   pk.z = pack_bf16x2(__uint_as_float(r[k + 4]), __uint_as_float(r[k + 5]));
                   pk.w = pack_bf16x2(__uint_as_float(r[k + 6]), __uint_as_float(r[k + 7]));
-                  const size_t zc = (size_t)(oz + j) * ncho + chunk0 + (cn >> 3);
-                  if (p.y_cp8) *reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8) = pk;
-                  if (p.y_ps8)
-                    *reinterpret_cast<uint4*>(p.y_ps8 + (zc * 4 * (size_t)p.Hso * p.Wso + pcell) * 8) = pk;
+                  if (p.y_cp8) store_cell(p, 0, oz + j, chunk0 + (cn >> 3), zpitch, cell, pk);
+                  if (p.y_ps8) store_cell(p, 1, oz + j, chunk0 + (cn >> 3), 4 * (size_t)p.Hso * p.Wso, pcell, pk);
                 }
               }
             }
@@ -1427,7 +1461,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
                      const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
                      const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
-                     int stats_rep_stride, const TcSlab* slab, cudaStream_t s) {
+                     int stats_rep_stride, const TcSlab* slab, const TcPeer* peer, cudaStream_t s) {
   if (cin != 8 && cin != 16 && cin != 32 && cin != 64) {
     set_error("conv3d(bf16/tcgen05): Cin=%d unsupported (need 8, 16, 32 or 64)", cin);
     return MVSB200_ERR_UNSUPPORTED;
@@ -1475,6 +1509,12 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     c.xbn = x_bn ? *x_bn : TcBnSrc{nullptr, nullptr, nullptr, 1.0, 0.f, 0, 1, 0};
     c.sbn = s_bn ? *s_bn : TcBnSrc{nullptr, nullptr, nullptr, 1.0, 0.f, 0, 1, 0};
     c.stats_reps = stats_reps > 0 ? stats_reps : 1; c.stats_rep_stride = stats_rep_stride;
+    for (int t = 0; t < 2; ++t) {
+      c.mir_prev[t] = peer ? (__nv_bfloat16*)peer->mir_prev[t] : nullptr;
+      c.mir_next[t] = peer ? (__nv_bfloat16*)peer->mir_next[t] : nullptr;
+      c.wait_flags[t] = peer ? peer->wait_flags[t] : nullptr;
+    }
+    c.wait_n = peer ? peer->wait_n : 0; c.wait_seq = peer ? peer->wait_seq : 0u; c.err_flag = peer ? peer->err_flag : nullptr;
     c.y_cp8 = (__nv_bfloat16*)y_cp8; c.y_ps8 = (__nv_bfloat16*)y_ps8; c.y_f32 = y_f32; c.stats = stats;
     // D-slab mode: the tensors hold D + 2 planes (halo before / after), local plane l is extended plane l + 1
     const int Dt = slab && slab->halo ? D + 2 : D;
@@ -1700,7 +1740,7 @@ int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, cons
   else if (via_f32) MVS_CUDA(tmp.alloc((void**)&yf, (size_t)Do * Ho * Wo * cout * sizeof(float)));
   else MVS_CUDA(tmp.alloc(&yp, planar_bytes(Do, Ho, Wo, cout, 0)));
   rc = launch_conv3d_tc(xp, xs, xb, kp, ss, sb, kernel_tf, D, H, W, cin, cout, stride, transposed, yp, nullptr, yf, stats,
-                        scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, s);
+                        scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, nullptr, s);
   if (rc) return rc;
   if (yp) rc = launch_planar_to_ndhwc(yp, Do, Ho, Wo, cout, y, s);
   else if (via_f32) rc = launch_f32_to_bf16(yf, (size_t)Do * Ho * Wo * cout, y, s);

@@ -17,6 +17,14 @@ struct TcBnSrc {
 // before and after the D local planes; planes outside [zv_lo, zv_hi) (extended coordinates) are SAME padding.
 struct TcSlab { int halo; int zv_lo; int zv_hi; };
 
+// D-slab mode over peer memory (NVLink): where the boundary planes of the output are mirrored (the neighbours' halo
+// planes, [0] chunk-planar / [1] parity-split, NULL = none) and which publication flags the kernel waits for before
+// it reads its inputs (per consumed layer `wait_n` words, one per rank, each >= wait_seq when published).
+struct TcPeer {
+  void* mir_prev[2]; void* mir_next[2];
+  const unsigned* wait_flags[2]; int wait_n; unsigned wait_seq; unsigned* err_flag;
+};
+
 // One job per layer of a network for conv3d_tc_pack_all; its launches (output-channel slices of 32) take
 // consecutive weight slots starting at slot0.
 struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0; };
@@ -27,7 +35,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
                      const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
                      const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
-                     int stats_rep_stride, const TcSlab* slab, cudaStream_t s);
+                     int stats_rep_stride, const TcSlab* slab, const TcPeer* peer, cudaStream_t s);
 int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
                            const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout,
                            int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "conv3d_tc.h"
 #include <stdlib.h>
+#include <string.h>
 
 namespace mvsb200 {
 
@@ -243,7 +244,7 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
                             L.stride, L.transposed, last ? nullptr : ws + p.raw_off[i],
                             (!last && p.has_ps8[i]) ? ws + p.ps8_off[i] : nullptr, last ? filtered : nullptr, st,
                             nullptr, L.src >= 0 ? &xbn : nullptr, L.skip >= 0 ? &sbn : nullptr,
-                            ws + p.scratch_off + (size_t)2 * i * conv3d_tc_pack_slot_bytes(), kStatsReps, rep_stride, nullptr, s);
+                            ws + p.scratch_off + (size_t)2 * i * conv3d_tc_pack_slot_bytes(), kStatsReps, rep_stride, nullptr, nullptr, s);
       if (rc) return rc;
     }
     if (profile) cudaEventRecord(pev[i + 1], s);
@@ -362,7 +363,9 @@ struct SlabPlan {
   size_t raw_plane[MVSB200_REGNET_LAYERS], ps8_plane[MVSB200_REGNET_LAYERS];  // bytes per plane
   size_t cost_cp8_off, cost_ps8_off, cost_cp8_plane, cost_ps8_plane;
   size_t hom_off, coef_off, pair_off, filtered_off, stats_off, stats_bytes, scratch_off, total;
-  int cpad;
+  size_t gstats_off, gstats_bytes;      // peer mode: statistics of every layer per source rank [layer][slabs][2*cpad]
+  size_t flags_off, flags_bytes;        // peer mode: publication flags [layer][slabs] + an error word
+  int cpad, slabs;
 };
 
 static int make_slab_plan(int n_views, int D, int slabs, int H, int W, int cin, int b, SlabPlan* sp) {
@@ -401,6 +404,11 @@ static int make_slab_plan(int n_views, int D, int slabs, int H, int W, int cin, 
   sp->stats_bytes = (size_t)MVSB200_REGNET_LAYERS * kStatsReps * 2 * sp->cpad * sizeof(double);
   sp->stats_off = off; off += align_up(sp->stats_bytes, 256);
   sp->scratch_off = off; off += align_up(conv3d_tc_pack_slot_bytes() * 2 * MVSB200_REGNET_LAYERS, 256);
+  sp->slabs = slabs;
+  sp->gstats_bytes = (size_t)MVSB200_REGNET_LAYERS * slabs * 2 * sp->cpad * sizeof(double);
+  sp->gstats_off = off; off += align_up(sp->gstats_bytes, 256);
+  sp->flags_bytes = (size_t)(MVSB200_REGNET_LAYERS * slabs + 1) * sizeof(unsigned);
+  sp->flags_off = off; off += align_up(sp->flags_bytes, 256);
   sp->total = off;
   return MVSB200_OK;
 }
@@ -508,7 +516,141 @@ extern "C" int mvsb200_slab_layer(int layer, int n_views, int depth_num, int sla
                           L.stride, L.transposed, y_cp8, y_ps8, last ? (float*)(ws + sp.filtered_off) : nullptr,
                           last ? nullptr : stats + (size_t)layer * lstride, nullptr, L.src >= 0 ? &xbn : nullptr,
                           L.skip >= 0 ? &sbn : nullptr, ws + sp.scratch_off + (size_t)2 * layer * conv3d_tc_pack_slot_bytes(),
-                          kStatsReps, 2 * sp.cpad, &win, s);
+                          kStatsReps, 2 * sp.cpad, &win, nullptr, s);
+}
+
+// ---- D-slab mode over peer memory (NVLink) -----------------------------------------------------------------------
+// The exchange between layers happens inside the kernels: the producing epilogue stores its boundary planes into the
+// neighbours' halo planes through peer pointers, a one-block publish kernel copies the layer's statistics into every
+// rank's per-source table and then raises this rank's flag on every rank, and the consuming kernel spins (bounded) on
+// its local flags before it reads anything.  No NCCL call between layers.
+namespace mvsb200 {
+__global__ void slab_publish_kernel(const double* __restrict__ local_stats, int reps, int rep_stride, int n,
+                                    char* const* __restrict__ peers, int slabs, int slab, size_t gstats_off,
+                                    size_t flags_off, int layer, int cpad, unsigned seq) {
+  // totals of this rank's partial copies -> slot `slab` of the layer's table on every rank
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < reps; ++r) t += local_stats[(size_t)r * rep_stride + c];
+    for (int q = 0; q < slabs; ++q) {
+      double* g = reinterpret_cast<double*>(peers[q] + gstats_off) + ((size_t)layer * slabs + slab) * 2 * cpad;
+      g[c] = t;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // (the layer kernel before us in the stream has completed, so its peer stores are done as well)
+  if (threadIdx.x < slabs) {
+    unsigned* f = reinterpret_cast<unsigned*>(peers[threadIdx.x] + flags_off) + layer * slabs + slab;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+  }
+}
+}  // namespace mvsb200
+
+// Layer `layer` on the local slab with the exchange fused in.  peers[slabs]: device-visible base addresses of every
+// rank's slab workspace (own one included, from mvsb200_ipc_open); seq: 1, 2, 3, ... per inference.
+extern "C" int mvsb200_slab_layer_p2p(int layer, int n_views, int depth_num, int slab, int slabs, int hf, int wf,
+                                      int channels, const mvsb200_regnet_params* params, int base_filter, float bn_eps,
+                                      void* workspace, void* const* peers_dev, void* const* peers_host, unsigned seq,
+                                      void* stream) {
+  MVS_CHECK_ARG(layer >= 0 && layer < MVSB200_REGNET_LAYERS && params && workspace && peers_dev && peers_host,
+                "slab_layer_p2p: bad arguments");
+  MVS_CHECK_ARG(slabs >= 1 && slabs <= 8 && slab >= 0 && slab < slabs, "slab_layer_p2p: slab %d of %d", slab, slabs);
+  SlabPlan sp;
+  int rc = make_slab_plan(n_views, depth_num, slabs, hf, wf, channels, base_filter, &sp);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const RegnetPlan& p = sp.net;
+  const LayerDesc& L = p.layer[layer];
+  const bool last = layer == MVSB200_L_3DCONV6_2;
+  const bool s2 = L.stride == 2 && !L.transposed;
+  const int* d = p.dims[L.in_level];
+  double* stats = (double*)(ws + sp.stats_off);
+  double* gstats = (double*)(ws + sp.gstats_off);
+  unsigned* flags = (unsigned*)(ws + sp.flags_off);
+  const int lstride = kStatsReps * 2 * sp.cpad, gstride = slabs * 2 * sp.cpad;
+  const void* x = L.src < 0 ? (const void*)(ws + (s2 ? sp.cost_ps8_off : sp.cost_cp8_off))
+                            : (const void*)(ws + (s2 ? sp.ps8_off[L.src] : sp.raw_off[L.src]));
+  const void* sk = L.skip < 0 ? nullptr : (const void*)(ws + sp.raw_off[L.skip]);
+  TcBnSrc xbn = {nullptr, nullptr, nullptr, 1.0, bn_eps, 0, 1, 0}, sbn = xbn;
+  if (L.src >= 0)
+    xbn = {gstats + (size_t)L.src * gstride, params->gamma[L.src], params->beta[L.src],
+           (double)p.vox[p.layer[L.src].out_level] * slabs, bn_eps, p.layer[L.src].cout, slabs, 2 * sp.cpad};
+  if (L.skip >= 0)
+    sbn = {gstats + (size_t)L.skip * gstride, params->gamma[L.skip], params->beta[L.skip],
+           (double)p.vox[p.layer[L.skip].out_level] * slabs, bn_eps, p.layer[L.skip].cout, slabs, 2 * sp.cpad};
+  const TcSlab win = {1, slab == 0 ? 1 : 0, slab == slabs - 1 ? d[0] + 1 : d[0] + 2};
+  TcPeer peer = {};
+  const int dlo = p.dims[L.out_level][0];
+  if (!last) {
+    const size_t off[2] = {sp.raw_off[layer], sp.ps8_off[layer]}, plane[2] = {sp.raw_plane[layer], sp.ps8_plane[layer]};
+    for (int t = 0; t < 2; ++t) {
+      if (!plane[t]) continue;
+      if (slab > 0) peer.mir_prev[t] = (char*)peers_host[slab - 1] + off[t] + plane[t] * (size_t)(dlo + 1);   // its AFTER halo
+      if (slab < slabs - 1) peer.mir_next[t] = (char*)peers_host[slab + 1] + off[t];                            // its BEFORE halo
+    }
+  }
+  peer.wait_n = slabs; peer.wait_seq = seq; peer.err_flag = flags + MVSB200_REGNET_LAYERS * slabs;
+  peer.wait_flags[0] = L.src >= 0 ? flags + L.src * slabs : nullptr;
+  peer.wait_flags[1] = L.skip >= 0 ? flags + L.skip * slabs : nullptr;
+  void* y_cp8 = last ? nullptr : ws + sp.raw_off[layer] + sp.raw_plane[layer];
+  void* y_ps8 = (!last && sp.ps8_plane[layer]) ? ws + sp.ps8_off[layer] + sp.ps8_plane[layer] : nullptr;
+  rc = launch_conv3d_tc(x, nullptr, nullptr, sk, nullptr, nullptr, params->kernel[layer], d[0], d[1], d[2], L.cin, L.cout,
+                        L.stride, L.transposed, y_cp8, y_ps8, last ? (float*)(ws + sp.filtered_off) : nullptr,
+                        last ? nullptr : stats + (size_t)layer * lstride, nullptr, L.src >= 0 ? &xbn : nullptr,
+                        L.skip >= 0 ? &sbn : nullptr, ws + sp.scratch_off + (size_t)2 * layer * conv3d_tc_pack_slot_bytes(),
+                        kStatsReps, 2 * sp.cpad, &win, &peer, s);
+  if (rc || last) return rc;
+  slab_publish_kernel<<<1, 128, 0, s>>>(stats + (size_t)layer * lstride, kStatsReps, 2 * sp.cpad, 2 * L.cout,
+                                        (char* const*)peers_dev, slabs, slab, sp.gstats_off, sp.flags_off, layer, sp.cpad,
+                                        seq);
+  MVS_LAUNCH_CHECK("slab_publish_kernel");
+  return MVSB200_OK;
+}
+
+// 1 when a consumer gave up waiting for a publication flag (a rank died or ran out of order); clears it
+extern "C" int mvsb200_slab_p2p_error(int n_views, int depth_num, int slabs, int hf, int wf, int channels, int base_filter,
+                                      void* workspace, void* stream) {
+  SlabPlan sp;
+  if (make_slab_plan(n_views, depth_num, slabs, hf, wf, channels, base_filter, &sp)) return MVSB200_ERR_INVALID;
+  unsigned v = 0;
+  unsigned* f = (unsigned*)((char*)workspace + sp.flags_off) + MVSB200_REGNET_LAYERS * slabs;
+  MVS_CUDA(cudaMemcpyAsync(&v, f, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  MVS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (v) MVS_CUDA(cudaMemsetAsync(f, 0, sizeof(v), (cudaStream_t)stream));
+  return (int)v;
+}
+
+// Peer-visible device memory for the slab workspace (cudaMalloc + CUDA IPC): ranks are separate processes.
+extern "C" int mvsb200_ipc_alloc(size_t bytes, void** ptr) {
+  MVS_CHECK_ARG(ptr && bytes > 0, "ipc_alloc: bad arguments");
+  MVS_CUDA(cudaMalloc(ptr, bytes));
+  MVS_CUDA(cudaMemset(*ptr, 0, bytes));
+  return MVSB200_OK;
+}
+extern "C" int mvsb200_ipc_free(void* ptr) {
+  MVS_CUDA(cudaFree(ptr));
+  return MVSB200_OK;
+}
+extern "C" int mvsb200_ipc_export(void* ptr, unsigned char* handle64) {
+  MVS_CHECK_ARG(ptr && handle64, "ipc_export: NULL pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  MVS_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return MVSB200_OK;
+}
+extern "C" int mvsb200_ipc_open(const unsigned char* handle64, void** ptr) {
+  MVS_CHECK_ARG(ptr && handle64, "ipc_open: NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  MVS_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MVSB200_OK;
+}
+extern "C" int mvsb200_ipc_close(void* ptr) {
+  MVS_CUDA(cudaIpcCloseMemHandle(ptr));
+  return MVSB200_OK;
 }
 
 // Regions the host exchanges after layer `layer` (byte offsets into the workspace):

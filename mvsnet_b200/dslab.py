@@ -12,6 +12,12 @@ depth window (include/mvsnet_b200.h, mvsb200_slab_*); this module is the exchang
     planes.
 
 `exchange_layer` only touches byte regions of a flat workspace tensor, so it is testable on CPU.
+
+With p2p=True the exchange moves INTO the kernels (no NCCL call between layers): the slab workspaces are CUDA-IPC
+mapped into every rank, the producing epilogue stores its boundary planes straight into the neighbours' halo planes
+over NVLink, a one-block kernel publishes the layer's statistics and raises a flag on every rank, and the consuming
+kernel waits on its local flags (mvsb200_slab_layer_p2p).  Only the final all-gather stays a collective; it is also the
+barrier that keeps a fast rank's next inference out of a slow rank's buffers.
 """
 from __future__ import annotations
 
@@ -89,7 +95,7 @@ class DSlabHotPath:
     `group`.  Every rank calls infer() with the same inputs and gets the same maps."""
 
     def __init__(self, n_views, depth_num, hf, wf, weights, channels=32, order="mem", inverse_depth=False, bn_eps=1e-5,
-                 device="cuda", group=None):
+                 device="cuda", group=None, p2p=False):
         from .engine import RegnetWeights
         self.lib = L.load()
         self.group = group
@@ -105,10 +111,52 @@ class DSlabHotPath:
         nbytes = self.lib.mvsb200_slab_workspace_bytes(n_views, depth_num, self.world, hf, wf, channels, self.base_filter)
         if nbytes == 0:
             raise L.MVSB200Error("slab_workspace_bytes rejected the shape: " + L.last_error())
-        self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        self.p2p = bool(p2p) and self.world > 1
+        self.seq = 0
+        if self.p2p:
+            self._map_peers(nbytes)
+        else:
+            self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
         self.regions = [layer_regions(i, n_views, depth_num, self.world, hf, wf, channels, self.base_filter)
                         for i in range(N_LAYERS)]
         self.filtered = torch.empty((depth_num, hf, wf), dtype=torch.float32, device=self.device)
+
+    def _map_peers(self, nbytes: int):
+        """Slab workspace in plain cudaMalloc memory, exported over CUDA IPC and opened by every other rank."""
+        with torch.cuda.device(self.device):
+            base = ctypes.c_void_p()
+            L.check(self.lib.mvsb200_ipc_alloc(nbytes, ctypes.byref(base)), "ipc_alloc")
+            handle = ctypes.create_string_buffer(64)
+            L.check(self.lib.mvsb200_ipc_export(base, handle), "ipc_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+            addrs = []
+            for q in range(self.world):
+                if q == self.rank:
+                    addrs.append(base.value)
+                else:
+                    peer = ctypes.c_void_p()
+                    L.check(self.lib.mvsb200_ipc_open(ctypes.create_string_buffer(handles[q], 64), ctypes.byref(peer)),
+                            "ipc_open")
+                    addrs.append(peer.value)
+        self._base, self._addrs, self._nbytes = base, addrs, nbytes
+        self.peers_host = (ctypes.c_void_p * self.world)(*addrs)
+        self.peers_dev = torch.tensor(addrs, dtype=torch.int64, device=self.device)
+
+        class _Raw:                                   # zero-copy torch view of the library-owned allocation
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (base.value, False), "version": 2}
+        self.ws = torch.as_tensor(_Raw(), device=self.device)
+
+    def close(self):
+        """Unmap the peers and free the IPC workspace (p2p mode); call it on every rank after a barrier."""
+        if getattr(self, "_base", None) is not None:
+            torch.cuda.synchronize(self.device)
+            for q, a in enumerate(self._addrs):
+                if q != self.rank:
+                    self.lib.mvsb200_ipc_close(ctypes.c_void_p(a))
+            self.ws = None
+            self.lib.mvsb200_ipc_free(self._base)
+            self._base = None
 
     def infer(self, feats: torch.Tensor, cams: torch.Tensor, depth_start: float, depth_interval: float):
         L.require_cuda(feats, cams)
@@ -118,6 +166,14 @@ class DSlabHotPath:
                                          ctypes.byref(self.weights.params), self.base_filter, L.ptr(self.ws),
                                          self.ws.numel(), L.stream_ptr())
         L.check(rc, "slab_begin")
+        if self.p2p:
+            self.seq += 1
+            for layer in SLAB_ORDER:
+                rc = self.lib.mvsb200_slab_layer_p2p(layer, *args, ctypes.byref(self.weights.params), self.base_filter,
+                                                     self.bn_eps, L.ptr(self.ws), L.ptr(self.peers_dev), self.peers_host,
+                                                     self.seq, L.stream_ptr())
+                L.check(rc, f"slab_layer_p2p {layer}")
+            return self._finish(depth_start, depth_interval)
         pending = {}
         for layer in SLAB_ORDER:
             for src in LAYER_INPUTS[layer]:                 # the exchanges this layer reads must have landed
@@ -132,6 +188,9 @@ class DSlabHotPath:
         for works in pending.values():
             for w in works:
                 w.wait()
+        return self._finish(depth_start, depth_interval)
+
+    def _finish(self, depth_start: float, depth_interval: float):
         off, nbytes = self.regions[N_LAYERS - 1]["filtered"]
         mine = self.ws[off:off + nbytes].view(torch.float32)
         dist.all_gather_into_tensor(self.filtered.view(-1), mine, group=self.group)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--config", default="small")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--iid", action="store_true", help="i.i.d. features (fast to build at the large configs)")
+    ap.add_argument("--p2p", action="store_true", help="also run the peer-memory variant (exchange inside the kernels)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -67,10 +68,22 @@ def main():
 
     res["single_gpu_ms"] = timeit(lambda: single.infer(feats, camsd, ds, di))
     res["dslab_ms"] = timeit(lambda: slab.infer(feats, camsd, ds, di))
+    if a.p2p:
+        fused = DSlabHotPath(n, D, hf, wf, single.weights, device=dev, p2p=True)
+        d3, p3 = fused.infer(feats, camsd, ds, di)
+        torch.cuda.synchronize()
+        res["p2p_max_abs_depth_diff_in_intervals"] = float((d1 - d3).abs().max()) / di
+        res["p2p_vs_nccl_max_abs_depth_diff_in_intervals"] = float((d2 - d3).abs().max()) / di
+        res["dslab_p2p_ms"] = timeit(lambda: fused.infer(feats, camsd, ds, di))
+        res["p2p_wait_timeouts"] = int(fused.lib.mvsb200_slab_p2p_error(n, D, world, hf, wf, 32, fused.base_filter,
+                                                                        fused.ws.data_ptr(), None))
+        dist.barrier()
+        fused.close()
     if rank == 0:
         print(json.dumps(res), flush=True)
     # same gate as the bf16 path against the oracle: depth within 0.1 interval (here: of the single-GPU result)
-    ok = res["max_abs_depth_diff_in_intervals"] <= 0.1
+    ok = res["max_abs_depth_diff_in_intervals"] <= 0.1 and res.get("p2p_max_abs_depth_diff_in_intervals", 0.0) <= 0.1 \
+        and res.get("p2p_wait_timeouts", 0) == 0
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -238,6 +238,16 @@ int mvsb200_slab_layer(int layer, int n_views, int depth_num, int slab, int slab
 int mvsb200_slab_regions(int layer, int n_views, int depth_num, int slabs, int hf, int wf, int channels,
                          int base_filter, unsigned long long* out);
 
+/* D-slab mode: the softmax over depth split over the ranks.  mvsb200_regress_partial reduces planes [d0, d0+dl) of
+ * the filtered volume to per-pixel (max of -F, sum of exp, depth-weighted sum) [3, npix]; after an all-gather of the
+ * partials mvsb200_regress_combine gives the depth map (identical on every rank) and this rank's share of the
+ * probability map (buckets of model.py:113-140 that fall into its planes; sum the shares over the ranks). */
+int mvsb200_regress_partial(const float* filtered, int dl, int d0, int depth_num, int npix, float depth_start,
+                            float depth_interval, int inverse_depth, float* partial, void* stream);
+int mvsb200_regress_combine(const float* partials, int slabs, const float* filtered, int dl, int d0, int depth_num,
+                            int npix, float depth_start, float depth_interval, int inverse_depth, int num_buckets,
+                            float* depth_map, float* prob_partial, void* stream);
+
 /* D-slab mode with the exchange fused into the kernels (peer memory over NVLink, no collective between layers).
  * The slab workspaces live in IPC-exportable memory (mvsb200_ipc_*) and every rank maps all of them:
  * peers_dev / peers_host = the same `slabs` base addresses as a device array and a host array (own workspace at

@@ -70,6 +70,9 @@ SIGNATURES = {
     "mvsb200_ipc_export": (c_int, [_P, _P]),
     "mvsb200_ipc_open": (c_int, [_P, _P]),
     "mvsb200_ipc_close": (c_int, [_P]),
+    "mvsb200_regress_partial": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, _P, _P]),
+    "mvsb200_regress_combine": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P,
+                                        _P]),
     "mvsb200_slab_regions": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mvsb200_infer_cost_offsets": (c_int, [c_int] * 7 + [_P, _P]),
     "mvsb200_infer_host_staging_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

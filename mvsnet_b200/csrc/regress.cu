@@ -99,6 +99,63 @@ __global__ void probability_map_kernel(const float* __restrict__ prob_volume, co
   prob_map[pix] = prob;
 }
 
+// ---- D-slab mode: the softmax over depth split over ranks -------------------------------------------------------
+// Each rank reduces its own planes to (m, s, w) = (max of -F, sum of exp(-F - m), sum of d_i exp(-F - m)) per pixel;
+// the partials of all ranks are combined as M = max m_r, S = sum s_r e^(m_r - M), W = sum w_r e^(m_r - M),
+// depth = W / S (model.py:472-495 up to the association of the sums); the probability map adds, on each rank, the
+// buckets of get_probability_map_slice (model.py:113-140) that fall into its slab, and the host sums the ranks.
+__global__ void regress_partial_kernel(const float* __restrict__ filtered, int dl, int d0, int D, int npix,
+                                       float depth_start, float depth_end, int inverse_depth,
+                                       float* __restrict__ partial) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  float m = -__ldg(filtered + pix);
+  for (int d = 1; d < dl; ++d) m = fmaxf(m, -__ldg(filtered + (size_t)d * npix + pix));
+  float s = 0.0f, w = 0.0f;
+  for (int d = 0; d < dl; ++d) {
+    const float e = expf(sub_(-__ldg(filtered + (size_t)d * npix + pix), m));
+    s = add_(s, e);
+    w = add_(w, mul_(depth_sample(d0 + d, D, depth_start, depth_end, inverse_depth), e));
+  }
+  partial[pix] = m;
+  partial[npix + pix] = s;
+  partial[2 * (size_t)npix + pix] = w;
+}
+
+__global__ void regress_combine_kernel(const float* __restrict__ partials, int slabs, const float* __restrict__ filtered,
+                                       int dl, int d0, int D, int npix, float depth_start, float depth_interval,
+                                       float depth_end, int inverse_depth, int num_buckets,
+                                       float* __restrict__ depth_map, float* __restrict__ prob_partial) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  float M = partials[pix];
+  for (int r = 1; r < slabs; ++r) M = fmaxf(M, partials[(size_t)r * 3 * npix + pix]);
+  float S = 0.0f, W = 0.0f;
+  for (int r = 0; r < slabs; ++r) {
+    const float* pr = partials + (size_t)r * 3 * npix;
+    const float sc = expf(sub_(pr[pix], M));
+    S = add_(S, mul_(pr[npix + pix], sc));
+    W = add_(W, mul_(pr[2 * (size_t)npix + pix], sc));
+  }
+  const float depth = div_(W, S);
+  depth_map[pix] = depth;
+  int b[4];
+  prob_buckets(depth, D, depth_start, depth_interval, depth_end, inverse_depth, b[0], b[2], b[1], b[3]);   // l0 r0 | l1 r1
+  float prob = 0.0f;
+  const int nb = num_buckets == 4 ? 4 : 2;
+  for (int k = 0; k < nb; ++k) {
+    const int i = b[k] - d0;
+    if (i >= 0 && i < dl) prob = add_(prob, div_(expf(sub_(-__ldg(filtered + (size_t)i * npix + pix), M)), S));
+  }
+  prob_partial[pix] = prob;
+}
+
+int launch_regress_partial(const float* filtered, int dl, int d0, int D, int npix, float depth_start,
+                           float depth_interval, int inverse_depth, float* partial, cudaStream_t s);
+int launch_regress_combine(const float* partials, int slabs, const float* filtered, int dl, int d0, int D, int npix,
+                           float depth_start, float depth_interval, int inverse_depth, int num_buckets, float* depth_map,
+                           float* prob_partial, cudaStream_t s);
+
 static float host_depth_end(int depth_num, float depth_start, float depth_interval) {
   // model.py:378-379 in fp32: start + (float(D) - 1) * interval
   volatile float dm1 = (float)depth_num - 1.0f;
@@ -137,9 +194,49 @@ int launch_depth_regress(const float* filtered, int depth_num, int hf, int wf, f
   return MVSB200_OK;
 }
 
+int launch_regress_partial(const float* filtered, int dl, int d0, int D, int npix, float depth_start,
+                           float depth_interval, int inverse_depth, float* partial, cudaStream_t s) {
+  MVS_CHECK_ARG(filtered && partial && dl >= 1 && d0 >= 0 && d0 + dl <= D && npix >= 1, "regress_partial: bad arguments");
+  regress_partial_kernel<<<ceil_div(npix, 128), 128, 0, s>>>(filtered, dl, d0, D, npix, depth_start,
+                                                             host_depth_end(D, depth_start, depth_interval),
+                                                             inverse_depth, partial);
+  MVS_LAUNCH_CHECK("regress_partial_kernel");
+  return MVSB200_OK;
+}
+
+int launch_regress_combine(const float* partials, int slabs, const float* filtered, int dl, int d0, int D, int npix,
+                           float depth_start, float depth_interval, int inverse_depth, int num_buckets, float* depth_map,
+                           float* prob_partial, cudaStream_t s) {
+  MVS_CHECK_ARG(partials && filtered && depth_map && prob_partial && slabs >= 1, "regress_combine: bad arguments");
+  MVS_CHECK_ARG(num_buckets == 2 || num_buckets == 4, "regress_combine: num_buckets must be 2 or 4 (got %d)", num_buckets);
+  regress_combine_kernel<<<ceil_div(npix, 128), 128, 0, s>>>(partials, slabs, filtered, dl, d0, D, npix, depth_start,
+                                                             depth_interval, host_depth_end(D, depth_start, depth_interval),
+                                                             inverse_depth, num_buckets, depth_map, prob_partial);
+  MVS_LAUNCH_CHECK("regress_combine_kernel");
+  return MVSB200_OK;
+}
+
 }  // namespace mvsb200
 
 using namespace mvsb200;
+
+// D-slab mode: soft-argmin partials of planes [d0, d0 + dl) of a depth_num-plane sweep: filtered [dl, npix] ->
+// partial [3, npix] = (max of -F, sum of exp, depth-weighted sum)
+extern "C" int mvsb200_regress_partial(const float* filtered, int dl, int d0, int depth_num, int npix, float depth_start,
+                                       float depth_interval, int inverse_depth, float* partial, void* stream) {
+  return launch_regress_partial(filtered, dl, d0, depth_num, npix, depth_start, depth_interval, inverse_depth, partial,
+                                (cudaStream_t)stream);
+}
+
+// partials [slabs, 3, npix] of all ranks -> depth_map [npix] (identical on every rank) and this rank's share of the
+// probability map (sum the shares of all ranks)
+extern "C" int mvsb200_regress_combine(const float* partials, int slabs, const float* filtered, int dl, int d0,
+                                       int depth_num, int npix, float depth_start, float depth_interval,
+                                       int inverse_depth, int num_buckets, float* depth_map, float* prob_partial,
+                                       void* stream) {
+  return launch_regress_combine(partials, slabs, filtered, dl, d0, depth_num, npix, depth_start, depth_interval,
+                                inverse_depth, num_buckets, depth_map, prob_partial, (cudaStream_t)stream);
+}
 
 extern "C" int mvsb200_depth_regress(const float* filtered, int depth_num, int hf, int wf, float depth_start,
                                      float depth_interval, int inverse_depth, int num_buckets, float* depth_map,

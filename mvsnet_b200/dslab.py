@@ -8,16 +8,17 @@ depth window (include/mvsnet_b200.h, mvsb200_slab_*); this module is the exchang
   * after every layer: all-reduce (SUM) of its batch statistics (BN uses statistics of the WHOLE volume,
     network.py:496) and a halo exchange of the boundary planes of its output with both neighbours (the 3x3x3
     receptive field of the consumers, network.py:210,327);
-  * after the last layer: all-gather of the filtered slabs so that the softmax over depth (model.py:474) sees all
-    planes.
+  * after the last layer: the softmax over depth (model.py:474) is split as well -- per-rank (max, sum of exp,
+    depth-weighted sum) partials, one 3-map all-gather, a combine, and a sum of the per-rank shares of the
+    probability map.
 
 `exchange_layer` only touches byte regions of a flat workspace tensor, so it is testable on CPU.
 
 With p2p=True the exchange moves INTO the kernels (no NCCL call between layers): the slab workspaces are CUDA-IPC
 mapped into every rank, the producing epilogue stores its boundary planes straight into the neighbours' halo planes
 over NVLink, a one-block kernel publishes the layer's statistics and raises a flag on every rank, and the consuming
-kernel waits on its local flags (mvsb200_slab_layer_p2p).  Only the final all-gather stays a collective; it is also the
-barrier that keeps a fast rank's next inference out of a slow rank's buffers.
+kernel waits on its local flags (mvsb200_slab_layer_p2p).  Only the small collectives of the regression remain; they
+are also the barrier that keeps a fast rank's next inference out of a slow rank's buffers.
 """
 from __future__ import annotations
 
@@ -119,7 +120,8 @@ class DSlabHotPath:
             self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
         self.regions = [layer_regions(i, n_views, depth_num, self.world, hf, wf, channels, self.base_filter)
                         for i in range(N_LAYERS)]
-        self.filtered = torch.empty((depth_num, hf, wf), dtype=torch.float32, device=self.device)
+        self.partial = torch.empty((3, hf * wf), dtype=torch.float32, device=self.device)
+        self.partials = torch.empty((self.world, 3, hf * wf), dtype=torch.float32, device=self.device)
 
     def _map_peers(self, nbytes: int):
         """Slab workspace in plain cudaMalloc memory, exported over CUDA IPC and opened by every other rank."""
@@ -191,7 +193,21 @@ class DSlabHotPath:
         return self._finish(depth_start, depth_interval)
 
     def _finish(self, depth_start: float, depth_interval: float):
+        """Softmax over depth across the slabs: per-rank partials, one small all-gather, combine, and a sum of the
+        per-rank shares of the probability map (no rank ever holds the whole filtered volume)."""
         off, nbytes = self.regions[N_LAYERS - 1]["filtered"]
         mine = self.ws[off:off + nbytes].view(torch.float32)
-        dist.all_gather_into_tensor(self.filtered.view(-1), mine, group=self.group)
-        return ops.depth_regress(self.filtered, depth_start, depth_interval, bool(self.inverse_depth))
+        npix, dl = self.hf * self.wf, self.end - self.begin
+        rc = self.lib.mvsb200_regress_partial(L.ptr(mine), dl, self.begin, self.depth_num, npix, float(depth_start),
+                                              float(depth_interval), self.inverse_depth, L.ptr(self.partial),
+                                              L.stream_ptr())
+        L.check(rc, "regress_partial")
+        dist.all_gather_into_tensor(self.partials.view(-1), self.partial.view(-1), group=self.group)
+        depth = torch.empty((self.hf, self.wf), dtype=torch.float32, device=self.device)
+        prob = torch.empty((self.hf, self.wf), dtype=torch.float32, device=self.device)
+        rc = self.lib.mvsb200_regress_combine(L.ptr(self.partials), self.world, L.ptr(mine), dl, self.begin,
+                                              self.depth_num, npix, float(depth_start), float(depth_interval),
+                                              self.inverse_depth, 4, L.ptr(depth), L.ptr(prob), L.stream_ptr())
+        L.check(rc, "regress_combine")
+        dist.all_reduce(prob, op=dist.ReduceOp.SUM, group=self.group)
+        return depth, prob

@@ -98,3 +98,35 @@ def test_reference_named_probability_map(ops, O):
     ref = O.get_probability_map(np.stack(Ps), np.stack(ds)[..., None], [400.0, 401.0], [3.0, 3.0])
     assert out.shape == (2, 6, 8, 1)
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("slabs", [1, 2, 4])
+def test_slab_regression_matches_whole_volume(ops, slabs):
+    """D-slab mode: per-slab soft-argmin partials + combine + summed probability shares equal the whole-volume
+    kernel up to the association of the sums (all slabs emulated on one GPU)."""
+    import ctypes
+    from mvsnet_b200 import _lib as L
+    lib = L.load()
+    D, hf, wf = 32, 24, 40
+    ds, di = 425.0, 2.5
+    g = torch.Generator(device="cuda").manual_seed(3)
+    F = torch.randn((D, hf, wf), device="cuda", generator=g) * 3.0
+    F[5, 3, 7] = -40.0                                   # a sharp minimum: exact-integer index, double-counted buckets
+    F[D - 1, 0, 0] = -40.0                               # and one at the clipped end
+    depth_ref, prob_ref = ops.depth_regress(F, ds, di)
+    npix, dl = hf * wf, D // slabs
+    partials = torch.empty((slabs, 3, npix), device="cuda")
+    for r in range(slabs):
+        L.check(lib.mvsb200_regress_partial(L.ptr(F[r * dl:(r + 1) * dl].contiguous()), dl, r * dl, D, npix, ds, di, 0,
+                                            L.ptr(partials[r]), L.stream_ptr()), "regress_partial")
+    prob = torch.zeros((hf, wf), device="cuda")
+    for r in range(slabs):
+        depth = torch.empty((hf, wf), device="cuda")
+        share = torch.empty((hf, wf), device="cuda")
+        L.check(lib.mvsb200_regress_combine(L.ptr(partials), slabs, L.ptr(F[r * dl:(r + 1) * dl].contiguous()), dl, r * dl,
+                                            D, npix, ds, di, 0, 4, L.ptr(depth), L.ptr(share), L.stream_ptr()),
+                "regress_combine")
+        prob += share
+        assert float((depth - depth_ref).abs().max()) <= 1e-5 * float(depth_ref.abs().max())
+    assert float((prob - prob_ref).abs().max()) <= 2e-5
+    assert abs(float(prob[3, 7]) - float(prob_ref[3, 7])) <= 2e-5 and float(prob_ref[3, 7]) > 1.5    # counted twice

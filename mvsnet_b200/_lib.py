@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint64, c_void_p
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmvsnet_b200.so")
+LIB_PATH = os.environ.get("MVSB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmvsnet_b200.so")   # MVSB200_LIB: development override (A/B builds)
 
 OK = 0
 ORDER_MEM, ORDER_TRAIN = 0, 1

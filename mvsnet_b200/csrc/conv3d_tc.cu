@@ -110,6 +110,7 @@ struct Params {
   int ring_pad;                  // zeroed bytes after the last slot (rows of the last block may read past their plane)
   int xf_k;                      // cells per transform thread and plane
   int dz_begin[kMaxSpan + 1];    // ops [dz_begin[d], dz_begin[d+1]) read input plane d of the step
+  float* rg_out; float rg_start, rg_step;   // fused soft-argmin partials of the last layer (NULL: off)
   int pdl;                       // programmatic dependent launch: 1 = let the next layer start at CTA start, 2 = at CTA end
   int dbg;                       // development switches (env MVSB200_TC_DBG): 1 no loads, 2 no MMA, 4 no stores
   long long* prof;               // development: per-role cycle counters of CTA 0 (env MVSB200_TC_PROF)
@@ -252,15 +253,18 @@ __device__ __forceinline__ void flush_stats(const Params& p, float (&sum)[NV], f
 
 // One 16-byte cell of the chunk-planar (cell index inside the plane, which = 0) or parity-split (which = 1) output;
 // boundary planes go to the neighbouring slabs' halo planes as well (peer memory over NVLink).
+template <bool PEER>
 __device__ __forceinline__ void store_cell(const Params& p, int which, int oz, int chunk, size_t plane_cells, size_t cell,
                                            const uint4& pk) {
   __nv_bfloat16* y = which ? p.y_ps8 : p.y_cp8;
   const int ncho = p.Cout >> 3;
   *reinterpret_cast<uint4*>(y + (((size_t)oz * ncho + chunk) * plane_cells + cell) * 8) = pk;
-  if (oz == 0 && p.mir_prev[which])
-    *reinterpret_cast<uint4*>(p.mir_prev[which] + ((size_t)chunk * plane_cells + cell) * 8) = pk;
-  if (oz == p.Do - 1 && p.mir_next[which])
-    *reinterpret_cast<uint4*>(p.mir_next[which] + ((size_t)chunk * plane_cells + cell) * 8) = pk;
+  if (PEER) {                           // peer-memory D-slab mode only (separate instantiation)
+    if (oz == 0 && p.mir_prev[which])
+      *reinterpret_cast<uint4*>(p.mir_prev[which] + ((size_t)chunk * plane_cells + cell) * 8) = pk;
+    if (oz == p.Do - 1 && p.mir_next[which])
+      *reinterpret_cast<uint4*>(p.mir_next[which] + ((size_t)chunk * plane_cells + cell) * 8) = pk;
+  }
 }
 
 // Issue the MMAs of ops [ob, oe) of one input plane: one 16-byte shared-memory record per op (the unrolled loop
@@ -281,9 +285,13 @@ __device__ __forceinline__ void issue_ops(const uint4* s_ops, int ob, int oe, ui
 
 // XFC = 0: classic epilogue (CP accumulator columns per row block); XFC = 1 / 2 / 4: x-fold epilogue for launches of
 // 8 * XFC output channels (Cout = 1 uses XFC = 1)
-template <int CP, int XFC>
+// FLAGS bit 0: D-slab mode over peer memory (flag wait in the prologue, boundary planes mirrored to the neighbours);
+// bit 1: the single-channel layer (Cout = 1, fp32 output, optional fused soft-argmin).  Separate instantiations, so
+// that neither costs the common path registers or instructions.
+template <int CP, int XFC, int FLAGS>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_constant__ Params p) {
   constexpr bool XF = XFC != 0;
+  constexpr bool PEER = (FLAGS & 1) != 0, C1 = (FLAGS & 2) != 0;
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [B image][R slots][skip slots][op table][plane op ranges][barriers][tmem ptr]
   unsigned char* s_b = smem;
@@ -355,22 +363,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   // D-slab mode over peer memory: the layers this one consumes must have been published by EVERY rank (their
   // statistics) -- which covers the two neighbours whose boundary planes landed in our halo planes.  One flag word
   // per (layer, rank) holds the sequence number of the last published inference.  The spin is bounded.
-  if (p.wait_n > 0 && threadIdx.x < 2 * p.wait_n) {
-    const unsigned* f = p.wait_flags[threadIdx.x / p.wait_n];
-    if (f) {
-      f += threadIdx.x % p.wait_n;
-      const long long t0 = clock64();
-      for (;;) {
-        unsigned v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        if ((int)(v - p.wait_seq) >= 0) break;
-        if (clock64() - t0 > 4000000000LL) { if (p.err_flag) atomicExch(p.err_flag, 1u); break; }
-        __nanosleep(200);
+  if (PEER) {
+    if (p.wait_n > 0 && threadIdx.x < 2 * p.wait_n) {
+      const unsigned* f = p.wait_flags[threadIdx.x / p.wait_n];
+      if (f) {
+        f += threadIdx.x % p.wait_n;
+        const long long t0 = clock64();
+        for (;;) {
+          unsigned v;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+          if ((int)(v - p.wait_seq) >= 0) break;
+          if (clock64() - t0 > 4000000000LL) { if (p.err_flag) atomicExch(p.err_flag, 1u); break; }
+          __nanosleep(200);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");      // the halo planes are read by the TMA unit (async proxy)
       }
-      asm volatile("fence.proxy.async;" ::: "memory");      // the halo planes are read by the TMA unit (async proxy)
     }
+    __syncthreads();
   }
-  __syncthreads();
   {
     // BN scale / shift of the input (and skip) channels, one thread per channel (fp64 moments are slow: not per
     // transform thread)
@@ -635,10 +645,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         for (int k = 0; k < NST; ++k) { sum[k] = 0.0f; sq[k] = 0.0f; }
         const int grp = 3 * p.cout_n, nchunk = p.cout_n >> 3;
         const size_t zpitch = (size_t)p.Ho * p.Wo;
-        const int ncho = p.Cout >> 3, chunk0 = p.cout_base >> 3;
+        const int chunk0 = p.cout_base >> 3;
         const int px_shift = 31 - __clz(p.PX);
         long long ew = 0, et0 = 0;
         if (p.prof) et0 = clock64();
+        float rg_m[kMaxMB], rg_s[kMaxMB], rg_w[kMaxMB];     // fused soft-argmin state of this thread's pixels
+#pragma unroll
+        for (int b = 0; b < kMaxMB; ++b) { rg_m[b] = -INFINITY; rg_s[b] = 0.0f; rg_w[b] = 0.0f; }
         for (int t = 0; t < nsteps; ++t) {
           const int stage = t & 1;
           long long ea = 0;
@@ -648,19 +661,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           if (p.prof) ew += clock64() - ea;
           const int mz = zb + t * p.zf;
           const int nlive = min(p.zf, ze - mz);
-          for (int b = 0; b < p.MB; ++b) {
-            const int m = b * 128 + warp * 32 + lane;
-            const int yy = m >> px_shift, xx = m & (p.PX - 1);
-            const bool valid = xx >= 1 && xx <= TXe && yy < TYe && !(p.dbg & 4);
-            const int oy = y0 + yy, ox = x0 + xx - 1;
-            const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((stage * p.MB + b) * p.NB);
-            if (p.cout_n == 1) {
-              // Cout = 1 (3dconv6_2): N = 3*zf <= 12 columns, fp32 [D,H,W] output
+          if (C1) {
+            // Cout = 1 (3dconv6_2): N = 3*zf <= 12 columns, fp32 [D,H,W] output.  When the CTA covers the whole depth
+            // range the soft-argmin of the regression (model.py:472-495) is folded in: every thread keeps the running
+            // (max of -F, sum of exp, depth-weighted sum) of its pixels, rescaled when the maximum moves.
+#pragma unroll
+            for (int b = 0; b < kMaxMB; ++b) {
+              if (b >= p.MB) break;
+              const int m = b * 128 + warp * 32 + lane;
+              const int yy = m >> px_shift, xx = m & (p.PX - 1);
+              const bool valid = xx >= 1 && xx <= TXe && yy < TYe && !(p.dbg & 4);
+              const int oy = y0 + yy, ox = x0 + xx - 1;
+              const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((stage * p.MB + b) * p.NB);
               uint32_t r[16];
               tmem_ld16(tb, r);
               tmem_ld_wait();
+              float xj[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
+                xj[j] = -INFINITY;
                 if (j < p.zf) {
                   const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(r[3 * j]), 1, p.PX);
                   const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(r[3 * j + 2]), 1, p.PX);
@@ -668,12 +687,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   if (valid && j < nlive) {
                     sum[0] += v; sq[0] = fmaf(v, v, sq[0]);
                     if (p.y_f32) p.y_f32[((size_t)(mz + j) * p.Ho + oy) * p.Wo + ox] = v;
+                    xj[j] = -v;
                   }
                 }
               }
+              if (p.rg_out && valid) {
+                // one rescale per step: new maximum over the old one and the step's planes, then the planes' terms
+                const float mx = fmaxf(fmaxf(rg_m[b], fmaxf(xj[0], xj[1])), fmaxf(xj[2], xj[3]));
+                const float sc = __expf(rg_m[b] - mx);          // 0 on the first step (rg_m starts at -inf)
+                float s_ = rg_s[b] * sc, w_ = rg_w[b] * sc;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float e = __expf(xj[j] - mx);           // 0 for planes outside the volume (-inf)
+                  const float dsample = __fadd_rn(p.rg_start, __fmul_rn(p.rg_step, (float)(mz + j)));   // tf.linspace
+                  s_ += e;
+                  w_ = fmaf(dsample, e, w_);
+                }
+                rg_m[b] = mx; rg_s[b] = s_; rg_w[b] = w_;
+              }
             }
           }
-          if (p.cout_n != 1) {
+          if (!C1) {
             // items (row block, output plane j, 8-channel chunk): the three TMEM loads of the next item are in flight
             // while this one is shuffled, reduced and stored
             const int nitems = p.MB * p.zf * nchunk;
@@ -730,10 +764,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                     uint4 pk;
                     pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
                     pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-                    if (p.y_cp8) store_cell(p, 0, oz, chunk0 + ck, zpitch, (size_t)oy * p.Wo + ox, pk);
+                    if (p.y_cp8) store_cell<PEER>(p, 0, oz, chunk0 + ck, zpitch, (size_t)oy * p.Wo + ox, pk);
                     if (p.y_ps8) {
                       const size_t pcell = ((size_t)((oy & 1) * 2 + (ox & 1)) * p.Hso + (oy >> 1)) * p.Wso + (ox >> 1);
-                      store_cell(p, 1, oz, chunk0 + ck, 4 * (size_t)p.Hso * p.Wso, pcell, pk);
+                      store_cell<PEER>(p, 1, oz, chunk0 + ck, 4 * (size_t)p.Hso * p.Wso, pcell, pk);
                     }
                   }
                 }
@@ -745,6 +779,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_acc_empty[stage]);
         }
+        if (C1 && p.rg_out) {
+          // (m, s, w) per pixel, [3][Ho*Wo]: combined and turned into depth + probability by regress_combine_kernel
+          const size_t npix = (size_t)p.Ho * p.Wo;
+#pragma unroll
+          for (int b = 0; b < kMaxMB; ++b) {
+            if (b >= p.MB) break;
+            const int m = b * 128 + warp * 32 + lane;
+            const int yy = m >> px_shift, xx = m & (p.PX - 1);
+            if (xx >= 1 && xx <= TXe && yy < TYe) {
+              const size_t pix = (size_t)(y0 + yy) * p.Wo + (x0 + xx - 1);
+              p.rg_out[pix] = rg_m[b]; p.rg_out[npix + pix] = rg_s[b]; p.rg_out[2 * npix + pix] = rg_w[b];
+            }
+          }
+        }
         if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
         if (p.stats && !(p.dbg & 8)) flush_stats<NST>(p, sum, sq, p.cout_n, false, s_red, warp, lane);
       } else {
@@ -755,7 +803,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       const int ncls = deconv ? 8 : 1;
       const int ncol = p.zf * p.cout_n;
       const size_t zpitch = (size_t)p.Ho * p.Wo;          // voxels per output plane
-      const int ncho = p.Cout >> 3, chunk0 = p.cout_base >> 3;
+      const int chunk0 = p.cout_base >> 3;
+      const int ncho = p.Cout >> 3;
       long long ew = 0, et0 = 0;
       if (p.prof) et0 = clock64();
       for (int t = 0; t < nsteps; ++t) {
@@ -811,8 +860,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                 c1.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
                 c1.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
                 c1.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
-                store_cell(p, 0, oz, chunk0, zpitch, cell, c0);
-                store_cell(p, 0, oz, chunk0, zpitch, cell + 1, c1);
+                if (PEER) {
+                  store_cell<true>(p, 0, oz, chunk0, zpitch, cell, c0);
+                  store_cell<true>(p, 0, oz, chunk0, zpitch, cell + 1, c1);
+                } else {
+                  const size_t zc = (size_t)oz * ncho + chunk0;
+                  uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
+                  dst[0] = c0; dst[1] = c1;
+                }
               } else {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -831,8 +886,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                     c1.y = pack_bf16x2(__uint_as_float(r[16 + k + 2]), __uint_as_float(r[16 + k + 3]));
                     c1.z = pack_bf16x2(__uint_as_float(r[16 + k + 4]), __uint_as_float(r[16 + k + 5]));
                     c1.w = pack_bf16x2(__uint_as_float(r[16 + k + 6]), __uint_as_float(r[16 + k + 7]));
-                    store_cell(p, 0, oz, chunk0 + (k >> 3), zpitch, cell, c0);
-                    store_cell(p, 0, oz, chunk0 + (k >> 3), zpitch, cell + 1, c1);
+                    if (PEER) {
+                      store_cell<true>(p, 0, oz, chunk0 + (k >> 3), zpitch, cell, c0);
+                      store_cell<true>(p, 0, oz, chunk0 + (k >> 3), zpitch, cell + 1, c1);
+                    } else {
+                      const size_t zc = (size_t)oz * ncho + chunk0 + (k >> 3);
+                      uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
+                      dst[0] = c0; dst[1] = c1;
+                    }
                   }
                 }
               }
@@ -896,8 +957,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   pk.y = pack_bf16x2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
                   pk.z = pack_bf16x2(__uint_as_float(r[k + 4]), __uint_as_float(r[k + 5]));
                   pk.w = pack_bf16x2(__uint_as_float(r[k + 6]), __uint_as_float(r[k + 7]));
-                  if (p.y_cp8) store_cell(p, 0, oz + j, chunk0 + (cn >> 3), zpitch, cell, pk);
-                  if (p.y_ps8) store_cell(p, 1, oz + j, chunk0 + (cn >> 3), 4 * (size_t)p.Hso * p.Wso, pcell, pk);
+                  if (p.y_cp8) store_cell<PEER>(p, 0, oz + j, chunk0 + (cn >> 3), zpitch, cell, pk);
+                  if (p.y_ps8) store_cell<PEER>(p, 1, oz + j, chunk0 + (cn >> 3), 4 * (size_t)p.Hso * p.Wso, pcell, pk);
                 }
               }
             }
@@ -1455,13 +1516,27 @@ int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStr
   return MVSB200_OK;
 }
 
+using TcKernel = void (*)(const Params);
+// 0: <16 classic>, 1: <32 classic>, 2 / 3 / 4: x-fold with 8 / 16 / 32 channels per launch, 5: x-fold, Cout = 1
+static TcKernel kernel_variant(int k, bool peer_mode) {
+  switch (k) {
+    case 0: return peer_mode ? conv3d_tc_kernel<16, 0, 1> : conv3d_tc_kernel<16, 0, 0>;
+    case 1: return peer_mode ? conv3d_tc_kernel<32, 0, 1> : conv3d_tc_kernel<32, 0, 0>;
+    case 2: return peer_mode ? conv3d_tc_kernel<32, 1, 1> : conv3d_tc_kernel<32, 1, 0>;
+    case 3: return peer_mode ? conv3d_tc_kernel<32, 2, 1> : conv3d_tc_kernel<32, 2, 0>;
+    case 4: return peer_mode ? conv3d_tc_kernel<32, 4, 1> : conv3d_tc_kernel<32, 4, 0>;
+    default: return peer_mode ? conv3d_tc_kernel<32, 1, 3> : conv3d_tc_kernel<32, 1, 2>;
+  }
+}
+
 // x: CP8 for stride-1 convs and transposed convs, PS8 for stride-2 convs.  skip: CP8.
 // Outputs: y_cp8 and / or y_ps8 (bf16, Cout % 8 == 0), or y_f32 (NDHWC fp32, any Cout).
 int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
                      const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
                      const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
-                     int stats_rep_stride, const TcSlab* slab, const TcPeer* peer, cudaStream_t s) {
+                     int stats_rep_stride, const TcSlab* slab, const TcPeer* peer, TcRegress* regress,
+                     cudaStream_t s) {
   if (cin != 8 && cin != 16 && cin != 32 && cin != 64) {
     set_error("conv3d(bf16/tcgen05): Cin=%d unsupported (need 8, 16, 32 or 64)", cin);
     return MVSB200_ERR_UNSUPPORTED;
@@ -1487,11 +1562,10 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
   }
   static bool attr_done = false;
   if (!attr_done) {
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    MVS_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    for (int peer_mode = 0; peer_mode < 2; ++peer_mode)
+      for (int k = 0; k < 6; ++k)
+        MVS_CUDA(cudaFuncSetAttribute((const void*)kernel_variant(k, peer_mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemBudget));
     attr_done = true;
   }
   const bool has_skip = skip != nullptr, transform = xs != nullptr || has_skip || (x_bn && x_bn->stats);
@@ -1515,6 +1589,15 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       c.wait_flags[t] = peer ? peer->wait_flags[t] : nullptr;
     }
     c.wait_n = peer ? peer->wait_n : 0; c.wait_seq = peer ? peer->wait_seq : 0u; c.err_flag = peer ? peer->err_flag : nullptr;
+    // soft-argmin folded into the epilogue: only the x-folded single-channel layer whose CTAs walk the whole depth
+    c.rg_out = nullptr; c.rg_start = 0.f; c.rg_step = 0.f;
+    if (regress) {
+      regress->fused = 0;
+      if (regress->partial && c.xfold && cout == 1 && c.zsplit == 1 && y_f32 && !(slab && slab->halo)) {
+        c.rg_out = regress->partial; c.rg_start = regress->start; c.rg_step = regress->step;
+        regress->fused = 1;
+      }
+    }
     c.y_cp8 = (__nv_bfloat16*)y_cp8; c.y_ps8 = (__nv_bfloat16*)y_ps8; c.y_f32 = y_f32; c.stats = stats;
     // D-slab mode: the tensors hold D + 2 planes (halo before / after), local plane l is extended plane l + 1
     const int Dt = slab && slab->halo ? D + 2 : D;
@@ -1569,17 +1652,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = c.pdl ? 1 : 0;
     cudaError_t lerr = cudaSuccess;
-    auto launch = [&]() {
-      if (c.xfold) {
-        if (c.cout_n <= 8) lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<32, 1>, c);
-        else if (c.cout_n <= 16) lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<32, 2>, c);
-        else lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<32, 4>, c);
-      } else if (c.CP == 16) {
-        lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<16, 0>, c);
-      } else {
-        lerr = cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<32, 0>, c);
-      }
-    };
+    // instantiation: epilogue shape x (peer-memory D-slab mode or not)
+    const int variant = c.xfold ? (c.cout_n == 1 ? 5 : c.cout_n <= 8 ? 2 : c.cout_n <= 16 ? 3 : 4) : (c.CP == 16 ? 0 : 1);
+    auto launch = [&]() { lerr = cudaLaunchKernelEx(&cfg, kernel_variant(variant, peer != nullptr), c); };
     launch();
     if (lerr != cudaSuccess) {
       set_error("launch of conv3d_tc_kernel failed: %s", cudaGetErrorString(lerr));
@@ -1740,7 +1815,7 @@ int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, cons
   else if (via_f32) MVS_CUDA(tmp.alloc((void**)&yf, (size_t)Do * Ho * Wo * cout * sizeof(float)));
   else MVS_CUDA(tmp.alloc(&yp, planar_bytes(Do, Ho, Wo, cout, 0)));
   rc = launch_conv3d_tc(xp, xs, xb, kp, ss, sb, kernel_tf, D, H, W, cin, cout, stride, transposed, yp, nullptr, yf, stats,
-                        scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, nullptr, s);
+                        scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, nullptr, nullptr, s);
   if (rc) return rc;
   if (yp) rc = launch_planar_to_ndhwc(yp, Do, Ho, Wo, cout, y, s);
   else if (via_f32) rc = launch_f32_to_bf16(yf, (size_t)Do * Ho * Wo * cout, y, s);

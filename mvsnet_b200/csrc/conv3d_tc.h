@@ -25,6 +25,11 @@ struct TcPeer {
   const unsigned* wait_flags[2]; int wait_n; unsigned wait_seq; unsigned* err_flag;
 };
 
+// Soft-argmin of the regression folded into the last layer's epilogue (linear depth sampling): partial [3][Ho*Wo]
+// = per-pixel (max of -F, sum of exp, depth-weighted sum) with depth_i = start + step * i (tf.linspace); the launch
+// sets `fused` when the plan allowed it (x-fold, one output channel, CTAs covering the whole depth range).
+struct TcRegress { float* partial; float start, step; int fused; };
+
 // One job per layer of a network for conv3d_tc_pack_all; its launches (output-channel slices of 32) take
 // consecutive weight slots starting at slot0.
 struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0; };
@@ -35,7 +40,8 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
                      const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout, int stride,
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
                      const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
-                     int stats_rep_stride, const TcSlab* slab, const TcPeer* peer, cudaStream_t s);
+                     int stats_rep_stride, const TcSlab* slab, const TcPeer* peer, TcRegress* regress,
+                     cudaStream_t s);
 int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
                            const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout,
                            int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);

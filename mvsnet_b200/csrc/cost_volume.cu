@@ -143,7 +143,7 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
   __syncthreads();
   const bool active = (x < Wf) && (y < Hf);
   const int xc = min(x, Wf - 1), yc = min(y, Hf - 1);
-  const size_t plane = (size_t)Hf * Wf * 32, plane16 = (size_t)Hf * (Wf + 1) * 64;
+  const size_t plane = (size_t)Hf * Wf * 32;
   const float4 r = ldg4(feats + ((size_t)yc * Wf + xc) * 32 + g * 4);
   const float4 rq = make_float4(r.x * r.x, r.y * r.y, r.z * r.z, r.w * r.w);
   const float inv_n = 1.0f / (float)n_views, inv_nn = 1.0f / (float)(n_views * n_views);

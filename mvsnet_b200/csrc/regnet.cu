@@ -147,7 +147,7 @@ static int check_regnet_shape(int D, int H, int W, int cin, int b) {
 // layouts at regnet_cost_planar() inside the workspace and `cost` is ignored.
 int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const mvsb200_regnet_params* params, int D,
                         int H, int W, int cin, int b, float eps, int precision, float* filtered, void* workspace,
-                        size_t workspace_bytes, cudaStream_t s) {
+                        size_t workspace_bytes, cudaStream_t s, TcRegress* regress = nullptr) {
   MVS_CHECK_ARG((cost || cost_planar) && params && filtered && workspace, "regnet_forward: NULL pointer");
   int rc = check_regnet_shape(D, H, W, cin, b);
   if (rc) return rc;
@@ -244,7 +244,8 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
                             L.stride, L.transposed, last ? nullptr : ws + p.raw_off[i],
                             (!last && p.has_ps8[i]) ? ws + p.ps8_off[i] : nullptr, last ? filtered : nullptr, st,
                             nullptr, L.src >= 0 ? &xbn : nullptr, L.skip >= 0 ? &sbn : nullptr,
-                            ws + p.scratch_off + (size_t)2 * i * conv3d_tc_pack_slot_bytes(), kStatsReps, rep_stride, nullptr, nullptr, s);
+                            ws + p.scratch_off + (size_t)2 * i * conv3d_tc_pack_slot_bytes(), kStatsReps, rep_stride, nullptr,
+                            nullptr, last ? regress : nullptr, s);
       if (rc) return rc;
     }
     if (profile) cudaEventRecord(pev[i + 1], s);
@@ -516,7 +517,7 @@ extern "C" int mvsb200_slab_layer(int layer, int n_views, int depth_num, int sla
                           L.stride, L.transposed, y_cp8, y_ps8, last ? (float*)(ws + sp.filtered_off) : nullptr,
                           last ? nullptr : stats + (size_t)layer * lstride, nullptr, L.src >= 0 ? &xbn : nullptr,
                           L.skip >= 0 ? &sbn : nullptr, ws + sp.scratch_off + (size_t)2 * layer * conv3d_tc_pack_slot_bytes(),
-                          kStatsReps, 2 * sp.cpad, &win, nullptr, s);
+                          kStatsReps, 2 * sp.cpad, &win, nullptr, nullptr, s);
 }
 
 // ---- D-slab mode over peer memory (NVLink) -----------------------------------------------------------------------
@@ -600,7 +601,7 @@ extern "C" int mvsb200_slab_layer_p2p(int layer, int n_views, int depth_num, int
                         L.stride, L.transposed, y_cp8, y_ps8, last ? (float*)(ws + sp.filtered_off) : nullptr,
                         last ? nullptr : stats + (size_t)layer * lstride, nullptr, L.src >= 0 ? &xbn : nullptr,
                         L.skip >= 0 ? &sbn : nullptr, ws + sp.scratch_off + (size_t)2 * layer * conv3d_tc_pack_slot_bytes(),
-                        kStatsReps, 2 * sp.cpad, &win, &peer, s);
+                        kStatsReps, 2 * sp.cpad, &win, &peer, nullptr, s);
   if (rc || last) return rc;
   slab_publish_kernel<<<1, 128, 0, s>>>(stats + (size_t)layer * lstride, kStatsReps, 2 * sp.cpad, 2 * L.cout,
                                         (char* const*)peers_dev, slabs, slab, sp.gstats_off, sp.flags_off, layer, sp.cpad,
@@ -694,9 +695,15 @@ int launch_cost_volume_coef(const float* feats, const float* homographies, const
                             void* out, cudaStream_t s);
 size_t cost_volume_pair_bytes(int n_views, int hf, int wf);
 }
+namespace mvsb200 {
+int launch_regress_combine(const float* partials, int slabs, const float* filtered, int dl, int d0, int D, int npix,
+                           float depth_start, float depth_interval, int inverse_depth, int num_buckets, float* depth_map,
+                           float* prob_partial, cudaStream_t s);
+}
 namespace {
+inline float sub_host(float a, float b) { volatile float r = a - b; return r; }
 struct InferPlan {
-  size_t hom_off, coef_off, cost_off, filtered_off, pair_off, regnet_off, total;
+  size_t hom_off, coef_off, cost_off, filtered_off, pair_off, partial_off, regnet_off, total;
   size_t regnet_bytes;
 };
 void make_infer_plan(int n_views, int D, int hf, int wf, int C, int b, int precision, InferPlan* ip) {
@@ -708,6 +715,7 @@ void make_infer_plan(int n_views, int D, int hf, int wf, int C, int b, int preci
   ip->cost_off = off;     off += align_up((size_t)D * hf * wf * C * (precision == MVSB200_PRECISION_BF16 ? 2 : 4), 256);
   ip->filtered_off = off; off += align_up((size_t)D * hf * wf * sizeof(float), 256);
   ip->pair_off = off;     off += align_up(cost_volume_pair_bytes(n_views, hf, wf), 256);
+  ip->partial_off = off;  off += align_up((size_t)3 * hf * wf * sizeof(float), 256);   // fused soft-argmin partials
   ip->regnet_off = off;
   ip->regnet_bytes = mvsb200_regnet_workspace_bytes(D, hf, wf, C, b, precision);
   off += ip->regnet_bytes;
@@ -800,12 +808,24 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   }
   if (rc) return rc;
   MVS_STAGE_EVENT(2);
+  // bf16 mode, linear depth: the soft-argmin runs inside the last layer's epilogue when its plan allows it
+  // (tf.linspace step in fp32, model.py:487-490)
+  volatile float lin_num = sub_host((float)depth_num, 1.0f);
+  volatile float lin_span = sub_host((float)depth_end, depth_start);
+  volatile float lin_step = depth_num > 1 ? lin_span / lin_num : 0.0f;
+  static const bool no_fused_regress = getenv("MVSB200_NO_FUSED_REGRESS") != nullptr;
+  TcRegress rg = {(float*)(ws + ip.partial_off), depth_start, (float)lin_step, 0};
+  const bool try_fuse = precision == MVSB200_PRECISION_BF16 && !inverse_depth && !no_fused_regress;
   rc = regnet_forward_impl(cost, cost_dtype, planar ? 1 : 0, params, depth_num, hf, wf, channels, base_filter, bn_eps,
-                           precision, filtered, ws + ip.regnet_off, ip.regnet_bytes, s);
+                           precision, filtered, ws + ip.regnet_off, ip.regnet_bytes, s, try_fuse ? &rg : nullptr);
   if (rc) return rc;
   MVS_STAGE_EVENT(3);
-  rc = launch_depth_regress(filtered, depth_num, hf, wf, depth_start, depth_interval, inverse_depth, 4, depth_map,
-                            prob_map, nullptr, s);
+  if (try_fuse && rg.fused)
+    rc = launch_regress_combine(rg.partial, 1, filtered, depth_num, 0, depth_num, hf * wf, depth_start, depth_interval,
+                                inverse_depth, 4, depth_map, prob_map, s);
+  else
+    rc = launch_depth_regress(filtered, depth_num, hf, wf, depth_start, depth_interval, inverse_depth, 4, depth_map,
+                              prob_map, nullptr, s);
   if (rc) return rc;
   MVS_STAGE_EVENT(4);
   return MVSB200_OK;

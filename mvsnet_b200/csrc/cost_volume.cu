@@ -208,10 +208,10 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
         float4 w;
         if (TAPS16) {
           // consecutive planes of a pixel often fall into the same source cell (the sample moves a fraction of a
-          // pixel per plane): the second plane of the pair then reuses the taps already in registers (a predicated
+          // pixel per plane): a later plane of the group then reuses the taps already in registers (a predicated
           // load makes no L1 traffic for the lanes that skip it)
-          if (!(HINT && kdc == 2 && (j & 1) && fi.x == prev_fi.x)) ta = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.x));
-          if (!(HINT && kdc == 2 && (j & 1) && fi.y == prev_fi.y)) tb = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.y));
+          if (!(HINT && (j % kdc) != 0 && fi.x == prev_fi.x)) ta = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.x));
+          if (!(HINT && (j % kdc) != 0 && fi.y == prev_fi.y)) tb = __ldg(reinterpret_cast<const uint4*>(base16 + (unsigned)fi.y));
           prev_fi = fi;
           const uint4 a = ta, b = tb;
           if (HINT) {

@@ -813,7 +813,7 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   volatile float lin_num = sub_host((float)depth_num, 1.0f);
   volatile float lin_span = sub_host((float)depth_end, depth_start);
   volatile float lin_step = depth_num > 1 ? lin_span / lin_num : 0.0f;
-  static const bool no_fused_regress = getenv("MVSB200_NO_FUSED_REGRESS") != nullptr;
+  const bool no_fused_regress = getenv("MVSB200_NO_FUSED_REGRESS") != nullptr;      // tests compare the two paths
   TcRegress rg = {(float*)(ws + ip.partial_off), depth_start, (float)lin_step, 0};
   const bool try_fuse = precision == MVSB200_PRECISION_BF16 && !inverse_depth && !no_fused_regress;
   rc = regnet_forward_impl(cost, cost_dtype, planar ? 1 : 0, params, depth_num, hf, wf, channels, base_filter, bn_eps,

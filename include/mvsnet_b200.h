@@ -268,6 +268,42 @@ int mvsb200_ipc_export(void* ptr, unsigned char* handle64);
 int mvsb200_ipc_open(const unsigned char* handle64, void** ptr);
 int mvsb200_ipc_close(void* ptr);
 
+/* ---- image feature tower (the step before the hot path) --------------------------------
+ * UNetDS2GN (cnn_wrapper/mvsnetworks.py:53-115), run per view with shared weights (model.py:392-406).  fp32, NHWC.
+ * Layer order = the order the reference builds them: 2dconv1_0 2_0 3_0 4_0 0_1 0_2 1_1 1_2 2_1 2_2 3_1 3_2 4_1 4_2
+ * 5_0 5_1 5_2 6_0 6_1 6_2 7_0 7_1 7_2 8_0 8_1 8_2 conv9_0 9_1 9_2 conv10_0 10_1 10_2.
+ * kernel[l]: `<layer>/kernel` [k,k,Cin,Cout] (conv) or [k,k,Cout,Cin] (the four deconvs 2dconv{5,6,7,8}_0);
+ * gamma/beta[l]: `<layer>/gn/{gamma,beta}` [Cout]; NULL for conv10_2 (no normalisation, mvsnetworks.py:113-115). */
+#define MVSB200_UNET_LAYERS 32
+typedef struct mvsb200_unet_params {
+  const float* kernel[MVSB200_UNET_LAYERS];
+  const float* gamma[MVSB200_UNET_LAYERS];
+  const float* beta[MVSB200_UNET_LAYERS];
+} mvsb200_unet_params;
+
+/* One conv_gn / deconv_gn building block, split in its two halves (network.py:218-276, :349-409):
+ * mvsb200_conv2d_layer: tf.layers.conv2d / conv2d_transpose, SAME, no bias, of the channel concatenation of xa
+ *   [N,H,W,ca] and xb [N,H,W,cb] (cb = 0: xa alone): y [N,Ho,Wo,cout] raw; ksize 3 or 5, stride 1 or 2, transposed
+ *   only 3x3 stride 2 (Ho = 2H).  stats (may be NULL): [N][cout/8][2] doubles, the kernel ADDS the sum and the sum
+ *   of squares of every (view, group of 8 channels) of y (the caller zeroes it).
+ * mvsb200_group_norm: y [N,pixels,channels] in place: ((y - mean) / sqrt(var + eps)) * gamma + beta, ReLU if relu. */
+int mvsb200_conv2d_layer(const float* xa, int ca, const float* xb, int cb, const float* kernel_tf, int n_views,
+                         int height, int width, int cout, int ksize, int stride, int transposed, float* y,
+                         double* stats, void* stream);
+int mvsb200_group_norm(float* y, const double* stats, const float* gamma, const float* beta, int n_views,
+                       int pixels, int channels, float eps, int relu, void* stream);
+
+/* Whole tower: images [N,H,W,3] (centred, mvs_data_generation/utils.py:33-38) -> feats [N,H/4,W/4,4*base_filter].
+ * H and W must be multiples of 16 and base_filter a multiple of 8 (network mode "normal").  0 bytes = bad shape. */
+size_t mvsb200_unet_workspace_bytes(int n_views, int height, int width, int base_filter);
+int mvsb200_unet_forward(const float* images, const mvsb200_unet_params* params, int n_views, int height,
+                         int width, int base_filter, float gn_eps, float* feats, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* After mvsb200_unet_forward: byte offset inside the workspace and {Ho, Wo, C} of a layer's (normalised) output
+ * (layer-wise parity tests).  The last layer is written to `feats`, not to the workspace. */
+int mvsb200_unet_layer_output(int n_views, int height, int width, int base_filter, int layer, size_t* offset,
+                              int* dims);
+
 /* Diagnostic (not on the product path): one 128 x n x (16*kblocks) tcgen05.mma tile computed from
  * caller-built shared-memory images of the A and B operands (no-swizzle K-major core-matrix
  * layout).  Pins the descriptor semantics conv3d_tc.cu relies on.  d_out [128*n] fp32. */

@@ -25,6 +25,33 @@ class MVSB200Error(RuntimeError):
     """A call into libmvsnet_b200.so returned a non-zero status."""
 
 
+UNET_LAYERS = 32
+# name, op, kernel, stride, filters / base_filter, sources (-1 = the images), group norm, relu: mvsnetworks.py:58-115
+UNET_LAYER_TABLE = [
+    ("2dconv1_0", "conv", 3, 2, 2, (-1,), True, True), ("2dconv2_0", "conv", 3, 2, 4, (0,), True, True),
+    ("2dconv3_0", "conv", 3, 2, 8, (1,), True, True), ("2dconv4_0", "conv", 3, 2, 16, (2,), True, True),
+    ("2dconv0_1", "conv", 3, 1, 1, (-1,), True, True), ("2dconv0_2", "conv", 3, 1, 1, (4,), True, True),
+    ("2dconv1_1", "conv", 3, 1, 2, (0,), True, True), ("2dconv1_2", "conv", 3, 1, 2, (6,), True, True),
+    ("2dconv2_1", "conv", 3, 1, 4, (1,), True, True), ("2dconv2_2", "conv", 3, 1, 4, (8,), True, True),
+    ("2dconv3_1", "conv", 3, 1, 8, (2,), True, True), ("2dconv3_2", "conv", 3, 1, 8, (10,), True, True),
+    ("2dconv4_1", "conv", 3, 1, 16, (3,), True, True), ("2dconv4_2", "conv", 3, 1, 16, (12,), True, True),
+    ("2dconv5_0", "deconv", 3, 2, 8, (13,), True, False), ("2dconv5_1", "conv", 3, 1, 8, (14, 11), True, True),
+    ("2dconv5_2", "conv", 3, 1, 8, (15,), True, True), ("2dconv6_0", "deconv", 3, 2, 4, (16,), True, False),
+    ("2dconv6_1", "conv", 3, 1, 4, (17, 9), True, True), ("2dconv6_2", "conv", 3, 1, 4, (18,), True, True),
+    ("2dconv7_0", "deconv", 3, 2, 2, (19,), True, False), ("2dconv7_1", "conv", 3, 1, 2, (20, 7), True, True),
+    ("2dconv7_2", "conv", 3, 1, 2, (21,), True, True), ("2dconv8_0", "deconv", 3, 2, 1, (22,), True, False),
+    ("2dconv8_1", "conv", 3, 1, 1, (23, 5), True, True), ("2dconv8_2", "conv", 3, 1, 1, (24,), True, True),
+    ("conv9_0", "conv", 5, 2, 2, (25,), True, True), ("conv9_1", "conv", 3, 1, 2, (26,), True, True),
+    ("conv9_2", "conv", 3, 1, 2, (27,), True, True), ("conv10_0", "conv", 5, 2, 4, (28,), True, True),
+    ("conv10_1", "conv", 3, 1, 4, (29,), True, True), ("conv10_2", "conv", 3, 1, 4, (30,), False, False),
+]
+UNET_LAYER_NAMES = [t[0] for t in UNET_LAYER_TABLE]
+
+
+class UnetParams(ctypes.Structure):
+    _fields_ = [("kernel", c_void_p * UNET_LAYERS), ("gamma", c_void_p * UNET_LAYERS), ("beta", c_void_p * UNET_LAYERS)]
+
+
 class RegnetParams(ctypes.Structure):
     _fields_ = [("kernel", c_void_p * REGNET_LAYERS), ("gamma", c_void_p * REGNET_LAYERS),
                 ("beta", c_void_p * REGNET_LAYERS)]
@@ -51,6 +78,11 @@ SIGNATURES = {
                                        c_int, _P, _P, c_size_t, _P]),
     "mvsb200_regnet_layer_raw": (c_void_p, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p),
                                             POINTER(c_void_p)]),
+    "mvsb200_conv2d_layer": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "mvsb200_group_norm": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P]),
+    "mvsb200_unet_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "mvsb200_unet_forward": (c_int, [_P, POINTER(UnetParams), c_int, c_int, c_int, c_int, c_float, _P, _P, c_size_t, _P]),
+    "mvsb200_unet_layer_output": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_int)]),
     "mvsb200_depth_regress": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P, _P, _P]),
     "mvsb200_probability_map": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P]),
     "mvsb200_infer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),

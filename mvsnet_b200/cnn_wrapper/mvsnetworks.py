@@ -1,4 +1,4 @@
-"""Drop-in for the 3-D branch of mvsnet/cnn_wrapper/mvsnetworks.py: RegNetUS0 (:122-158)."""
+"""Drop-in for mvsnet/cnn_wrapper/mvsnetworks.py: RegNetUS0 (:122-158) and the image tower UNetDS2GN (:53-115)."""
 from __future__ import annotations
 
 import ctypes
@@ -70,4 +70,53 @@ class RegNetUS0:
                                                    nbytes, L.stream_ptr()), "regnet_forward")
                 outs.append(out)
             self._output = torch.stack(outs, dim=0)[..., None]
+        return self._output
+
+
+_UNET_VARIABLES = {}
+
+
+def set_unet_variables(weights: dict) -> None:
+    """Register UNetDS2GN variables ('2dconv0_1/kernel', '2dconv0_1/gn/gamma', ...), shared by every tower like the
+    reference's reuse=True variable scope (model.py:392-406)."""
+    _UNET_VARIABLES.clear()
+    _UNET_VARIABLES.update(weights)
+    _UNET_CACHE.clear()
+
+
+_UNET_CACHE = {}
+
+
+class UNetDS2GN:
+    """UNetDS2GN({'data': image}, trainable=, training=, mode=, reuse=).get_output() -> [B,H/4,W/4,32].
+
+    `image` is [B,H,W,3] fp32 (centred).  Group normalisation has no batch dependence, so a batch of B images is B
+    independent towers (upstream builds one tower per view and batch_size 1)."""
+
+    def __init__(self, inputs, trainable=True, training=True, mode="normal", reuse=False, epsilon=1e-5, **kwargs):
+        if mode not in NETWORK_MODE_DIVISOR:
+            raise ValueError(f"unknown network mode {mode!r}")
+        if regnet_base_filter(mode) % 8:
+            raise NotImplementedError(f"UNetDS2GN mode {mode!r}: groups of fewer than 8 channels are not built")
+        self.base_divisor = NETWORK_MODE_DIVISOR[mode]
+        self.base_filter = regnet_base_filter(mode)
+        self.epsilon = float(epsilon)
+        self.layers = dict(inputs)
+        self._output = None
+
+    def get_output(self):
+        if self._output is None:
+            from ..features import FeatureTower
+            image = self.layers["data"]
+            if image.dim() != 4:
+                raise ValueError("Improper input rank for layer: 2dconv1_0")
+            if not _UNET_VARIABLES:
+                raise RuntimeError("UNetDS2GN variables not set: call mvsnetworks.set_unet_variables(weights)")
+            key = (str(image.device), self.epsilon)
+            if key not in _UNET_CACHE:
+                _UNET_CACHE[key] = FeatureTower(_UNET_VARIABLES, self.epsilon, image.device)
+            tower = _UNET_CACHE[key]
+            if tower.weights.base_filter != self.base_filter:
+                raise ValueError(f"variables are for base_filter {tower.weights.base_filter}, mode needs {self.base_filter}")
+            self._output = tower(image.to(torch.float32))
         return self._output

@@ -1,9 +1,10 @@
 """Drop-in for the 3DCNN part of mvsnet/model.py: inference (:257), inference_mem (:374),
 get_probability_map (:20), get_probability_map_slice (:45) with the reference's argument order.
 
-The feature UNet (UNetDS2GN, model.py:272,392) is out of scope and stays whatever the caller uses:
-register it with `set_feature_extractor(fn)` (fn: images [B,H,W,3] -> features [B,H/4,W/4,C]); or pass
-the feature towers directly as `images` [B,N,Hf,Wf,C] (any last dimension other than 3).
+`images` is either the reference's [B,N,H,W,3] (then every view goes through the UNetDS2GN tower of this package,
+model.py:392-406, once its variables are registered with `mvsnetworks.set_unet_variables`, or through a caller's own
+extractor registered with `set_feature_extractor(fn)`, fn: images [B,H,W,3] -> features [B,H/4,W/4,C]), or the
+feature towers themselves, [B,N,Hf,Wf,C] (any last dimension other than 3).
 """
 from __future__ import annotations
 
@@ -50,20 +51,27 @@ def get_probability_map(cv_batch, depth_map_batch, depth_start_batch, depth_inte
     return torch.cat(outs, dim=0)
 
 
-def _towers(images):
+def _towers(images, network_mode="normal"):
     if images.shape[-1] != 3:
         return images                                    # already feature towers [B,N,Hf,Wf,C]
-    if _feature_extractor is None:
-        raise RuntimeError("images given but no feature extractor registered (model.set_feature_extractor); "
-                           "the feature UNet is outside this package")
     n = images.shape[1]
-    return torch.stack([_feature_extractor(images[:, v]) for v in range(n)], dim=1)
+    if _feature_extractor is not None:
+        return torch.stack([_feature_extractor(images[:, v]) for v in range(n)], dim=1)
+    if not mvsnetworks._UNET_VARIABLES:
+        raise RuntimeError("images given but neither UNetDS2GN variables (mvsnetworks.set_unet_variables) nor a "
+                           "feature extractor (model.set_feature_extractor) is registered")
+    # one tower per view with shared variables (model.py:392-406); the views of a batch are independent, so they
+    # go through the tower together
+    b, _, h, w, _ = images.shape
+    tower = mvsnetworks.UNetDS2GN({"data": images.reshape(b * n, h, w, 3)}, mode=network_mode, reuse=True)
+    f = tower.get_output()
+    return f.reshape(b, n, f.shape[1], f.shape[2], f.shape[3])
 
 
 def _run(images, cams, depth_num, depth_start, depth_interval, network_mode, inverse_depth, order):
     if not isinstance(depth_num, int):
         raise TypeError("depth_num must be a Python int (model.py:427 iterates range(depth_num))")
-    feats = _towers(images).to(torch.float32)
+    feats = _towers(images, network_mode).to(torch.float32)
     B, N, hf, wf, c = feats.shape
     if FLAGS.view_num is not None and FLAGS.view_num != N:
         raise ValueError(f"FLAGS.view_num={FLAGS.view_num} but {N} views given")

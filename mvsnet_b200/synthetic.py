@@ -61,6 +61,48 @@ def make_regnet_weights(in_channels=32, base_filter=8, seed=42):
     return w
 
 
+def unet_channels(base_filter=8, in_channels=3):
+    """[(name, op, k, stride, Cin, Cout, has_gn)] of UNetDS2GN in the reference's build order (mvsnetworks.py:58-115)."""
+    from ._lib import UNET_LAYER_TABLE
+    out, ch = [], []
+    for name, op, k, stride, mult, srcs, gn, _relu in UNET_LAYER_TABLE:
+        cin = sum(in_channels if s < 0 else ch[s] for s in srcs)
+        ch.append(base_filter * mult)
+        out.append((name, op, k, stride, cin, ch[-1], gn))
+    return out
+
+
+def make_unet_weights(base_filter=8, seed=43):
+    """TF-layout weights of the feature tower: conv '<l>/kernel' [k,k,Cin,Cout], deconv [k,k,Cout,Cin]; '<l>/gn/gamma',
+    '<l>/gn/beta' (network.py:256-266).  Glorot-uniform kernels (tf.layers default), gamma ~ U(0.5,1.5), beta ~ N(0,0.1)."""
+    rng = np.random.RandomState(seed)
+    w = {}
+    for name, op, k, _stride, cin, cout, gn in unet_channels(base_filter):
+        limit = np.sqrt(6.0 / (k * k * cin + k * k * cout))
+        shape = (k, k, cin, cout) if op == "conv" else (k, k, cout, cin)
+        w[name + "/kernel"] = rng.uniform(-limit, limit, size=shape).astype(F32)
+        if gn:
+            w[name + "/gn/gamma"] = rng.uniform(0.5, 1.5, size=(cout,)).astype(F32)
+            w[name + "/gn/beta"] = rng.normal(0.0, 0.1, size=(cout,)).astype(F32)
+    return w
+
+
+def make_images(n_views, height, width, seed=91):
+    """Centred images [N,H,W,3] (zero mean, unit variance per image: mvs_data_generation/utils.py:33-38): a smooth
+    random texture plus noise, a different crop per view."""
+    rng = np.random.RandomState(seed)
+    base = rng.normal(size=(height + 64, width + 64, 3))
+    for _ in range(2):                                     # cheap blur: neighbour averages along both axes
+        base = (base + np.roll(base, 1, 0) + np.roll(base, -1, 0)) / 3.0
+        base = (base + np.roll(base, 1, 1) + np.roll(base, -1, 1)) / 3.0
+    imgs = []
+    for v in range(n_views):
+        oy, ox = rng.randint(0, 64, size=2)
+        im = base[oy:oy + height, ox:ox + width] + 0.05 * rng.normal(size=(height, width, 3))
+        imgs.append((im - im.mean()) / np.sqrt(im.var() + 1e-8))
+    return np.stack(imgs).astype(F32)
+
+
 def _look_at(cam_pos, target, roll_deg):
     """World->camera rotation for a camera at cam_pos looking at target (z forward, y down)."""
     z = target - cam_pos

@@ -1,0 +1,114 @@
+"""Image feature tower on the GPU (csrc/feature2d.cu) against the CPU restatement: every kind of
+layer of UNetDS2GN alone (3x3 / 5x5, stride 1 / 2, transposed, concatenated sources, odd extents), the group
+normalisation, the whole 32-layer tower layer by layer, and images -> depth map through the reference-named API."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from conftest import to_dev  # noqa: E402
+from mvsnet_b200 import synthetic  # noqa: E402
+
+
+def _rand(shape, seed):
+    return np.random.RandomState(seed).normal(size=shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("case", [
+    dict(h=18, w=22, ca=3, cout=8, k=3, s=1), dict(h=18, w=22, ca=3, cout=16, k=3, s=2),
+    dict(h=16, w=24, ca=8, cout=16, k=5, s=2), dict(h=17, w=23, ca=8, cout=16, k=5, s=2),
+    dict(h=9, w=13, ca=64, cb=64, cout=64, k=3, s=1), dict(h=12, w=20, ca=16, cb=8, cout=8, k=3, s=1),
+    dict(h=7, w=9, ca=128, cout=128, k=3, s=1), dict(h=6, w=10, ca=16, cout=8, k=3, s=2, t=True),
+    dict(h=5, w=7, ca=128, cout=64, k=3, s=2, t=True)])
+def test_conv2d_layer_vs_oracle(case):
+    import oracle.feature_oracle as FO
+    from mvsnet_b200 import features
+    n, h, w, ca, cb = 2, case["h"], case["w"], case["ca"], case.get("cb", 0)
+    cout, k, s, t = case["cout"], case["k"], case["s"], case.get("t", False)
+    xa, xb = _rand((n, h, w, ca), 1), (_rand((n, h, w, cb), 2) if cb else None)
+    kern = _rand((k, k, cout, ca + cb) if t else (k, k, ca + cb, cout), 3) * np.float32(0.2)
+    x = xa if xb is None else np.concatenate([xa, xb], axis=-1)
+    ref = FO.conv2d_transpose_same(x, kern) if t else FO.conv2d_same(x, kern, s)
+    y, stats = features.conv2d_layer(to_dev(xa), to_dev(kern), s, t, xb=None if xb is None else to_dev(xb))
+    assert tuple(y.shape) == ref.shape
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-4, atol=2e-5 * float(np.abs(ref).max()))
+    # the statistics are the sums of what was stored, per (view, group of 8 channels)
+    g = y.double().reshape(n, -1, cout // 8, 8)
+    np.testing.assert_allclose(stats[..., 0].cpu().numpy(), g.sum(dim=(1, 3)).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (g * g).sum(dim=(1, 3)).cpu().numpy(), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("c,relu", [(8, True), (32, False), (128, True)])
+def test_group_norm_vs_oracle(c, relu):
+    import oracle.feature_oracle as FO
+    from mvsnet_b200 import features
+    x = _rand((2, 11, 13, c), 5) * np.float32(2.5) + np.float32(0.7)
+    gam = np.random.RandomState(6).uniform(0.5, 1.5, c).astype(np.float32)
+    bet = _rand((c,), 7)
+    ref = FO.group_norm(x, gam, bet, 1e-5, relu)
+    y = to_dev(x)
+    g = y.double().reshape(2, -1, c // 8, 8)
+    stats = torch.stack([g.sum(dim=(1, 3)), (g * g).sum(dim=(1, 3))], dim=-1).contiguous()
+    features.group_norm_(y, stats, to_dev(gam), to_dev(bet), 1e-5, relu)
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+
+
+def test_whole_tower_layer_by_layer():
+    import oracle.feature_oracle as FO
+    from mvsnet_b200 import _lib as L
+    from mvsnet_b200.features import FeatureTower
+    w = synthetic.make_unet_weights(8)
+    im = synthetic.make_images(2, 64, 80)
+    ref, outs = FO.unet_ds2gn(im, w, return_layers=True)
+    tower = FeatureTower(w)
+    f = tower(to_dev(im))
+    assert tuple(f.shape) == (2, 16, 20, 32)
+    for i, name in enumerate(L.UNET_LAYER_NAMES[:-1]):
+        got = tower.layer_output(i).cpu().numpy()
+        assert got.shape == outs[name].shape, name
+        # normalised activations are O(1); 32 layers of fp32 with different summation orders
+        assert float(np.abs(got - outs[name]).max()) <= 5e-4, (name, float(np.abs(got - outs[name]).max()))
+    assert float(np.abs(f.cpu().numpy() - ref).max()) <= 5e-4 * max(1.0, float(np.abs(ref).max()))
+    # same images, same features (no state between calls; fp64 atomics only reorder the statistics)
+    np.testing.assert_allclose(tower(to_dev(im)).cpu().numpy(), f.cpu().numpy(), rtol=0, atol=1e-5)
+
+
+def test_tower_rejects_shapes_the_reference_graph_cannot_build():
+    from mvsnet_b200 import _lib as L
+    from mvsnet_b200.features import FeatureTower
+    tower = FeatureTower(synthetic.make_unet_weights(8))
+    with pytest.raises(L.MVSB200Error, match="multiples of 16"):
+        tower(torch.zeros((1, 40, 64, 3), device="cuda"))
+    with pytest.raises(ValueError):
+        tower(torch.zeros((1, 32, 64, 4), device="cuda"))
+
+
+def test_images_to_depth_map_through_the_reference_names(tiny_problem):
+    """model.inference_mem(images [B,N,H,W,3], ...) with the package's own UNetDS2GN towers against the oracle run on
+    the same images: depth within 0.1 interval on >= 99.9 % of the pixels (fp32 mode)."""
+    import oracle as O
+    import oracle.feature_oracle as FO
+    from mvsnet_b200 import model
+    from mvsnet_b200.cnn_wrapper import mvsnetworks
+    p = tiny_problem
+    h, w = p["hf"] * 4, p["wf"] * 4
+    if h % 16 or w % 16:
+        pytest.skip("tiny problem is not a multiple of 16")
+    uw = synthetic.make_unet_weights(8)
+    im = synthetic.make_images(p["n_views"], h, w)
+    feats = FO.unet_ds2gn(im, uw)
+    rd, rp = O.inference_from_features(feats, p["cams"], p["depth_num"], p["depth_start"], p["depth_interval"], p["weights"])
+    mvsnetworks.set_variables(p["weights"])
+    mvsnetworks.set_unet_variables(uw)
+    model.set_feature_extractor(None)
+    old = (model.FLAGS.precision, model.FLAGS.view_num)
+    model.FLAGS.precision, model.FLAGS.view_num = "fp32", p["n_views"]
+    try:
+        d, pm = model.inference_mem(to_dev(im)[None], to_dev(p["cams"])[None], p["depth_num"],
+                                    torch.tensor([p["depth_start"]]), torch.tensor([p["depth_interval"]]), "normal")
+    finally:
+        model.FLAGS.precision, model.FLAGS.view_num = old
+        mvsnetworks.set_unet_variables({})
+    d = d[0, ..., 0].cpu().numpy()
+    assert float(np.mean(np.abs(d - rd) <= 0.1 * p["depth_interval"])) >= 0.999

@@ -27,7 +27,8 @@ def main():
     d, h, wd = D >> l, hf >> l, wf >> l
     x = torch.randn((d, h, wd, cin), device="cuda").to(torch.bfloat16)
     kern = torch.from_numpy(w[a.layer + "/kernel"]).cuda()
-    aff = (torch.ones(cin, device="cuda"), torch.zeros(cin, device="cuda")) if a.layer != "3dconv0_1" else None
+    # the two layers that read the cost volume have no normalisation on their input
+    aff = (torch.ones(cin, device="cuda"), torch.zeros(cin, device="cuda")) if a.layer not in ("3dconv0_1", "3dconv1_0") else None
     skip = x if a.layer in ("3dconv5_0", "3dconv6_0", "3dconv6_2") else None
     od = torch.float32 if a.layer == "3dconv6_2" else torch.bfloat16
     ts = []

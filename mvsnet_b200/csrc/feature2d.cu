@@ -5,6 +5,8 @@
 // reference's op order (network.py:237-276, :349-409: groups of 8 channels, biased variance, eps 1e-5; conv_gn has a
 // ReLU, deconv_gn has none).  This is the step before the hot path; the tcgen05 version
 // is round-2 work, this file is the parity-first CUDA implementation.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mvsb200 {
@@ -12,7 +14,7 @@ namespace mvsb200 {
 namespace {
 
 constexpr int kCoT = 8;            // output channels per block = one normalisation group (group_channel = 8)
-constexpr int kPxT = 4;            // consecutive output pixels (along x) per thread
+constexpr int kPxT = 4;            // output rows per thread (8 rows: 198 registers and no faster, measured)
 constexpr int kThreads2d = 128;
 
 struct F2Layer {
@@ -42,9 +44,10 @@ const F2Layer kUnet[MVSB200_UNET_LAYERS] = {
     {"conv10_1", 0, 3, 1, 4, 29, -2, 1, 1},   {"conv10_2", 0, 3, 1, 4, 30, -2, 0, 0},
 };
 
-// One thread = kPxT consecutive output pixels of a row x kCoT output channels; the weights of the block's channel
-// chunk sit in shared memory as [tap][ci][kCoT].  Sources a and b are the two halves of a channel concatenation
-// (cb = 0: single source).  blockIdx = (pixel segments, output-channel chunk, view).
+// One thread = kPxT output pixels (the same column of kPxT consecutive rows) x kCoT output channels; a warp covers
+// 32 consecutive columns, so its loads and stores run along x.  The weights of the block's channel chunk sit in
+// shared memory as [tap][ci][kCoT].  Sources a and b are the two halves of a channel concatenation (cb = 0: single
+// source).  blockIdx = (warp tiles of 32 columns x kPxT rows, output-channel chunk, view).
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(kThreads2d)
 conv2d_direct_kernel(const float* __restrict__ xa, int ca, const float* __restrict__ xb, int cb,
@@ -60,10 +63,11 @@ conv2d_direct_kernel(const float* __restrict__ xa, int ca, const float* __restri
                         : kernel_tf[((size_t)tap * Cin + ci) * Cout + (co0 + co)];      // [kh,kw,Cin,Cout]
   }
   __syncthreads();
-  const int segs = (Wo + kPxT - 1) / kPxT;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = q < Ho * segs;
-  const int oy = live ? q / segs : 0, ox0 = live ? (q - oy * segs) * kPxT : 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int xt = (Wo + 31) / 32;                                   // warp tiles per row band
+  const int q = blockIdx.x * (kThreads2d / 32) + warp;             // warp tile index
+  const int oy0 = (q / xt) * kPxT, ox = (q % xt) * 32 + lane;
+  const bool live = oy0 < Ho && ox < Wo;
   float acc[kPxT][kCoT];
 #pragma unroll
   for (int j = 0; j < kPxT; ++j)
@@ -72,21 +76,21 @@ conv2d_direct_kernel(const float* __restrict__ xa, int ca, const float* __restri
   if (live) {
     const float* xa_n = xa + (size_t)n * H * W * ca;
     const float* xb_n = cb ? xb + (size_t)n * H * W * cb : nullptr;
-    for (int kh = 0; kh < K; ++kh) {
-      int iy;
-      if (TRANSPOSED) { const int t = oy - kh; if (t < 0 || (t & 1)) continue; iy = t >> 1; }
-      else iy = oy * stride + kh - pad_h;
-      if (iy < 0 || iy >= H) continue;
-      for (int kw = 0; kw < K; ++kw) {
-        int ix[kPxT];
+    for (int kw = 0; kw < K; ++kw) {
+      int ix;
+      if (TRANSPOSED) { const int t = ox - kw; ix = (t < 0 || (t & 1)) ? -1 : (t >> 1); }
+      else ix = ox * stride + kw - pad_w;
+      if (ix < 0 || ix >= W) continue;
+      for (int kh = 0; kh < K; ++kh) {
+        int iy[kPxT];
         bool any = false;
 #pragma unroll
         for (int j = 0; j < kPxT; ++j) {
           int v;
-          if (TRANSPOSED) { const int t = ox0 + j - kw; v = (t < 0 || (t & 1)) ? -1 : (t >> 1); }
-          else v = (ox0 + j) * stride + kw - pad_w;
-          if (v >= W || ox0 + j >= Wo) v = -1;
-          ix[j] = v;
+          if (TRANSPOSED) { const int t = oy0 + j - kh; v = (t < 0 || (t & 1)) ? -1 : (t >> 1); }
+          else v = (oy0 + j) * stride + kh - pad_h;
+          if (v >= H || oy0 + j >= Ho) v = -1;
+          iy[j] = v;
           any |= v >= 0;
         }
         if (!any) continue;
@@ -97,13 +101,14 @@ conv2d_direct_kernel(const float* __restrict__ xa, int ca, const float* __restri
           const int cs = src ? cb : ca;
           if (cs == 0) continue;
           const float* ws = wt + (src ? ca * kCoT : 0);
-          const float* row = xs + (size_t)iy * W * cs;
+          const float* col = xs + (size_t)ix * cs;
+          const size_t rowp = (size_t)W * cs;
           if ((cs & 3) == 0) {
             for (int ci = 0; ci < cs; ci += 4) {
               float4 v[kPxT];
 #pragma unroll
               for (int j = 0; j < kPxT; ++j)
-                v[j] = ix[j] >= 0 ? __ldg(reinterpret_cast<const float4*>(row + (size_t)ix[j] * cs + ci))
+                v[j] = iy[j] >= 0 ? __ldg(reinterpret_cast<const float4*>(col + (size_t)iy[j] * rowp + ci))
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
@@ -125,7 +130,7 @@ conv2d_direct_kernel(const float* __restrict__ xa, int ca, const float* __restri
               const float4 w1 = *reinterpret_cast<const float4*>(ws + ci * kCoT + 4);
 #pragma unroll
               for (int j = 0; j < kPxT; ++j) {
-                const float a = ix[j] >= 0 ? __ldg(row + (size_t)ix[j] * cs + ci) : 0.0f;
+                const float a = iy[j] >= 0 ? __ldg(col + (size_t)iy[j] * rowp + ci) : 0.0f;
                 acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
                 acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
                 acc[j][4] = fmaf(a, w1.x, acc[j][4]); acc[j][5] = fmaf(a, w1.y, acc[j][5]);
@@ -136,11 +141,10 @@ conv2d_direct_kernel(const float* __restrict__ xa, int ca, const float* __restri
         }
       }
     }
-    float* yo = y + (((size_t)n * Ho + oy) * Wo + ox0) * Cout + co0;
 #pragma unroll
     for (int j = 0; j < kPxT; ++j)
-      if (ox0 + j < Wo) {
-        float4* o = reinterpret_cast<float4*>(yo + (size_t)j * Cout);
+      if (oy0 + j < Ho) {
+        float4* o = reinterpret_cast<float4*>(y + (((size_t)n * Ho + oy0 + j) * Wo + ox) * Cout + co0);
         o[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
         o[1] = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
       }
@@ -151,7 +155,7 @@ conv2d_direct_kernel(const float* __restrict__ xa, int ca, const float* __restri
   if (live) {
 #pragma unroll
     for (int j = 0; j < kPxT; ++j)
-      if (ox0 + j < Wo) {
+      if (oy0 + j < Ho) {
 #pragma unroll
         for (int k = 0; k < kCoT; ++k) { s += acc[j][k]; sq = fmaf(acc[j][k], acc[j][k], sq); }
       }
@@ -161,7 +165,6 @@ conv2d_direct_kernel(const float* __restrict__ xa, int ca, const float* __restri
     s += __shfl_xor_sync(0xffffffffu, s, o);
     sq += __shfl_xor_sync(0xffffffffu, sq, o);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { s_red[0][warp] = s; s_red[1][warp] = sq; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -214,8 +217,8 @@ int launch_conv2d(const float* xa, int ca, const float* xb, int cb, const float*
     set_error("conv2d: %d input channels exceed the shared-memory weight tile", ca + cb);
     return MVSB200_ERR_UNSUPPORTED;
   }
-  const int segs = (wo + kPxT - 1) / kPxT;
-  dim3 grid(ceil_div(ho * segs, kThreads2d), cout / kCoT, n);
+  const int tiles = ceil_div(wo, 32) * ceil_div(ho, kPxT);          // one warp per 32 columns x kPxT rows
+  dim3 grid(ceil_div(tiles, kThreads2d / 32), cout / kCoT, n);
   if (transposed)
     conv2d_direct_kernel<true><<<grid, kThreads2d, smem, s>>>(xa, ca, xb, cb, kernel_tf, h, w, cout, k, stride, ho, wo, 0, 0,
                                                               y, stats);
@@ -318,6 +321,13 @@ extern "C" int mvsb200_unet_forward(const float* images, const mvsb200_unet_para
   double* stats = (double*)(ws + p.stats_off);
   MVS_CUDA(cudaMemsetAsync(stats, 0, p.stats_bytes, s));
   const int gmax = 16 * base_filter / kCoT;
+  // development aid: MVSB200_UNET_PROFILE=1 prints per-layer device times (synchronises; not for timed runs)
+  static const bool profile = getenv("MVSB200_UNET_PROFILE") != nullptr;
+  cudaEvent_t pev[MVSB200_UNET_LAYERS + 1];
+  if (profile) {
+    for (int i = 0; i <= MVSB200_UNET_LAYERS; ++i) cudaEventCreate(&pev[i]);
+    cudaEventRecord(pev[0], s);
+  }
   for (int l = 0; l < MVSB200_UNET_LAYERS; ++l) {
     const F2Layer& L = kUnet[l];
     MVS_CHECK_ARG(params->kernel[l] != nullptr, "unet_forward: kernel[%d] (%s) is NULL", l, L.name);
@@ -338,6 +348,19 @@ extern "C" int mvsb200_unet_forward(const float* images, const mvsb200_unet_para
       rc = launch_group_norm(y, st, params->gamma[l], params->beta[l], n_views, p.h[l] * p.w[l], p.c[l], gn_eps, L.relu, s);
       if (rc) return rc;
     }
+    if (profile) cudaEventRecord(pev[l + 1], s);
+  }
+  if (profile) {
+    cudaStreamSynchronize(s);
+    float total = 0.f;
+    for (int l = 0; l < MVSB200_UNET_LAYERS; ++l) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pev[l], pev[l + 1]);
+      total += ms;
+      fprintf(stderr, "[unet] %-10s %4dx%-4d C=%-3d %.3f ms\n", kUnet[l].name, p.h[l], p.w[l], p.c[l], ms);
+    }
+    fprintf(stderr, "[unet] total %.3f ms\n", total);
+    for (int i = 0; i <= MVSB200_UNET_LAYERS; ++i) cudaEventDestroy(pev[i]);
   }
   return MVSB200_OK;
 }

@@ -1554,19 +1554,17 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     set_error("conv3d(bf16/tcgen05): cuTensorMapEncodeTiled is not available from the driver");
     return MVSB200_ERR_CUDA;
   }
-  int sm_count = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
+  int sm_count = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  // function attributes are per device: once per device of this process (a set bit is only ever re-set to itself)
+  static std::atomic<uint64_t> attr_done{0};
+  if (!(attr_done.load(std::memory_order_acquire) >> (dev & 63) & 1u)) {
     for (int peer_mode = 0; peer_mode < 2; ++peer_mode)
       for (int k = 0; k < 6; ++k)
         MVS_CUDA(cudaFuncSetAttribute((const void*)kernel_variant(k, peer_mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemBudget));
-    attr_done = true;
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   const bool has_skip = skip != nullptr, transform = xs != nullptr || has_skip || (x_bn && x_bn->stats);
   int launch_idx = 0;

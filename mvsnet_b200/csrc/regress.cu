@@ -176,11 +176,13 @@ int launch_depth_regress(const float* filtered, int depth_num, int hf, int wf, f
   const size_t smem = (size_t)depth_num * kRegPix * sizeof(float);
   const int blocks = ceil_div(npix, kRegPix);
   if (smem <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};      // per device of this process
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_set.load(std::memory_order_acquire) >> (dev & 63) & 1u)) {
       MVS_CUDA(cudaFuncSetAttribute(depth_regress_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     200 * 1024));
-      attr_set = true;
+      attr_set.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     depth_regress_kernel<true><<<blocks, kRegPix, smem, s>>>(filtered, depth_num, npix, depth_start, depth_interval,
                                                             depth_end, inverse_depth, num_buckets, depth_map,

@@ -291,6 +291,13 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"kernel": "cost_volume_c32_kernel (fused warp + variance)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes": cv_bytes, "avg_launch_ms": cv_ms},
+        # the second stage as a whole (13 launches of conv3d_tc_kernel): SURVEY 8(d) unfused compulsory bytes 230 B
+        # per voxel and 22 896 FLOP per voxel, against the same measured HBM peak
+        "roofline_regularizer": {"kernel": "conv3d_tc_kernel x13 (RegNetUS0, bf16 tcgen05)", "bound": "hbm",
+                                 "achieved": 230.0 * V / (float(stage_ms[2]) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": 230.0 * V / (float(stage_ms[2]) * 1e-3) / 1e9 / peak,
+                                 "algorithmic_bytes": 230 * V, "tflops": 22896.0 * V / (float(stage_ms[2]) * 1e-3) / 1e12,
+                                 "stage_ms": float(stage_ms[2])},
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

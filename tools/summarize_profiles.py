@@ -8,6 +8,8 @@ from collections import OrderedDict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+if tag.startswith("-"):
+    sys.exit("usage: summarize_profiles.py [tag]   (reads gpurun_out/, writes profiles/<tag>_*)")
 
 
 def read_csv(path):

@@ -71,17 +71,22 @@ __device__ __forceinline__ void store_cost4(void* out, size_t elem, float4 c, bo
 }
 
 // x-paired fp16 copy of the source-view features (see TAPS16 below): out [N][Hf][Wf+1][8][2][4]
-__global__ void pair_features_kernel(const float* __restrict__ feats, int n_views, int Hf, int Wf,
+// pad_rows = 0: out [N][Hf][Wf+1][8][2][4]; pad_rows = 1: [N][Hf+3][...], image row y at row y + 2, rows 0, 1 and
+// Hf + 2 zero (the 8-byte footprint records of HINT = 2 rely on them instead of validity masks)
+__global__ void pair_features_kernel(const float* __restrict__ feats, int n_views, int Hf, int Wf, int pad_rows,
                                      __half* __restrict__ out) {
-  const size_t total = (size_t)n_views * Hf * (Wf + 1) * 8;
+  const int rows = pad_rows ? Hf + 3 : Hf;
+  const size_t total = (size_t)n_views * rows * (Wf + 1) * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int g = (int)(i & 7);
     size_t t = i >> 3;
     const int j = (int)(t % (Wf + 1)); t /= (Wf + 1);     // pair j = pixels (j-1, j)
-    const size_t row = t;                                  // view * Hf + y
+    const int y = (int)(t % rows) - (pad_rows ? 2 : 0);
+    const size_t row = (t / rows) * Hf + (size_t)max(y, 0);    // view * Hf + y
+    const bool in_y = y >= 0 && y < Hf;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (j >= 1) a = ldg4(feats + (row * Wf + (j - 1)) * 32 + g * 4);
-    if (j < Wf) b = ldg4(feats + (row * Wf + j) * 32 + g * 4);
+    if (in_y && j >= 1) a = ldg4(feats + (row * Wf + (j - 1)) * 32 + g * 4);
+    if (in_y && j < Wf) b = ldg4(feats + (row * Wf + j) * 32 + g * 4);
     __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y),
                     __floats2half2_rn(b.z, b.w)};
     *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(h);
@@ -113,8 +118,10 @@ constexpr int kPlaneChunk = 48;
 // (half the L1 wavefronts and load instructions of the fp32 path).  The reference view stays fp32.
 // HINT (with TAPS16): the 4-tap blend itself runs in packed fp16 (HFMA2, two channels per instruction, no
 // per-tap conversions); the blended value is widened once and the running sums stay fp32.  The blend error
-// (~1e-3 relative) is below the bf16 rounding of the volume this variant writes.
-template <int OUT, int TX, int TY, int KDC, bool TAPS16, bool HINT, int MINB = (KDC == 2 ? 4 : (KDC == 4 ? 3 : 2))>
+// (~1e-3 relative) is below the bf16 rounding of the volume this variant writes.  HINT = 2: the footprint travels as
+// an 8-byte record (offset of the first row pair + the two fractions as halves; the copy has zero guard rows, so no
+// validity masks are needed and the second row is always one row further): half the broadcast wavefronts.
+template <int OUT, int TX, int TY, int KDC, bool TAPS16, int HINT, int MINB = (KDC == 2 ? 4 : (KDC == 4 ? 3 : 2))>
 __global__ void __launch_bounds__(256, MINB)
 cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict__ feats16,
                        const float* __restrict__ coef, int n_views, int D, int d0g, int Dloc, int Hf, int Wf,
@@ -127,6 +134,7 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
   __shared__ float s_coef[kMaxSrcViews * kPlaneChunk * 8];
   __shared__ float4 s_fw[32][9];          // per pixel: bilinear weights of one round (+1: bank spread)
   __shared__ int2 s_fi[32][9];            // per pixel: packed clamped tap columns / rows
+  __shared__ uint2 s_f8[HINT == 2 ? 32 : 1][9];   // HINT = 2: (byte offset of the first row pair, half2(fx, fy))
   __shared__ uint4 s_cells[OUT == 2 ? KDC * 4 * 32 + 16 : 1];   // one group of output cells (planar layouts)
   const int tid = threadIdx.x;
   const int g = tid & 7;            // channel group (4 channels) and footprint slot of the round
@@ -150,6 +158,7 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
   const int dend = min(Dloc, dbeg + kPlaneChunk);
   const int rounds = (KDC * n_src) / 8;       // the launcher picks KDC so that this is exact
   const char* base16 = reinterpret_cast<const char*>(feats16) + g * 16;
+  const unsigned row16 = (unsigned)(Wf + 1) * 128u;      // bytes per row of the paired copy
   // footprint slot g of a round: view (round*VPR + g / KDC), plane g % KDC of the group
   const int my_dd = g % KDC, my_dv = g / KDC;
   for (int d0 = dbeg; d0 < dend; d0 += KDC) {
@@ -174,7 +183,14 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
           const unsigned vbase = (unsigned)(v + 1) * (unsigned)(Hf * (Wf + 1));
           const unsigned off0 = (vbase + (unsigned)(cy0 * (Wf + 1) + xp)) * 128u;
           const unsigned off1 = (vbase + (unsigned)(cy1 * (Wf + 1) + xp)) * 128u;
-          if (HINT) {
+          if (HINT == 2) {
+            // 8-byte record: footprints with no tap inside the image point at the two zero rows on top
+            const bool any = (f.vx0 || f.vx1) && (f.vy0 || f.vy1);
+            const unsigned cell = (unsigned)(v + 1) * (unsigned)((Hf + 3) * (Wf + 1)) +
+                                  (unsigned)((any ? f.y0 + 2 : 0) * (Wf + 1) + (any ? f.x0 + 1 : 0));
+            const __half2 fr = __floats2half2_rn(any ? f.wxr : 0.0f, any ? f.wyr : 0.0f);
+            s_f8[p][g] = make_uint2(cell * 128u, *reinterpret_cast<const uint32_t*>(&fr));
+          } else if (HINT) {
             // one 16-byte record per footprint (a 128-bit shared load costs 4 data-pipe wavefronts per warp whatever
             // it broadcasts, so the weights travel as four halves next to the two offsets)
             const __half2 hx = __floats2half2_rn(l_wyl * l_wxl, l_wyl * l_wxr);
@@ -201,10 +217,23 @@ cost_volume_c32_kernel(const float* __restrict__ feats, const __half* __restrict
       for (int j = 0; j < 8; ++j) {
         constexpr int kdc = KDC;
         const int dd = j % kdc;                       // compile-time after unrolling
-        const float4 fw = s_fw[p][j];
+        float4 fw;
         int2 fi;
-        if (TAPS16 && HINT) fi = make_int2(__float_as_int(fw.z), __float_as_int(fw.w));
-        else fi = s_fi[p][j];
+        if (HINT == 2) {
+          const uint2 rec = s_f8[p][j];
+          const __half2 fr = *reinterpret_cast<const __half2*>(&rec.y);          // (fx, fy)
+          const __half2 gr = __hsub2(__float2half2_rn(1.0f), fr);                 // (1 - fx, 1 - fy)
+          const __half2 xw = __halves2half2(__low2half(gr), __low2half(fr));      // (wxl, wxr)
+          const __half2 r0 = __hmul2(xw, __high2half2(gr)), r1 = __hmul2(xw, __high2half2(fr));
+          fw.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&r0));        // (w00, w01)
+          fw.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&r1));        // (w10, w11)
+          fw.z = fw.w = 0.0f;
+          fi = make_int2((int)rec.x, (int)(rec.x + row16));
+        } else {
+          fw = s_fw[p][j];
+          if (TAPS16 && HINT) fi = make_int2(__float_as_int(fw.z), __float_as_int(fw.w));
+          else fi = s_fi[p][j];
+        }
         float4 w;
         if (TAPS16) {
           // consecutive planes of a pixel often fall into the same source cell (the sample moves a fraction of a
@@ -467,6 +496,10 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
       cost_volume_c32_kernel<O, TX_, TY_, 2, true, true, 2><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,   \
                                                                                coef, n_views, depth_num, d0g, dloc, hf, wf, \
                                                                                order, out, planar_ps8);           \
+    else if (O == 2 && feats16 && half_interp && rec8)                                                            \
+      cost_volume_c32_kernel<O, TX_, TY_, K_, true, 2><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,        \
+                                                                            coef, n_views, depth_num, d0g, dloc, hf, wf, \
+                                                                            order, out, planar_ps8);              \
     else if (O == 2 && feats16 && half_interp)                                                                    \
       cost_volume_c32_kernel<O, TX_, TY_, K_, true, true><<<grid, 256, 0, s>>>(feats, (const __half*)feats16,     \
                                                                                coef, n_views, depth_num, d0g, dloc, hf, wf, \
@@ -488,12 +521,15 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
   } while (0)
     if (planar && ((hf | wf) & 1) && planar_ps8)
       MVS_CUDA(cudaMemsetAsync(planar_ps8, 0, (size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) * 16, s));
+    static const bool half_interp = getenv("MVSB200_CV_FP32_BLEND") == nullptr;     // fp16 blend unless asked otherwise
+    static const int minb_env = getenv("MVSB200_CV_MINB") ? atoi(getenv("MVSB200_CV_MINB")) : 0;   // tuning
+    // 8-byte footprint records over the zero-padded paired copy (MVSB200_CV_REC16=1: the 16-byte records)
+    const bool rec8 = planar && feats16 && half_interp && minb_env == 0 && getenv("MVSB200_CV_REC16") == nullptr &&
+                      (size_t)n_views * (hf + 3) * (wf + 1) < ((size_t)1 << 25);
     if (planar && feats16) {
-      pair_features_kernel<<<148 * 8, 256, 0, s>>>(feats, n_views, hf, wf, (__half*)feats16);
+      pair_features_kernel<<<148 * 8, 256, 0, s>>>(feats, n_views, hf, wf, rec8 ? 1 : 0, (__half*)feats16);
       MVS_LAUNCH_CHECK("pair_features_kernel");
     }
-    static const bool half_interp = getenv("MVSB200_CV_FP32_BLEND") == nullptr;
-    static const int minb_env = getenv("MVSB200_CV_MINB") ? atoi(getenv("MVSB200_CV_MINB")) : 0;   // tuning   // fp16 blend unless asked otherwise
     // planes per thread: the smallest of 2 / 4 / 8 whose footprints fill whole rounds of 8 lanes
     const int n_src = n_views - 1;
     int kdc = (2 * n_src) % 8 == 0 ? 2 : ((4 * n_src) % 8 == 0 ? 4 : 8);
@@ -549,7 +585,7 @@ bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sample
 }
 
 // feats16: scratch of cost_volume_pair_bytes() for the x-paired fp16 copy of the features (NULL: fp32 taps)
-size_t cost_volume_pair_bytes(int n_views, int hf, int wf) { return (size_t)n_views * hf * (wf + 1) * 128; }
+size_t cost_volume_pair_bytes(int n_views, int hf, int wf) { return (size_t)n_views * (hf + 3) * (wf + 1) * 128; }
 
 int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                               int wf, int channels, int order, int sampler, void* cp8, void* ps8, void* feats16,

@@ -147,7 +147,9 @@ static int check_regnet_shape(int D, int H, int W, int cin, int b) {
 // layouts at regnet_cost_planar() inside the workspace and `cost` is ignored.
 int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const mvsb200_regnet_params* params, int D,
                         int H, int W, int cin, int b, float eps, int precision, float* filtered, void* workspace,
-                        size_t workspace_bytes, cudaStream_t s, TcRegress* regress = nullptr) {
+                        size_t workspace_bytes, cudaStream_t s, TcRegress* regress = nullptr, bool inspect = true) {
+  // inspect: also materialise every layer's BN scale / shift for mvsb200_regnet_layer_raw (the whole-path entry
+  // points do not need them: one launch less on the critical path)
   MVS_CHECK_ARG((cost || cost_planar) && params && filtered && workspace, "regnet_forward: NULL pointer");
   int rc = check_regnet_shape(D, H, W, cin, b);
   if (rc) return rc;
@@ -250,7 +252,7 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
     }
     if (profile) cudaEventRecord(pev[i + 1], s);
   }
-  if (bf16) {
+  if (bf16 && inspect) {
     // scale / shift of every layer for mvsb200_regnet_layer_raw (inspection only; the layers above do not read them)
     const float* gam[MVSB200_REGNET_LAYERS];
     const float* bet[MVSB200_REGNET_LAYERS];
@@ -817,7 +819,7 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   TcRegress rg = {(float*)(ws + ip.partial_off), depth_start, (float)lin_step, 0};
   const bool try_fuse = precision == MVSB200_PRECISION_BF16 && !inverse_depth && !no_fused_regress;
   rc = regnet_forward_impl(cost, cost_dtype, planar ? 1 : 0, params, depth_num, hf, wf, channels, base_filter, bn_eps,
-                           precision, filtered, ws + ip.regnet_off, ip.regnet_bytes, s, try_fuse ? &rg : nullptr);
+                           precision, filtered, ws + ip.regnet_off, ip.regnet_bytes, s, try_fuse ? &rg : nullptr, false);
   if (rc) return rc;
   MVS_STAGE_EVENT(3);
   if (try_fuse && rg.fused)

@@ -210,6 +210,18 @@ int mvsb200_infer_host_async(const float* feats_host, const float* cams_host, in
                              int base_filter, float bn_eps, int precision, float* depth_map_host,
                              float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
                              void* stream);
+/* Same, with the copies on `copy_stream` and the kernels on `compute_stream`, chained by events (feed -> kernels ->
+ * fetch).  A caller that alternates two (staging buffer, workspace, copy stream) sets over ONE compute stream keeps the
+ * kernels of consecutive reference views back to back while the 40 MB feed of the next view and the fetch of the
+ * previous one run beside them (two compute streams would let the next view's first kernels take SMs from the current
+ * view's single-wave layers).  The copy stream also orders the re-use of its staging buffer, so use one copy stream per
+ * staging buffer.  Host buffers must be pinned; outputs are valid once copy_stream is synchronised. */
+int mvsb200_infer_host_pipelined(const float* feats_host, const float* cams_host, int n_views, int depth_num,
+                                 int hf, int wf, int channels, float depth_start, float depth_interval,
+                                 int inverse_depth, int order, int sampler, const mvsb200_regnet_params* params,
+                                 int base_filter, float bn_eps, int precision, float* depth_map_host,
+                                 float* prob_map_host, void* staging_dev, void* workspace, size_t workspace_bytes,
+                                 void* compute_stream, void* copy_stream);
 
 /* ---- D-slab mode (BASELINE config 5): ONE volume split along depth over `slabs` GPUs ------------
  * Rank `slab` runs the bf16 path on depth_num/slabs consecutive planes (a multiple of 8).  Tensors in the slab

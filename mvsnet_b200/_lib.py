@@ -112,6 +112,8 @@ SIGNATURES = {
                                    POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "mvsb200_infer_host_async": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
                                    POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "mvsb200_infer_host_pipelined": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
+                                   POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P, _P]),
     "mvsb200_umma_probe": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, _P, _P]),
     "mvsb200_launch_count": (c_uint64, []),

@@ -839,14 +839,18 @@ extern "C" size_t mvsb200_infer_host_staging_bytes(int n_views, int hf, int wf, 
          align_up((size_t)n_views * 32 * sizeof(float), 256) + 2 * align_up((size_t)hf * wf * sizeof(float), 256);
 }
 
+// copies on `copy_stream`, kernels on `stream`; when they differ the two are chained with events (feed -> kernels ->
+// fetch), so that a caller with one compute stream and one copy stream keeps the kernels of consecutive reference
+// views back to back while the feed of the next view and the fetch of the previous one run beside them
 static int infer_host_enqueue(const float* feats_host, const float* cams_host, int n_views, int depth_num, int hf,
                               int wf, int channels, float depth_start, float depth_interval, int inverse_depth, int order,
                               int sampler, const mvsb200_regnet_params* params, int base_filter, float bn_eps,
                               int precision, float* depth_map_host, float* prob_map_host, void* staging_dev,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+                              void* workspace, size_t workspace_bytes, void* stream, void* copy_stream) {
   MVS_CHECK_ARG(feats_host && cams_host && depth_map_host && prob_map_host && staging_dev, "infer_host: NULL pointer");
   MVS_CHECK_ARG(n_views >= 2 && hf > 0 && wf > 0 && channels > 0, "infer_host: bad shape");
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = (cudaStream_t)copy_stream, sk = (cudaStream_t)stream;
+  const bool split = s != sk;
   char* st = (char*)staging_dev;
   const size_t feat_bytes = (size_t)n_views * hf * wf * channels * sizeof(float);
   const size_t cam_bytes = (size_t)n_views * 32 * sizeof(float);
@@ -857,9 +861,22 @@ static int infer_host_enqueue(const float* feats_host, const float* cams_host, i
   float* d_prob = (float*)((char*)d_depth + align_up(map_bytes, 256));
   MVS_CUDA(cudaMemcpyAsync(d_feats, feats_host, feat_bytes, cudaMemcpyHostToDevice, s));
   MVS_CUDA(cudaMemcpyAsync(d_cams, cams_host, cam_bytes, cudaMemcpyHostToDevice, s));
+  cudaEvent_t ev = nullptr;
+  if (split) {
+    MVS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaEventRecord(ev, s);
+    cudaStreamWaitEvent(sk, ev, 0);
+  }
   int rc = mvsb200_infer(d_feats, d_cams, n_views, depth_num, hf, wf, channels, depth_start, depth_interval,
                          inverse_depth, order, sampler, params, base_filter, bn_eps, precision, d_depth, d_prob,
                          workspace, workspace_bytes, stream);
+  if (split) {
+    if (!rc) {
+      cudaEventRecord(ev, sk);              // re-recording is fine: the wait above captured the first record
+      cudaStreamWaitEvent(s, ev, 0);
+    }
+    cudaEventDestroy(ev);                   // released once the pending work on it has completed
+  }
   if (rc) return rc;
   MVS_CUDA(cudaMemcpyAsync(depth_map_host, d_depth, map_bytes, cudaMemcpyDeviceToHost, s));
   MVS_CUDA(cudaMemcpyAsync(prob_map_host, d_prob, map_bytes, cudaMemcpyDeviceToHost, s));
@@ -874,7 +891,7 @@ extern "C" int mvsb200_infer_host(const float* feats_host, const float* cams_hos
                                   void* stream) {
   int rc = infer_host_enqueue(feats_host, cams_host, n_views, depth_num, hf, wf, channels, depth_start, depth_interval,
                               inverse_depth, order, sampler, params, base_filter, bn_eps, precision, depth_map_host,
-                              prob_map_host, staging_dev, workspace, workspace_bytes, stream);
+                              prob_map_host, staging_dev, workspace, workspace_bytes, stream, stream);
   if (rc) return rc;
   MVS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return MVSB200_OK;
@@ -888,5 +905,17 @@ extern "C" int mvsb200_infer_host_async(const float* feats_host, const float* ca
                                         void* workspace, size_t workspace_bytes, void* stream) {
   return infer_host_enqueue(feats_host, cams_host, n_views, depth_num, hf, wf, channels, depth_start, depth_interval,
                             inverse_depth, order, sampler, params, base_filter, bn_eps, precision, depth_map_host,
-                            prob_map_host, staging_dev, workspace, workspace_bytes, stream);
+                            prob_map_host, staging_dev, workspace, workspace_bytes, stream, stream);
+}
+
+extern "C" int mvsb200_infer_host_pipelined(const float* feats_host, const float* cams_host, int n_views, int depth_num,
+                                            int hf, int wf, int channels, float depth_start, float depth_interval,
+                                            int inverse_depth, int order, int sampler,
+                                            const mvsb200_regnet_params* params, int base_filter, float bn_eps,
+                                            int precision, float* depth_map_host, float* prob_map_host,
+                                            void* staging_dev, void* workspace, size_t workspace_bytes,
+                                            void* compute_stream, void* copy_stream) {
+  return infer_host_enqueue(feats_host, cams_host, n_views, depth_num, hf, wf, channels, depth_start, depth_interval,
+                            inverse_depth, order, sampler, params, base_filter, bn_eps, precision, depth_map_host,
+                            prob_map_host, staging_dev, workspace, workspace_bytes, compute_stream, copy_stream);
 }

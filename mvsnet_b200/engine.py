@@ -131,6 +131,25 @@ class HotPath:
         L.check(rc, "infer_host_async")
         return depth_out, prob_out
 
+    def infer_host_pipelined(self, feats_host: torch.Tensor, cams_host: torch.Tensor, depth_start: float,
+                             depth_interval: float, depth_out: torch.Tensor, prob_out: torch.Tensor,
+                             compute_stream: torch.cuda.Stream, copy_stream: torch.cuda.Stream):
+        """infer_host_async with the copies on `copy_stream` and the kernels on `compute_stream` (chained by events).
+        Two engines, each with its own copy stream, alternating over ONE compute stream keep the kernels back to back
+        while the feed of the next reference view runs beside them; the outputs are valid once copy_stream has been
+        synchronised."""
+        for t in (feats_host, cams_host, depth_out, prob_out):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_pinned():
+                raise ValueError("infer_host_pipelined takes contiguous fp32 PINNED host tensors")
+        rc = self.lib.mvsb200_infer_host_pipelined(
+            L.ptr(feats_host), L.ptr(cams_host), self.n_views, self.depth_num, self.hf, self.wf, self.channels,
+            float(depth_start), float(depth_interval), self.inverse_depth, self.order, self.sampler,
+            ctypes.byref(self.weights.params), self.base_filter, self.bn_eps, self.precision, L.ptr(depth_out),
+            L.ptr(prob_out), L.ptr(self.staging), L.ptr(self.workspace), self.workspace.numel(),
+            ctypes.c_void_p(compute_stream.cuda_stream), ctypes.c_void_p(copy_stream.cuda_stream))
+        L.check(rc, "infer_host_pipelined")
+        return depth_out, prob_out
+
     def set_stage_events(self, events) -> None:
         """events: five torch.cuda.Event(enable_timing=True) (or None) recorded at the stage boundaries of infer()."""
         if events is None:

@@ -138,3 +138,27 @@ def test_infer_host_async_two_streams(tiny_problem):
     for k in range(2):
         assert torch.equal(outs[k][0], ref[k][0])
         assert torch.equal(outs[k][1], ref[k][1])
+
+
+def test_infer_host_pipelined_one_compute_stream(tiny_problem):
+    """Feed / kernels / fetch on separate streams chained by events: same maps as the synchronous host entry point,
+    for several views in flight over one compute stream and one copy stream per staging buffer."""
+    from mvsnet_b200.engine import HotPath
+    p = tiny_problem
+    engs = [HotPath(p["n_views"], p["depth_num"], p["hf"], p["wf"], p["weights"], precision="bf16") for _ in range(2)]
+    fh = [torch.from_numpy(p["feats"] * s).pin_memory() for s in (1.0, 0.5, 2.0)]
+    ch = torch.from_numpy(p["cams"]).pin_memory()
+    ref = []
+    for f in fh:
+        d, q = torch.empty((p["hf"], p["wf"])).pin_memory(), torch.empty((p["hf"], p["wf"])).pin_memory()
+        engs[0].infer_host(f, ch, p["depth_start"], p["depth_interval"], d, q)
+        ref.append((d.clone(), q.clone()))
+    compute, copies = torch.cuda.Stream(), [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [(torch.empty((p["hf"], p["wf"])).pin_memory(), torch.empty((p["hf"], p["wf"])).pin_memory()) for _ in fh]
+    for i, f in enumerate(fh):
+        engs[i % 2].infer_host_pipelined(f, ch, p["depth_start"], p["depth_interval"], outs[i][0], outs[i][1], compute,
+                                         copies[i % 2])
+    torch.cuda.synchronize()
+    for (d, q), (rd, rq) in zip(outs, ref):
+        assert np.allclose(d.numpy(), rd.numpy(), rtol=1e-4, atol=1e-2)
+        assert np.allclose(q.numpy(), rq.numpy(), atol=1e-2)

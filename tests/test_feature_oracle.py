@@ -101,3 +101,29 @@ def test_tower_shapes_and_deconv_without_relu():
     assert outs["2dconv5_0"].min() < 0.0 and outs["2dconv0_1"].min() >= 0.0
     with pytest.raises(ValueError):
         FO.unet_ds2gn(im[:, :30], w)
+
+
+def test_c_abi_tower_plan_is_host_only_and_matches_the_layer_table():
+    """mvsb200_unet_workspace_bytes / _layer_output do no device work: extents and channel counts of every layer as the
+    library lays them out equal the restatement's, offsets are disjoint and inside the workspace, bad shapes give 0."""
+    import ctypes
+    lib = L.load()
+    n, h, w = 3, 64, 96
+    total = lib.mvsb200_unet_workspace_bytes(n, h, w, 8)
+    assert total > 0
+    im = np.zeros((1, h, w, 3), F32)
+    shapes = {"data": (h, w)}
+    ends = []
+    for i, (name, op, k, s, cin, cout, srcs, gn, relu) in enumerate(FO.unet_layer_specs(8)):
+        ih, iw = shapes[srcs[0]]
+        shapes[name] = (2 * ih, 2 * iw) if op == "deconv" else (-(-ih // s), -(-iw // s))
+        off, dims = ctypes.c_size_t(), (ctypes.c_int * 3)()
+        L.check(lib.mvsb200_unet_layer_output(n, h, w, 8, i, ctypes.byref(off), dims), "unet_layer_output")
+        assert tuple(dims) == (*shapes[name], cout), name
+        ends.append((off.value, off.value + n * dims[0] * dims[1] * dims[2] * 4))
+    ends.sort()
+    assert all(a[1] <= b[0] for a, b in zip(ends, ends[1:])) and ends[-1][1] <= total
+    assert shapes["conv10_2"] == (h // 4, w // 4)
+    for bad in [(n, 40, 96, 8), (n, 64, 100, 8), (0, 64, 96, 8), (n, 64, 96, 4)]:
+        assert lib.mvsb200_unet_workspace_bytes(*bad) == 0
+    assert b"multiples of 16" in lib.mvsb200_last_error() or b"base_filter" in lib.mvsb200_last_error()

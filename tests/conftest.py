@@ -22,6 +22,11 @@ def golden_tiny():
 
 
 @pytest.fixture(scope="session")
+def golden_tower():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "tiny_tower.npz")))
+
+
+@pytest.fixture(scope="session")
 def tiny_problem():
     from mvsnet_b200 import synthetic
     return synthetic.make_problem("tiny")

@@ -127,3 +127,18 @@ def test_c_abi_tower_plan_is_host_only_and_matches_the_layer_table():
     for bad in [(n, 40, 96, 8), (n, 64, 100, 8), (0, 64, 96, 8), (n, 64, 96, 4)]:
         assert lib.mvsb200_unet_workspace_bytes(*bad) == 0
     assert b"multiples of 16" in lib.mvsb200_last_error() or b"base_filter" in lib.mvsb200_last_error()
+
+
+def test_golden_tower_fixture_matches_the_restatement(golden_tower):
+    """tests/golden/tiny_tower.npz (made by tests/golden/make_golden_tower.py) freezes the restatement's output."""
+    g = golden_tower
+    w = synthetic.make_unet_weights(8)
+    np.testing.assert_allclose(np.array([np.float64(np.abs(w[k]).sum()) for k in sorted(w)]), g["weight_digest"], rtol=1e-12)
+    np.testing.assert_array_equal(synthetic.make_images(2, 32, 48), g["images"])
+    feats, outs = FO.unet_ds2gn(g["images"], w, return_layers=True)
+    # torch-CPU convolutions may pick different kernels on different hosts: a few ulps, not bit equality
+    np.testing.assert_allclose(feats, g["feats"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(outs["2dconv5_0"], g["l2dconv5_0"], rtol=0, atol=2e-5)
+    names = [s[0] for s in FO.unet_layer_specs(8)]
+    digest = np.array([[outs[n].mean(), np.abs(outs[n]).mean(), outs[n].max()] for n in names], dtype=np.float64)
+    np.testing.assert_allclose(digest, g["layer_digest"], rtol=1e-4, atol=1e-5)

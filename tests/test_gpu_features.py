@@ -74,6 +74,20 @@ def test_whole_tower_layer_by_layer():
     np.testing.assert_allclose(tower(to_dev(im)).cpu().numpy(), f.cpu().numpy(), rtol=0, atol=1e-5)
 
 
+def test_tower_against_the_golden_fixture(golden_tower):
+    """The committed vectors (tests/golden/tiny_tower.npz): images -> features, and two intermediate layers."""
+    from mvsnet_b200 import _lib as L
+    from mvsnet_b200.features import FeatureTower
+    g = golden_tower
+    tower = FeatureTower(synthetic.make_unet_weights(8))
+    f = tower(to_dev(g["images"]))
+    assert float(np.abs(f.cpu().numpy() - g["feats"]).max()) <= 5e-4 * max(1.0, float(np.abs(g["feats"]).max()))
+    l5 = tower.layer_output(L.UNET_LAYER_NAMES.index("2dconv5_0")).cpu().numpy()
+    assert float(np.abs(l5 - g["l2dconv5_0"]).max()) <= 5e-4
+    l8 = tower.layer_output(L.UNET_LAYER_NAMES.index("2dconv8_2")).cpu().numpy()[:, ::4, ::4, :]
+    assert float(np.abs(l8 - g["l2dconv8_2"]).max()) <= 5e-4
+
+
 def test_tower_rejects_shapes_the_reference_graph_cannot_build():
     from mvsnet_b200 import _lib as L
     from mvsnet_b200.features import FeatureTower

@@ -4,7 +4,7 @@
 // group statistics of the result reduced in the epilogue, and group normalisation (+ ReLU) applied in place in the
 // reference's op order (network.py:237-276, :349-409: groups of 8 channels, biased variance, eps 1e-5; conv_gn has a
 // ReLU, deconv_gn has none).  This is the step before the hot path; the tcgen05 version
-// is round-2 work, this file is the parity-first CUDA implementation.
+// is round-2 work, this file is the parity-first CUDA implementation (8.8 ms for 5 views at 1152x864).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -201,6 +201,123 @@ __global__ void group_norm_kernel(float* __restrict__ y, const double* __restric
   }
 }
 
+// Shared-memory tiled variant for the ordinary convolutions whose sources have multiples of 8 channels (28 of the 32
+// layers): a block computes 32 columns x 16 rows x kCoT output channels.  Eight input channels at a time, the haloed
+// input tile is staged in shared memory (coalesced loads; split in two 4-channel planes so that a warp's 128-bit
+// reads run along x) next to that chunk's weights; a thread keeps the NR = 3 S + K input rows of its column in
+// registers and reuses them for its 4 output rows and the K vertical taps.  SAME padding = zeros staged for the
+// pixels outside the image.
+constexpr int kTileRows = 16;
+template <int K, int S>
+__global__ void __launch_bounds__(kThreads2d)
+conv2d_tile_kernel(const float* __restrict__ xa, int ca, const float* __restrict__ xb, int cb,
+                   const float* __restrict__ kernel_tf, int H, int W, int Cout, int Ho, int Wo, int pad_h, int pad_w,
+                   float* __restrict__ y, double* __restrict__ stats) {
+  constexpr int IR = (kTileRows - 1) * S + K, IC = 31 * S + K, NR = 3 * S + K;
+  extern __shared__ float4 s_tile[];                  // [2 halves][IR][IC] float4, then weights [K*K][8 ci][8 co]
+  float* s_wt = reinterpret_cast<float*>(s_tile + 2 * IR * IC);
+  __shared__ float s_red[2][kThreads2d / 32];
+  const int Cin = ca + cb;
+  const int co0 = blockIdx.y * kCoT, n = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int xt = (Wo + 31) / 32;
+  const int oy_t = (blockIdx.x / xt) * kTileRows, ox_t = (blockIdx.x % xt) * 32;
+  const int oy0 = oy_t + warp * kPxT, ox = ox_t + lane;
+  const int gy0 = oy_t * S - pad_h, gx0 = ox_t * S - pad_w;        // image position of tile cell (0, 0)
+  float acc[kPxT][kCoT];
+#pragma unroll
+  for (int j = 0; j < kPxT; ++j)
+#pragma unroll
+    for (int k = 0; k < kCoT; ++k) acc[j][k] = 0.0f;
+  for (int c8 = 0; c8 < Cin; c8 += 8) {
+    const bool from_b = c8 >= ca;
+    const float* xs = from_b ? xb + (size_t)n * H * W * cb : xa + (size_t)n * H * W * ca;
+    const int cs = from_b ? cb : ca, cl = from_b ? c8 - ca : c8;   // channel offset inside the source
+    __syncthreads();                                               // the previous chunk has been consumed
+    for (int i = threadIdx.x; i < 2 * IR * IC; i += kThreads2d) {
+      const int half = i & 1, cell = i >> 1;
+      const int r = cell / IC, c = cell - r * IC;
+      const int gy = gy0 + r, gx = gx0 + c;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = __ldg(reinterpret_cast<const float4*>(xs + ((size_t)gy * W + gx) * cs + cl + half * 4));
+      s_tile[(half * IR + r) * IC + c] = v;
+    }
+    for (int i = threadIdx.x; i < K * K * 64; i += kThreads2d) {
+      const int co = i & 7, ci = (i >> 3) & 7, tap = i >> 6;
+      s_wt[i] = kernel_tf[((size_t)tap * Cin + c8 + ci) * Cout + co0 + co];      // [kh,kw,Cin,Cout]
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 rowv[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) rowv[r] = s_tile[(half * IR + warp * kPxT * S + r) * IC + lane * S + kw];
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float* wp = s_wt + ((kh * K + kw) * 8 + half * 4 + c) * 8;
+            const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+            for (int j = 0; j < kPxT; ++j) {
+              const float4 rv = rowv[j * S + kh];
+              const float a = c == 0 ? rv.x : (c == 1 ? rv.y : (c == 2 ? rv.z : rv.w));
+              acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
+              acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
+              acc[j][4] = fmaf(a, w1.x, acc[j][4]); acc[j][5] = fmaf(a, w1.y, acc[j][5]);
+              acc[j][6] = fmaf(a, w1.z, acc[j][6]); acc[j][7] = fmaf(a, w1.w, acc[j][7]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const bool live = ox < Wo;
+  float sm = 0.0f, sq = 0.0f;
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < kPxT; ++j)
+      if (oy0 + j < Ho) {
+        float4* o = reinterpret_cast<float4*>(y + (((size_t)n * Ho + oy0 + j) * Wo + ox) * Cout + co0);
+        o[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        o[1] = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+#pragma unroll
+        for (int k = 0; k < kCoT; ++k) { sm += acc[j][k]; sq = fmaf(acc[j][k], acc[j][k], sq); }
+      }
+  }
+  if (stats == nullptr) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) { s_red[0][warp] = sm; s_red[1][warp] = sq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ds = 0.0, dq = 0.0;
+    for (int w = 0; w < kThreads2d / 32; ++w) { ds += (double)s_red[0][w]; dq += (double)s_red[1][w]; }
+    double* st = stats + ((size_t)n * (Cout / kCoT) + blockIdx.y) * 2;
+    atomicAdd(st, ds);
+    atomicAdd(st + 1, dq);
+  }
+}
+
+template <int K, int S>
+int launch_conv2d_tile(const float* xa, int ca, const float* xb, int cb, const float* kernel_tf, int n, int h, int w,
+                       int cout, int ho, int wo, float* y, double* stats, cudaStream_t s) {
+  constexpr int IR = (kTileRows - 1) * S + K, IC = 31 * S + K;
+  const size_t smem = (size_t)2 * IR * IC * sizeof(float4) + (size_t)K * K * 64 * sizeof(float);
+  MVS_CUDA(cudaFuncSetAttribute(conv2d_tile_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(wo, 32) * ceil_div(ho, kTileRows), cout / kCoT, n);
+  conv2d_tile_kernel<K, S><<<grid, kThreads2d, smem, s>>>(xa, ca, xb, cb, kernel_tf, h, w, cout, ho, wo,
+                                                          tf_same_pad_before(h, K, S), tf_same_pad_before(w, K, S), y, stats);
+  MVS_LAUNCH_CHECK("conv2d_tile_kernel");
+  return MVSB200_OK;
+}
+
 int out_extent(int in, int stride, int transposed) { return transposed ? in * 2 : (in + stride - 1) / stride; }
 
 int launch_conv2d(const float* xa, int ca, const float* xb, int cb, const float* kernel_tf, int n, int h, int w, int cout,
@@ -212,6 +329,12 @@ int launch_conv2d(const float* xa, int ca, const float* xb, int cb, const float*
   MVS_CHECK_ARG(!transposed || (k == 3 && stride == 2), "conv2d: the transposed convolution is 3x3 stride 2");
   MVS_CHECK_ARG(n <= 65535, "conv2d: too many views");
   const int ho = out_extent(h, stride, transposed), wo = out_extent(w, stride, transposed);
+  static const bool no_tile = getenv("MVSB200_UNET_NO_TILE") != nullptr;       // development switch
+  if (!transposed && ca % 8 == 0 && cb % 8 == 0 && !no_tile) {
+    if (k == 3 && stride == 1) return launch_conv2d_tile<3, 1>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
+    if (k == 3 && stride == 2) return launch_conv2d_tile<3, 2>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
+    if (k == 5 && stride == 2) return launch_conv2d_tile<5, 2>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
+  }
   const size_t smem = (size_t)k * k * (ca + cb) * kCoT * sizeof(float);
   if (smem > 48 * 1024) {
     set_error("conv2d: %d input channels exceed the shared-memory weight tile", ca + cb);

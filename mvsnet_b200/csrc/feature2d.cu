@@ -202,18 +202,20 @@ __global__ void group_norm_kernel(float* __restrict__ y, const double* __restric
 }
 
 // Shared-memory tiled variant for the ordinary convolutions whose sources have multiples of 8 channels (28 of the 32
-// layers): a block computes 32 columns x 16 rows x kCoT output channels.  Eight input channels at a time, the haloed
+// layers): a block computes 32 columns x 4 R rows x kCoT output channels (R = 4 rows per thread; R = 8 at stride 1
+// needs 126 registers and was slower: 10.3 vs 8.8 ms for the tower).  Eight input channels at a time, the haloed
 // input tile is staged in shared memory (coalesced loads; split in two 4-channel planes so that a warp's 128-bit
-// reads run along x) next to that chunk's weights; a thread keeps the NR = 3 S + K input rows of its column in
-// registers and reuses them for its 4 output rows and the K vertical taps.  SAME padding = zeros staged for the
+// reads run along x) next to that chunk's weights; a thread keeps the NR = (R - 1) S + K input rows of its column in
+// registers and reuses them for its R output rows and the K vertical taps.  SAME padding = zeros staged for the
 // pixels outside the image.
-constexpr int kTileRows = 16;
-template <int K, int S>
+// R = output rows per thread (the block covers 4 R rows): each weight read from shared memory feeds R pixels
+template <int K, int S, int R>
 __global__ void __launch_bounds__(kThreads2d)
 conv2d_tile_kernel(const float* __restrict__ xa, int ca, const float* __restrict__ xb, int cb,
                    const float* __restrict__ kernel_tf, int H, int W, int Cout, int Ho, int Wo, int pad_h, int pad_w,
                    float* __restrict__ y, double* __restrict__ stats) {
-  constexpr int IR = (kTileRows - 1) * S + K, IC = 31 * S + K, NR = 3 * S + K;
+  constexpr int kTileRows = 4 * R;
+  constexpr int IR = (kTileRows - 1) * S + K, IC = 31 * S + K, NR = (R - 1) * S + K;
   extern __shared__ float4 s_tile[];                  // [2 halves][IR][IC] float4, then weights [K*K][8 ci][8 co]
   float* s_wt = reinterpret_cast<float*>(s_tile + 2 * IR * IC);
   __shared__ float s_red[2][kThreads2d / 32];
@@ -222,11 +224,11 @@ conv2d_tile_kernel(const float* __restrict__ xa, int ca, const float* __restrict
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int xt = (Wo + 31) / 32;
   const int oy_t = (blockIdx.x / xt) * kTileRows, ox_t = (blockIdx.x % xt) * 32;
-  const int oy0 = oy_t + warp * kPxT, ox = ox_t + lane;
+  const int oy0 = oy_t + warp * R, ox = ox_t + lane;
   const int gy0 = oy_t * S - pad_h, gx0 = ox_t * S - pad_w;        // image position of tile cell (0, 0)
-  float acc[kPxT][kCoT];
+  float acc[R][kCoT];
 #pragma unroll
-  for (int j = 0; j < kPxT; ++j)
+  for (int j = 0; j < R; ++j)
 #pragma unroll
     for (int k = 0; k < kCoT; ++k) acc[j][k] = 0.0f;
   for (int c8 = 0; c8 < Cin; c8 += 8) {
@@ -254,7 +256,7 @@ conv2d_tile_kernel(const float* __restrict__ xa, int ca, const float* __restrict
       for (int half = 0; half < 2; ++half) {
         float4 rowv[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) rowv[r] = s_tile[(half * IR + warp * kPxT * S + r) * IC + lane * S + kw];
+        for (int r = 0; r < NR; ++r) rowv[r] = s_tile[(half * IR + warp * R * S + r) * IC + lane * S + kw];
 #pragma unroll
         for (int kh = 0; kh < K; ++kh) {
 #pragma unroll
@@ -262,7 +264,7 @@ conv2d_tile_kernel(const float* __restrict__ xa, int ca, const float* __restrict
             const float* wp = s_wt + ((kh * K + kw) * 8 + half * 4 + c) * 8;
             const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll
-            for (int j = 0; j < kPxT; ++j) {
+            for (int j = 0; j < R; ++j) {
               const float4 rv = rowv[j * S + kh];
               const float a = c == 0 ? rv.x : (c == 1 ? rv.y : (c == 2 ? rv.z : rv.w));
               acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
@@ -279,7 +281,7 @@ conv2d_tile_kernel(const float* __restrict__ xa, int ca, const float* __restrict
   float sm = 0.0f, sq = 0.0f;
   if (live) {
 #pragma unroll
-    for (int j = 0; j < kPxT; ++j)
+    for (int j = 0; j < R; ++j)
       if (oy0 + j < Ho) {
         float4* o = reinterpret_cast<float4*>(y + (((size_t)n * Ho + oy0 + j) * Wo + ox) * Cout + co0);
         o[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
@@ -305,14 +307,15 @@ conv2d_tile_kernel(const float* __restrict__ xa, int ca, const float* __restrict
   }
 }
 
-template <int K, int S>
+template <int K, int S, int R>
 int launch_conv2d_tile(const float* xa, int ca, const float* xb, int cb, const float* kernel_tf, int n, int h, int w,
                        int cout, int ho, int wo, float* y, double* stats, cudaStream_t s) {
+  constexpr int kTileRows = 4 * R;
   constexpr int IR = (kTileRows - 1) * S + K, IC = 31 * S + K;
   const size_t smem = (size_t)2 * IR * IC * sizeof(float4) + (size_t)K * K * 64 * sizeof(float);
-  MVS_CUDA(cudaFuncSetAttribute(conv2d_tile_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MVS_CUDA(cudaFuncSetAttribute(conv2d_tile_kernel<K, S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(wo, 32) * ceil_div(ho, kTileRows), cout / kCoT, n);
-  conv2d_tile_kernel<K, S><<<grid, kThreads2d, smem, s>>>(xa, ca, xb, cb, kernel_tf, h, w, cout, ho, wo,
+  conv2d_tile_kernel<K, S, R><<<grid, kThreads2d, smem, s>>>(xa, ca, xb, cb, kernel_tf, h, w, cout, ho, wo,
                                                           tf_same_pad_before(h, K, S), tf_same_pad_before(w, K, S), y, stats);
   MVS_LAUNCH_CHECK("conv2d_tile_kernel");
   return MVSB200_OK;
@@ -331,9 +334,9 @@ int launch_conv2d(const float* xa, int ca, const float* xb, int cb, const float*
   const int ho = out_extent(h, stride, transposed), wo = out_extent(w, stride, transposed);
   static const bool no_tile = getenv("MVSB200_UNET_NO_TILE") != nullptr;       // development switch
   if (!transposed && ca % 8 == 0 && cb % 8 == 0 && !no_tile) {
-    if (k == 3 && stride == 1) return launch_conv2d_tile<3, 1>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
-    if (k == 3 && stride == 2) return launch_conv2d_tile<3, 2>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
-    if (k == 5 && stride == 2) return launch_conv2d_tile<5, 2>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
+    if (k == 3 && stride == 1) return launch_conv2d_tile<3, 1, 4>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
+    if (k == 3 && stride == 2) return launch_conv2d_tile<3, 2, 4>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
+    if (k == 5 && stride == 2) return launch_conv2d_tile<5, 2, 4>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
   }
   const size_t smem = (size_t)k * k * (ca + cb) * kCoT * sizeof(float);
   if (smem > 48 * 1024) {

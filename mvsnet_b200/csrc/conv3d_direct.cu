@@ -2,7 +2,7 @@
 // on CUDA cores with TF SAME padding (network.py:210, :327), the producer's batch-norm + ReLU and
 // the skip-connection add folded into the input read (network.py:459, :496-508), and the batch
 // statistics of the result reduced in the epilogue.  This is the bit-faithful fp32 path used for
-// parity against the oracle; the bf16 tcgen05 path lives in conv3d_umma.cu.
+// parity against the oracle; the bf16 tcgen05 path lives in conv3d_tc.cu.
 #include "common.cuh"
 
 namespace mvsb200 {

@@ -129,11 +129,13 @@ def group_norm(x, gamma, beta, eps=1e-5, relu=True, group_channel=8):
     return y
 
 
-def unet_ds2gn(images, weights, base_filter=8, eps=1e-5, return_layers=False):
+def unet_ds2gn(images, weights, base_filter=8, eps=1e-5, return_layers=False, round_fn=None):
     """UNetDS2GN forward (mvsnetworks.py:53-115).  images [N,H,W,3] (centred, mvs_data_generation/utils.py:33-38)
     -> features [N,H/4,W/4,4*base_filter].  H and W must be multiples of 16 (the concats need equal extents).
 
     weights: TF variable names '<layer>/kernel' ([k,k,Cin,Cout]; deconv [k,k,Cout,Cin]), '<layer>/gn/gamma', '<layer>/gn/beta'.
+    round_fn (optional) is applied to every convolution input and kernel -- used by tests to model an implementation
+    with bf16 operands and fp32 accumulation; the reference itself is plain fp32.
     """
     images = _f(images)
     if images.shape[1] % 16 or images.shape[2] % 16:
@@ -142,6 +144,8 @@ def unet_ds2gn(images, weights, base_filter=8, eps=1e-5, return_layers=False):
     for name, op, k, stride, cin, cout, srcs, gn, relu in unet_layer_specs(base_filter, images.shape[-1]):
         x = outs[srcs[0]] if len(srcs) == 1 else np.concatenate([outs[s] for s in srcs], axis=-1)
         kern = weights[name + "/kernel"]
+        if round_fn is not None:
+            x, kern = round_fn(x), round_fn(kern)
         y = conv2d_same(x, kern, stride) if op == "conv" else conv2d_transpose_same(x, kern)
         if gn:
             y = group_norm(y, weights[name + "/gn/gamma"], weights[name + "/gn/beta"], eps, relu)

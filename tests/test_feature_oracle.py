@@ -142,3 +142,20 @@ def test_golden_tower_fixture_matches_the_restatement(golden_tower):
     names = [s[0] for s in FO.unet_layer_specs(8)]
     digest = np.array([[outs[n].mean(), np.abs(outs[n]).mean(), outs[n].max()] for n in names], dtype=np.float64)
     np.testing.assert_allclose(digest, g["layer_digest"], rtol=1e-4, atol=1e-5)
+
+
+def test_bf16_operand_model_stays_close_to_fp32():
+    """round_fn models a tensor-core tower (bf16 operands, fp32 accumulation, fp32 normalisation): on the seeded
+    problem the features move by about 1 % of their range -- the tolerance budget of the round-2 implementation."""
+    import torch
+
+    def bf16(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=F32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+    w = synthetic.make_unet_weights(8)
+    im = synthetic.make_images(1, 32, 48)
+    f32 = FO.unet_ds2gn(im, w)
+    f16 = FO.unet_ds2gn(im, w, round_fn=bf16)
+    err = np.abs(f16 - f32)
+    scale = float(np.abs(f32).max())
+    assert float(err.max()) <= 0.08 * scale and float(err.mean()) <= 0.01 * scale, (float(err.max()), float(err.mean()), scale)

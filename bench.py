@@ -290,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": eng.d2h_bytes, "ms_per_step": ms_e2e / args.steps, "depth_checksum": checksum},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "cost_volume_c32_kernel (fused warp + variance)", "bound": "hbm",
+        "roofline": {"kernel": "cost_volume_window_kernel (fused warp + variance, TMA-staged source windows)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes": cv_bytes, "avg_launch_ms": cv_ms},
         # the second stage as a whole (13 launches of conv3d_tc_kernel): SURVEY 8(d) unfused compulsory bytes 230 B

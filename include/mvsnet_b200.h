@@ -181,6 +181,11 @@ int mvsb200_infer(const float* feats, const float* cams, int n_views, int depth_
  * (bf16 mode): chunk-planar [D][C/8][Hf][Wf][8] and parity-split [D][C/8][4][Hf/2][Wf/2][8] bf16. */
 int mvsb200_infer_cost_offsets(int n_views, int depth_num, int hf, int wf, int channels, int base_filter,
                                int precision, size_t* cp8_offset, size_t* ps8_offset);
+/* Byte offset, inside the mvsb200_infer workspace, of the filtered cost volume [D,Hf,Wf] fp32 (the squeezed output of
+ * RegNetUS0, model.py:468-469) the last call left there: lets a test run the reference's regression (model.py:472-498)
+ * on exactly the volume the fused soft-argmin saw. */
+int mvsb200_infer_filtered_offset(int n_views, int depth_num, int hf, int wf, int channels, int base_filter,
+                                  int precision, size_t* offset);
 
 /* Optional instrumentation: five cudaEvent_t handles recorded by mvsb200_infer on its stream at the
  * stage boundaries (start, after homographies, after cost volume, after regularizer, after regression);
@@ -325,6 +330,16 @@ int mvsb200_umma_probe(const void* a_image, int a_bytes, const void* b_image, in
 
 /* Number of kernel launches issued through this library by the calling process so far. */
 uint64_t mvsb200_launch_count(void);
+
+/* Development counter of the fused warp + variance kernel (cost_volume_win.cu): (voxel, view) pairs whose taps came
+ * from global memory because their footprint was not inside the shared-memory window, since the last reset.  Counted
+ * only while the tuning switch CV_STATS is on.  Synchronises the device.  No counterpart in the reference. */
+int mvsb200_cost_volume_window_stats(unsigned long long* slow_pairs, int reset);
+
+/* Development / tuning switch by name, e.g. ("NO_FUSED_REGRESS", "1"), ("CV_KERNEL", "1"), ("TC_TILE", "14x8").
+ * The MVSB200_<NAME> environment variables are only the initial values, read once at first use; nothing on the hot
+ * path reads the environment.  value NULL restores the default.  No counterpart in the reference. */
+int mvsb200_set_tuning(const char* name, const char* value);
 
 #ifdef __cplusplus
 }

@@ -107,6 +107,7 @@ SIGNATURES = {
                                         _P]),
     "mvsb200_slab_regions": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mvsb200_infer_cost_offsets": (c_int, [c_int] * 7 + [_P, _P]),
+    "mvsb200_infer_filtered_offset": (c_int, [c_int] * 7 + [_P]),
     "mvsb200_infer_host_staging_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mvsb200_infer_host": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
                                    POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
@@ -117,6 +118,8 @@ SIGNATURES = {
     "mvsb200_umma_probe": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, _P, _P]),
     "mvsb200_launch_count": (c_uint64, []),
+    "mvsb200_set_tuning": (c_int, [c_char_p, c_char_p]),
+    "mvsb200_cost_volume_window_stats": (c_int, [POINTER(c_uint64), c_int]),
 }
 
 _lib = None
@@ -138,6 +141,12 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def set_tuning(name: str, value=None) -> None:
+    """Development / tuning switch of the library (MVSB200_<name> in the environment is only its initial value)."""
+    v = None if value is None else str(int(value) if isinstance(value, bool) else value).encode()
+    check(load().mvsb200_set_tuning(name.encode(), v), f"set_tuning({name})")
 
 
 def last_error() -> str:
@@ -162,6 +171,18 @@ def stream_ptr():
 
 
 def require_cuda(*tensors):
+    """Every tensor must live on the CURRENT CUDA device: the library launches on the current device and on its
+    current stream, so a tensor of another GPU would be dereferenced by the wrong one (wrap the call in
+    `torch.cuda.device(t.device)`, as engine.HotPath does)."""
+    import torch
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise MVSB200Error("mvsnet_b200 needs CUDA tensors: there is no CPU path")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise MVSB200Error(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: "
+                               "wrap the call in torch.cuda.device(tensor.device)")

@@ -10,6 +10,7 @@ from .. import ops
 from ..engine import NETWORK_MODE_DIVISOR, RegnetWeights, regnet_base_filter
 
 _VARIABLES = {}      # the "checkpoint": TF variable name -> array, shared like a TF variable scope
+_VARIABLES_VERSION = [0]   # bumped by every set_variables(): device copies made from an older checkpoint are stale
 
 
 def set_variables(weights: dict) -> None:
@@ -17,6 +18,11 @@ def set_variables(weights: dict) -> None:
     _VARIABLES.clear()
     _VARIABLES.update(weights)
     _VARIABLES.pop("__device__", None)
+    _VARIABLES_VERSION[0] += 1
+
+
+def variables_version() -> int:
+    return _VARIABLES_VERSION[0]
 
 
 def get_variables() -> dict:
@@ -44,6 +50,18 @@ class RegNetUS0:
         self.layers = dict(inputs)
         self._output = None
 
+    def _forward_one(self, lib, w, prec, c):
+        if self.precision == "bf16" and c.dtype != torch.bfloat16:
+            c = c.to(torch.bfloat16)
+        d, hf, wf, ch = c.shape
+        nbytes = lib.mvsb200_regnet_workspace_bytes(d, hf, wf, ch, w.base_filter, prec)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=c.device)
+        out = torch.empty((d, hf, wf), dtype=torch.float32, device=c.device)
+        L.check(lib.mvsb200_regnet_forward(L.ptr(c), ops._DTYPE[c.dtype], ctypes.byref(w.params), d, hf, wf, ch,
+                                           w.base_filter, self.epsilon, prec, L.ptr(out), L.ptr(ws), nbytes,
+                                           L.stream_ptr()), "regnet_forward")
+        return out
+
     def get_output(self):
         if self._output is None:
             cost = self.layers["data"]
@@ -57,18 +75,9 @@ class RegNetUS0:
             lib = L.load()
             outs = []
             prec = ops._PRECISION[self.precision]
-            for b in range(cost.shape[0]):
-                c = cost[b].contiguous()
-                if self.precision == "bf16" and c.dtype != torch.bfloat16:
-                    c = c.to(torch.bfloat16)
-                d, hf, wf, ch = c.shape
-                nbytes = lib.mvsb200_regnet_workspace_bytes(d, hf, wf, ch, w.base_filter, prec)
-                ws = torch.empty((nbytes,), dtype=torch.uint8, device=c.device)
-                out = torch.empty((d, hf, wf), dtype=torch.float32, device=c.device)
-                L.check(lib.mvsb200_regnet_forward(L.ptr(c), ops._DTYPE[c.dtype], ctypes.byref(w.params), d, hf, wf,
-                                                   ch, w.base_filter, self.epsilon, prec, L.ptr(out), L.ptr(ws),
-                                                   nbytes, L.stream_ptr()), "regnet_forward")
-                outs.append(out)
+            with torch.cuda.device(cost.device):
+                for b in range(cost.shape[0]):
+                    outs.append(self._forward_one(lib, w, prec, cost[b].contiguous()))
             self._output = torch.stack(outs, dim=0)[..., None]
         return self._output
 

@@ -16,6 +16,25 @@ extern std::atomic<uint64_t> g_launch_count;
 
 inline void count_launch(int n = 1) { g_launch_count.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+// Development / tuning switches.  One immutable snapshot, read with a single atomic load per use: it is filled from
+// the MVSB200_* environment variables ONCE (first use) and replaced as a whole by mvsb200_set_tuning(); nothing on
+// the hot path calls getenv().  -1 = not set for the fields that distinguish "unset" from 0.
+struct Tuning {
+  int no_fused_regress = 0;   // NO_FUSED_REGRESS: stand-alone regression kernel instead of the 3dconv6_2 epilogue
+  int cv_fp32_taps = 0;       // CV_FP32_TAPS: product-mode cost volume from fp32 features (north_star arithmetic)
+  int cv_kernel = 0;          // CV_KERNEL: 0 = shared-memory window kernel (TMA), 1 = the round-1 gather kernel
+  int cv_fp32_blend = 0, cv_minb = 0, cv_rec16 = 0, cv_kdc = 0;      // round-1 gather kernel variants
+  int cv_planes = 0, cv_stats = 0;                                   // window kernel: planes per block; fit counters
+  int tc_zf = -1, tc_xfold = -1, tc_zsplit = 0, tc_dbg = 0, tc_verbose = 0, tc_prof = 0, tc_exact_smem = 0, tc_no_pdl = 0;
+  int tc_tile_x = 0, tc_tile_y = 0;
+  int tc_layer_set = 0, tc_layer[3] = {0, 0, 0};                     // TC_LAYER="cin,cout,mode": restrict the tc_* switches
+  int regnet_profile = 0, unet_no_tile = 0, unet_profile = 0, unet_fp32 = 0;
+};
+const Tuning& tuning();
+
+// multiprocessor count of the current device (cached per device)
+int sm_count_current();
+
 #define MVS_CHECK_ARG(cond, ...)                         \
   do {                                                   \
     if (!(cond)) {                                       \

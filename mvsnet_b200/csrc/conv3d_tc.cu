@@ -1337,24 +1337,17 @@ using namespace tc;
 // Plan (tile, folds, z split, op table) of one launch: output channels [cb, cb+cn) of a layer.  Cached per shape.
 static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, int cn, bool has_skip, bool transform,
                       int sm_count, Plan* out, int* dbg_out) {
-  // tuning / debugging switches; MVSB200_TC_LAYER="cin,cout,mode" restricts them to one layer shape
-  const char* zf_env = getenv("MVSB200_TC_ZF");
-  const char* tile_env = getenv("MVSB200_TC_TILE");     // "TXxTY" forces the tile
-  const char* dbg_env = getenv("MVSB200_TC_DBG");
-  const char* zs_env = getenv("MVSB200_TC_ZSPLIT");
-  const char* xf_env = getenv("MVSB200_TC_XFOLD");     // 0 switches the x-fold off
-  if (const char* only = getenv("MVSB200_TC_LAYER")) {
-    int a = 0, b = 0, m = 0;
-    sscanf(only, "%d,%d,%d", &a, &b, &m);
-    if (a != cin || b != cout || m != mode) zf_env = tile_env = dbg_env = zs_env = xf_env = nullptr;
-  }
-  int force_tx = 0, force_ty = 0;
-  if (tile_env) sscanf(tile_env, "%dx%d", &force_tx, &force_ty);
-  const int force_zs = zs_env ? atoi(zs_env) : 0;
-  const bool no_xfold = xf_env && atoi(xf_env) == 0;
+  // tuning / debugging switches (mvsb200_set_tuning); TC_LAYER="cin,cout,mode" restricts them to one layer shape
+  const Tuning& tn = tuning();
+  const bool mine = !tn.tc_layer_set || (tn.tc_layer[0] == cin && tn.tc_layer[1] == cout && tn.tc_layer[2] == mode);
+  const int zf_forced = mine ? tn.tc_zf : -1;                    // -1: planner's choice
+  const int force_tx = mine ? tn.tc_tile_x : 0, force_ty = mine ? tn.tc_tile_y : 0;
+  const int force_zs = mine ? tn.tc_zsplit : 0;
+  const bool no_xfold = mine && tn.tc_xfold == 0;
+  const int dbg_forced = mine ? tn.tc_dbg : 0;
     const int Mx = mode == MODE_CONV2 ? ceil_div(W, 2) : W, My = mode == MODE_CONV2 ? ceil_div(H, 2) : H,
               Mz = mode == MODE_CONV2 ? ceil_div(D, 2) : D;
-    const std::array<int, 14> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_env ? atoi(zf_env) : 0,
+    const std::array<int, 14> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_forced > 0 ? zf_forced : 0,
                                      force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0)};
     Plan best;
     bool found = false;
@@ -1368,8 +1361,8 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
       for (int zi = 0; zi < 3; ++zi) {
         const int zf = zf_cands[zi];
         if (mode != MODE_CONV1 && zf != 1) continue;
-        if (zf_env && atoi(zf_env) != zf && mode == MODE_CONV1) continue;
-        if (zf > 1 && !zf_env && Mz < 2 * zf) continue;
+        if (zf_forced > 0 && zf_forced != zf && mode == MODE_CONV1) continue;
+        if (zf > 1 && zf_forced <= 0 && Mz < 2 * zf) continue;
         for (int xf = (mode == MODE_CONV1 && !no_xfold) ? 1 : 0; xf >= 0; --xf)
         for (int TX = 4; TX <= 30; ++TX) {
           if (xf && TX != 6 && TX != 14 && TX != 30) continue;
@@ -1409,7 +1402,7 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
       }
     }
     if (found) *out = best;
-    if (dbg_out) *dbg_out = dbg_env ? atoi(dbg_env) : 0;
+    if (dbg_out) *dbg_out = dbg_forced;
     return found;
 }
 
@@ -1485,12 +1478,7 @@ int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStr
   static PackAll a;      // too large for the stack of some callers; filled and consumed under the launch below
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
-  int sm_count = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sm_count = sm_count_current();
   a.n = 0;
   for (int j = 0; j < njobs; ++j) {
     const TcPackJob& jb = jobs[j];
@@ -1554,9 +1542,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     set_error("conv3d(bf16/tcgen05): cuTensorMapEncodeTiled is not available from the driver");
     return MVSB200_ERR_CUDA;
   }
-  int sm_count = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const int sm_count = sm_count_current();
+  int dev = 0;
+  MVS_CUDA(cudaGetDevice(&dev));
   // function attributes are per device: once per device of this process (a set bit is only ever re-set to itself)
   static std::atomic<uint64_t> attr_done{0};
   if (!(attr_done.load(std::memory_order_acquire) >> (dev & 63) & 1u)) {
@@ -1612,7 +1600,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     }
     {
       c.dbg = dbg_flags;
-      if (getenv("MVSB200_TC_VERBOSE"))
+      if (tuning().tc_verbose)
         fprintf(stderr, "[tc] mode=%d Cin=%d Cout=%d(+%d) tile %dx%d PX=%d RY=%d MB=%d N=%d R=%d zf=%d xf=%d zsplit=%d grid=%d smem=%zu "
                 "RS=%d nops=%d b=%dB xf=%d/%d est=%.0f clk\n",
                 mode, cin, cn, cb, c.TX, c.TY, c.PX, c.RY, c.MB, c.CP, c.R, c.zf, c.xfold, c.zsplit, c.tiles_x * c.tiles_y * c.zsplit,
@@ -1632,16 +1620,16 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     const int grid = c.tiles_x * c.tiles_y * c.zsplit;
     static long long* prof_buf = nullptr;
     c.prof = nullptr;
-    if (getenv("MVSB200_TC_PROF")) {
+    if (tuning().tc_prof) {
       if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 256 + 16 * 4096));
       c.prof = prof_buf;
     }
     // every launch asks for the same (maximum) dynamic shared memory: a different carve-out per layer makes the
     // SMs re-partition L1 / shared memory between launches
-    static const bool exact_smem = getenv("MVSB200_TC_EXACT_SMEM") != nullptr;
+    const bool exact_smem = tuning().tc_exact_smem != 0;
     const size_t smem_launch = exact_smem ? best.smem : kSmemBudget;
     // programmatic dependent launch (prologue of this layer under the tail of the previous kernel)
-    static const bool no_pdl = getenv("MVSB200_TC_NO_PDL") != nullptr;
+    const bool no_pdl = tuning().tc_no_pdl != 0;
     c.pdl = no_pdl ? 0 : (grid <= sm_count ? 1 : 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_launch; cfg.stream = s;
@@ -1716,7 +1704,7 @@ int conv3d_tc_describe(int D, int H, int W, int cin, int cout, int stride, int t
   for (int cb = 0; cb < cout; cb += 32, ++launches) {
     const int cn = cout - cb < 32 ? cout - cb : 32;
     Plan pl;
-    if (!find_plan(mode, D, H, W, cin, cout, cb, cn, has_skip != 0, transform != 0, sm_count > 0 ? sm_count : 148, &pl,
+    if (!find_plan(mode, D, H, W, cin, cout, cb, cn, has_skip != 0, transform != 0, sm_count > 0 ? sm_count : 148 /* B200: host-only planning without a device */, &pl,
                    nullptr)) {
       set_error("conv3d(bf16/tcgen05): no tile fits (Cin=%d Cout=%d mode=%d)", cin, cout, mode);
       return MVSB200_ERR_UNSUPPORTED;
@@ -1744,11 +1732,16 @@ size_t planar_bytes(int D, int H, int W, int C, int parity_split) {
   return (size_t)D * (C / 8) * 4 * ((H + 1) / 2) * ((W + 1) / 2) * 16;
 }
 
+static unsigned grid_for(size_t items) {       // 256-thread blocks, at most 32 per multiprocessor
+  const size_t cap = (size_t)sm_count_current() * 32, want = (items + 255) / 256;
+  return (unsigned)(want < cap ? want : cap);
+}
+
 int launch_ndhwc_to_planar(const void* x_ndhwc, int D, int H, int W, int C, void* cp8, void* ps8, cudaStream_t s) {
   MVS_CHECK_ARG(C % 8 == 0, "layout: C must be a multiple of 8 (got %d)", C);
   if (ps8 && ((H | W) & 1)) MVS_CUDA(cudaMemsetAsync(ps8, 0, planar_bytes(D, H, W, C, 1), s));
   const size_t total = (size_t)D * H * W * (C / 8);
-  const unsigned blocks = (unsigned)((total + 255) / 256 < 148u * 32u ? (total + 255) / 256 : 148u * 32u);
+  const unsigned blocks = grid_for(total);
   ndhwc_to_planar_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x_ndhwc, D, H, W, C, (__nv_bfloat16*)cp8,
                                                 (__nv_bfloat16*)ps8);
   MVS_LAUNCH_CHECK("ndhwc_to_planar_kernel");
@@ -1758,14 +1751,14 @@ int launch_ndhwc_to_planar(const void* x_ndhwc, int D, int H, int W, int C, void
 int launch_planar_to_ndhwc(const void* cp8, int D, int H, int W, int C, void* y_ndhwc, cudaStream_t s) {
   MVS_CHECK_ARG(C % 8 == 0, "layout: C must be a multiple of 8 (got %d)", C);
   const size_t total = (size_t)D * H * W * (C / 8);
-  const unsigned blocks = (unsigned)((total + 255) / 256 < 148u * 32u ? (total + 255) / 256 : 148u * 32u);
+  const unsigned blocks = grid_for(total);
   planar_to_ndhwc_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)cp8, D, H, W, C, (__nv_bfloat16*)y_ndhwc);
   MVS_LAUNCH_CHECK("planar_to_ndhwc_kernel");
   return MVSB200_OK;
 }
 
 int launch_f32_to_bf16(const float* x, size_t n, void* y, cudaStream_t s) {
-  const unsigned blocks = (unsigned)((n + 255) / 256 < 148u * 32u ? (n + 255) / 256 : 148u * 32u);
+  const unsigned blocks = grid_for(n);
   f32_to_bf16_kernel<<<blocks, 256, 0, s>>>(x, n, (__nv_bfloat16*)y);
   MVS_LAUNCH_CHECK("f32_to_bf16_kernel");
   return MVSB200_OK;

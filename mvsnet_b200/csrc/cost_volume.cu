@@ -439,6 +439,13 @@ cost_volume_generic_kernel(const float* __restrict__ feats, const float* __restr
   }
 }
 
+size_t cost_volume_pair_bytes(int n_views, int hf, int wf);
+size_t cost_volume_window_scratch_bytes(int n_views, int hf, int wf);
+bool cost_volume_window_ok(int n_views, int hf, int wf, int channels, int sampler);
+int launch_cost_volume_window(const float* feats, const float* coef_table, int n_views, int depth_num, int d0g, int dloc,
+                              int hf, int wf, int order, void* cp8, void* ps8, void* feats16, int blend32,
+                              unsigned long long* stats, cudaStream_t s);
+
 // planar_ps8 != NULL or planar != 0: write the bf16 planar layouts (out = CP8, planar_ps8 = PS8); fast path only
 static int launch_cost_volume_any(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                                   int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
@@ -481,6 +488,11 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
     set_error("cost_volume: variant %d needs sampler=transform, C=32, n_views<=8", variant);
     return MVSB200_ERR_UNSUPPORTED;
   }
+  // product mode: the shared-memory window kernel (cost_volume_win.cu) unless the round-1 gather kernel is asked for
+  if (planar && feats16 && coef && variant == 3 && tuning().cv_kernel == 0 &&
+      cost_volume_window_ok(n_views, hf, wf, channels, sampler))
+    return launch_cost_volume_window(feats, coef, n_views, depth_num, d0g, dloc, hf, wf, order, out, planar_ps8, feats16,
+                                     tuning().cv_fp32_blend, nullptr, s);
   if (variant >= 2) {
     const bool wide = variant == 2;
     const int tx = wide ? 32 : 16, ty = wide ? 1 : 2;
@@ -521,22 +533,23 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
   } while (0)
     if (planar && ((hf | wf) & 1) && planar_ps8)
       MVS_CUDA(cudaMemsetAsync(planar_ps8, 0, (size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) * 16, s));
-    static const bool half_interp = getenv("MVSB200_CV_FP32_BLEND") == nullptr;     // fp16 blend unless asked otherwise
-    static const int minb_env = getenv("MVSB200_CV_MINB") ? atoi(getenv("MVSB200_CV_MINB")) : 0;   // tuning
-    // 8-byte footprint records over the zero-padded paired copy (MVSB200_CV_REC16=1: the 16-byte records)
-    const bool rec8 = planar && feats16 && half_interp && minb_env == 0 && getenv("MVSB200_CV_REC16") == nullptr &&
+    const Tuning& tn = tuning();
+    const bool half_interp = tn.cv_fp32_blend == 0;     // fp16 blend unless asked otherwise
+    const int minb_env = tn.cv_minb;                    // tuning
+    // the paired copy is addressed with 32-bit byte offsets: past 4 GiB the taps come from the fp32 features
+    if (feats16 && cost_volume_pair_bytes(n_views, hf, wf) >= ((size_t)1 << 32)) feats16 = nullptr;
+    // 8-byte footprint records over the zero-padded paired copy (tuning CV_REC16=1: the 16-byte records)
+    const bool rec8 = planar && feats16 && half_interp && minb_env == 0 && tn.cv_rec16 == 0 &&
                       (size_t)n_views * (hf + 3) * (wf + 1) < ((size_t)1 << 25);
     if (planar && feats16) {
-      pair_features_kernel<<<148 * 8, 256, 0, s>>>(feats, n_views, hf, wf, rec8 ? 1 : 0, (__half*)feats16);
+      pair_features_kernel<<<sm_count_current() * 8, 256, 0, s>>>(feats, n_views, hf, wf, rec8 ? 1 : 0, (__half*)feats16);
       MVS_LAUNCH_CHECK("pair_features_kernel");
     }
     // planes per thread: the smallest of 2 / 4 / 8 whose footprints fill whole rounds of 8 lanes
     const int n_src = n_views - 1;
     int kdc = (2 * n_src) % 8 == 0 ? 2 : ((4 * n_src) % 8 == 0 ? 4 : 8);
-    if (const char* e = getenv("MVSB200_CV_KDC")) {           // tuning: 2 / 4 / 8 when it still fills whole rounds
-      const int k = atoi(e);
+    if (const int k = tn.cv_kdc)                              // tuning: 2 / 4 / 8 when it still fills whole rounds
       if ((k == 2 || k == 4 || k == 8) && (k * n_src) % 8 == 0) kdc = k;
-    }
     if (planar) { if (wide) CV_FAST_K(2, 32, 1); else CV_FAST_K(2, 16, 2); }
     else if (wide) { if (bf16) CV_FAST_K(1, 32, 1); else CV_FAST_K(0, 32, 1); }
     else           { if (bf16) CV_FAST_K(1, 16, 2); else CV_FAST_K(0, 16, 2); }

@@ -332,7 +332,7 @@ int launch_conv2d(const float* xa, int ca, const float* xb, int cb, const float*
   MVS_CHECK_ARG(!transposed || (k == 3 && stride == 2), "conv2d: the transposed convolution is 3x3 stride 2");
   MVS_CHECK_ARG(n <= 65535, "conv2d: too many views");
   const int ho = out_extent(h, stride, transposed), wo = out_extent(w, stride, transposed);
-  static const bool no_tile = getenv("MVSB200_UNET_NO_TILE") != nullptr;       // development switch
+  const bool no_tile = tuning().unet_no_tile != 0;       // development switch
   if (!transposed && ca % 8 == 0 && cb % 8 == 0 && !no_tile) {
     if (k == 3 && stride == 1) return launch_conv2d_tile<3, 1, 4>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
     if (k == 3 && stride == 2) return launch_conv2d_tile<3, 2, 4>(xa, ca, xb, cb, kernel_tf, n, h, w, cout, ho, wo, y, stats, s);
@@ -361,7 +361,7 @@ int launch_group_norm(float* y, const double* stats, const float* gamma, const f
   MVS_CHECK_ARG(y && stats && gamma && beta && n >= 1 && hw >= 1 && c >= kCoT && c % kCoT == 0,
                 "group_norm: bad arguments (C=%d must be a multiple of %d)", c, kCoT);
   const size_t total4 = (size_t)n * hw * c / 4;
-  const int blocks = (int)((total4 + 255) / 256 < 148 * 16 ? (total4 + 255) / 256 : 148 * 16);
+  const int blocks = (int)((total4 + 255) / 256 < (size_t)sm_count_current() * 16 ? (total4 + 255) / 256 : (size_t)sm_count_current() * 16);
   group_norm_kernel<<<blocks, 256, 0, s>>>(y, stats, gamma, beta, hw, c, eps, relu, total4);
   MVS_LAUNCH_CHECK("group_norm_kernel");
   return MVSB200_OK;
@@ -448,7 +448,7 @@ extern "C" int mvsb200_unet_forward(const float* images, const mvsb200_unet_para
   MVS_CUDA(cudaMemsetAsync(stats, 0, p.stats_bytes, s));
   const int gmax = 16 * base_filter / kCoT;
   // development aid: MVSB200_UNET_PROFILE=1 prints per-layer device times (synchronises; not for timed runs)
-  static const bool profile = getenv("MVSB200_UNET_PROFILE") != nullptr;
+  const bool profile = tuning().unet_profile != 0;
   cudaEvent_t pev[MVSB200_UNET_LAYERS + 1];
   if (profile) {
     for (int i = 0; i <= MVSB200_UNET_LAYERS; ++i) cudaEventCreate(&pev[i]);

@@ -177,7 +177,7 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
     if (rc) return rc;
   }
   // development aid: MVSB200_REGNET_PROFILE=1 prints per-layer device times (synchronises; not for timed runs)
-  static const bool profile = getenv("MVSB200_REGNET_PROFILE") != nullptr;
+  const bool profile = tuning().regnet_profile != 0;
   cudaEvent_t pev[MVSB200_REGNET_LAYERS + 1];
   if (profile) {
     for (int i = 0; i <= MVSB200_REGNET_LAYERS; ++i) cudaEventCreate(&pev[i]);
@@ -765,6 +765,19 @@ extern "C" int mvsb200_infer_cost_offsets(int n_views, int depth_num, int hf, in
   return MVSB200_OK;
 }
 
+// Byte offset, inside the whole-path workspace, of the filtered cost volume [D,Hf,Wf] fp32 (output of 3dconv6_2) that
+// the last mvsb200_infer call left there (tests: the regression stage against the oracle on the same volume)
+extern "C" int mvsb200_infer_filtered_offset(int n_views, int depth_num, int hf, int wf, int channels, int base_filter,
+                                             int precision, size_t* offset) {
+  MVS_CHECK_ARG(offset != nullptr && n_views >= 2, "infer_filtered_offset: bad arguments");
+  int rc = check_regnet_shape(depth_num, hf, wf, channels, base_filter);
+  if (rc) return rc;
+  InferPlan ip;
+  make_infer_plan(n_views, depth_num, hf, wf, channels, base_filter, precision, &ip);
+  *offset = ip.filtered_off;
+  return MVSB200_OK;
+}
+
 extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views, int depth_num, int hf, int wf,
                              int channels, float depth_start, float depth_interval, int inverse_depth, int order,
                              int sampler, const mvsb200_regnet_params* params, int base_filter, float bn_eps,
@@ -801,7 +814,7 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   if (planar) {
     void *cp8 = nullptr, *ps8 = nullptr;
     regnet_cost_planar(ws + ip.regnet_off, depth_num, hf, wf, channels, base_filter, &cp8, &ps8);
-    static const bool fp32_taps = getenv("MVSB200_CV_FP32_TAPS") != nullptr;
+    const bool fp32_taps = tuning().cv_fp32_taps != 0;
     rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8,
                                    fp32_taps ? nullptr : ws + ip.pair_off, coefs, s);
   } else {
@@ -815,7 +828,7 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   volatile float lin_num = sub_host((float)depth_num, 1.0f);
   volatile float lin_span = sub_host((float)depth_end, depth_start);
   volatile float lin_step = depth_num > 1 ? lin_span / lin_num : 0.0f;
-  const bool no_fused_regress = getenv("MVSB200_NO_FUSED_REGRESS") != nullptr;      // tests compare the two paths
+  const bool no_fused_regress = tuning().no_fused_regress != 0;      // tests compare the two paths
   TcRegress rg = {(float*)(ws + ip.partial_off), depth_start, (float)lin_step, 0};
   const bool try_fuse = precision == MVSB200_PRECISION_BF16 && !inverse_depth && !no_fused_regress;
   rc = regnet_forward_impl(cost, cost_dtype, planar ? 1 : 0, params, depth_num, hf, wf, channels, base_filter, bn_eps,
@@ -837,6 +850,17 @@ extern "C" size_t mvsb200_infer_host_staging_bytes(int n_views, int hf, int wf, 
   if (n_views < 2 || hf <= 0 || wf <= 0 || channels <= 0) return 0;
   return align_up((size_t)n_views * hf * wf * channels * sizeof(float), 256) +
          align_up((size_t)n_views * 32 * sizeof(float), 256) + 2 * align_up((size_t)hf * wf * sizeof(float), 256);
+}
+
+// one disable-timing event per (host thread, device), created on first use and kept for the life of the thread
+static int chain_event(cudaEvent_t* out) {
+  static thread_local cudaEvent_t pool[64] = {};
+  int dev = 0;
+  MVS_CUDA(cudaGetDevice(&dev));
+  cudaEvent_t& e = pool[dev & 63];
+  if (!e) MVS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *out = e;
+  return MVSB200_OK;
 }
 
 // copies on `copy_stream`, kernels on `stream`; when they differ the two are chained with events (feed -> kernels ->
@@ -861,23 +885,23 @@ static int infer_host_enqueue(const float* feats_host, const float* cams_host, i
   float* d_prob = (float*)((char*)d_depth + align_up(map_bytes, 256));
   MVS_CUDA(cudaMemcpyAsync(d_feats, feats_host, feat_bytes, cudaMemcpyHostToDevice, s));
   MVS_CUDA(cudaMemcpyAsync(d_cams, cams_host, cam_bytes, cudaMemcpyHostToDevice, s));
+  // the two streams are chained feed -> kernels -> fetch through ONE pooled event per (thread, device): a wait
+  // captures the record that precedes it, so the event can be re-recorded at once and is never destroyed per call
   cudaEvent_t ev = nullptr;
   if (split) {
-    MVS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    cudaEventRecord(ev, s);
-    cudaStreamWaitEvent(sk, ev, 0);
+    int rc_ev = chain_event(&ev);
+    if (rc_ev) return rc_ev;
+    MVS_CUDA(cudaEventRecord(ev, s));
+    MVS_CUDA(cudaStreamWaitEvent(sk, ev, 0));
   }
   int rc = mvsb200_infer(d_feats, d_cams, n_views, depth_num, hf, wf, channels, depth_start, depth_interval,
                          inverse_depth, order, sampler, params, base_filter, bn_eps, precision, d_depth, d_prob,
                          workspace, workspace_bytes, stream);
-  if (split) {
-    if (!rc) {
-      cudaEventRecord(ev, sk);              // re-recording is fine: the wait above captured the first record
-      cudaStreamWaitEvent(s, ev, 0);
-    }
-    cudaEventDestroy(ev);                   // released once the pending work on it has completed
-  }
   if (rc) return rc;
+  if (split) {
+    MVS_CUDA(cudaEventRecord(ev, sk));
+    MVS_CUDA(cudaStreamWaitEvent(s, ev, 0));
+  }
   MVS_CUDA(cudaMemcpyAsync(depth_map_host, d_depth, map_bytes, cudaMemcpyDeviceToHost, s));
   MVS_CUDA(cudaMemcpyAsync(prob_map_host, d_prob, map_bytes, cudaMemcpyDeviceToHost, s));
   return MVSB200_OK;

@@ -71,6 +71,14 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, in
       : "memory");
 }
 
+// 3-D tiled tensor-map load (same semantics; the cost-volume kernel's source windows)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------- TMEM
 // Allocate `cols` (power of two >= 32) TMEM columns; the base address is written to *smem_dst.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {

@@ -14,13 +14,27 @@ from . import _lib as L
 from . import ops
 
 NETWORK_MODE_DIVISOR = {  # cnn_wrapper/network.py:75-85
-    "normal": 1.0, "semilite": 4 / 3, "lite": 2.0, "ultralite": 4.0, "fat": 0.5, "ultrafat": 0.25,
+    # 'semilite' is written `4/3` upstream (network.py:77) and the reference runs on Python 2.7 (xrange, iteritems),
+    # where that is INTEGER division = 1: semilite checkpoints have base_filter 8, like 'normal'
+    "normal": 1.0, "semilite": 1.0, "lite": 2.0, "ultralite": 4.0, "fat": 0.5, "ultrafat": 0.25,
 }
 
 
 def regnet_base_filter(network_mode: str = "normal") -> int:
     """mvsnetworks.py:126-127: max(1, int(8 / base_divisor))."""
     return max(1, int(8 / NETWORK_MODE_DIVISOR[network_mode]))
+
+
+def _on_own_device(method):
+    """Run a HotPath / FeatureTower method with the object's GPU as the current device: the library launches on the
+    current device and the current stream, whatever device its pointer arguments live on."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapper
 
 
 class RegnetWeights:
@@ -60,6 +74,10 @@ class HotPath:
                  sampler="transform", inverse_depth=False, bn_eps=1e-5, device="cuda"):
         self.lib = L.load()
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.MVSB200Error("mvsnet_b200 needs a CUDA device: there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.n_views, self.depth_num, self.hf, self.wf, self.channels = n_views, depth_num, hf, wf, channels
         self.precision = ops._PRECISION[precision]
         self.precision_name = precision
@@ -84,6 +102,7 @@ class HotPath:
         self.d2h_bytes = 2 * hf * wf * 4
 
     # -- whole path, device buffers --------------------------------------------------------------
+    @_on_own_device
     def infer(self, feats: torch.Tensor, cams: torch.Tensor, depth_start: float, depth_interval: float,
               depth_map: torch.Tensor | None = None, prob_map: torch.Tensor | None = None):
         L.require_cuda(feats, cams)
@@ -102,6 +121,7 @@ class HotPath:
         return depth_map, prob_map
 
     # -- whole path, host buffers (feed/fetch boundary of sess.run, inference.py:111) -----------------
+    @_on_own_device
     def infer_host(self, feats_host: torch.Tensor, cams_host: torch.Tensor, depth_start: float,
                    depth_interval: float, depth_out: torch.Tensor, prob_out: torch.Tensor):
         for t in (feats_host, cams_host, depth_out, prob_out):
@@ -115,6 +135,7 @@ class HotPath:
         L.check(rc, "infer_host")
         return depth_out, prob_out
 
+    @_on_own_device
     def infer_host_async(self, feats_host: torch.Tensor, cams_host: torch.Tensor, depth_start: float,
                          depth_interval: float, depth_out: torch.Tensor, prob_out: torch.Tensor):
         """infer_host without the final synchronisation: everything is enqueued on the current stream and the
@@ -131,6 +152,7 @@ class HotPath:
         L.check(rc, "infer_host_async")
         return depth_out, prob_out
 
+    @_on_own_device
     def infer_host_pipelined(self, feats_host: torch.Tensor, cams_host: torch.Tensor, depth_start: float,
                              depth_interval: float, depth_out: torch.Tensor, prob_out: torch.Tensor,
                              compute_stream: torch.cuda.Stream, copy_stream: torch.cuda.Stream):
@@ -150,6 +172,7 @@ class HotPath:
         L.check(rc, "infer_host_pipelined")
         return depth_out, prob_out
 
+    @_on_own_device
     def set_stage_events(self, events) -> None:
         """events: five torch.cuda.Event(enable_timing=True) (or None) recorded at the stage boundaries of infer()."""
         if events is None:
@@ -161,6 +184,7 @@ class HotPath:
         L.check(self.lib.mvsb200_infer_set_stage_events(arr), "set_stage_events")
 
     # -- stages (tests, profiling) ---------------------------------------------------------------------
+    @_on_own_device
     def cost_volume_planar(self, feats: torch.Tensor, cams: torch.Tensor, depth_start: float, depth_interval: float):
         """Run the whole path once and return views of the cost volume inside the workspace in the regularizer's two
         layouts: CP8 [D, C/8, Hf, Wf, 8] and PS8 [D, C/8, 4, Hf/2, Wf/2, 8] (bf16 mode, even Hf / Wf)."""
@@ -174,6 +198,16 @@ class HotPath:
         ps8 = self.workspace[ps8_off.value:ps8_off.value + n].view(torch.bfloat16)
         return cp8, ps8
 
+    def filtered_volume(self) -> torch.Tensor:
+        """The filtered cost volume [D,Hf,Wf] fp32 the last infer() left in the workspace (a view, not a copy)."""
+        off = ctypes.c_size_t()
+        L.check(self.lib.mvsb200_infer_filtered_offset(self.n_views, self.depth_num, self.hf, self.wf, self.channels,
+                                                       self.base_filter, self.precision, ctypes.byref(off)),
+                "infer_filtered_offset")
+        n = self.depth_num * self.hf * self.wf * 4
+        return self.workspace[off.value:off.value + n].view(torch.float32).view(self.depth_num, self.hf, self.wf)
+
+    @_on_own_device
     def regnet(self, cost: torch.Tensor) -> torch.Tensor:
         d, hf, wf, c = cost.shape
         nbytes = self.lib.mvsb200_regnet_workspace_bytes(d, hf, wf, c, self.base_filter, self.precision)

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .engine import _on_own_device
 
 
 class UnetWeights:
@@ -48,6 +49,8 @@ class FeatureTower:
     def __init__(self, weights, epsilon=1e-5, device="cuda"):
         self.lib = L.load()
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.weights = weights if isinstance(weights, UnetWeights) else UnetWeights(weights, self.device)
         self.epsilon = float(epsilon)
         self._ws = None
@@ -65,6 +68,7 @@ class FeatureTower:
     def __call__(self, images: torch.Tensor) -> torch.Tensor:
         return self.forward(images)
 
+    @_on_own_device
     def forward(self, images: torch.Tensor) -> torch.Tensor:
         L.require_cuda(images)
         if images.dim() != 4 or images.shape[-1] != 3 or images.dtype != torch.float32:

@@ -78,8 +78,9 @@ def _run(images, cams, depth_num, depth_start, depth_interval, network_mode, inv
     weights = mvsnetworks.get_variables()
     if not weights:
         raise RuntimeError("RegNetUS0 variables not set: call mvsnetworks.set_variables(weights)")
-    key = (N, depth_num, hf, wf, c, network_mode, bool(inverse_depth), order, FLAGS.precision, id(weights),
-           feats.device.index)
+    # the checkpoint version, not id(weights): set_variables() refills the same dict in place
+    key = (N, depth_num, hf, wf, c, network_mode, bool(inverse_depth), order, FLAGS.precision,
+           mvsnetworks.variables_version(), feats.device.index)
     eng = _engines.get(key)
     if eng is None:
         w = RegnetWeights(weights, feats.device)

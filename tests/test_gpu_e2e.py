@@ -44,8 +44,8 @@ def test_bf16_path_vs_oracle(small_problem, oracle_small):
     assert frac >= 0.95, frac
 
 
-def test_fused_soft_argmin_matches_regression_kernel(small_problem, monkeypatch):
-    """bf16 mode folds the soft-argmin (model.py:472-495) into the epilogue of 3dconv6_2; MVSB200_NO_FUSED_REGRESS=1
+def test_fused_soft_argmin_matches_regression_kernel(small_problem, tuning):
+    """bf16 mode folds the soft-argmin (model.py:472-495) into the epilogue of 3dconv6_2; the tuning switch NO_FUSED_REGRESS
     runs the stand-alone regression kernel on the filtered volume instead.  Same volume, same answer: depth to a
     thousandth of an interval (fast exp, different summation order); the probability sum of the four planes around
     the estimate may pick different planes only where the index sits on an integer."""
@@ -54,7 +54,7 @@ def test_fused_soft_argmin_matches_regression_kernel(small_problem, monkeypatch)
     eng = HotPath(p["n_views"], p["depth_num"], p["hf"], p["wf"], p["weights"], precision="bf16")
     feats, cams = to_dev(p["feats"]), to_dev(p["cams"])
     d1, p1 = [t.clone() for t in eng.infer(feats, cams, p["depth_start"], p["depth_interval"])]
-    monkeypatch.setenv("MVSB200_NO_FUSED_REGRESS", "1")
+    tuning("NO_FUSED_REGRESS", 1)
     d2, p2 = [t.clone() for t in eng.infer(feats, cams, p["depth_start"], p["depth_interval"])]
     assert float((d1 - d2).abs().max()) <= 1e-3 * p["depth_interval"]
     assert float(((p1 - p2).abs() <= 1e-4).float().mean()) >= 0.999

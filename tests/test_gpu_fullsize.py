@@ -88,13 +88,13 @@ def test_whole_path_is_deterministic_and_bounded(big):
     assert torch.isfinite(d1).all() and torch.isfinite(p1).all()
 
 
-def test_fused_soft_argmin_matches_regression_kernel_at_full_size(big, monkeypatch):
+def test_fused_soft_argmin_matches_regression_kernel_at_full_size(big, tuning):
     """At this size every CTA of 3dconv6_2 walks the whole depth range, so the soft-argmin is folded into its
     epilogue; the stand-alone regression kernel on the same filtered volume must agree (see test_gpu_e2e)."""
     from mvsnet_b200.engine import HotPath
     eng = HotPath(N, D, HF, WF, synthetic.make_regnet_weights(), precision="bf16")
     d1, p1 = [t.clone() for t in eng.infer(big["feats"], big["cams"], big["ds"], big["di"])]
-    monkeypatch.setenv("MVSB200_NO_FUSED_REGRESS", "1")
+    tuning("NO_FUSED_REGRESS", 1)
     d2, p2 = [t.clone() for t in eng.infer(big["feats"], big["cams"], big["ds"], big["di"])]
     assert float((d1 - d2).abs().max()) <= 2e-3 * big["di"]
     assert float(((p1 - p2).abs() <= 1e-4).float().mean()) >= 0.999

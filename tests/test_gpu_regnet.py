@@ -155,13 +155,22 @@ def test_bf16_layer_with_affine_relu_and_skip(ops, O):
 
 
 def test_regnet_bf16_vs_oracle(O, small_problem):
+    """Whole bf16 RegNetUS0 against (a) the oracle run with bf16-rounded conv operands (round_fn: the arithmetic this
+    mode implements -- what is left is the bf16 storage of the raw layer outputs and summation order) and (b) the plain
+    fp32 oracle (the distance the bf16 operands themselves cost)."""
     p = small_problem
     H = np.stack([O.get_homographies(p["cams"][0:1], p["cams"][v:v + 1], p["depth_num"], p["depth_start"],
                                      p["depth_interval"])[0] for v in range(1, p["n_views"])])
-    cost = O.cost_volume(p["feats"], H)
-    ref = O.regnet_us0(cost, p["weights"])
+    cost = bf16_round(O.cost_volume(p["feats"], H))
     out = _regnet("bf16", p, cost)
+    ref_model = O.regnet_us0(cost, p["weights"], round_fn=bf16_round)
+    ref = O.regnet_us0(cost, p["weights"])
+    rel_model = np.abs(out - ref_model).max() / np.abs(ref_model).max()
+    rms_model = np.sqrt(np.mean((out - ref_model) ** 2)) / np.sqrt(np.mean(ref_model ** 2))
     rel = np.abs(out - ref).max() / np.abs(ref).max()
+    print(f"bf16 RegNetUS0 vs bf16-operand oracle: max {rel_model:.4f} rms {rms_model:.5f} of range; vs fp32 oracle: max {rel:.4f}")
+    assert rel_model <= 0.03, rel_model
+    assert rms_model <= 0.004, rms_model
     assert rel <= 0.08, rel
     assert np.corrcoef(out.ravel(), ref.ravel())[0, 1] >= 0.999
 
@@ -171,7 +180,7 @@ def test_regnet_bf16_vs_oracle(O, small_problem):
 @pytest.mark.parametrize("case", [(8, 16, 24, 32, 8, 1, False), (7, 9, 11, 16, 16, 1, False), (10, 16, 24, 8, 1, 1, False),
                                   (18, 20, 40, 32, 8, 1, False), (8, 16, 24, 32, 16, 2, False),
                                   (7, 9, 11, 32, 16, 2, False)])
-def test_bf16_zfold_variants(ops, O, monkeypatch, case, zf, xfold):
+def test_bf16_zfold_variants(ops, O, tuning, case, zf, xfold):
     """z-fold (several output planes per MMA N, master B images) and x-fold (kw taps in N, shuffled epilogue)
     against the oracle, incl. ragged D and tiles wider than the volume."""
     D, H, W, cin, cout, stride, tr = case
@@ -179,8 +188,8 @@ def test_bf16_zfold_variants(ops, O, monkeypatch, case, zf, xfold):
         pytest.skip("z-fold applies to stride-1 convs only")
     if zf * cout > 32 or (xfold and stride != 1):
         pytest.skip("fold does not apply")
-    monkeypatch.setenv("MVSB200_TC_ZF", str(zf))
-    monkeypatch.setenv("MVSB200_TC_XFOLD", str(xfold))
+    tuning("TC_ZF", zf)
+    tuning("TC_XFOLD", xfold)
     rng = np.random.RandomState(41)
     x = bf16_round(rng.randn(D, H, W, cin))
     w = (rng.randn(3, 3, 3, cin, cout) * 0.1).astype(np.float32)

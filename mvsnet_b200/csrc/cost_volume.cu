@@ -490,7 +490,8 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
   }
   // product mode: the shared-memory window kernel (cost_volume_win.cu) unless the round-1 gather kernel is asked for
   if (planar && feats16 && coef && variant == 3 && tuning().cv_kernel == 0 &&
-      cost_volume_window_ok(n_views, hf, wf, channels, sampler))
+      cost_volume_window_ok(n_views, hf, wf, channels, sampler) &&
+      (size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) < ((size_t)1 << 31))      // 32-bit cell indices
     return launch_cost_volume_window(feats, coef, n_views, depth_num, d0g, dloc, hf, wf, order, out, planar_ps8, feats16,
                                      tuning().cv_fp32_blend, nullptr, s);
   if (variant >= 2) {

@@ -3,37 +3,39 @@
 // the running-sum ops of model.py:423-463 (inference_mem) / model.py:315-334 (inference); the warped volume is
 // never written.
 //
-// Work item = 32 x 4 reference pixels x 8 consecutive depth planes (1 024 voxels).  Consecutive planes of a pixel
+// Work item = 32 x 3 reference pixels x 10 consecutive depth planes (960 voxels).  Consecutive planes of a pixel
 // sample a source view a fraction of a pixel apart, so the taps of a whole work item fall into
 // one small window of each source view: the bounding box of the 8 corner samples (the sample position is projective
-// in (x, y) and a Moebius function of the depth, hence monotone along every edge of the box).  Warp 0
+// in (x, y) and a Moebius function of the depth, hence monotone along every edge of the box).  A producer warp
 // computes that box per (work item, view) and has the TMA unit copy it from an fp16 chunk-planar copy of the
 // features ([N][4][Hf][Wf] cells of 8 channels = 16 bytes) into a shared-memory ring -- cells outside the image are
 // zero-filled by the TMA unit, which IS the reference's zero fill -- one 8-channel chunk at a time (stage = work
-// item x chunk; 48 x 16 cells per view, loaded as one or two boxes of 8 rows).  the 512 threads own two voxels
-// each: the bilinear footprint of a voxel in every view (two IEEE divisions, weights) is computed once per work
-// item and kept in registers (3 words per view), then every stage costs 4 conflict-free 16-byte shared-memory loads
-// and 16 packed-half FMAs per (voxel, view); running sum and squared sum stay in fp32 registers across the views;
-// the variance goes out as whole 16-byte cells of the regularizer's two planar layouts (lanes run along x: 512
-// contiguous bytes per warp, no staging).  A voxel whose footprint is not inside the staged window (wild geometry,
-// rounding at a box edge, window larger than the buffer) reads its taps from global memory instead: correctness
-// never depends on the window.
+// item x chunk; 48 x 16 cells per view, loaded as one or two boxes of 8 rows); it also stages the item's transform
+// rows.  15 consumer warps own two voxels per lane: the bilinear footprint of a voxel in every view (one reciprocal,
+// weights) is computed once per work item and kept in registers (3 words per view), then every stage costs 4
+// conflict-free 16-byte shared-memory loads and 16 packed-half FMAs per (voxel, view); running sum and squared sum
+// stay in fp32 registers across the views; the variance goes out as whole 16-byte cells of the regularizer's two
+// planar layouts (lanes run along x: 512 contiguous bytes per warp, no staging).  A voxel whose footprint is not
+// inside the staged window (wild geometry, window larger than the buffer) reads its taps from global memory instead:
+// correctness never depends on the window.
 #include "geometry.cuh"
 #include "umma.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <mutex>
 #include <string.h>
+#include <type_traits>
 
 namespace mvsb200 {
 using namespace umma;
 
 namespace cvw {
 
-constexpr int TXP = 32, TYP = 4, PL = 8;                 // reference pixels x planes of a work item
-constexpr int kItems = TXP * TYP * PL;                   // 1 024 voxels
-constexpr int kThreads = 512, kIPT = kItems / kThreads;  // 16 warps = 4 per scheduler: 128 registers per thread
-constexpr int kWarps = kThreads / 32;
+constexpr int TXP = 32, TYP = 3, PL = 10;                // reference pixels x planes of a work item
+constexpr int kItems = TXP * TYP * PL;                   // 960 voxels = 15 consumer warps x 2 voxels per lane
+constexpr int kIPT = 2;                                  // voxels per consumer thread
+constexpr int kConsumers = kItems / kIPT, kConsumerWarps = kConsumers / 32;
+constexpr int kThreads = kConsumers + 32;                // + the producer warp: 16 warps = 4 per scheduler, 128 registers
 constexpr int WX = 48, WROWS = 8, WBOXES = 2, WY = WROWS * WBOXES;
 constexpr int kBoxBytes = WX * WROWS * 16;               // one TMA box: 8 rows of 48 cells
 constexpr int kViewBytes = kBoxBytes * WBOXES;           // window buffer of one view: 48 x 16 cells
@@ -52,6 +54,7 @@ struct Params {
   int n_src, D, d0g, Dloc, Hf, Wf, order;
   int tiles_x, tiles_y, nwork, nstages;
   unsigned long long* stats;         // optional: [0] (voxel, view) pairs served from global memory
+  int dbg;                           // development (tuning CV_DBG): 1 = no TMA loads, 2 = no blend, 4 = no parity-split store, 8 = no stores
 };
 
 __global__ void planar_half_features_kernel(const float* __restrict__ feats, int n_views, int Hf, int Wf,
@@ -89,26 +92,49 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
 
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// Sample position of reference pixel (x, y) for product mode: the arithmetic of transform_coords (geometry.cuh) with
+// ONE approximate reciprocal instead of two IEEE divisions (<= 2 ulp of the coordinate, ~1e-5 px: far below the fp16
+// rounding of the taps this mode reads; the fp32 parity kernels keep the exact divisions)
+__device__ __forceinline__ void fast_coords(const float4 c0, const float4 c1, float x, float y, float& ix, float& iy) {
+  const float rp = rcp_approx(fmaf(c1.z, x, fmaf(c1.w, y, 1.0f)));
+  ix = fmaf(c0.x, x, fmaf(c0.y, y, c0.z)) * rp;
+  iy = fmaf(c0.w, x, fmaf(c1.x, y, c1.y)) * rp;
+}
+
 // NV = number of source views; BLEND32: the 4-tap blend in fp32 (taps still fp16-rounded) instead of packed fp16
 template <int NV, bool BLEND32>
 __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const __grid_constant__ Params p) {
+  constexpr int IPT = kIPT;
   extern __shared__ __align__(128) unsigned char smem[];
   const int stage_bytes = NV * kViewBytes;
   unsigned char* s_ring = smem;
-  Meta* s_meta = reinterpret_cast<Meta*>(smem + (size_t)p.nstages * stage_bytes);      // [2][NV]
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_meta + 2 * kMaxSrc);
+  Meta* s_meta = reinterpret_cast<Meta*>(smem + (size_t)p.nstages * stage_bytes);      // [2][kMaxSrc]
+  float4* s_coef = reinterpret_cast<float4*>(s_meta + 2 * kMaxSrc);                     // [2][kMaxSrc][PL][2]: transform rows
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_coef + 2 * kMaxSrc * PL * 2);
   uint64_t* bar_empty = bar_full + kMaxStages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], kWarps); }
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], kConsumerWarps); }
     fence_mbar_init();
   }
   __syncthreads();
   const int ns = p.nstages;
   const int nmine = p.nwork > (int)blockIdx.x ? (p.nwork - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  // ---- producer duty of warp 0 (it is a consumer like the others): stage g of this CTA = (work item g / 4, chunk g % 4);
-  // at chunk 0 lanes < NV first work out the window of the item in "their" view and publish it in s_meta
+  // ---- producer warp: stage g of this CTA = (work item g / 4, chunk g % 4); at chunk 0 lanes < NV first work out the
+  // window of the item in "their" view and publish it in s_meta.  (A consumer warp that also produced would be the
+  // slowest warp and pace all the others: measured, 9 of 16 warps spinning on the full barrier.)
   int m_wx0 = 0, m_wy0 = 0, m_rows = 0;        // lane v of warp 0: window of view v of the item being produced
   uint32_t m_bytes = 0;
   auto produce = [&](int g) {
@@ -128,26 +154,39 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int d = min(max(p.d0g + ((k & 4) ? lh : ll), 0), p.D - 1);
+          const float4* row = reinterpret_cast<const float4*>(p.coef + ((size_t)lane * p.D + d) * 8);
           float ix, iy;
-          transform_coords(p.coef + ((size_t)lane * p.D + d) * 8, (float)((k & 1) ? xh : xl), (float)((k & 2) ? yh : yl),
-                           ix, iy);
+          fast_coords(__ldg(row), __ldg(row + 1), (float)((k & 1) ? xh : xl), (float)((k & 2) ? yh : yl), ix, iy);
           finite = finite && fabsf(ix) <= 1.0e9f && fabsf(iy) <= 1.0e9f;      // false for NaN, inf and absurd values
           mnx = fminf(mnx, ix); mxx = fmaxf(mxx, ix); mny = fminf(mny, iy); mxy = fmaxf(mxy, iy);
         }
+        int outside = 0;
         if (finite) {
-          const float fx0 = floorf(mnx), fx1 = floorf(mxx) + 1.0f, fy0 = floorf(mny), fy1 = floorf(mxy) + 1.0f;
+          // one source pixel of slack on every side: the corners bound the samples up to rounding
+          const float fx0 = floorf(mnx) - 1.0f, fx1 = floorf(mxx) + 2.0f, fy0 = floorf(mny) - 1.0f, fy1 = floorf(mxy) + 2.0f;
           if (fx1 >= 0.0f && fx0 <= (float)(p.Wf - 1) && fy1 >= 0.0f && fy0 <= (float)(p.Hf - 1)) {
-            m_wx0 = (int)fmaxf(fx0, (float)-WX);
-            m_wy0 = (int)fmaxf(fy0, (float)-WY);
-            m_rows = ((int)fminf(fy1, (float)p.Hf) - m_wy0 + 1 <= WROWS) ? WROWS : WY;
+            // rows above / left of the image hold zeros only: start the window at -1 at the earliest
+            m_wx0 = (int)fmaxf(floorf(mnx), -1.0f);
+            m_wy0 = (int)fmaxf(floorf(mny), -1.0f);
+            m_rows = ((int)fminf(floorf(mxy) + 1.0f, (float)p.Hf) - m_wy0 + 1 <= WROWS) ? WROWS : WY;
+          } else {
+            outside = 1;             // no tap of this work item touches the image: the view contributes exact zeros
           }
         }
-        s_meta[(it & 1) * kMaxSrc + lane] = Meta{m_wx0, m_wy0, m_rows, 0};
+        s_meta[(it & 1) * kMaxSrc + lane] = Meta{m_wx0, m_wy0, m_rows, outside};
+      }
+      // the transform rows of the item's planes for every view: the consumers read them from shared memory
+      for (int i = lane; i < NV * PL * 2; i += 32) {
+        const int v = i / (PL * 2), r = i - v * (PL * 2);
+        const int d = min(max(p.d0g + dc * PL + (r >> 1), 0), p.D - 1);
+        s_coef[((it & 1) * kMaxSrc + v) * (PL * 2) + r] =
+            __ldg(reinterpret_cast<const float4*>(p.coef + ((size_t)v * p.D + d) * 8) + (r & 1));
       }
       // bytes of one stage of this work item (sum over the views, the same for its four chunks)
       m_bytes = (uint32_t)(m_rows * kRowBytes);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m_bytes += __shfl_xor_sync(0xffffffffu, m_bytes, o);
+      if (p.dbg & 1) m_bytes = 0;
     }
     const int stage = g % ns;
     const uint32_t round = (uint32_t)(g / ns);                // how many times the ring has wrapped
@@ -161,17 +200,20 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
     const int v = lane >> 1, b = lane & 1;
     const int rows_v = __shfl_sync(0xffffffffu, m_rows, v), wx0_v = __shfl_sync(0xffffffffu, m_wx0, v),
               wy0_v = __shfl_sync(0xffffffffu, m_wy0, v);
-    if (v < NV && b * WROWS < rows_v)
+    if (v < NV && b * WROWS < rows_v && !(p.dbg & 1))
       tma_load_3d(s_ring + (size_t)stage * stage_bytes + (size_t)v * kViewBytes + (size_t)b * kBoxBytes, &p.tmap,
                   wx0_v * 4, wy0_v + b * WROWS, (v + 1) * 4 + c, &bar_full[stage]);
   };
-  if (warp == 0)
-    for (int g = 0; g < ns - 1; ++g) produce(g);
+  if (warp == kConsumerWarps) {
+    for (int g = 0; g < 4 * nmine; ++g) produce(g);
+    return;
+  }
 
   // ===================================== consumers =====================================
   const int t = threadIdx.x;
-  const int px = t & (TXP - 1), py = (t >> 5) & (TYP - 1), pl0 = t >> 7;      // planes pl0 and pl0 + 4 of the work item
+  const int px = t & (TXP - 1), py = (t >> 5) % TYP, pl0 = (t >> 5) / TYP;     // planes pl0 and pl0 + PL / 2 of the item
   const float inv_n = 1.0f / (float)(NV + 1), inv_nn = 1.0f / (float)((NV + 1) * (NV + 1));
+  const float2 inv_n2 = make_float2(inv_n, inv_n), ninv_nn2 = make_float2(-inv_nn, -inv_nn);
   const size_t plane_cells = (size_t)p.Hf * p.Wf;
   const int Hs = (p.Hf + 1) >> 1, Ws = (p.Wf + 1) >> 1;
   const uint32_t ring_u32 = smem_u32(s_ring);
@@ -182,74 +224,35 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
     const int tx = wi % p.tiles_x, ty = (wi / p.tiles_x) % p.tiles_y, dc = wi / (p.tiles_x * p.tiles_y);
     const int x = tx * TXP + px, y = ty * TYP + py;
     const int xc = min(x, p.Wf - 1), yc = min(y, p.Hf - 1);
-    // footprints of this thread's two voxels in every source view, in image coordinates: top-left tap (x0, y0)
-    // packed as (y0 + 2) << 15 | (x0 + 2), and the four tap weights
-    uint32_t fo[kIPT][NV];
-    uint32_t wa[kIPT][NV], wb[kIPT][NV];       // fp16 blend: half2 (w00, w01), (w10, w11); fp32 blend: wxr, wyr bits
-    bool live[kIPT];
+    uint32_t fo[IPT][NV];              // per (voxel, view): byte offset of the top-left tap in the view's window, or
+                                       // bit 31 | (y0 + 2) << 15 | (x0 + 2) when the footprint is outside the window
+    uint32_t wa[IPT][NV], wb[IPT][NV]; // fp16 blend: half2 (w00, w01), (w10, w11); fp32 blend: wxr, wyr bits
+    bool live[IPT];
+    uint32_t cell_cp8[IPT], cell_ps8[IPT];       // chunk-0 cell index of the voxel in the two output layouts
 #pragma unroll
-    for (int i = 0; i < kIPT; ++i) {
-      const int l = dc * PL + pl0 + i * (PL / kIPT);
-      const int dg = p.d0g + l;
-      live[i] = x < p.Wf && y < p.Hf && l < p.Dloc && (unsigned)dg < (unsigned)p.D;
-      const int d = min(max(dg, 0), p.D - 1);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const float4* row = reinterpret_cast<const float4*>(p.coef + ((size_t)v * p.D + d) * 8);
-        const float4 c0 = __ldg(row), c1 = __ldg(row + 1);
-        const float tc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        float ix, iy;
-        transform_coords(tc, (float)xc, (float)yc, ix, iy);
-        const Footprint f = make_footprint(ix, iy, p.Wf, p.Hf);
-        fo[i][v] = (uint32_t)((f.y0 + 2) << 15) | (uint32_t)(f.x0 + 2);
-        if (BLEND32) {
-          wa[i][v] = __float_as_uint(f.wxr); wb[i][v] = __float_as_uint(f.wyr);
-          if (f.wxl == 0.0f && f.wxr == 0.0f) { wa[i][v] = 0x7fc00000u; }      // non-finite sample: marks "all weights 0"
-        } else {
-          const __half2 h0 = __floats2half2_rn(f.wyl * f.wxl, f.wyl * f.wxr), h1 = __floats2half2_rn(f.wyr * f.wxl, f.wyr * f.wxr);
-          wa[i][v] = *reinterpret_cast<const uint32_t*>(&h0); wb[i][v] = *reinterpret_cast<const uint32_t*>(&h1);
-        }
-      }
+    for (int i = 0; i < IPT; ++i) {
+      const int l = dc * PL + pl0 + i * (PL / IPT);
+      live[i] = x < p.Wf && y < p.Hf && l < p.Dloc && (unsigned)(p.d0g + l) < (unsigned)p.D;
+      cell_cp8[i] = (uint32_t)(((size_t)l * 4 * p.Hf + y) * p.Wf + x);
+      cell_ps8[i] = (uint32_t)((((size_t)l * 16 + (y & 1) * 2 + (x & 1)) * Hs + (y >> 1)) * Ws + (x >> 1));
     }
-    for (int c = 0; c < 4; ++c) {
-      // reference view: S = r, Q = r^2 (model.py:436-437)
-      float2 S[kIPT][4], Q[kIPT][4];
-      {
-        const float4* rp = reinterpret_cast<const float4*>(p.feats + ((size_t)yc * p.Wf + xc) * 32 + c * 8);
-        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-#pragma unroll
-        for (int i = 0; i < kIPT; ++i) {
-          S[i][0] = make_float2(r0.x, r0.y); S[i][1] = make_float2(r0.z, r0.w);
-          S[i][2] = make_float2(r1.x, r1.y); S[i][3] = make_float2(r1.z, r1.w);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) Q[i][k] = make_float2(S[i][k].x * S[i][k].x, S[i][k].y * S[i][k].y);
-        }
-      }
-      if (warp == 0) produce(4 * it + c + ns - 1);       // keep ns - 1 stages in flight
-      mbar_wait(&bar_full[stage], round & 1u);
-      if (c == 0) {
-        // window-relative tap offsets: bit 31 clear = byte offset of the top-left cell inside the view's buffer
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const Meta m = s_meta[(it & 1) * kMaxSrc + v];
-#pragma unroll
-          for (int i = 0; i < kIPT; ++i) {
-            const int x0 = (int)(fo[i][v] & 0x7fffu) - 2, y0 = (int)(fo[i][v] >> 15) - 2;
-            const int cx = x0 - m.wx0, cy = y0 - m.wy0;
-            const unsigned ry = m.rows > 0 ? (unsigned)(m.rows - 1) : 0u;       // both tap rows must have landed
-            if ((unsigned)cx < (unsigned)(WX - 1) && (unsigned)cy < ry) fo[i][v] = (uint32_t)((cy * WX + cx) * 16);
-            else fo[i][v] |= 0x80000000u;
-          }
-        }
-      }
-      const uint32_t sbase = ring_u32 + (uint32_t)(stage * stage_bytes);
+    // reference cell of chunk 0 (in flight while the window of the item is awaited)
+    uint4 rcell = __ldg(p.feats16 + (size_t)yc * p.Wf + xc);
+    unsigned skip = 0;                 // views that contribute exact zeros to this work item
+    bool slow_warp = false;            // some voxel of this warp reads a view from global memory
+    float2 S[IPT][4], Q[IPT][4];
+
+    // the taps of one (voxel, view) blended into the running sums; CHECK: the footprint may lie outside the window
+    auto blend = [&](auto check_tag, int c, uint32_t sbase) {
+      constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
+        if (skip & (1u << v)) continue;
 #pragma unroll
-        for (int i = 0; i < kIPT; ++i) {
+        for (int i = 0; i < IPT; ++i) {
           uint4 ta, tb, tc4, td;
           const uint32_t o = fo[i][v];
-          if (!(o & 0x80000000u)) {
+          if (!CHECK || !(o & 0x80000000u)) {
             const uint32_t a = sbase + (uint32_t)(v * kViewBytes) + o;
             ta = lds128(a); tb = lds128(a + 16); tc4 = lds128(a + kRowBytes); td = lds128(a + kRowBytes + 16);
           } else {
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
             tb = (vy0 && vx1) ? __ldg(img + (size_t)y0 * p.Wf + x0 + 1) : z;
             tc4 = (vy1 && vx0) ? __ldg(img + (size_t)(y0 + 1) * p.Wf + x0) : z;
             td = (vy1 && vx1) ? __ldg(img + (size_t)(y0 + 1) * p.Wf + x0 + 1) : z;
-            if (p.stats && c == 0) atomicAdd(p.stats, 1ull);
+            if (p.stats && c == 0 && (vx0 || vx1) && (vy0 || vy1)) atomicAdd(p.stats, 1ull);
           }
           const uint32_t* A = reinterpret_cast<const uint32_t*>(&ta);
           const uint32_t* B = reinterpret_cast<const uint32_t*>(&tb);
@@ -297,38 +300,97 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
           }
         }
       }
+    };
+
+    for (int c = 0; c < 4; ++c) {
+      // reference view: S = r, Q = r^2 (model.py:436-437), read like the source views from the fp16 copy (one
+      // coalesced 16-byte load per thread, issued one chunk ahead; an fp32 NHWC pixel would cost a 128-byte line per lane)
+      {
+        const uint32_t* R = reinterpret_cast<const uint32_t*>(&rcell);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(as_h2(R[k]));
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) { S[i][k] = f; Q[i][k] = fmul2(f, f); }
+        }
+        if (c < 3) rcell = __ldg(p.feats16 + (size_t)(c + 1) * plane_cells + (size_t)yc * p.Wf + xc);
+      }
+      mbar_wait(&bar_full[stage], round & 1u);
+      if (c == 0) {
+        // the item's window and transform rows have been published (ordered by the barrier): bilinear footprint of
+        // every (voxel, view), once per work item.  Sample position as in transform_coords (geometry.cuh); a footprint
+        // whose four taps sit inside the landed rows of the window becomes a shared-memory offset.
+        bool slow = false;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const Meta m = s_meta[(it & 1) * kMaxSrc + v];
+          if (m.pad) skip |= 1u << v;
+          const unsigned ry = m.rows > 0 ? (unsigned)(m.rows - 1) : 0u;       // both tap rows must have landed
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) {
+            const float4* row = s_coef + ((it & 1) * kMaxSrc + v) * (PL * 2) + (pl0 + i * (PL / IPT)) * 2;
+            float ix, iy;
+            fast_coords(row[0], row[1], (float)xc, (float)yc, ix, iy);
+            const bool finite = fabsf(ix) <= 1.0e9f && fabsf(iy) <= 1.0e9f;   // false for NaN and inf
+            const float xf = floorf(ix), yf = floorf(iy);
+            float wxr = ix - xf, wyr = iy - yf;
+            int x0 = (int)fminf(fmaxf(xf, -2.0f), (float)p.Wf), y0 = (int)fminf(fmaxf(yf, -2.0f), (float)p.Hf);
+            if (!finite) { x0 = -2; y0 = -2; wxr = 0.0f; wyr = 0.0f; }       // reads as outside: contributes 0
+            if (BLEND32) {
+              wa[i][v] = finite ? __float_as_uint(wxr) : 0x7fc00000u;        // marker: all four weights 0
+              wb[i][v] = __float_as_uint(wyr);
+            } else {
+              const float wxl = finite ? 1.0f - wxr : 0.0f, wyl = 1.0f - wyr;
+              const __half2 h0 = __floats2half2_rn(wyl * wxl, wyl * wxr), h1 = __floats2half2_rn(wyr * wxl, wyr * wxr);
+              wa[i][v] = *reinterpret_cast<const uint32_t*>(&h0); wb[i][v] = *reinterpret_cast<const uint32_t*>(&h1);
+            }
+            const int cx = x0 - m.wx0, cy = y0 - m.wy0;
+            if ((unsigned)cx < (unsigned)(WX - 1) && (unsigned)cy < ry) {
+              fo[i][v] = (uint32_t)((cy * WX + cx) * 16);
+            } else if (m.rows > 0 && (x0 + 1 < 0 || x0 >= p.Wf || y0 + 1 < 0 || y0 >= p.Hf)) {
+              // all four taps outside the image: zero weights on the first cells of the window (landed, finite)
+              fo[i][v] = 0u;
+              wa[i][v] = BLEND32 ? 0x7fc00000u : 0u; wb[i][v] = 0u;
+            } else {
+              fo[i][v] = 0x80000000u | (uint32_t)((y0 + 2) << 15) | (uint32_t)(x0 + 2);
+              slow = slow || !m.pad;
+            }
+          }
+        }
+        slow_warp = __any_sync(0xffffffffu, slow);
+      }
+      const uint32_t sbase = ring_u32 + (uint32_t)(stage * stage_bytes);
+      if (!(p.dbg & 2)) {
+        if (slow_warp) blend(std::true_type{}, c, sbase);
+        else blend(std::false_type{}, c, sbase);
+      }
       // this warp is done with the stage: hand the buffer back to the producer
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[stage]);
       if (++stage == ns) { stage = 0; ++round; }
-      // variance with reciprocal multiplies (<= 1 ulp from the reference's divisions, model.py:458-461 / :330-332)
+      // variance with reciprocal multiplies, two channels per instruction (within an ulp or two of the reference's
+      // divisions, model.py:458-461 / :330-332; this mode stores bf16)
 #pragma unroll
-      for (int i = 0; i < kIPT; ++i) {
+      for (int i = 0; i < IPT; ++i) {
         if (!live[i]) continue;
-        float cst[8];
+        uint4 cell;
+        uint32_t* cw = reinterpret_cast<uint32_t*>(&cell);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+          float2 cst;
           if (p.order == MVSB200_ORDER_MEM) {
-            cst[2 * k] = Q[i][k].x * inv_n - (S[i][k].x * S[i][k].x) * inv_nn;
-            cst[2 * k + 1] = Q[i][k].y * inv_n - (S[i][k].y * S[i][k].y) * inv_nn;
+            cst = ffma2(Q[i][k], inv_n2, fmul2(fmul2(S[i][k], S[i][k]), ninv_nn2));
           } else {
-            const float mx = S[i][k].x * inv_n, my = S[i][k].y * inv_n;
-            cst[2 * k] = Q[i][k].x * inv_n - mx * mx;
-            cst[2 * k + 1] = Q[i][k].y * inv_n - my * my;
+            const float2 m = fmul2(S[i][k], inv_n2);
+            cst = ffma2(Q[i][k], inv_n2, fmul2(fmul2(m, m), make_float2(-1.0f, -1.0f)));
           }
+          const __nv_bfloat162 b = __floats2bfloat162_rn(cst.x, cst.y);
+          cw[k] = *reinterpret_cast<const uint32_t*>(&b);
         }
-        uint4 cell;
-        {
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(cst[0], cst[1]), b1 = __floats2bfloat162_rn(cst[2], cst[3]);
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(cst[4], cst[5]), b3 = __floats2bfloat162_rn(cst[6], cst[7]);
-          cell.x = *reinterpret_cast<uint32_t*>(&b0); cell.y = *reinterpret_cast<uint32_t*>(&b1);
-          cell.z = *reinterpret_cast<uint32_t*>(&b2); cell.w = *reinterpret_cast<uint32_t*>(&b3);
-        }
-        const int l = dc * PL + pl0 + i * (PL / kIPT);
-        const size_t zc = (size_t)l * 4 + c;
-        if (p.cp8) *reinterpret_cast<uint4*>(p.cp8 + ((zc * p.Hf + y) * p.Wf + x) * 8) = cell;
-        if (p.ps8)
-          *reinterpret_cast<uint4*>(p.ps8 + (((zc * 4 + (y & 1) * 2 + (x & 1)) * Hs + (y >> 1)) * Ws + (x >> 1)) * 8) = cell;
+        if (p.cp8 && !(p.dbg & 8))
+          *reinterpret_cast<uint4*>(p.cp8 + ((size_t)cell_cp8[i] + (size_t)c * plane_cells) * 8) = cell;
+        if (p.ps8 && !(p.dbg & 12))
+          *reinterpret_cast<uint4*>(p.ps8 + ((size_t)cell_ps8[i] + (size_t)c * 4 * Hs * Ws) * 8) = cell;
       }
     }
   }
@@ -428,7 +490,11 @@ int launch_cost_volume_window(const float* feats, const float* coef_table, int n
   p.nstages = nstages > kMaxStages ? kMaxStages : nstages;
   MVS_CHECK_ARG(p.nstages >= 2, "cost_volume(window): shared-memory ring too small");
   p.stats = stats ? stats : (tuning().cv_stats ? window_stats_buffer() : nullptr);
-  const size_t smem = (size_t)p.nstages * stage_bytes + 2 * kMaxSrc * sizeof(Meta) + 2 * kMaxStages * sizeof(uint64_t);
+  const size_t smem = (size_t)p.nstages * stage_bytes + 2 * kMaxSrc * sizeof(Meta) + 2 * kMaxSrc * PL * 2 * sizeof(float4) +
+                      2 * kMaxStages * sizeof(uint64_t);
+  MVS_CHECK_ARG((size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) < ((size_t)1 << 31) && (size_t)dloc * 4 * hf * wf < ((size_t)1 << 31),
+                "cost_volume(window): volume too large for 32-bit cell indices");
+  p.dbg = tuning().cv_dbg;
   Kernel k = blend32 ? pick<true>(nv) : pick<false>(nv);
   // the attribute is per device and per function: set it every time (cheap, and a set value is only re-set to itself)
   MVS_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

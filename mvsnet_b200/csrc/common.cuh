@@ -24,7 +24,7 @@ struct Tuning {
   int cv_fp32_taps = 0;       // CV_FP32_TAPS: product-mode cost volume from fp32 features (north_star arithmetic)
   int cv_kernel = 0;          // CV_KERNEL: 0 = shared-memory window kernel (TMA), 1 = the round-1 gather kernel
   int cv_fp32_blend = 0, cv_minb = 0, cv_rec16 = 0, cv_kdc = 0;      // round-1 gather kernel variants
-  int cv_planes = 0, cv_stats = 0, cv_dbg = 0, cv_ipt = 0;                                   // window kernel: planes per block; fit counters
+  int cv_planes = 0, cv_stats = 0, cv_dbg = 0;                                   // window kernel: planes per block; fit counters
   int tc_zf = -1, tc_xfold = -1, tc_zsplit = 0, tc_dbg = 0, tc_verbose = 0, tc_prof = 0, tc_exact_smem = 0, tc_no_pdl = 0;
   int tc_tile_x = 0, tc_tile_y = 0;
   int tc_layer_set = 0, tc_layer[3] = {0, 0, 0};                     // TC_LAYER="cin,cout,mode": restrict the tc_* switches

@@ -33,9 +33,10 @@ namespace cvw {
 
 constexpr int TXP = 32, TYP = 3, PL = 10;                // reference pixels x planes of a work item
 constexpr int kItems = TXP * TYP * PL;                   // 960 voxels = 15 consumer warps x 2 voxels per lane
-constexpr int kIPT = 2;                                  // voxels per consumer thread
-constexpr int kConsumers = kItems / kIPT, kConsumerWarps = kConsumers / 32;
-constexpr int kThreads = kConsumers + 32;                // + the producer warp: 16 warps = 4 per scheduler, 128 registers
+// 2 voxels per consumer thread: 15 consumer warps + the producer warp = 16 warps = 4 per scheduler at <= 128 registers
+// (measured at config 2: 0.71 ms; 1 voxel per thread = 30 + 1 warps at <= 64 registers: 0.79 ms)
+constexpr int kIPT = 2;
+constexpr int kThreads = kItems / kIPT + 32;
 constexpr int WX = 48, WROWS = 8, WBOXES = 2, WY = WROWS * WBOXES;
 constexpr int kBoxBytes = WX * WROWS * 16;               // one TMA box: 8 rows of 48 cells
 constexpr int kViewBytes = kBoxBytes * WBOXES;           // window buffer of one view: 48 x 16 cells
@@ -115,7 +116,7 @@ __device__ __forceinline__ void fast_coords(const float4 c0, const float4 c1, fl
 // NV = number of source views; BLEND32: the 4-tap blend in fp32 (taps still fp16-rounded) instead of packed fp16
 template <int NV, bool BLEND32>
 __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const __grid_constant__ Params p) {
-  constexpr int IPT = kIPT;
+  constexpr int IPT = kIPT, kConsumerWarps = kItems / IPT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const int stage_bytes = NV * kViewBytes;
   unsigned char* s_ring = smem;
@@ -135,15 +136,14 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
   // ---- producer warp: stage g of this CTA = (work item g / 4, chunk g % 4); at chunk 0 lanes < NV first work out the
   // window of the item in "their" view and publish it in s_meta.  (A consumer warp that also produced would be the
   // slowest warp and pace all the others: measured, 9 of 16 warps spinning on the full barrier.)
-  int m_wx0 = 0, m_wy0 = 0, m_rows = 0;        // lane v of warp 0: window of view v of the item being produced
-  uint32_t m_bytes = 0;
-  auto produce = [&](int g) {
-    if (g >= 4 * nmine) return;
-    const int it = g >> 2, c = g & 3;
-    if (c == 0) {
+  if (warp == kConsumerWarps) {
+    // window of work item `it` in view `lane` (lanes < NV) + the item's transform rows -> s_meta / s_coef [it & 1]
+    int n_wx0 = 0, n_wy0 = 0, n_rows = 0;       // ... of the item prepared last
+    auto prepare = [&](int it) {
+      n_wx0 = n_wy0 = n_rows = 0;
+      if (it >= nmine) return;
       const int wi = (int)blockIdx.x + it * (int)gridDim.x;
       const int tx = wi % p.tiles_x, ty = (wi / p.tiles_x) % p.tiles_y, dc = wi / (p.tiles_x * p.tiles_y);
-      m_wx0 = m_wy0 = m_rows = 0;
       if (lane < NV) {
         // bounding box of the work item's samples in source view `lane`: the 8 corners of (x, y, plane)
         const int xl = tx * TXP, xh = min(xl + TXP - 1, p.Wf - 1);
@@ -166,14 +166,14 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
           const float fx0 = floorf(mnx) - 1.0f, fx1 = floorf(mxx) + 2.0f, fy0 = floorf(mny) - 1.0f, fy1 = floorf(mxy) + 2.0f;
           if (fx1 >= 0.0f && fx0 <= (float)(p.Wf - 1) && fy1 >= 0.0f && fy0 <= (float)(p.Hf - 1)) {
             // rows above / left of the image hold zeros only: start the window at -1 at the earliest
-            m_wx0 = (int)fmaxf(floorf(mnx), -1.0f);
-            m_wy0 = (int)fmaxf(floorf(mny), -1.0f);
-            m_rows = ((int)fminf(floorf(mxy) + 1.0f, (float)p.Hf) - m_wy0 + 1 <= WROWS) ? WROWS : WY;
+            n_wx0 = (int)fmaxf(floorf(mnx), -1.0f);
+            n_wy0 = (int)fmaxf(floorf(mny), -1.0f);
+            n_rows = ((int)fminf(floorf(mxy) + 1.0f, (float)p.Hf) - n_wy0 + 1 <= WROWS) ? WROWS : WY;
           } else {
             outside = 1;             // no tap of this work item touches the image: the view contributes exact zeros
           }
         }
-        s_meta[(it & 1) * kMaxSrc + lane] = Meta{m_wx0, m_wy0, m_rows, outside};
+        s_meta[(it & 1) * kMaxSrc + lane] = Meta{n_wx0, n_wy0, n_rows, outside};
       }
       // the transform rows of the item's planes for every view: the consumers read them from shared memory
       for (int i = lane; i < NV * PL * 2; i += 32) {
@@ -182,30 +182,39 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
         s_coef[((it & 1) * kMaxSrc + v) * (PL * 2) + r] =
             __ldg(reinterpret_cast<const float4*>(p.coef + ((size_t)v * p.D + d) * 8) + (r & 1));
       }
+      __syncwarp();        // every lane's stores precede lane 0's arrive on the item's first full barrier
+    };
+    prepare(0);
+    for (int it = 0; it < nmine; ++it) {
+      const int m_wx0 = n_wx0, m_wy0 = n_wy0, m_rows = n_rows;
       // bytes of one stage of this work item (sum over the views, the same for its four chunks)
-      m_bytes = (uint32_t)(m_rows * kRowBytes);
+      uint32_t m_bytes = (uint32_t)(m_rows * kRowBytes);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m_bytes += __shfl_xor_sync(0xffffffffu, m_bytes, o);
       if (p.dbg & 1) m_bytes = 0;
+      // lanes 2v and 2v+1 issue the one or two boxes of view v
+      const int v = lane >> 1, b = lane & 1;
+      const int rows_v = __shfl_sync(0xffffffffu, m_rows, v), wx0_v = __shfl_sync(0xffffffffu, m_wx0, v),
+                wy0_v = __shfl_sync(0xffffffffu, m_wy0, v);
+      for (int c = 0; c < 4; ++c) {
+        const int g = 4 * it + c;
+        const int stage = g % ns;
+        const uint32_t round = (uint32_t)(g / ns);              // how many times the ring has wrapped
+        if (round > 0) mbar_wait(&bar_empty[stage], (round - 1) & 1u);
+        if (lane == 0) {
+          if (m_bytes) mbar_arrive_expect_tx(&bar_full[stage], m_bytes);    // (orders the s_meta / s_coef stores before the readers' wait)
+          else mbar_arrive(&bar_full[stage]);
+        }
+        __syncwarp();
+        if (v < NV && b * WROWS < rows_v && !(p.dbg & 1))
+          tma_load_3d(s_ring + (size_t)stage * stage_bytes + (size_t)v * kViewBytes + (size_t)b * kBoxBytes, &p.tmap,
+                      wx0_v * 4, wy0_v + b * WROWS, (v + 1) * 4 + c, &bar_full[stage]);
+        // the next item's window while this item's boxes are in flight.  Its slot [(it + 1) & 1] was last read at chunk 0
+        // of item it - 1, which every consumer has left: the stage just armed reuses a buffer they have all released
+        // after it (ns <= 4 stages per item)
+        if (c == 0) prepare(it + 1);
+      }
     }
-    const int stage = g % ns;
-    const uint32_t round = (uint32_t)(g / ns);                // how many times the ring has wrapped
-    if (round > 0) mbar_wait(&bar_empty[stage], (round - 1) & 1u);
-    if (lane == 0) {
-      if (m_bytes) mbar_arrive_expect_tx(&bar_full[stage], m_bytes);    // (orders the s_meta stores before the wait of the readers)
-      else mbar_arrive(&bar_full[stage]);
-    }
-    __syncwarp();
-    // lanes 2v and 2v+1 issue the one or two boxes of view v
-    const int v = lane >> 1, b = lane & 1;
-    const int rows_v = __shfl_sync(0xffffffffu, m_rows, v), wx0_v = __shfl_sync(0xffffffffu, m_wx0, v),
-              wy0_v = __shfl_sync(0xffffffffu, m_wy0, v);
-    if (v < NV && b * WROWS < rows_v && !(p.dbg & 1))
-      tma_load_3d(s_ring + (size_t)stage * stage_bytes + (size_t)v * kViewBytes + (size_t)b * kBoxBytes, &p.tmap,
-                  wx0_v * 4, wy0_v + b * WROWS, (v + 1) * 4 + c, &bar_full[stage]);
-  };
-  if (warp == kConsumerWarps) {
-    for (int g = 0; g < 4 * nmine; ++g) produce(g);
     return;
   }
 
@@ -302,97 +311,103 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
       }
     };
 
-    for (int c = 0; c < 4; ++c) {
-      // reference view: S = r, Q = r^2 (model.py:436-437), read like the source views from the fp16 copy (one
-      // coalesced 16-byte load per thread, issued one chunk ahead; an fp32 NHWC pixel would cost a 128-byte line per lane)
-      {
-        const uint32_t* R = reinterpret_cast<const uint32_t*>(&rcell);
+    // ---- chunk 0's stage carries the item's window and transform rows (published before the barrier was armed):
+    // bilinear footprint of every (voxel, view), once per work item.  Sample position as in transform_coords
+    // (geometry.cuh), clamped to [-2, W] x [-2, H]: beyond that every tap is outside the image anyway (and NaN / inf
+    // land on the bound: "outside", as the reference's zero fill has it).  A footprint whose four taps sit inside
+    // the landed rows of the window becomes a shared-memory offset.
+    mbar_wait(&bar_full[stage], round & 1u);
+    {
+      bool slow = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = __half22float2(as_h2(R[k]));
+      for (int v = 0; v < NV; ++v) {
+        const Meta m = s_meta[(it & 1) * kMaxSrc + v];
+        if (m.pad) skip |= 1u << v;
+        const unsigned ry = m.rows > 0 ? (unsigned)(m.rows - 1) : 0u;       // both tap rows must have landed
 #pragma unroll
-          for (int i = 0; i < IPT; ++i) { S[i][k] = f; Q[i][k] = fmul2(f, f); }
-        }
-        if (c < 3) rcell = __ldg(p.feats16 + (size_t)(c + 1) * plane_cells + (size_t)yc * p.Wf + xc);
-      }
-      mbar_wait(&bar_full[stage], round & 1u);
-      if (c == 0) {
-        // the item's window and transform rows have been published (ordered by the barrier): bilinear footprint of
-        // every (voxel, view), once per work item.  Sample position as in transform_coords (geometry.cuh); a footprint
-        // whose four taps sit inside the landed rows of the window becomes a shared-memory offset.
-        bool slow = false;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const Meta m = s_meta[(it & 1) * kMaxSrc + v];
-          if (m.pad) skip |= 1u << v;
-          const unsigned ry = m.rows > 0 ? (unsigned)(m.rows - 1) : 0u;       // both tap rows must have landed
-#pragma unroll
-          for (int i = 0; i < IPT; ++i) {
-            const float4* row = s_coef + ((it & 1) * kMaxSrc + v) * (PL * 2) + (pl0 + i * (PL / IPT)) * 2;
-            float ix, iy;
-            fast_coords(row[0], row[1], (float)xc, (float)yc, ix, iy);
-            const bool finite = fabsf(ix) <= 1.0e9f && fabsf(iy) <= 1.0e9f;   // false for NaN and inf
-            const float xf = floorf(ix), yf = floorf(iy);
-            float wxr = ix - xf, wyr = iy - yf;
-            int x0 = (int)fminf(fmaxf(xf, -2.0f), (float)p.Wf), y0 = (int)fminf(fmaxf(yf, -2.0f), (float)p.Hf);
-            if (!finite) { x0 = -2; y0 = -2; wxr = 0.0f; wyr = 0.0f; }       // reads as outside: contributes 0
-            if (BLEND32) {
-              wa[i][v] = finite ? __float_as_uint(wxr) : 0x7fc00000u;        // marker: all four weights 0
-              wb[i][v] = __float_as_uint(wyr);
-            } else {
-              const float wxl = finite ? 1.0f - wxr : 0.0f, wyl = 1.0f - wyr;
-              const __half2 h0 = __floats2half2_rn(wyl * wxl, wyl * wxr), h1 = __floats2half2_rn(wyr * wxl, wyr * wxr);
-              wa[i][v] = *reinterpret_cast<const uint32_t*>(&h0); wb[i][v] = *reinterpret_cast<const uint32_t*>(&h1);
-            }
-            const int cx = x0 - m.wx0, cy = y0 - m.wy0;
-            if ((unsigned)cx < (unsigned)(WX - 1) && (unsigned)cy < ry) {
-              fo[i][v] = (uint32_t)((cy * WX + cx) * 16);
-            } else if (m.rows > 0 && (x0 + 1 < 0 || x0 >= p.Wf || y0 + 1 < 0 || y0 >= p.Hf)) {
-              // all four taps outside the image: zero weights on the first cells of the window (landed, finite)
-              fo[i][v] = 0u;
-              wa[i][v] = BLEND32 ? 0x7fc00000u : 0u; wb[i][v] = 0u;
-            } else {
-              fo[i][v] = 0x80000000u | (uint32_t)((y0 + 2) << 15) | (uint32_t)(x0 + 2);
-              slow = slow || !m.pad;
-            }
-          }
-        }
-        slow_warp = __any_sync(0xffffffffu, slow);
-      }
-      const uint32_t sbase = ring_u32 + (uint32_t)(stage * stage_bytes);
-      if (!(p.dbg & 2)) {
-        if (slow_warp) blend(std::true_type{}, c, sbase);
-        else blend(std::false_type{}, c, sbase);
-      }
-      // this warp is done with the stage: hand the buffer back to the producer
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_empty[stage]);
-      if (++stage == ns) { stage = 0; ++round; }
-      // variance with reciprocal multiplies, two channels per instruction (within an ulp or two of the reference's
-      // divisions, model.py:458-461 / :330-332; this mode stores bf16)
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) {
-        if (!live[i]) continue;
-        uint4 cell;
-        uint32_t* cw = reinterpret_cast<uint32_t*>(&cell);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float2 cst;
-          if (p.order == MVSB200_ORDER_MEM) {
-            cst = ffma2(Q[i][k], inv_n2, fmul2(fmul2(S[i][k], S[i][k]), ninv_nn2));
+        for (int i = 0; i < IPT; ++i) {
+          const float4* row = s_coef + ((it & 1) * kMaxSrc + v) * (PL * 2) + (pl0 + i * (PL / IPT)) * 2;
+          float ix, iy;
+          fast_coords(row[0], row[1], (float)xc, (float)yc, ix, iy);
+          ix = fminf(fmaxf(ix, -2.0f), (float)p.Wf);
+          iy = fminf(fmaxf(iy, -2.0f), (float)p.Hf);
+          const float xf = floorf(ix), yf = floorf(iy);
+          const float wxr = ix - xf, wyr = iy - yf;
+          const int x0 = (int)xf, y0 = (int)yf;
+          if (BLEND32) {
+            wa[i][v] = __float_as_uint(wxr); wb[i][v] = __float_as_uint(wyr);
           } else {
-            const float2 m = fmul2(S[i][k], inv_n2);
-            cst = ffma2(Q[i][k], inv_n2, fmul2(fmul2(m, m), make_float2(-1.0f, -1.0f)));
+            const float wxl = 1.0f - wxr, wyl = 1.0f - wyr;
+            const __half2 h0 = __floats2half2_rn(wyl * wxl, wyl * wxr), h1 = __floats2half2_rn(wyr * wxl, wyr * wxr);
+            wa[i][v] = *reinterpret_cast<const uint32_t*>(&h0); wb[i][v] = *reinterpret_cast<const uint32_t*>(&h1);
           }
-          const __nv_bfloat162 b = __floats2bfloat162_rn(cst.x, cst.y);
-          cw[k] = *reinterpret_cast<const uint32_t*>(&b);
+          const int cx = x0 - m.wx0, cy = y0 - m.wy0;
+          if ((unsigned)cx < (unsigned)(WX - 1) && (unsigned)cy < ry) {
+            fo[i][v] = (uint32_t)((cy * WX + cx) * 16);
+          } else if (m.rows > 0 && (x0 + 1 < 0 || x0 >= p.Wf || y0 + 1 < 0 || y0 >= p.Hf)) {
+            // all four taps outside the image: zero weights on the first cells of the window (landed, finite)
+            fo[i][v] = 0u;
+            wa[i][v] = BLEND32 ? 0x7fc00000u : 0u; wb[i][v] = 0u;
+          } else {
+            fo[i][v] = 0x80000000u | (uint32_t)((y0 + 2) << 15) | (uint32_t)(x0 + 2);
+            slow = slow || !m.pad;
+          }
         }
-        if (p.cp8 && !(p.dbg & 8))
-          *reinterpret_cast<uint4*>(p.cp8 + ((size_t)cell_cp8[i] + (size_t)c * plane_cells) * 8) = cell;
-        if (p.ps8 && !(p.dbg & 12))
-          *reinterpret_cast<uint4*>(p.ps8 + ((size_t)cell_ps8[i] + (size_t)c * 4 * Hs * Ws) * 8) = cell;
       }
+      slow_warp = __any_sync(0xffffffffu, slow);
     }
+
+    // ---- the four chunks of the item; instantiated twice (with / without the global-memory path) so that the
+    // common case carries neither its branches nor its registers
+    auto chunks = [&](auto check_tag) {
+      for (int c = 0; c < 4; ++c) {
+        // reference view: S = r, Q = r^2 (model.py:436-437), read like the source views from the fp16 copy (one
+        // coalesced 16-byte load per thread, issued one chunk ahead; an fp32 NHWC pixel would cost a 128-byte line
+        // per lane)
+        {
+          const uint32_t* R = reinterpret_cast<const uint32_t*>(&rcell);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(as_h2(R[k]));
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) { S[i][k] = f; Q[i][k] = fmul2(f, f); }
+          }
+          if (c < 3) rcell = __ldg(p.feats16 + (size_t)(c + 1) * plane_cells + (size_t)yc * p.Wf + xc);
+        }
+        if (c > 0) mbar_wait(&bar_full[stage], round & 1u);
+        if (!(p.dbg & 2)) blend(check_tag, c, ring_u32 + (uint32_t)(stage * stage_bytes));
+        // this warp is done with the stage: hand the buffer back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[stage]);
+        if (++stage == ns) { stage = 0; ++round; }
+        // variance with reciprocal multiplies, two channels per instruction (within an ulp or two of the reference's
+        // divisions, model.py:458-461 / :330-332; this mode stores bf16)
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+          if (!live[i]) continue;
+          uint4 cell;
+          uint32_t* cw = reinterpret_cast<uint32_t*>(&cell);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float2 cst;
+            if (p.order == MVSB200_ORDER_MEM) {
+              cst = ffma2(Q[i][k], inv_n2, fmul2(fmul2(S[i][k], S[i][k]), ninv_nn2));
+            } else {
+              const float2 m = fmul2(S[i][k], inv_n2);
+              cst = ffma2(Q[i][k], inv_n2, fmul2(fmul2(m, m), make_float2(-1.0f, -1.0f)));
+            }
+            const __nv_bfloat162 b = __floats2bfloat162_rn(cst.x, cst.y);
+            cw[k] = *reinterpret_cast<const uint32_t*>(&b);
+          }
+          if (p.cp8 && !(p.dbg & 8))
+            *reinterpret_cast<uint4*>(p.cp8 + ((size_t)cell_cp8[i] + (size_t)c * plane_cells) * 8) = cell;
+          if (p.ps8 && !(p.dbg & 12))
+            *reinterpret_cast<uint4*>(p.ps8 + ((size_t)cell_ps8[i] + (size_t)c * 4 * Hs * Ws) * 8) = cell;
+        }
+      }
+    };
+    if (slow_warp) chunks(std::true_type{});
+    else chunks(std::false_type{});
   }
 }
 

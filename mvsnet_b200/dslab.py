@@ -211,3 +211,96 @@ class DSlabHotPath:
         L.check(rc, "regress_combine")
         dist.all_reduce(prob, op=dist.ReduceOp.SUM, group=self.group)
         return depth, prob
+
+
+class LocalSlabHotPath:
+    """The D-slab path with every slab on ONE GPU, in ONE process: the same library calls as DSlabHotPath
+    (mvsb200_slab_begin / _layer / _regress_partial / _combine on `slabs` workspaces), with the exchange step done by
+    device copies between the workspaces and the statistics summed in place.  No torch.distributed: this is how a
+    single-GPU box checks the slab kernels (depth windows, halo planes, global batch statistics, split softmax) against
+    the oracle; it is not a fast path."""
+
+    def __init__(self, n_views, depth_num, hf, wf, weights, slabs, channels=32, order="mem", inverse_depth=False,
+                 bn_eps=1e-5, device="cuda"):
+        from .engine import RegnetWeights
+        self.lib = L.load()
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.world = int(slabs)
+        slab_range(depth_num, 0, self.world)                      # validates the split
+        self.n_views, self.depth_num, self.hf, self.wf, self.channels = n_views, depth_num, hf, wf, channels
+        self.order = ops._ORDER[order]
+        self.inverse_depth = int(bool(inverse_depth))
+        self.bn_eps = float(bn_eps)
+        self.weights = weights if isinstance(weights, RegnetWeights) else RegnetWeights(weights, self.device)
+        self.base_filter = self.weights.base_filter
+        nbytes = self.lib.mvsb200_slab_workspace_bytes(n_views, depth_num, self.world, hf, wf, channels, self.base_filter)
+        if nbytes == 0:
+            raise L.MVSB200Error("slab_workspace_bytes rejected the shape: " + L.last_error())
+        self.ws = [torch.zeros((nbytes,), dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+        self.regions = [layer_regions(i, n_views, depth_num, self.world, hf, wf, channels, self.base_filter)
+                        for i in range(N_LAYERS)]
+
+    def _exchange(self, layer: int):
+        reg = self.regions[layer]
+        off, nbytes = reg["stats"]
+        if nbytes:
+            total = sum(w[off:off + nbytes].view(torch.float64) for w in self.ws)
+            for w in self.ws:
+                w[off:off + nbytes].view(torch.float64).copy_(total)
+        for t in reg["tensors"]:
+            n = t["plane"]
+            for r in range(self.world):
+                if r > 0:        # my first plane is the previous slab's AFTER halo
+                    self.ws[r - 1][t["after"]:t["after"] + n].copy_(self.ws[r][t["first"]:t["first"] + n])
+                if r < self.world - 1:
+                    self.ws[r + 1][t["before"]:t["before"] + n].copy_(self.ws[r][t["last"]:t["last"] + n])
+
+    def infer(self, feats: torch.Tensor, cams: torch.Tensor, depth_start: float, depth_interval: float):
+        with torch.cuda.device(self.device):
+            L.require_cuda(feats, cams)
+            feats, cams = feats.contiguous(), cams.contiguous()
+            common = (self.n_views, self.depth_num)
+            shape = (self.hf, self.wf, self.channels)
+            for r in range(self.world):
+                rc = self.lib.mvsb200_slab_begin(L.ptr(feats), L.ptr(cams), *common, r, self.world, *shape,
+                                                 float(depth_start), float(depth_interval), self.inverse_depth, self.order,
+                                                 ctypes.byref(self.weights.params), self.base_filter, L.ptr(self.ws[r]),
+                                                 self.ws[r].numel(), L.stream_ptr())
+                L.check(rc, "slab_begin")
+            for layer in SLAB_ORDER:
+                for r in range(self.world):
+                    rc = self.lib.mvsb200_slab_layer(layer, *common, r, self.world, *shape,
+                                                     ctypes.byref(self.weights.params), self.base_filter, self.bn_eps,
+                                                     L.ptr(self.ws[r]), L.stream_ptr())
+                    L.check(rc, f"slab_layer {layer}")
+                if layer != N_LAYERS - 1:
+                    self._exchange(layer)
+            # softmax over depth across the slabs (model.py:474): per-slab partials, combine, summed probability shares
+            npix, dl = self.hf * self.wf, self.depth_num // self.world
+            off, nbytes = self.regions[N_LAYERS - 1]["filtered"]
+            partials = torch.empty((self.world, 3, npix), dtype=torch.float32, device=self.device)
+            for r in range(self.world):
+                mine = self.ws[r][off:off + nbytes].view(torch.float32)
+                rc = self.lib.mvsb200_regress_partial(L.ptr(mine), dl, r * dl, self.depth_num, npix, float(depth_start),
+                                                      float(depth_interval), self.inverse_depth, L.ptr(partials[r]),
+                                                      L.stream_ptr())
+                L.check(rc, "regress_partial")
+            depth = torch.empty((self.hf, self.wf), dtype=torch.float32, device=self.device)
+            prob = torch.zeros((self.hf, self.wf), dtype=torch.float32, device=self.device)
+            share = torch.empty_like(prob)
+            for r in range(self.world):
+                mine = self.ws[r][off:off + nbytes].view(torch.float32)
+                rc = self.lib.mvsb200_regress_combine(L.ptr(partials), self.world, L.ptr(mine), dl, r * dl, self.depth_num,
+                                                      npix, float(depth_start), float(depth_interval), self.inverse_depth,
+                                                      4, L.ptr(depth), L.ptr(share), L.stream_ptr())
+                L.check(rc, "regress_combine")
+                prob += share
+            return depth, prob
+
+    def filtered_volume(self) -> torch.Tensor:
+        """The filtered cost volume [D,Hf,Wf] fp32 of the last infer(), assembled from the slabs."""
+        off, nbytes = self.regions[N_LAYERS - 1]["filtered"]
+        dl = self.depth_num // self.world
+        return torch.cat([w[off:off + nbytes].view(torch.float32).view(dl, self.hf, self.wf) for w in self.ws], dim=0)

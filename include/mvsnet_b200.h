@@ -321,6 +321,21 @@ int mvsb200_unet_forward(const float* images, const mvsb200_unet_params* params,
 int mvsb200_unet_layer_output(int n_views, int height, int width, int base_filter, int layer, size_t* offset,
                               int* dims);
 
+/* ---- refinement glue after the path (model.py:753-811 `depth_refine`) ------------------------------
+ * tf.image.resize_bilinear of TF 1.x (align_corners = False): x [n,height,width,channels] fp32 -> y [n,out_height,
+ * out_width,channels], then y = (y - subtract) * multiply (the depth normalisation of model.py:763-765 in the same pass;
+ * pass 0 and 1 for a plain resize; equal sizes make it a pure affine). */
+int mvsb200_resize_bilinear(const float* x, int n, int height, int width, int channels, float* y, int out_height,
+                            int out_width, float subtract, float multiply, void* stream);
+/* scaled = x * multiply; sum = scaled + add (either output may be NULL; add NULL: sum = scaled): the residual back in
+ * millimetres and the refined depth map, model.py:803-809. */
+int mvsb200_scale_add(const float* x, float multiply, const float* add, size_t count, float* scaled, float* sum,
+                      void* stream);
+/* tf.layers.conv2d(3x3, SAME, stride 1, use_bias=True) of concat(xa, xb) with optional ReLU: the layers of RefineNetConv
+ * (mvsnetworks.py:178-193, network.py:171-206).  kernel_tf [3,3,ca+cb,cout], bias [cout] or NULL. */
+int mvsb200_conv2d_bias(const float* xa, int ca, const float* xb, int cb, const float* kernel_tf, const float* bias, int n,
+                        int height, int width, int cout, int relu, float* y, void* stream);
+
 /* Diagnostic (not on the product path): one 128 x n x (16*kblocks) tcgen05.mma tile computed from
  * caller-built shared-memory images of the A and B operands (no-swizzle K-major core-matrix
  * layout).  Pins the descriptor semantics conv3d_tc.cu relies on.  d_out [128*n] fp32. */

@@ -117,6 +117,9 @@ SIGNATURES = {
                                    POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P, _P]),
     "mvsb200_umma_probe": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, _P, _P]),
+    "mvsb200_resize_bilinear": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, c_float, _P]),
+    "mvsb200_scale_add": (c_int, [_P, c_float, _P, c_size_t, _P, _P, _P]),
+    "mvsb200_conv2d_bias": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "mvsb200_launch_count": (c_uint64, []),
     "mvsb200_set_tuning": (c_int, [c_char_p, c_char_p]),
     "mvsb200_cost_volume_window_stats": (c_int, [POINTER(c_uint64), c_int]),

@@ -129,3 +129,53 @@ class UNetDS2GN:
                 raise ValueError(f"variables are for base_filter {tower.weights.base_filter}, mode needs {self.base_filter}")
             self._output = tower(image.to(torch.float32))
         return self._output
+
+
+_REFINE_VARIABLES = {}
+
+
+def set_refine_variables(weights: dict) -> None:
+    """Register the variables of the refinement tower: 'refine_conv{0..3}/kernel' [3,3,Cin,Cout] and '/bias' [Cout]."""
+    _REFINE_VARIABLES.clear()
+    _REFINE_VARIABLES.update(weights)
+
+
+class RefineNetConv:
+    """RefineNetConv({'color_image': image, 'depth_image': data}, ...).get_output() -> [B,H,W,1]: the refinement tower of
+    network_type 'original' (mvsnetworks.py:178-193): concat, three biased 3x3 convolutions with ReLU, a biased 3x3
+    convolution to one channel."""
+
+    def __init__(self, inputs, trainable=True, training=True, mode="normal", reuse=False, **kwargs):
+        if mode not in NETWORK_MODE_DIVISOR:
+            raise ValueError(f"unknown network mode {mode!r}")
+        self.base_filter = max(1, int(32 / NETWORK_MODE_DIVISOR[mode]))
+        self.layers = dict(inputs)
+        self._output = None
+
+    def get_output(self):
+        if self._output is None:
+            color, depth = self.layers["color_image"], self.layers["depth_image"]
+            if color.dim() != 4 or depth.dim() != 4:
+                raise ValueError("Improper input rank for layer: refine_conv0")
+            if not _REFINE_VARIABLES:
+                raise RuntimeError("refinement variables not set: call mvsnetworks.set_refine_variables(weights)")
+            lib = L.load()
+            with torch.cuda.device(color.device):
+                L.require_cuda(color, depth)
+                n, h, w, _ = color.shape
+                xa, xb = color.to(torch.float32).contiguous(), depth.to(torch.float32).contiguous()
+                for i in range(4):
+                    k = torch.as_tensor(_REFINE_VARIABLES[f"refine_conv{i}/kernel"], dtype=torch.float32).to(color.device).contiguous()
+                    b = torch.as_tensor(_REFINE_VARIABLES[f"refine_conv{i}/bias"], dtype=torch.float32).to(color.device).contiguous()
+                    ca, cb = xa.shape[3], 0 if xb is None else xb.shape[3]
+                    if tuple(k.shape[:3]) != (3, 3, ca + cb):
+                        raise ValueError(f"refine_conv{i}/kernel must be [3,3,{ca + cb},*], got {tuple(k.shape)}")
+                    if i < 3 and k.shape[3] != self.base_filter:
+                        raise ValueError(f"variables are for {k.shape[3]} filters, mode needs {self.base_filter}")
+                    y = torch.empty((n, h, w, k.shape[3]), dtype=torch.float32, device=color.device)
+                    L.check(lib.mvsb200_conv2d_bias(L.ptr(xa), ca, L.ptr(xb) if xb is not None else None, cb, L.ptr(k),
+                                                    L.ptr(b), n, h, w, int(k.shape[3]), int(i < 3), L.ptr(y),
+                                                    L.stream_ptr()), "conv2d_bias")
+                    xa, xb = y, None
+            self._output = xa
+        return self._output

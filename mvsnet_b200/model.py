@@ -114,3 +114,71 @@ def inference_mem(images, cams, depth_num, depth_start, depth_interval, network_
         raise NotImplementedError("inference_mem(training=False) is never exercised by the reference "
                                   "(predictlib.py:83-84 leaves the default)")
     return _run(images, cams, depth_num, depth_start, depth_interval, network_mode, inverse_depth, "mem")
+
+
+def _resize_bilinear(x, out_h, out_w, subtract=0.0, multiply=1.0):
+    """tf.image.resize_bilinear (TF 1.x, align_corners=False) of x [B,H,W,C], then (y - subtract) * multiply."""
+    from . import _lib as L
+    x = x.to(torch.float32).contiguous()
+    b, h, w, c = x.shape
+    y = torch.empty((b, out_h, out_w, c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.require_cuda(x)
+        L.check(L.load().mvsb200_resize_bilinear(L.ptr(x), b, h, w, c, L.ptr(y), out_h, out_w, float(subtract),
+                                                 float(multiply), L.stream_ptr()), "resize_bilinear")
+    return y
+
+
+def depth_refine(init_depth_map, image, prob_map, depth_num, depth_start, depth_interval, network_mode, network_type,
+                 is_master_gpu=True, training=True, trainable=True, upsample_depth=False, refine_with_confidence=False,
+                 stereo_image=None, residual_refinement=True):
+    """model.py:753-811: refine the depth map with the reference image.  init_depth_map, prob_map [B,Hd,Wd,1]; image
+    [B,H,W,3] -> (refined_depth_map, residual_depth_map).  The depth map is normalised to [0,1] over the sweep (:763),
+    depth or image are resized with tf.image.resize_bilinear (:766-777), the tower sees concat(image, depth[, prob][,
+    stereo image]) and predicts a residual in normalised units, which is scaled back and added (:803-809).
+    network_type 'original' = RefineNetConv; 'unet' (RefineUNetConv) is outside this package's scope."""
+    import numpy as np
+
+    from . import _lib as L
+    if network_type == "unet":
+        raise NotImplementedError("depth_refine: network_type 'unet' (RefineUNetConv) is not built; use 'original'")
+    if network_type != "original":
+        raise NotImplementedError                                                      # model.py:801
+    init = init_depth_map.to(torch.float32).contiguous()
+    b, hd, wd, _ = init.shape
+    if b != 1 and (isinstance(depth_start, torch.Tensor) and depth_start.numel() > 1):
+        raise NotImplementedError("depth_refine: one depth range per call (batch_size 1, as predictlib.py:86-91 runs it)")
+    ds, di = np.float32(_sc(depth_start, 0)), np.float32(_sc(depth_interval, 0))
+    depth_end = np.float32(ds + np.float32(np.float32(depth_num) - np.float32(1.0)) * di)
+    depth_scale = np.float32(depth_end - ds)
+    inv_scale_note = float(depth_scale)
+    if upsample_depth:
+        h, w = int(image.shape[1]), int(image.shape[2])
+        # (x - start) / scale is a division upstream; resize first, then the same division (tf.div before the resize is
+        # the same values up to rounding: both are linear) -- kept in the reference's order: normalise, then resize
+        norm = _resize_bilinear((init - float(ds)) / inv_scale_note, h, w)
+        init = _resize_bilinear(init, h, w)
+        if refine_with_confidence:
+            prob_map = _resize_bilinear(prob_map, h, w)
+    else:
+        norm = (init - float(ds)) / inv_scale_note
+        image = _resize_bilinear(image, hd, wd)
+        if stereo_image is not None:
+            stereo_image = _resize_bilinear(stereo_image, hd, wd)
+    data = norm
+    if refine_with_confidence:
+        data = torch.cat([data, prob_map.to(torch.float32)], dim=3)
+    if stereo_image is not None:
+        data = torch.cat([data, stereo_image.to(torch.float32)], dim=3)
+    tower = mvsnetworks.RefineNetConv({"color_image": image.to(torch.float32), "depth_image": data},
+                                      trainable=trainable, training=training, mode=network_mode,
+                                      reuse=not is_master_gpu or FLAGS.reuse_vars)
+    residual_norm = tower.get_output().contiguous()
+    residual = torch.empty_like(residual_norm)
+    refined = torch.empty_like(residual_norm)
+    with torch.cuda.device(residual_norm.device):
+        L.check(L.load().mvsb200_scale_add(L.ptr(residual_norm), float(depth_scale),
+                                           L.ptr(init.contiguous()) if residual_refinement else None,
+                                           residual_norm.numel(), L.ptr(residual), L.ptr(refined), L.stream_ptr()),
+                "scale_add")
+    return refined, residual

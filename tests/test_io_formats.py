@@ -94,9 +94,63 @@ def test_png_conversions_and_probability_filter(tmp_path):
                                   np.array([[500.0, 0.0], [700.0, 0.0]], np.float32))    # strict <, depthfusion.py:188
     folder = tmp_path / "dense"
     cam = F.load_cam(io.StringIO(CAM_TXT), max_d=192)
-    F.write_output_slice(str(folder / "depths_mvsnet"), depth[None, :, :, None], prob[None, :, :, None], cam[None], 7)
-    (folder / "depths_mvsnet" / "7.jpg").write_bytes(b"")                               # the glob key of the reference
-    assert sorted(os.listdir(folder / "depths_mvsnet")) == ["7.jpg", "7.txt", "7_init.pfm", "7_prob.pfm"]
+    out_dir = folder / "depths_mvsnet"
+    F.write_output_slice(str(out_dir), depth[None, :, :, None], prob[None, :, :, None], cam[None], 7)
+    assert sorted(os.listdir(out_dir)) == ["7.txt", "7_depth.png", "7_init.pfm", "7_prob.pfm", "7_prob.png"]
+    with pytest.raises(FileNotFoundError):              # depthfusion.py finds the views by <index>.jpg: none written yet
+        F.probability_filter(str(folder), 0.3)
+    image = np.linspace(-1.0, 1.0, 2 * 2 * 3, dtype=np.float32).reshape(2, 2, 3)         # a centred image
+    F.write_output_slice(str(out_dir), depth, prob, cam, 7, out_ref_image=image)
+    assert (out_dir / "7.jpg").read_bytes()[:3] == b"\xff\xd8\xff"                       # a JPEG
+    np.testing.assert_array_equal(F.read_png16(str(out_dir / "7_depth.png")), np.array([[500, 600], [700, 800]], np.uint16))
+    np.testing.assert_array_equal(F.read_png16(str(out_dir / "7_prob.png")), F.confidence_map_to_uint16(prob))
     F.probability_filter(str(folder), 0.3)
-    with open(folder / "depths_mvsnet" / "7_prob_filtered.pfm", "rb") as f:
+    with open(out_dir / "7_prob_filtered.pfm", "rb") as f:
         np.testing.assert_array_equal(F.load_pfm(f), np.array([[500.0, 0.0], [700.0, 0.0]], np.float32))
+
+
+def test_png16_is_a_standard_png(tmp_path):
+    img = (np.arange(5 * 7, dtype=np.uint32).reshape(5, 7) * 1999 % 65536).astype(np.uint16)
+    p = str(tmp_path / "x.png")
+    F.write_png16(p, img)
+    np.testing.assert_array_equal(F.read_png16(p), img)
+    cv2 = pytest.importorskip("cv2")
+    back = cv2.imread(p, cv2.IMREAD_UNCHANGED)                                          # an independent decoder
+    assert back.dtype == np.uint16
+    np.testing.assert_array_equal(back, img)
+    with pytest.raises(ValueError):
+        F.write_png16(p, img.astype(np.uint8))
+
+
+def _camera_json(tx):
+    pose = {"{},{}".format(i, j): float(i == j) for i in range(4) for j in range(4)}
+    pose["0,3"], pose["1,3"], pose["2,3"] = tx, 0.25, -0.5                              # metres
+    return {"pose": {"matrix": pose}, "intrinsics": {"fx": 700.0, "fy": 710.0, "px": 320.0, "py": 240.0}}
+
+
+def test_cluster_and_covisibility(tmp_path):
+    """mvs_cluster.py:91-140, cluster_generator.py:139-156: camera JSON -> cam [2,4,4] (translation in mm, depth row),
+    view lists padded with the reference, empty clusters skipped."""
+    import json
+    session = tmp_path / "session"
+    (session / "cameras").mkdir(parents=True)
+    for i in range(4):
+        (session / "cameras" / f"{i}.json").write_text(json.dumps(_camera_json(0.1 * i)))
+    covis = {"0": {"views": [1, 2, 3], "min_depth": 400.0, "max_depth": 900.0},
+             "1": {"views": [0], "min_depth": 410.0, "max_depth": 910.0},
+             "2": {"views": [], "min_depth": 420.0, "max_depth": 920.0},
+             "3": {"views": [2, 1, 0], "min_depth": 430.0, "max_depth": 930.0}}
+    (session / "covisibility.json").write_text(json.dumps(covis))
+    clusters = F.load_covisibility(str(session), view_num=3, depth_num=128, interval_scale=1.06)
+    assert [c.ref_index for c in clusters] == [0, 1, 3]                                  # the empty one is skipped
+    assert clusters[0].indices == [0, 1, 2] and clusters[1].indices == [1, 0, 1] and clusters[2].indices == [3, 2, 1]
+    assert [c.ref_index for c in F.load_covisibility(str(session), 3, include_empty=True)] == [0, 1, 2, 3]
+    assert len(F.load_covisibility(str(session), 3, max_clusters=2)) == 2
+    cams = clusters[1].cameras()
+    assert cams.shape == (3, 2, 4, 4) and cams.dtype == np.float32
+    np.testing.assert_allclose(cams[0, 0, :3, 3], [100.0, 250.0, -500.0])                # metres -> millimetres
+    np.testing.assert_array_equal(cams[0], cams[2])                                      # padded with the reference view
+    np.testing.assert_allclose(cams[0, 1, :3, :3], [[700.0, 0, 320.0], [0, 710.0, 240.0], [0, 0, 1.0]])
+    interval = (910.0 - 410.0) / 127 * 1.06
+    np.testing.assert_allclose(cams[0, 1, 3], [410.0, interval, 128, 910.0], rtol=1e-6)
+    assert clusters[0].image_path(2).endswith(os.path.join("images", "2.jpg"))

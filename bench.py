@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2]
     python bench.py --config cfg3 [--gpus N]                 BASELINE config 3: 49 reference views sharded over the ranks
+    python bench.py --config cfg4 [--gpus N]                 BASELINE config 4: training step (forward + backward)
     python bench.py --config cfg5 --mode dslab [--gpus N]    BASELINE config 5: ONE volume, depth slabs over the ranks
 
 A step = one pass of the hot path over one reference view (cluster): feats [5,216,288,32] + cams
@@ -575,13 +576,83 @@ def run_dslab(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 4: training step (forward + backward) of the path, 3 views 640x512, D=128
+# ------------------------------------------------------------------------------------------------
+def run_train(args, rank, world, local_rank):
+    """A step = forward in the fp32 parity mode + mvsnet_regression_loss + the gradients of every RegNetUS0 variable and
+    of the feature maps (mvsb200_train_step; train.py:314-315,429).  Ranks hold replicas and take different clusters
+    (data parallel without a gradient exchange: the optimizer and its all-reduce are outside the path)."""
+    import torch
+    import torch.distributed as dist
+
+    from mvsnet_b200 import ops, synthetic
+    from mvsnet_b200.train import TrainStep
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synthetic.CONFIGS["cfg1"]                    # config 4 has config 1's shape
+    n, D = cfg["n_views"], cfg["depth_num"]
+    hf, wf = cfg["height"] // 4, cfg["width"] // 4
+    V = D * hf * wf
+    ts = TrainStep(n, D, hf, wf, synthetic.make_regnet_weights(), order="train", device=dev)
+    _, cams_h, feats_d, cams_d = make_clusters(synthetic, cfg, 2, rank * 2, dev)
+    ds, di = float(cams_h[0][0, 1, 3, 0]), float(cams_h[0][0, 1, 3, 1])
+    rng = np.random.RandomState(11 + rank)
+    gt = (ds + di * rng.uniform(2, D - 3, size=(hf, wf))).astype(np.float32)
+    gt[rng.rand(hf, wf) < 0.2] = 0.0
+    gt_d = torch.from_numpy(gt).to(dev)
+    for i in range(args.warmup):
+        ts.step(feats_d[i % 2], cams_d[i % 2], gt_d, ds, di)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = ts.step(feats_d[i % 2], cams_d[i % 2], gt_d, ds, di)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = ops.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    if rank == 0:
+        value = args.steps * world / (ms / 1e3)
+        loss = float(out["metrics"][0])
+        line = {
+            "metric": "train_steps_per_s", "value": value, "unit": "training steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg4: MVSNet training step fwd+bwd of the 3DCNN path, 3 views 640x512, D=128 (feature "
+                                   "maps 160x128x32 in; loss + gradients of RegNetUS0 and of the feature maps out)",
+                       "voxels_per_map": V},
+            "detail": {"loss": loss, "arithmetic": "fp32 on CUDA cores (parity mode); bilinear-warp backward = exact adjoint scatter",
+                       "gvox_per_s": value * V / 1e9},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", help="cfg1 | cfg2 (BASELINE metric config) | cfg3 (49-view batch) | cfg5")
+    ap.add_argument("--config", default="cfg2", help="cfg1 | cfg2 (BASELINE metric config) | cfg3 (49-view batch) | cfg4 (training step) | cfg5")
     ap.add_argument("--mode", default="views", choices=["views", "dslab"],
                     help="views: every rank whole reference views; dslab: ONE volume, depth slabs over the ranks (cfg5)")
     ap.add_argument("--no-p2p", action="store_true", help="dslab: exchange by NCCL between layers instead of peer memory")
@@ -604,6 +675,8 @@ def main():
         run_reference(args, rank, world)
     elif args.config == "cfg3":
         run_cfg3(args, rank, world, local_rank)
+    elif args.config == "cfg4":
+        run_train(args, rank, world, local_rank)
     elif args.mode == "dslab":
         run_dslab(args, rank, world, local_rank)
     else:

@@ -321,6 +321,27 @@ int mvsb200_unet_forward(const float* images, const mvsb200_unet_params* params,
 int mvsb200_unet_layer_output(int n_views, int height, int width, int base_filter, int layer, size_t* offset,
                               int* dims);
 
+/* ---- training step of the path (BASELINE config 4; train.py:314-315 `inference` inside get_loss, loss.py:190-220
+ * mvsnet_regression_loss with loss_type 'original', train.py:429 opt.compute_gradients) ------------------------------
+ * Gradient buffers in the layout of the variables they belong to (fp32, device memory); gamma/beta[10] unused. */
+typedef struct mvsb200_regnet_grads {
+  float* kernel[MVSB200_REGNET_LAYERS];
+  float* gamma[MVSB200_REGNET_LAYERS];
+  float* beta[MVSB200_REGNET_LAYERS];
+} mvsb200_regnet_grads;
+size_t mvsb200_train_workspace_bytes(int n_views, int depth_num, int hf, int wf, int channels, int base_filter);
+/* Forward in the fp32 parity mode (variance order `order`: MVSB200_ORDER_TRAIN is model.py:330-332), loss against
+ * gt_depth [Hf,Wf] (0 = invalid pixel, loss.py:21), backward.
+ *   grads     d loss / d every RegNetUS0 variable
+ *   dfeats    d loss / d feats [n_views,Hf,Wf,32]; the warp's gradient is the exact adjoint (scatter) of the bilinear
+ *             zero-fill gather -- TF 1.12 registers a resampling with the inverse transform instead
+ *   depth_map out [Hf,Wf]; metrics out [3] (device): loss, less_one_accuracy, less_three_accuracy (loss.py:161-187) */
+int mvsb200_train_step(const float* feats, const float* cams, const float* gt_depth, int n_views, int depth_num, int hf,
+                       int wf, int channels, float depth_start, float depth_interval, int order,
+                       const mvsb200_regnet_params* params, int base_filter, float bn_eps,
+                       const mvsb200_regnet_grads* grads, float* dfeats, float* depth_map, float* metrics, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* ---- refinement glue after the path (model.py:753-811 `depth_refine`) ------------------------------
  * tf.image.resize_bilinear of TF 1.x (align_corners = False): x [n,height,width,channels] fp32 -> y [n,out_height,
  * out_width,channels], then y = (y - subtract) * multiply (the depth normalisation of model.py:763-765 in the same pass;

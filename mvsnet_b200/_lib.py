@@ -57,6 +57,11 @@ class RegnetParams(ctypes.Structure):
                 ("beta", c_void_p * REGNET_LAYERS)]
 
 
+class RegnetGrads(ctypes.Structure):
+    _fields_ = [("kernel", c_void_p * REGNET_LAYERS), ("gamma", c_void_p * REGNET_LAYERS),
+                ("beta", c_void_p * REGNET_LAYERS)]
+
+
 # name -> (restype, argtypes); every symbol include/mvsnet_b200.h declares
 _P = c_void_p
 SIGNATURES = {
@@ -117,6 +122,9 @@ SIGNATURES = {
                                    POINTER(RegnetParams), c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P, _P]),
     "mvsb200_umma_probe": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, _P, _P]),
+    "mvsb200_train_workspace_bytes": (c_size_t, [c_int] * 6),
+    "mvsb200_train_step": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                                   POINTER(RegnetParams), c_int, c_float, POINTER(RegnetGrads), _P, _P, _P, _P, c_size_t, _P]),
     "mvsb200_resize_bilinear": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, c_float, _P]),
     "mvsb200_scale_add": (c_int, [_P, c_float, _P, c_size_t, _P, _P, _P]),
     "mvsb200_conv2d_bias": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),

@@ -27,7 +27,7 @@ conv3d_direct_kernel(const TIN* __restrict__ x, const float* __restrict__ x_scal
                      const TIN* __restrict__ skip, const float* __restrict__ skip_scale,
                      const float* __restrict__ skip_shift, const float* __restrict__ kernel_tf, int D, int H, int W,
                      int Cin, int Cout, int stride, int Do, int Ho, int Wo, int pad_d, int pad_h, int pad_w,
-                     TOUT* __restrict__ y, double* __restrict__ stats) {
+                     TOUT* __restrict__ y, double* __restrict__ stats, int accumulate) {
   extern __shared__ float s_w[];                      // [27][Cin][CO_T]
   __shared__ float s_red[2][4][CO_T];
   const int co0 = blockIdx.y * CO_T;
@@ -79,7 +79,7 @@ conv3d_direct_kernel(const TIN* __restrict__ x, const float* __restrict__ x_scal
     for (int k = 0; k < CO_T; ++k)
       if (co0 + k < Cout) {
         if (sizeof(TOUT) == 2) reinterpret_cast<__nv_bfloat16*>(yo)[k] = __float2bfloat16_rn(acc[k]);
-        else reinterpret_cast<float*>(yo)[k] = acc[k];
+        else reinterpret_cast<float*>(yo)[k] = accumulate ? reinterpret_cast<float*>(yo)[k] + acc[k] : acc[k];
       }
   }
   if (stats == nullptr) return;
@@ -167,7 +167,7 @@ int launch_bn_finalize_all(const double* stats, const float* const* gamma, const
 template <typename TIN, typename TOUT, bool TRANSPOSED>
 static int launch_direct_t(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
                            const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout,
-                           int stride, void* y, double* stats, cudaStream_t s) {
+                           int stride, void* y, double* stats, cudaStream_t s, int accumulate) {
   int Do, Ho, Wo, pd = 0, ph = 0, pw = 0;
   if (TRANSPOSED) { Do = 2 * D; Ho = 2 * H; Wo = 2 * W; }
   else {
@@ -185,7 +185,7 @@ static int launch_direct_t(const void* x, const float* xs, const float* xb, cons
     auto kfn = conv3d_direct_kernel<TIN, TOUT, CO, TRANSPOSED>;                                                  \
     MVS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                \
     kfn<<<grid, 128, smem, s>>>((const TIN*)x, xs, xb, (const TIN*)skip, ss, sb, kernel_tf, D, H, W, cin, cout,  \
-                                stride, Do, Ho, Wo, pd, ph, pw, (TOUT*)y, stats);                                \
+                                stride, Do, Ho, Wo, pd, ph, pw, (TOUT*)y, stats, accumulate);                    \
   } while (0)
   if (co_t == 16) DIRECT(16); else if (co_t == 8) DIRECT(8); else DIRECT(1);
 #undef DIRECT
@@ -195,12 +195,16 @@ static int launch_direct_t(const void* x, const float* xs, const float* xb, cons
 
 int launch_conv3d_direct(const void* x, int x_dtype, const float* xs, const float* xb, const void* skip,
                          const float* ss, const float* sb, const float* kernel_tf, int D, int H, int W, int cin,
-                         int cout, int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s) {
+                         int cout, int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s,
+                         int accumulate) {
+  // accumulate != 0 (fp32 output only): y += result instead of y = result (the backward pass sums the input gradients
+  // of every consumer of an activation)
+  MVS_CHECK_ARG(!accumulate || y_dtype == MVSB200_F32, "conv3d(fp32): accumulate needs an fp32 output");
 #define GO(TI, TO)                                                                                                   \
   (transposed ? launch_direct_t<TI, TO, true>(x, xs, xb, skip, ss, sb, kernel_tf, D, H, W, cin, cout, stride, y,     \
-                                              stats, s)                                                              \
+                                              stats, s, accumulate)                                                  \
               : launch_direct_t<TI, TO, false>(x, xs, xb, skip, ss, sb, kernel_tf, D, H, W, cin, cout, stride, y,    \
-                                               stats, s))
+                                               stats, s, accumulate))
   if (x_dtype == MVSB200_F32 && y_dtype == MVSB200_F32) return GO(float, float);
   if (x_dtype == MVSB200_BF16 && y_dtype == MVSB200_F32) return GO(__nv_bfloat16, float);
   if (x_dtype == MVSB200_F32 && y_dtype == MVSB200_BF16) return GO(float, __nv_bfloat16);

@@ -169,9 +169,10 @@ def test_regnet_bf16_vs_oracle(O, small_problem):
     rms_model = np.sqrt(np.mean((out - ref_model) ** 2)) / np.sqrt(np.mean(ref_model ** 2))
     rel = np.abs(out - ref).max() / np.abs(ref).max()
     print(f"bf16 RegNetUS0 vs bf16-operand oracle: max {rel_model:.4f} rms {rms_model:.5f} of range; vs fp32 oracle: max {rel:.4f}")
-    assert rel_model <= 0.03, rel_model
-    assert rms_model <= 0.004, rms_model
-    assert rel <= 0.08, rel
+    # measured on B200: 0.0064 / 0.0034 / 0.0058
+    assert rel_model <= 0.015, rel_model
+    assert rms_model <= 0.006, rms_model
+    assert rel <= 0.02, rel
     assert np.corrcoef(out.ravel(), ref.ravel())[0, 1] >= 0.999
 
 

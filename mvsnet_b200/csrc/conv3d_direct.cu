@@ -129,12 +129,12 @@ int launch_bn_finalize(const double* stats, const float* gamma, const float* bet
 
 // all layers of a network in one launch (block = layer); scale / shift rows are `cpad` apart, stats rows 2*cpad
 struct BnAll {
-  const float* gamma[16]; const float* beta[16]; int channels[16]; double count[16];
+  const float* gamma[16]; const float* beta[16]; int channels[16]; int channels_true[16]; double count[16];
 };
 __global__ void bn_finalize_all_kernel(const double* __restrict__ stats, const __grid_constant__ BnAll a, int cpad, int reps,
                                        int layers, float eps, float* __restrict__ scale, float* __restrict__ shift) {
-  const int l = blockIdx.x, C = a.channels[l];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  const int l = blockIdx.x, C = a.channels[l];      // C: row pitch of the statistics; gamma / beta hold channels_true
+  for (int c = threadIdx.x; c < a.channels_true[l]; c += blockDim.x) {
     double sm = 0.0, sq = 0.0;
     for (int r = 0; r < reps; ++r) {          // partial copies [rep][layer][2*cpad]
       const double* st = stats + ((size_t)r * layers + l) * 2 * cpad;
@@ -151,13 +151,14 @@ __global__ void bn_finalize_all_kernel(const double* __restrict__ stats, const _
 }
 
 int launch_bn_finalize_all(const double* stats, const float* const* gamma, const float* const* beta, const int* channels,
-                           const double* counts, int layers, int cpad, int reps, float eps, float* scale, float* shift,
-                           cudaStream_t s) {
+                           const int* channels_true, const double* counts, int layers, int cpad, int reps, float eps,
+                           float* scale, float* shift, cudaStream_t s) {
   MVS_CHECK_ARG(layers > 0 && layers <= 16, "bn_finalize_all: bad layer count");
   BnAll a;
   for (int i = 0; i < 16; ++i) {
     a.gamma[i] = i < layers ? gamma[i] : nullptr; a.beta[i] = i < layers ? beta[i] : nullptr;
     a.channels[i] = i < layers ? channels[i] : 0; a.count[i] = i < layers ? counts[i] : 1.0;
+    a.channels_true[i] = i < layers ? channels_true[i] : 0;
   }
   bn_finalize_all_kernel<<<layers, 64, 0, s>>>(stats, a, cpad, reps, layers, eps, scale, shift);
   MVS_LAUNCH_CHECK("bn_finalize_all_kernel");

@@ -124,6 +124,7 @@ struct PackOp { int16_t tap[2]; int16_t cbase[2]; };
 struct PackParams {
   const float* kernel_tf; uint16_t* out;
   int Cin, Cout, cout_base, cout_n, CP, transposed, nops, zf, master, xfold, dmerge, cw;
+  int CinT, CoutT;       // channel counts of kernel_tf itself (<= Cin / Cout: channels padded to whole cells hold zeros)
   PackOp ops[kMaxOps];   // per-op images: tap = kd*9+kh*3+kw per K half (-1 = zero half);
                          // master images: tap = kh*3+kw (kd comes from the row group), one per (kh,kw,pair)
 };
@@ -141,9 +142,9 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
       const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
       const int sz = (sh >> 2) & 1, sy = (sh >> 1) & 1, sx = sh & 1;
       float w = 0.0f;
-      if ((!sz || !pz) && (!sy || !py) && (!sx || !px) && cn < p.cout_n && ci < p.Cin) {
+      if ((!sz || !pz) && (!sy || !py) && (!sx || !px) && cn < p.cout_n && ci < p.CinT && p.cout_base + cn < p.CoutT) {
         const int tap = ((pz + 2 * sz) * 3 + (py + 2 * sy)) * 3 + (px + 2 * sx);
-        w = p.kernel_tf[((size_t)tap * p.Cout + p.cout_base + cn) * p.Cin + ci];
+        w = p.kernel_tf[((size_t)tap * p.CoutT + p.cout_base + cn) * p.CinT + ci];
       }
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
       p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
@@ -162,10 +163,10 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
       const int ci = p.ops[op].cbase[half] + k8;
       if (tap >= 0) tap += (p.xfold ? kw : 0) - 9 * j;       // x-fold: the op's tap code has kw = 0
       float w = 0.0f;
-      if (tap >= 0 && tap < 27 && j < p.zf && ci < p.Cin) {
+      if (tap >= 0 && tap < 27 && j < p.zf && ci < p.CinT && p.cout_base + cn < p.CoutT) {
         const int co = p.cout_base + cn;
-        w = p.transposed ? p.kernel_tf[((size_t)tap * p.Cout + co) * p.Cin + ci]
-                         : p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + co];
+        w = p.transposed ? p.kernel_tf[((size_t)tap * p.CoutT + co) * p.CinT + ci]
+                         : p.kernel_tf[((size_t)tap * p.CinT + ci) * p.CoutT + co];
       }
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
       p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
@@ -179,9 +180,9 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
       const int g = row / grp, rem = row - g * grp, kw = rem / p.cout_n, cn = rem - kw * p.cout_n, kd = p.zf + 1 - g;
       const int ci = p.ops[m].cbase[half] + k8;
       float w = 0.0f;
-      if (kd >= 0 && kd < 3 && ci < p.Cin) {
+      if (kd >= 0 && kd < 3 && ci < p.CinT && p.cout_base + cn < p.CoutT) {
         const int tap = kd * 9 + p.ops[m].tap[0] + (p.xfold ? kw : 0);
-        w = p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + p.cout_base + cn];
+        w = p.kernel_tf[((size_t)tap * p.CinT + ci) * p.CoutT + p.cout_base + cn];
       }
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
       p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
@@ -204,6 +205,7 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 // scale / shift of channel c from batch statistics: the arithmetic of bn_finalize_kernel (conv3d_direct.cu), i.e.
 // fp64 moments rounded once, then tf.nn.batch_normalization in fp32 (network.py:496-506, Appendix A.6)
 __device__ __forceinline__ void bn_scale_shift(const TcBnSrc& b, int c, float& scale, float& shift) {
+  if (b.channels_true > 0 && c >= b.channels_true) { scale = 0.0f; shift = 0.0f; return; }     // padding channel: stays 0
   double sm = 0.0, sq = 0.0;
   for (int r = 0; r < b.reps; ++r) {
     sm += b.stats[(size_t)r * b.rep_stride + c];
@@ -1248,6 +1250,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   for (int d = kMaxSpan - 1; d >= 0; --d) if (c.dz_begin[d] > c.dz_begin[d + 1]) c.dz_begin[d] = c.dz_begin[d + 1];
   pk.zf = zf; pk.master = master ? 1 : 0; pk.xfold = xfold ? 1 : 0; pk.dmerge = c.dmerge; pk.cw = c.cw;
   pk.nops = nimg; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
+  pk.CinT = cin; pk.CoutT = cout;
   pk.transposed = mode == MODE_DECONV;
   const size_t fixed = (size_t)c.b_bytes + (size_t)c.ring_pad + (size_t)kMaxOps * 16 + 32 + 2048 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
   c.RS = has_skip ? kMinSkipRing : 0;
@@ -1429,9 +1432,9 @@ __global__ void pack_all_kernel(const __grid_constant__ PackAll a) {
       const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
       const int sz = (sh >> 2) & 1, sy = (sh >> 1) & 1, sx = sh & 1;
       float w = 0.0f;
-      if ((!sz || !pz) && (!sy || !py) && (!sx || !px) && cn < p.cout_n && ci < p.Cin) {
+      if ((!sz || !pz) && (!sy || !py) && (!sx || !px) && cn < p.cout_n && ci < p.CinT && p.cout_base + cn < p.CoutT) {
         const int tap = ((pz + 2 * sz) * 3 + (py + 2 * sy)) * 3 + (px + 2 * sx);
-        w = p.kernel_tf[((size_t)tap * p.Cout + p.cout_base + cn) * p.Cin + ci];
+        w = p.kernel_tf[((size_t)tap * p.CoutT + p.cout_base + cn) * p.CinT + ci];
       }
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
       p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
@@ -1448,10 +1451,10 @@ __global__ void pack_all_kernel(const __grid_constant__ PackAll a) {
       const int ci = p.ops[op].cbase[half] + k8;
       if (tap >= 0) tap += (p.xfold ? kw : 0) - 9 * j;
       float w = 0.0f;
-      if (tap >= 0 && tap < 27 && j < p.zf && ci < p.Cin) {
+      if (tap >= 0 && tap < 27 && j < p.zf && ci < p.CinT && p.cout_base + cn < p.CoutT) {
         const int co = p.cout_base + cn;
-        w = p.transposed ? p.kernel_tf[((size_t)tap * p.Cout + co) * p.Cin + ci]
-                         : p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + co];
+        w = p.transposed ? p.kernel_tf[((size_t)tap * p.CoutT + co) * p.CinT + ci]
+                         : p.kernel_tf[((size_t)tap * p.CinT + ci) * p.CoutT + co];
       }
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
       p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
@@ -1464,9 +1467,9 @@ __global__ void pack_all_kernel(const __grid_constant__ PackAll a) {
       const int g = row / grp, rem = row - g * grp, kw = rem / p.cout_n, cn = rem - kw * p.cout_n, kd = p.zf + 1 - g;
       const int ci = p.ops[m].cbase[half] + k8;
       float w = 0.0f;
-      if (kd >= 0 && kd < 3 && ci < p.Cin) {
+      if (kd >= 0 && kd < 3 && ci < p.CinT && p.cout_base + cn < p.CoutT) {
         const int tap = kd * 9 + p.ops[m].tap[0] + (p.xfold ? kw : 0);
-        w = p.kernel_tf[((size_t)tap * p.Cin + ci) * p.Cout + p.cout_base + cn];
+        w = p.kernel_tf[((size_t)tap * p.CinT + ci) * p.CoutT + p.cout_base + cn];
       }
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
       p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
@@ -1495,6 +1498,8 @@ int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStr
       MVS_CHECK_ARG(a.n < kMaxPackJobs, "conv3d_tc_pack_all: too many launches");
       a.job[a.n] = pl.pp;
       a.job[a.n].kernel_tf = jb.kernel_tf;
+      if (jb.cin_true > 0) a.job[a.n].CinT = jb.cin_true;
+      if (jb.cout_true > 0) a.job[a.n].CoutT = jb.cout_true;
       a.job[a.n].out = (uint16_t*)((unsigned char*)dst_base + (size_t)slot * conv3d_tc_pack_slot_bytes());
       ++a.n;
     }

@@ -11,6 +11,7 @@ namespace mvsb200 {
 struct TcBnSrc {
   const double* stats; const float* gamma; const float* beta; double count; float eps; int channels;
   int reps; int rep_stride;
+  int channels_true;      // > 0: gamma / beta hold this many entries; channels beyond are padding (scale = shift = 0)
 };
 
 // D-slab mode (one volume split along z over several GPUs): the input (and skip) tensor carries one halo plane
@@ -32,7 +33,8 @@ struct TcRegress { float* partial; float start, step; int fused; };
 
 // One job per layer of a network for conv3d_tc_pack_all; its launches (output-channel slices of 32) take
 // consecutive weight slots starting at slot0.
-struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0; };
+// cin_true / cout_true > 0: channel counts of kernel_tf itself when the layer runs with channels padded to whole cells.
+struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0, cin_true, cout_true; };
 
 // x: CP8 for stride-1 convs and transposed convs, PS8 for stride-2 convs.  skip: CP8.
 // Outputs: y_cp8 and / or y_ps8 (bf16, Cout % 8 == 0), or y_f32 (NDHWC fp32, any Cout).

@@ -18,8 +18,8 @@ int launch_conv3d_direct(const void* x, int x_dtype, const float* xs, const floa
                          int cout, int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s,
                          int accumulate = 0);
 int launch_bn_finalize_all(const double* stats, const float* const* gamma, const float* const* beta, const int* channels,
-                           const double* counts, int layers, int cpad, int reps, float eps, float* scale, float* shift,
-                           cudaStream_t s);
+                           const int* channels_true, const double* counts, int layers, int cpad, int reps, float eps,
+                           float* scale, float* shift, cudaStream_t s);
 
 int launch_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const float* x_shift, const void* skip,
                         const float* skip_scale, const float* skip_shift, const float* kernel_tf, int depth,
@@ -62,8 +62,7 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
   MVS_CHECK_ARG(precision == MVSB200_PRECISION_FP32 || precision == MVSB200_PRECISION_BF16,
                 "regnet_forward: bad precision %d", precision);
   const bool bf16 = precision == MVSB200_PRECISION_BF16;
-  if (bf16) MVS_CHECK_ARG(cin % 8 == 0 && b % 8 == 0, "regnet_forward(bf16): channel counts must be multiples of 8 "
-                          "(in_channels=%d base_filter=%d)", cin, b);
+  if (bf16) MVS_CHECK_ARG(cin % 8 == 0, "regnet_forward(bf16): in_channels must be a multiple of 8 (got %d)", cin);
   RegnetPlan p;
   make_plan(D, H, W, cin, b, precision, &p);
   if (workspace_bytes < p.total) {
@@ -101,7 +100,7 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
       const LayerDesc& L = p.layer[i];
       const int* d = p.dims[L.in_level];
       jobs[i] = {params->kernel[i], d[0], d[1], d[2], L.cin, L.cout, L.stride, L.transposed, L.skip >= 0 ? 1 : 0,
-                 (L.src >= 0 || L.skip >= 0) ? 1 : 0, 2 * i};
+                 (L.src >= 0 || L.skip >= 0) ? 1 : 0, 2 * i, L.cin_true, L.cout_true};
     }
     rc = conv3d_tc_pack_all(jobs, MVSB200_REGNET_LAYERS, ws + p.scratch_off, s);
     if (rc) return rc;
@@ -144,10 +143,12 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
       TcBnSrc xbn = {nullptr, nullptr, nullptr, 1.0, eps, 0, 1, 0}, sbn = xbn;
       if (L.src >= 0)
         xbn = {stats + (size_t)L.src * 2 * cpad, params->gamma[L.src], params->beta[L.src],
-               (double)p.vox[p.layer[L.src].out_level], eps, p.layer[L.src].cout, kStatsReps, rep_stride};
+               (double)p.vox[p.layer[L.src].out_level], eps, p.layer[L.src].cout, kStatsReps, rep_stride,
+               p.layer[L.src].cout_true};
       if (L.skip >= 0)
         sbn = {stats + (size_t)L.skip * 2 * cpad, params->gamma[L.skip], params->beta[L.skip],
-               (double)p.vox[p.layer[L.skip].out_level], eps, p.layer[L.skip].cout, kStatsReps, rep_stride};
+               (double)p.vox[p.layer[L.skip].out_level], eps, p.layer[L.skip].cout, kStatsReps, rep_stride,
+               p.layer[L.skip].cout_true};
       rc = launch_conv3d_tc(x, nullptr, nullptr, sk, nullptr, nullptr, params->kernel[i], d[0], d[1], d[2], L.cin, L.cout,
                             L.stride, L.transposed, last ? nullptr : ws + p.raw_off[i],
                             (!last && p.has_ps8[i]) ? ws + p.ps8_off[i] : nullptr, last ? filtered : nullptr, st,
@@ -162,14 +163,16 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
     // scale / shift of every layer for mvsb200_regnet_layer_raw (inspection only; the layers above do not read them)
     const float* gam[MVSB200_REGNET_LAYERS];
     const float* bet[MVSB200_REGNET_LAYERS];
-    int chans[MVSB200_REGNET_LAYERS];
+    int chans[MVSB200_REGNET_LAYERS], chans_true[MVSB200_REGNET_LAYERS];
     double counts[MVSB200_REGNET_LAYERS];
     for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
       gam[i] = params->gamma[i]; bet[i] = params->beta[i];
       chans[i] = i == MVSB200_L_3DCONV6_2 ? 0 : p.layer[i].cout;
+      chans_true[i] = i == MVSB200_L_3DCONV6_2 ? 0 : p.layer[i].cout_true;
       counts[i] = (double)p.vox[p.layer[i].out_level];
     }
-    rc = launch_bn_finalize_all(stats, gam, bet, chans, counts, MVSB200_REGNET_LAYERS, cpad, kStatsReps, eps, scale, shift, s);
+    rc = launch_bn_finalize_all(stats, gam, bet, chans, chans_true, counts, MVSB200_REGNET_LAYERS, cpad, kStatsReps, eps, scale,
+                                shift, s);
     if (rc) return rc;
   }
   if (profile) {

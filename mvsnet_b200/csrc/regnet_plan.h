@@ -15,6 +15,7 @@ struct LayerDesc {
   int in_level, out_level;     // U-Net level of input / output volume (0 = full resolution)
   int src;                     // producing layer of the input, -1 = cost volume
   int skip;                    // layer added to the input (skip connection), -1 = none
+  int cin_true, cout_true;     // channel counts of the layer's variables; cin / cout may be padded to whole 8-channel cells
 };
 
 struct RegnetPlan {
@@ -53,11 +54,21 @@ inline void make_plan(int D, int H, int W, int cin, int b, int precision, Regnet
   p->elem = precision == MVSB200_PRECISION_BF16 ? 2 : 4;
   size_t off = 0;
   int max_c = 0;
+  // bf16 mode keeps activations in 16-byte cells of 8 channels: the narrow network modes (network.py:75-85: lite = 4,
+  // ultralite = 2 base filters) run with every channel count padded to a whole cell; padded channels carry zero weights
+  // and zero scale / shift, so they hold exact zeros everywhere
+  const bool pad8 = precision == MVSB200_PRECISION_BF16 && b % 8 != 0;
   for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
     p->layer[i] = L[i];
+    p->layer[i].cin_true = L[i].cin;
+    p->layer[i].cout_true = L[i].cout;
+    if (pad8) {
+      p->layer[i].cin = (L[i].cin + 7) / 8 * 8;
+      if (i != MVSB200_L_3DCONV6_2) p->layer[i].cout = (L[i].cout + 7) / 8 * 8;
+    }
     p->raw_off[i] = off;
-    if (i != MVSB200_L_3DCONV6_2) off += align_up(p->vox[L[i].out_level] * L[i].cout * p->elem, 256);
-    if (L[i].cout > max_c) max_c = L[i].cout;
+    if (i != MVSB200_L_3DCONV6_2) off += align_up(p->vox[L[i].out_level] * p->layer[i].cout * p->elem, 256);
+    if (p->layer[i].cout > max_c) max_c = p->layer[i].cout;
     p->has_ps8[i] = false;
     p->ps8_off[i] = 0;
   }
@@ -70,7 +81,7 @@ inline void make_plan(int D, int H, int W, int cin, int b, int precision, Regnet
       if (p->has_ps8[i]) {
         const int* d = p->dims[L[i].out_level];
         p->ps8_off[i] = off;
-        off += align_up(planar_bytes(d[0], d[1], d[2], L[i].cout, 1), 256);
+        off += align_up(planar_bytes(d[0], d[1], d[2], p->layer[i].cout, 1), 256);
       }
     p->cost_cp8_off = off; off += align_up(planar_bytes(D, H, W, cin, 0), 256);
     p->cost_ps8_off = off; off += align_up(planar_bytes(D, H, W, cin, 1), 256);

@@ -37,11 +37,14 @@ def gather_maps(local_indices: Sequence[int], local_maps, num_views: int, group=
     if max_n == 0:
         return [] if rank == 0 else None
     ref = local_maps[0] if len(local_maps) else None
-    shape = torch.tensor(list(ref.shape) if ref is not None else [0, 0], dtype=torch.int64)
+    # NCCL moves device tensors only: the shape exchange and the buffers of a rank without views live on its GPU
+    on_gpu = dist.get_backend(group) == "nccl"
+    device = ref.device if ref is not None else (torch.device("cuda", torch.cuda.current_device()) if on_gpu
+                                                 else torch.device("cpu"))
+    shape = torch.tensor(list(ref.shape) if ref is not None else [0, 0], dtype=torch.int64, device=device)
     shapes = [torch.zeros_like(shape) for _ in range(world)]
     dist.all_gather(shapes, shape, group=group)
     shp = next((tuple(int(v) for v in s) for s in shapes if int(s.sum()) > 0), None)
-    device = ref.device if ref is not None else torch.device("cpu")
     buf = torch.zeros((max_n,) + shp, dtype=torch.float32, device=device)
     for i, m in enumerate(local_maps):
         buf[i] = m

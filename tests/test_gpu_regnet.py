@@ -176,6 +176,39 @@ def test_regnet_bf16_vs_oracle(O, small_problem):
     assert np.corrcoef(out.ravel(), ref.ravel())[0, 1] >= 0.999
 
 
+@pytest.mark.parametrize("mode,base_filter", [("lite", 4), ("ultralite", 2)])
+def test_regnet_bf16_narrow_network_modes(O, small_problem, mode, base_filter):
+    """network_mode lite / ultralite (network.py:75-85; train.py:80 defaults to lite): 4 / 2 base filters.  The tensor-core
+    path pads every channel count to whole 8-channel cells (zero weights, zero scale / shift); against the oracle run
+    with bf16-rounded operands, and through the reference-named entry point."""
+    from mvsnet_b200 import model, synthetic
+    from mvsnet_b200.cnn_wrapper import mvsnetworks
+    from mvsnet_b200.engine import HotPath, regnet_base_filter
+    assert regnet_base_filter(mode) == base_filter and regnet_base_filter("semilite") == 8
+    p = small_problem
+    weights = synthetic.make_regnet_weights(32, base_filter, seed=7)
+    H = np.stack([O.get_homographies(p["cams"][0:1], p["cams"][v:v + 1], p["depth_num"], p["depth_start"],
+                                     p["depth_interval"])[0] for v in range(1, p["n_views"])])
+    cost = bf16_round(O.cost_volume(p["feats"], H))
+    ref = O.regnet_us0(cost, weights, round_fn=bf16_round)
+    eng = HotPath(p["n_views"], p["depth_num"], p["hf"], p["wf"], weights, precision="bf16")
+    out = eng.regnet(to_dev(cost).to(torch.bfloat16)).cpu().numpy()
+    rel = np.abs(out - ref).max() / np.abs(ref).max()
+    print(f"{mode}: bf16 RegNetUS0 (base filter {base_filter}) vs bf16-operand oracle: max {rel:.4f} of range")
+    assert rel <= 0.02, rel
+    # whole path by its reference name
+    rd, _ = O.inference_from_features(p["feats"], p["cams"], p["depth_num"], p["depth_start"], p["depth_interval"], weights)
+    mvsnetworks.set_variables(weights)
+    model.FLAGS.view_num, model.FLAGS.precision = p["n_views"], "bf16"
+    depth, _ = model.inference_mem(to_dev(p["feats"])[None], to_dev(p["cams"])[None], p["depth_num"],
+                                   torch.tensor([p["depth_start"]]), torch.tensor([p["depth_interval"]]), mode)
+    frac = float(np.mean(np.abs(depth[0, :, :, 0].cpu().numpy() - rd) <= 0.1 * p["depth_interval"]))
+    assert frac >= 0.95, frac
+    with pytest.raises(ValueError):            # the checkpoint's width must match the mode
+        model.inference_mem(to_dev(p["feats"])[None], to_dev(p["cams"])[None], p["depth_num"],
+                            torch.tensor([p["depth_start"]]), torch.tensor([p["depth_interval"]]), "normal")
+
+
 @pytest.mark.parametrize("xfold", [0, 1])
 @pytest.mark.parametrize("zf", [1, 2, 4])
 @pytest.mark.parametrize("case", [(8, 16, 24, 32, 8, 1, False), (7, 9, 11, 16, 16, 1, False), (10, 16, 24, 8, 1, 1, False),

@@ -51,6 +51,11 @@ def raw_metrics(path):
     return rows[start], rows[start + 1], rows[start + 2:]
 
 
+def tensor_keys(hdr):
+    """Every tensor-pipe / TMEM counter the capture holds (the hmma sub-pipe counter does not see tcgen05's UTCHMMA)."""
+    return [k for k in hdr if any(t in k for t in ("pipe_tensor", "tmem", "utc", "tcgen")) and ("pct_of_peak" in k or k.endswith(".sum"))]
+
+
 KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -74,7 +79,7 @@ def summarise(src, dst, names=None):
         rec = OrderedDict(kernel=r[hdr.index("Kernel Name")].split("(")[0])
         if names:
             rec["layer"] = names[i] if i < len(names) else ""
-        for k in KEYS:
+        for k in KEYS + [t for t in tensor_keys(hdr) if t not in KEYS]:
             if k in hdr and r[hdr.index(k)] not in ("", "n/a"):
                 rec[k] = r[hdr.index(k)] + " " + units[hdr.index(k)]
         if "dram__bytes_read.sum" in hdr:
@@ -86,8 +91,11 @@ def summarise(src, dst, names=None):
 
 
 cv = summarise(os.path.join(G, "prof_cv_raw.csv"), os.path.join(P, f"{tag}_cost_volume_ncu.json"))
-json.dump({"kernel": cv[0]["kernel"], "dram_bytes_per_launch": cv[0]["dram_bytes"],
-           "source": f"profiles/{tag}_cost_volume_ncu.json (ncu --set full, one launch at cfg2)"},
+if "cost_volume_window_kernel" not in cv[0]["kernel"]:
+    sys.exit(f"captured kernel {cv[0]['kernel']!r} is not the one bench.py reports the roofline of")
+json.dump({"kernel": cv[0]["kernel"], "config": "cfg2", "dram_bytes_per_launch": cv[0]["dram_bytes"],
+           "source": f"profiles/{tag}_cost_volume_ncu.json (ncu --set full, one launch at cfg2: dram__bytes_read.sum + "
+                     "dram__bytes_write.sum)"},
           open(os.path.join(P, "cost_volume_traffic.json"), "w"), indent=1)
 layers = ["3dconv1_0", "3dconv2_0", "3dconv3_0[0:32]", "3dconv3_0[32:64]", "3dconv0_1", "3dconv1_1", "3dconv2_1",
           "3dconv3_1[0:32]", "3dconv3_1[32:64]", "3dconv4_0", "3dconv5_0", "3dconv6_0", "3dconv6_2"]

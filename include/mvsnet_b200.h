@@ -278,6 +278,11 @@ int mvsb200_slab_layer_p2p(int layer, int n_views, int depth_num, int slab, int 
                            void* const* peers_dev, void* const* peers_host, unsigned seq, void* stream);
 int mvsb200_slab_p2p_error(int n_views, int depth_num, int slabs, int hf, int wf, int channels, int base_filter,
                            void* workspace, void* stream);
+/* Release every kernel of this rank that is waiting for another rank's publication flag: it gives up at once and raises
+ * the error word (mvsb200_slab_p2p_error then returns 1 and clears both).  For a watchdog that has lost a rank; the write
+ * uses a stream of its own, the compute stream being the one that is stuck. */
+int mvsb200_slab_p2p_abort(int n_views, int depth_num, int slabs, int hf, int wf, int channels, int base_filter,
+                           void* workspace);
 /* cudaMalloc'ed, zeroed device memory and its CUDA-IPC handle (64 bytes) / mapping in another process */
 int mvsb200_ipc_alloc(size_t bytes, void** ptr);
 int mvsb200_ipc_free(void* ptr);

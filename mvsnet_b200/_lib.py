@@ -102,6 +102,7 @@ SIGNATURES = {
     "mvsb200_slab_layer_p2p": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, _P, _P,
                                        ctypes.c_uint, _P]),
     "mvsb200_slab_p2p_error": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "mvsb200_slab_p2p_abort": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mvsb200_ipc_alloc": (c_int, [c_size_t, _P]),
     "mvsb200_ipc_free": (c_int, [_P]),
     "mvsb200_ipc_export": (c_int, [_P, _P]),

@@ -375,7 +375,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           unsigned v;
           asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
           if ((int)(v - p.wait_seq) >= 0) break;
-          if (clock64() - t0 > 4000000000LL) { if (p.err_flag) atomicExch(p.err_flag, 1u); break; }
+          // give up when the host raised the abort word (the word after the error word: a watchdog that lost a rank
+          // releases every kernel waiting for it at once) or after ~2 s
+          unsigned stop = 0u;
+          if (p.err_flag) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(stop) : "l"(p.err_flag + 1) : "memory");
+          if (stop || clock64() - t0 > 4000000000LL) { if (p.err_flag) atomicExch(p.err_flag, 1u); break; }
           __nanosleep(200);
         }
         asm volatile("fence.proxy.async;" ::: "memory");      // the halo planes are read by the TMA unit (async proxy)

@@ -276,7 +276,7 @@ struct SlabPlan {
   size_t cost_cp8_off, cost_ps8_off, cost_cp8_plane, cost_ps8_plane;
   size_t hom_off, coef_off, pair_off, filtered_off, stats_off, stats_bytes, scratch_off, total;
   size_t gstats_off, gstats_bytes;      // peer mode: statistics of every layer per source rank [layer][slabs][2*cpad]
-  size_t flags_off, flags_bytes;        // peer mode: publication flags [layer][slabs] + an error word
+  size_t flags_off, flags_bytes;        // peer mode: publication flags [layer][slabs] + an error word + an abort word
   int cpad, slabs;
 };
 
@@ -319,7 +319,7 @@ static int make_slab_plan(int n_views, int D, int slabs, int H, int W, int cin, 
   sp->slabs = slabs;
   sp->gstats_bytes = (size_t)MVSB200_REGNET_LAYERS * slabs * 2 * sp->cpad * sizeof(double);
   sp->gstats_off = off; off += align_up(sp->gstats_bytes, 256);
-  sp->flags_bytes = (size_t)(MVSB200_REGNET_LAYERS * slabs + 1) * sizeof(unsigned);
+  sp->flags_bytes = (size_t)(MVSB200_REGNET_LAYERS * slabs + 2) * sizeof(unsigned);
   sp->flags_off = off; off += align_up(sp->flags_bytes, 256);
   sp->total = off;
   return MVSB200_OK;
@@ -530,8 +530,27 @@ extern "C" int mvsb200_slab_p2p_error(int n_views, int depth_num, int slabs, int
   unsigned* f = (unsigned*)((char*)workspace + sp.flags_off) + MVSB200_REGNET_LAYERS * slabs;
   MVS_CUDA(cudaMemcpyAsync(&v, f, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   MVS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  if (v) MVS_CUDA(cudaMemsetAsync(f, 0, sizeof(v), (cudaStream_t)stream));
+  if (v) MVS_CUDA(cudaMemsetAsync(f, 0, 2 * sizeof(v), (cudaStream_t)stream));       // error word + abort word
   return (int)v;
+}
+
+// Release every kernel of THIS rank that is waiting for a publication flag (it gives up at once and raises the error
+// word): what a watchdog calls on the surviving ranks when a rank is lost, instead of sitting out the ~2 s bound per
+// layer.  The write goes out on a stream of its own -- the compute stream is the one that is stuck.  Cleared by
+// mvsb200_slab_p2p_error.
+extern "C" int mvsb200_slab_p2p_abort(int n_views, int depth_num, int slabs, int hf, int wf, int channels, int base_filter,
+                                      void* workspace) {
+  SlabPlan sp;
+  if (!workspace || make_slab_plan(n_views, depth_num, slabs, hf, wf, channels, base_filter, &sp)) return MVSB200_ERR_INVALID;
+  static thread_local cudaStream_t side[64] = {};
+  int dev = 0;
+  MVS_CUDA(cudaGetDevice(&dev));
+  if (!side[dev & 63]) MVS_CUDA(cudaStreamCreateWithFlags(&side[dev & 63], cudaStreamNonBlocking));
+  static const unsigned one = 1u;
+  unsigned* f = (unsigned*)((char*)workspace + sp.flags_off) + MVSB200_REGNET_LAYERS * slabs + 1;
+  MVS_CUDA(cudaMemcpyAsync(f, &one, sizeof(one), cudaMemcpyHostToDevice, side[dev & 63]));
+  MVS_CUDA(cudaStreamSynchronize(side[dev & 63]));
+  return MVSB200_OK;
 }
 
 // Peer-visible device memory for the slab workspace (cudaMalloc + CUDA IPC): ranks are separate processes.

@@ -160,6 +160,22 @@ class DSlabHotPath:
             self.lib.mvsb200_ipc_free(self._base)
             self._base = None
 
+    def abort(self):
+        """p2p mode: release this rank's kernels that wait for another rank's publication flag (a watchdog that has
+        lost a rank calls this on the survivors; the next p2p_error() reports it).  Safe from another host thread."""
+        if self.p2p:
+            with torch.cuda.device(self.device):
+                L.check(self.lib.mvsb200_slab_p2p_abort(self.n_views, self.depth_num, self.world, self.hf, self.wf,
+                                                        self.channels, self.base_filter, L.ptr(self.ws)), "slab_p2p_abort")
+
+    def p2p_error(self) -> bool:
+        """True when a kernel of the last inference gave up waiting (time-out or abort()); clears the flags."""
+        if not self.p2p:
+            return False
+        with torch.cuda.device(self.device):
+            return bool(self.lib.mvsb200_slab_p2p_error(self.n_views, self.depth_num, self.world, self.hf, self.wf,
+                                                        self.channels, self.base_filter, L.ptr(self.ws), L.stream_ptr()))
+
     def infer(self, feats: torch.Tensor, cams: torch.Tensor, depth_start: float, depth_interval: float):
         L.require_cuda(feats, cams)
         args = (self.n_views, self.depth_num, self.rank, self.world, self.hf, self.wf, self.channels)

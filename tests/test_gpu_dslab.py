@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_two_slabs_match_one_gpu():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "dslab_check.py"), "--config", "small",
-           "--iters", "2", "--p2p"]
+           "--iters", "2", "--p2p", "--abort-test"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = next(l for l in out.stdout.splitlines() if l.startswith("{"))
@@ -25,6 +25,8 @@ def test_two_slabs_match_one_gpu():
     assert res["world"] == 2 and res["max_abs_depth_diff_in_intervals"] <= 0.1
     # the peer-memory variant (exchange inside the kernels) computes exactly what the NCCL-driven one does
     assert res["p2p_vs_nccl_max_abs_depth_diff_in_intervals"] == 0.0 and res["p2p_wait_timeouts"] == 0
+    # a rank that waits for peers that never publish is released by abort() (not after 11 x 2 s) and says so
+    assert res["abort_reported"] and res["abort_released_ms"] < 1500.0
 
 
 @pytest.mark.parametrize("slabs", [2, 4])

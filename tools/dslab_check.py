@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--iid", action="store_true", help="i.i.d. features (fast to build at the large configs)")
     ap.add_argument("--p2p", action="store_true", help="also run the peer-memory variant (exchange inside the kernels)")
+    ap.add_argument("--abort-test", action="store_true",
+                    help="with --p2p: rank 0 runs the layers alone (nobody publishes), a timer calls abort(): the waits give up")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -77,13 +79,41 @@ def main():
         res["dslab_p2p_ms"] = timeit(lambda: fused.infer(feats, camsd, ds, di))
         res["p2p_wait_timeouts"] = int(fused.lib.mvsb200_slab_p2p_error(n, D, world, hf, wf, 32, fused.base_filter,
                                                                         fused.ws.data_ptr(), None))
+        if a.abort_test:
+            # rank 0 runs the layers of one more inference ALONE: every consumer kernel waits for flags the other ranks
+            # never raise.  A host timer aborts after 50 ms; without it each layer would sit out its ~2 s bound.
+            import ctypes
+            import threading
+            import time
+            from mvsnet_b200 import _lib as L
+            from mvsnet_b200.dslab import SLAB_ORDER
+            dist.barrier()
+            if rank == 0:
+                fused.seq += 1
+                args = (n, D, rank, world, hf, wf, 32)
+                t0 = time.perf_counter()
+                timer = threading.Timer(0.05, fused.abort)
+                timer.start()
+                L.check(fused.lib.mvsb200_slab_begin(L.ptr(feats), L.ptr(camsd), *args, ds, di, 0, 0,
+                                                     ctypes.byref(fused.weights.params), fused.base_filter, L.ptr(fused.ws),
+                                                     fused.ws.numel(), L.stream_ptr()), "slab_begin")
+                for layer in SLAB_ORDER:
+                    L.check(fused.lib.mvsb200_slab_layer_p2p(layer, *args, ctypes.byref(fused.weights.params), fused.base_filter,
+                                                             fused.bn_eps, L.ptr(fused.ws), L.ptr(fused.peers_dev),
+                                                             fused.peers_host, fused.seq, L.stream_ptr()), "slab_layer_p2p")
+                torch.cuda.synchronize()
+                timer.join()
+                res["abort_released_ms"] = 1e3 * (time.perf_counter() - t0)
+                res["abort_reported"] = bool(fused.p2p_error())
+            dist.barrier()
         dist.barrier()
         fused.close()
     if rank == 0:
         print(json.dumps(res), flush=True)
     # same gate as the bf16 path against the oracle: depth within 0.1 interval (here: of the single-GPU result)
     ok = res["max_abs_depth_diff_in_intervals"] <= 0.1 and res.get("p2p_max_abs_depth_diff_in_intervals", 0.0) <= 0.1 \
-        and res.get("p2p_wait_timeouts", 0) == 0
+        and res.get("p2p_wait_timeouts", 0) == 0 and res.get("abort_reported", True) \
+        and res.get("abort_released_ms", 0.0) < 1500.0
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

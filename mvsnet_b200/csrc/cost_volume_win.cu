@@ -55,7 +55,6 @@ struct Params {
   int n_src, D, d0g, Dloc, Hf, Wf, order;
   int tiles_x, tiles_y, nwork, nstages;
   unsigned long long* stats;         // optional: [0] (voxel, view) pairs served from global memory
-  int dbg;                           // development (tuning CV_DBG): 1 = no TMA loads, 2 = no blend, 4 = no parity-split store, 8 = no stores
 };
 
 __global__ void planar_half_features_kernel(const float* __restrict__ feats, int n_views, int Hf, int Wf,
@@ -113,9 +112,14 @@ __device__ __forceinline__ void fast_coords(const float4 c0, const float4 c1, fl
   iy = fmaf(c0.w, x, fmaf(c1.x, y, c1.y)) * rp;
 }
 
-// NV = number of source views; BLEND32: the 4-tap blend in fp32 (taps still fp16-rounded) instead of packed fp16
-template <int NV, bool BLEND32>
+// NV = number of source views.  MODE selects the arithmetic of the blend and of the running sums:
+//   0  4-tap blend in packed fp16 on the DIFFERENCE to the reference pixel (d_v = warped_v - r; the variance does not move
+//      with a shift, and differences keep Q/n - (S/n)^2 away from cancellation), sums of d and d^2 in fp32;
+//   1  blend in fp32 in the reference's association, sums of the warped values and their squares in fp32 (taps fp16);
+//   2  as 0 with the sums of d and d^2 kept in packed fp16 as well (converted once per chunk).
+template <int NV, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const __grid_constant__ Params p) {
+  constexpr bool BLEND32 = MODE == 1, ACC16 = MODE == 2;
   constexpr int IPT = kIPT, kConsumerWarps = kItems / IPT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const int stage_bytes = NV * kViewBytes;
@@ -160,20 +164,17 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
           finite = finite && fabsf(ix) <= 1.0e9f && fabsf(iy) <= 1.0e9f;      // false for NaN, inf and absurd values
           mnx = fminf(mnx, ix); mxx = fmaxf(mxx, ix); mny = fminf(mny, iy); mxy = fmaxf(mxy, iy);
         }
-        int outside = 0;
+        // A window always lands (8 rows at least, at a position clamped to the image with its one-cell zero border):
+        // a view none of whose taps touches the image gets zero weights on landed, finite cells, exactly like single
+        // footprints outside the image -- the consumers carry no "skip this view" branch.  Rows above / left of the image
+        // hold zeros only: the window starts at -1 at the earliest.
+        n_rows = WROWS;
         if (finite) {
-          // one source pixel of slack on every side: the corners bound the samples up to rounding
-          const float fx0 = floorf(mnx) - 1.0f, fx1 = floorf(mxx) + 2.0f, fy0 = floorf(mny) - 1.0f, fy1 = floorf(mxy) + 2.0f;
-          if (fx1 >= 0.0f && fx0 <= (float)(p.Wf - 1) && fy1 >= 0.0f && fy0 <= (float)(p.Hf - 1)) {
-            // rows above / left of the image hold zeros only: start the window at -1 at the earliest
-            n_wx0 = (int)fmaxf(floorf(mnx), -1.0f);
-            n_wy0 = (int)fmaxf(floorf(mny), -1.0f);
-            n_rows = ((int)fminf(floorf(mxy) + 1.0f, (float)p.Hf) - n_wy0 + 1 <= WROWS) ? WROWS : WY;
-          } else {
-            outside = 1;             // no tap of this work item touches the image: the view contributes exact zeros
-          }
+          n_wx0 = (int)fminf(fmaxf(floorf(mnx), -1.0f), (float)(p.Wf - 1));
+          n_wy0 = (int)fminf(fmaxf(floorf(mny), -1.0f), (float)(p.Hf - 1));
+          if ((int)fminf(floorf(mxy) + 1.0f, (float)p.Hf) - n_wy0 + 1 > WROWS) n_rows = WY;
         }
-        s_meta[(it & 1) * kMaxSrc + lane] = Meta{n_wx0, n_wy0, n_rows, outside};
+        s_meta[(it & 1) * kMaxSrc + lane] = Meta{n_wx0, n_wy0, n_rows, 0};
       }
       // the transform rows of the item's planes for every view: the consumers read them from shared memory
       for (int i = lane; i < NV * PL * 2; i += 32) {
@@ -191,7 +192,6 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
       uint32_t m_bytes = (uint32_t)(m_rows * kRowBytes);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m_bytes += __shfl_xor_sync(0xffffffffu, m_bytes, o);
-      if (p.dbg & 1) m_bytes = 0;
       // lanes 2v and 2v+1 issue the one or two boxes of view v
       const int v = lane >> 1, b = lane & 1;
       const int rows_v = __shfl_sync(0xffffffffu, m_rows, v), wx0_v = __shfl_sync(0xffffffffu, m_wx0, v),
@@ -201,12 +201,9 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
         const int stage = g % ns;
         const uint32_t round = (uint32_t)(g / ns);              // how many times the ring has wrapped
         if (round > 0) mbar_wait(&bar_empty[stage], (round - 1) & 1u);
-        if (lane == 0) {
-          if (m_bytes) mbar_arrive_expect_tx(&bar_full[stage], m_bytes);    // (orders the s_meta / s_coef stores before the readers' wait)
-          else mbar_arrive(&bar_full[stage]);
-        }
+        if (lane == 0) mbar_arrive_expect_tx(&bar_full[stage], m_bytes);   // (orders the s_meta / s_coef stores before the readers' wait)
         __syncwarp();
-        if (v < NV && b * WROWS < rows_v && !(p.dbg & 1))
+        if (v < NV && b * WROWS < rows_v)
           tma_load_3d(s_ring + (size_t)stage * stage_bytes + (size_t)v * kViewBytes + (size_t)b * kBoxBytes, &p.tmap,
                       wx0_v * 4, wy0_v + b * WROWS, (v + 1) * 4 + c, &bar_full[stage]);
         // the next item's window while this item's boxes are in flight.  Its slot [(it + 1) & 1] was last read at chunk 0
@@ -223,8 +220,9 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
   const int px = t & (TXP - 1), py = (t >> 5) % TYP, pl0 = (t >> 5) / TYP;     // planes pl0 and pl0 + PL / 2 of the item
   const float inv_n = 1.0f / (float)(NV + 1), inv_nn = 1.0f / (float)((NV + 1) * (NV + 1));
   const float2 inv_n2 = make_float2(inv_n, inv_n), ninv_nn2 = make_float2(-inv_nn, -inv_nn);
-  const size_t plane_cells = (size_t)p.Hf * p.Wf;
+  const uint32_t plane_cells = (uint32_t)(p.Hf * p.Wf);
   const int Hs = (p.Hf + 1) >> 1, Ws = (p.Wf + 1) >> 1;
+  const uint32_t ps8_chunk = (uint32_t)(4 * Hs * Ws);
   const uint32_t ring_u32 = smem_u32(s_ring);
   int stage = 0;
   uint32_t round = 0;
@@ -246,70 +244,9 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
       cell_ps8[i] = (uint32_t)((((size_t)l * 16 + (y & 1) * 2 + (x & 1)) * Hs + (y >> 1)) * Ws + (x >> 1));
     }
     // reference cell of chunk 0 (in flight while the window of the item is awaited)
-    uint4 rcell = __ldg(p.feats16 + (size_t)yc * p.Wf + xc);
-    unsigned skip = 0;                 // views that contribute exact zeros to this work item
+    const uint4* rptr = p.feats16 + (size_t)yc * p.Wf + xc;
+    uint4 rcell = __ldg(rptr);
     bool slow_warp = false;            // some voxel of this warp reads a view from global memory
-    float2 S[IPT][4], Q[IPT][4];
-
-    // the taps of one (voxel, view) blended into the running sums; CHECK: the footprint may lie outside the window
-    auto blend = [&](auto check_tag, int c, uint32_t sbase) {
-      constexpr bool CHECK = decltype(check_tag)::value;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        if (skip & (1u << v)) continue;
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-          uint4 ta, tb, tc4, td;
-          const uint32_t o = fo[i][v];
-          if (!CHECK || !(o & 0x80000000u)) {
-            const uint32_t a = sbase + (uint32_t)(v * kViewBytes) + o;
-            ta = lds128(a); tb = lds128(a + 16); tc4 = lds128(a + kRowBytes); td = lds128(a + kRowBytes + 16);
-          } else {
-            // footprint outside the staged window: the same taps from global memory, zero outside the image
-            const int x0 = (int)(o & 0x7fffu) - 2, y0 = (int)((o >> 15) & 0xffffu) - 2;
-            const uint4* img = p.feats16 + ((size_t)(v + 1) * 4 + c) * plane_cells;
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            const bool vx0 = (unsigned)x0 < (unsigned)p.Wf, vx1 = (unsigned)(x0 + 1) < (unsigned)p.Wf;
-            const bool vy0 = (unsigned)y0 < (unsigned)p.Hf, vy1 = (unsigned)(y0 + 1) < (unsigned)p.Hf;
-            ta = (vy0 && vx0) ? __ldg(img + (size_t)y0 * p.Wf + x0) : z;
-            tb = (vy0 && vx1) ? __ldg(img + (size_t)y0 * p.Wf + x0 + 1) : z;
-            tc4 = (vy1 && vx0) ? __ldg(img + (size_t)(y0 + 1) * p.Wf + x0) : z;
-            td = (vy1 && vx1) ? __ldg(img + (size_t)(y0 + 1) * p.Wf + x0 + 1) : z;
-            if (p.stats && c == 0 && (vx0 || vx1) && (vy0 || vy1)) atomicAdd(p.stats, 1ull);
-          }
-          const uint32_t* A = reinterpret_cast<const uint32_t*>(&ta);
-          const uint32_t* B = reinterpret_cast<const uint32_t*>(&tb);
-          const uint32_t* C = reinterpret_cast<const uint32_t*>(&tc4);
-          const uint32_t* Dd = reinterpret_cast<const uint32_t*>(&td);
-          if (BLEND32) {
-            float wxr = __uint_as_float(wa[i][v]), wyr = __uint_as_float(wb[i][v]);
-            float wxl = 1.0f - wxr, wyl = 1.0f - wyr;
-            if (wa[i][v] == 0x7fc00000u) { wxl = wxr = wyl = wyr = 0.0f; }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 a = __half22float2(as_h2(A[k])), b = __half22float2(as_h2(B[k]));
-              const float2 cc = __half22float2(as_h2(C[k])), d = __half22float2(as_h2(Dd[k]));
-              // the reference's association: wyl * (wxl*p00 + wxr*p01) + wyr * (wxl*p10 + wxr*p11)  (Appendix A.3)
-              float2 w;
-              w.x = wyl * (wxl * a.x + wxr * b.x) + wyr * (wxl * cc.x + wxr * d.x);
-              w.y = wyl * (wxl * a.y + wxr * b.y) + wyr * (wxl * cc.y + wxr * d.y);
-              S[i][k] = fadd2(S[i][k], w);
-              Q[i][k] = ffma2(w, w, Q[i][k]);
-            }
-          } else {
-            const __half2 h0 = as_h2(wa[i][v]), h1 = as_h2(wb[i][v]);
-            const __half2 w00 = __low2half2(h0), w01 = __high2half2(h0), w10 = __low2half2(h1), w11 = __high2half2(h1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const __half2 h = __hfma2(w11, as_h2(Dd[k]), __hfma2(w10, as_h2(C[k]), __hfma2(w01, as_h2(B[k]), __hmul2(w00, as_h2(A[k])))));
-              const float2 w = __half22float2(h);
-              S[i][k] = fadd2(S[i][k], w);
-              Q[i][k] = ffma2(w, w, Q[i][k]);
-            }
-          }
-        }
-      }
-    };
 
     // ---- chunk 0's stage carries the item's window and transform rows (published before the barrier was armed):
     // bilinear footprint of every (voxel, view), once per work item.  Sample position as in transform_coords
@@ -322,8 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const Meta m = s_meta[(it & 1) * kMaxSrc + v];
-        if (m.pad) skip |= 1u << v;
-        const unsigned ry = m.rows > 0 ? (unsigned)(m.rows - 1) : 0u;       // both tap rows must have landed
+        const unsigned ry = (unsigned)(m.rows - 1);       // both tap rows must have landed
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
           const float4* row = s_coef + ((it & 1) * kMaxSrc + v) * (PL * 2) + (pl0 + i * (PL / IPT)) * 2;
@@ -344,13 +280,13 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
           const int cx = x0 - m.wx0, cy = y0 - m.wy0;
           if ((unsigned)cx < (unsigned)(WX - 1) && (unsigned)cy < ry) {
             fo[i][v] = (uint32_t)((cy * WX + cx) * 16);
-          } else if (m.rows > 0 && (x0 + 1 < 0 || x0 >= p.Wf || y0 + 1 < 0 || y0 >= p.Hf)) {
+          } else if (x0 + 1 < 0 || x0 >= p.Wf || y0 + 1 < 0 || y0 >= p.Hf) {
             // all four taps outside the image: zero weights on the first cells of the window (landed, finite)
             fo[i][v] = 0u;
             wa[i][v] = BLEND32 ? 0x7fc00000u : 0u; wb[i][v] = 0u;
           } else {
             fo[i][v] = 0x80000000u | (uint32_t)((y0 + 2) << 15) | (uint32_t)(x0 + 2);
-            slow = slow || !m.pad;
+            slow = true;
           }
         }
       }
@@ -360,49 +296,118 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
     // ---- the four chunks of the item; instantiated twice (with / without the global-memory path) so that the
     // common case carries neither its branches nor its registers
     auto chunks = [&](auto check_tag) {
+      constexpr bool CHECK = decltype(check_tag)::value;
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        // reference view: S = r, Q = r^2 (model.py:436-437), read like the source views from the fp16 copy (one
-        // coalesced 16-byte load per thread, issued one chunk ahead; an fp32 NHWC pixel would cost a 128-byte line
-        // per lane)
-        {
-          const uint32_t* R = reinterpret_cast<const uint32_t*>(&rcell);
+        // the reference pixel's cell of this chunk, read like the source views from the fp16 copy (one coalesced
+        // 16-byte load per thread, issued one chunk ahead; an fp32 NHWC pixel would cost a 128-byte line per lane)
+        const uint4 rc = rcell;
+        if (c < 3) rcell = __ldg(rptr + (size_t)(c + 1) * plane_cells);
+        const uint32_t* R = reinterpret_cast<const uint32_t*>(&rc);
+        float2 S[IPT][4], Q[IPT][4];           // fp32 sums (MODE 0, 1)
+        __half2 S2[IPT][4], Q2[IPT][4];        // packed fp16 sums (MODE 2)
+        if (BLEND32) {
+          // S = r, Q = r^2 (model.py:436-437)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float2 f = __half22float2(as_h2(R[k]));
 #pragma unroll
             for (int i = 0; i < IPT; ++i) { S[i][k] = f; Q[i][k] = fmul2(f, f); }
           }
-          if (c < 3) rcell = __ldg(p.feats16 + (size_t)(c + 1) * plane_cells + (size_t)yc * p.Wf + xc);
         }
         if (c > 0) mbar_wait(&bar_full[stage], round & 1u);
-        if (!(p.dbg & 2)) blend(check_tag, c, ring_u32 + (uint32_t)(stage * stage_bytes));
+        const uint32_t sbase = ring_u32 + (uint32_t)(stage * stage_bytes);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) {
+            uint4 ta, tb, tc4, td;
+            const uint32_t o = fo[i][v];
+            if (!CHECK || !(o & 0x80000000u)) {
+              const uint32_t a = sbase + (uint32_t)(v * kViewBytes) + o;
+              ta = lds128(a); tb = lds128(a + 16); tc4 = lds128(a + kRowBytes); td = lds128(a + kRowBytes + 16);
+            } else {
+              // footprint outside the staged window: the same taps from global memory, zero outside the image
+              const int x0 = (int)(o & 0x7fffu) - 2, y0 = (int)((o >> 15) & 0xffffu) - 2;
+              const uint4* img = p.feats16 + ((size_t)(v + 1) * 4 + c) * plane_cells;
+              const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+              const bool vx0 = (unsigned)x0 < (unsigned)p.Wf, vx1 = (unsigned)(x0 + 1) < (unsigned)p.Wf;
+              const bool vy0 = (unsigned)y0 < (unsigned)p.Hf, vy1 = (unsigned)(y0 + 1) < (unsigned)p.Hf;
+              ta = (vy0 && vx0) ? __ldg(img + (size_t)y0 * p.Wf + x0) : z;
+              tb = (vy0 && vx1) ? __ldg(img + (size_t)y0 * p.Wf + x0 + 1) : z;
+              tc4 = (vy1 && vx0) ? __ldg(img + (size_t)(y0 + 1) * p.Wf + x0) : z;
+              td = (vy1 && vx1) ? __ldg(img + (size_t)(y0 + 1) * p.Wf + x0 + 1) : z;
+              if (p.stats && c == 0 && (vx0 || vx1) && (vy0 || vy1)) atomicAdd(p.stats, 1ull);
+            }
+            const uint32_t* A = reinterpret_cast<const uint32_t*>(&ta);
+            const uint32_t* B = reinterpret_cast<const uint32_t*>(&tb);
+            const uint32_t* C = reinterpret_cast<const uint32_t*>(&tc4);
+            const uint32_t* Dd = reinterpret_cast<const uint32_t*>(&td);
+            if (BLEND32) {
+              float wxr = __uint_as_float(wa[i][v]), wyr = __uint_as_float(wb[i][v]);
+              float wxl = 1.0f - wxr, wyl = 1.0f - wyr;
+              if (wa[i][v] == 0x7fc00000u) { wxl = wxr = wyl = wyr = 0.0f; }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 a = __half22float2(as_h2(A[k])), b = __half22float2(as_h2(B[k]));
+                const float2 cc = __half22float2(as_h2(C[k])), d = __half22float2(as_h2(Dd[k]));
+                // the reference's association: wyl * (wxl*p00 + wxr*p01) + wyr * (wxl*p10 + wxr*p11)  (Appendix A.3)
+                float2 w;
+                w.x = wyl * (wxl * a.x + wxr * b.x) + wyr * (wxl * cc.x + wxr * d.x);
+                w.y = wyl * (wxl * a.y + wxr * b.y) + wyr * (wxl * cc.y + wxr * d.y);
+                S[i][k] = fadd2(S[i][k], w);
+                Q[i][k] = ffma2(w, w, Q[i][k]);
+              }
+            } else {
+              const __half2 h0 = as_h2(wa[i][v]), h1 = as_h2(wb[i][v]);
+              const __half2 w00 = __low2half2(h0), w01 = __high2half2(h0), w10 = __low2half2(h1), w11 = __high2half2(h1);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                // d = warped - r: the chain starts from -r (sign bits flipped)
+                const __half2 h = __hfma2(w11, as_h2(Dd[k]), __hfma2(w10, as_h2(C[k]), __hfma2(w01, as_h2(B[k]),
+                                  __hfma2(w00, as_h2(A[k]), as_h2(R[k] ^ 0x80008000u)))));
+                if (ACC16) {
+                  if (v == 0) { S2[i][k] = h; Q2[i][k] = __hmul2(h, h); }
+                  else { S2[i][k] = __hadd2(S2[i][k], h); Q2[i][k] = __hfma2(h, h, Q2[i][k]); }
+                } else {
+                  const float2 w = __half22float2(h);
+                  if (v == 0) { S[i][k] = w; Q[i][k] = fmul2(w, w); }
+                  else { S[i][k] = fadd2(S[i][k], w); Q[i][k] = ffma2(w, w, Q[i][k]); }
+                }
+              }
+            }
+          }
+        }
         // this warp is done with the stage: hand the buffer back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[stage]);
         if (++stage == ns) { stage = 0; ++round; }
         // variance with reciprocal multiplies, two channels per instruction (within an ulp or two of the reference's
-        // divisions, model.py:458-461 / :330-332; this mode stores bf16)
+        // divisions, model.py:458-461 / :330-332; this mode stores bf16).  On differences both op orders of the
+        // reference reduce to Q/n - (S/n)^2.
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
-          if (!live[i]) continue;
           uint4 cell;
           uint32_t* cw = reinterpret_cast<uint32_t*>(&cell);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            float2 s, q;
+            if (ACC16) { s = __half22float2(S2[i][k]); q = __half22float2(Q2[i][k]); }
+            else { s = S[i][k]; q = Q[i][k]; }
             float2 cst;
-            if (p.order == MVSB200_ORDER_MEM) {
-              cst = ffma2(Q[i][k], inv_n2, fmul2(fmul2(S[i][k], S[i][k]), ninv_nn2));
+            if (!BLEND32 || p.order == MVSB200_ORDER_MEM) {
+              cst = ffma2(q, inv_n2, fmul2(fmul2(s, s), ninv_nn2));
             } else {
-              const float2 m = fmul2(S[i][k], inv_n2);
-              cst = ffma2(Q[i][k], inv_n2, fmul2(fmul2(m, m), make_float2(-1.0f, -1.0f)));
+              const float2 m = fmul2(s, inv_n2);
+              cst = ffma2(q, inv_n2, fmul2(fmul2(m, m), make_float2(-1.0f, -1.0f)));
             }
             const __nv_bfloat162 b = __floats2bfloat162_rn(cst.x, cst.y);
             cw[k] = *reinterpret_cast<const uint32_t*>(&b);
           }
-          if (p.cp8 && !(p.dbg & 8))
-            *reinterpret_cast<uint4*>(p.cp8 + ((size_t)cell_cp8[i] + (size_t)c * plane_cells) * 8) = cell;
-          if (p.ps8 && !(p.dbg & 12))
-            *reinterpret_cast<uint4*>(p.ps8 + ((size_t)cell_ps8[i] + (size_t)c * 4 * Hs * Ws) * 8) = cell;
+          if (live[i]) {
+            if (p.cp8) *reinterpret_cast<uint4*>(p.cp8 + (size_t)(cell_cp8[i] + (uint32_t)c * plane_cells) * 8) = cell;
+            if (p.ps8) *reinterpret_cast<uint4*>(p.ps8 + (size_t)(cell_ps8[i] + (uint32_t)c * ps8_chunk) * 8) = cell;
+          }
         }
       }
     };
@@ -428,7 +433,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 using Kernel = void (*)(const Params);
-template <bool B32>
+template <int B32>
 static Kernel pick(int nv) {
   switch (nv) {
     case 1: return cost_volume_window_kernel<1, B32>;
@@ -509,8 +514,7 @@ int launch_cost_volume_window(const float* feats, const float* coef_table, int n
                       2 * kMaxStages * sizeof(uint64_t);
   MVS_CHECK_ARG((size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) < ((size_t)1 << 31) && (size_t)dloc * 4 * hf * wf < ((size_t)1 << 31),
                 "cost_volume(window): volume too large for 32-bit cell indices");
-  p.dbg = tuning().cv_dbg;
-  Kernel k = blend32 ? pick<true>(nv) : pick<false>(nv);
+  Kernel k = blend32 == 1 ? pick<1>(nv) : (blend32 == 2 ? pick<2>(nv) : pick<0>(nv));
   // the attribute is per device and per function: set it every time (cheap, and a set value is only re-set to itself)
   MVS_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.nwork < sm ? p.nwork : sm;

@@ -73,7 +73,7 @@ def test_cfg2_bf16_depth_vs_oracle(oracle_cfg2):
 
 
 # ---------------------------------------------------------------------------------------------- cost volume
-@pytest.mark.parametrize("blend32", [0, 1])
+@pytest.mark.parametrize("blend32", [0, 1, 2])
 def test_product_cost_volume_vs_oracle_small(small_problem, tuning, blend32):
     import oracle as O
     p = small_problem

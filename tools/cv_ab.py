@@ -14,13 +14,9 @@ from mvsnet_b200 import _lib, synthetic  # noqa: E402
 from mvsnet_b200.engine import HotPath  # noqa: E402
 
 VARIANTS = {
-    "window_fp16_blend": {},
+    "window_fp16_blend_fp32_sums": {},
+    "window_fp16_blend_fp16_sums": {"CV_FP32_BLEND": 2},
     "window_fp32_blend": {"CV_FP32_BLEND": 1},
-    "window_no_blend(dbg)": {"CV_DBG": 2},
-    "window_no_ps8(dbg)": {"CV_DBG": 4},
-    "window_no_stores(dbg)": {"CV_DBG": 8},
-    "window_no_blend_no_ps8(dbg)": {"CV_DBG": 6},
-    "window_no_blend_no_stores(dbg)": {"CV_DBG": 10},
     "gather_fp16_taps": {"CV_KERNEL": 1},
     "gather_fp32_taps": {"CV_KERNEL": 1, "CV_FP32_TAPS": 1},
 }

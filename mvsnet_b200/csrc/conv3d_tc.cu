@@ -111,6 +111,11 @@ struct Params {
   int xf_k;                      // cells per transform thread and plane
   int dz_begin[kMaxSpan + 1];    // ops [dz_begin[d], dz_begin[d+1]) read input plane d of the step
   float* rg_out; float rg_start, rg_step;   // fused soft-argmin partials of the last layer (NULL: off)
+  // "rider" (3dconv0_1 + 3dconv1_0 in one pass over the cost volume): a stride-2 conv with the same input is the
+  // stride-1 conv of its filter evaluated at the odd (z, y, x) positions only (TF SAME padding, even extents), so its
+  // n2 output channels ride along as extra MMA columns of the odd output plane of a 2-plane step
+  int n2, Cout2, Ho2, Wo2, Hso2, Wso2;      // rider channels of this launch (0: off), its whole output volume
+  __nv_bfloat16* y2_cp8; __nv_bfloat16* y2_ps8; double* stats2;
   int pdl;                       // programmatic dependent launch: 1 = let the next layer start at CTA start, 2 = at CTA end
   int dbg;                       // development switches (env MVSB200_TC_DBG): 1 no loads, 2 no MMA, 4 no stores
   long long* prof;               // development: per-role cycle counters of CTA 0 (env MVSB200_TC_PROF)
@@ -125,11 +130,36 @@ struct PackParams {
   const float* kernel_tf; uint16_t* out;
   int Cin, Cout, cout_base, cout_n, CP, transposed, nops, zf, master, xfold, dmerge, cw;
   int CinT, CoutT;       // channel counts of kernel_tf itself (<= Cin / Cout: channels padded to whole cells hold zeros)
+  const float* kernel_tf2; int n2, CoutT2;   // rider: filter [3,3,3,CinT,CoutT2] of the stride-2 conv, n2 columns per kw
   PackOp ops[kMaxOps];   // per-op images: tap = kd*9+kh*3+kw per K half (-1 = zero half);
                          // master images: tap = kh*3+kw (kd comes from the row group), one per (kh,kw,pair)
 };
 
+// Rider launch (3dconv0_1 + 3dconv1_0): image of an op = [2 halves][CP rows][8]; row n = column n of the step:
+// [even plane: kw x n1 channels of the stride-1 filter][odd plane: kw x (n1 channels of the stride-1 filter | n2 of the
+// stride-2 filter)]; the op's tap code is dz*9 + kh*3 of its input plane dz (kw lives in the column, kd = dz - j).
+__device__ __forceinline__ void pack_rider(const PackParams& p) {
+  const int n1 = p.cout_n, g0 = 3 * n1, g1 = 3 * (n1 + p.n2);
+  const int total = p.nops * 2 * p.CP * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k8 = i & 7, n = (i >> 3) % p.CP, half = (i / (8 * p.CP)) & 1, op = i / (16 * p.CP);
+    const int ci = p.ops[op].cbase[half] + k8;
+    int j = 0, kw = 0, c = -1;
+    if (n < g0) { kw = n / n1; c = n - kw * n1; }
+    else if (n < g0 + g1) { j = 1; const int r = n - g0; kw = r / (n1 + p.n2); c = r - kw * (n1 + p.n2); }
+    const int tap = p.ops[op].tap[half] + kw - 9 * j;
+    float w = 0.0f;
+    if (c >= 0 && tap >= 0 && tap < 27 && ci < p.CinT) {
+      if (c < n1) { if (p.cout_base + c < p.CoutT) w = p.kernel_tf[((size_t)tap * p.CinT + ci) * p.CoutT + p.cout_base + c]; }
+      else if (c - n1 < p.CoutT2) w = p.kernel_tf2[((size_t)tap * p.CinT + ci) * p.CoutT2 + (c - n1)];
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    p.out[i] = *reinterpret_cast<const uint16_t*>(&h);
+  }
+}
+
 __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
+  if (p.n2) { pack_rider(p); return; }
   if (p.dmerge) {
     // transposed conv, classes merged: image = [2 halves][8 classes x cw rows][8]; the op's tap code is its input
     // shift (bit 2: z-1, bit 1: y-1, bit 0: x-1); class (pz,py,px) takes filter tap k = parity + 2 on a shifted axis
@@ -253,6 +283,41 @@ __device__ __forceinline__ void flush_stats(const Params& p, float (&sum)[NV], f
   }
 }
 
+// Rider launch: three groups of four epilogue warps.  Groups 0 and 1 hold the stride-1 layer's cout_n (8) channels of
+// the even / odd planes, group 2 the rider's n2 (<= 16) channels; each group reduces in its own 128 floats of shared
+// memory behind its own named barrier.
+template <int N2>
+__device__ __forceinline__ void flush_stats_rider(const Params& p, float (&sum)[8], float (&sq)[8], float (&sum2)[N2],
+                                                  float (&sq2)[N2], int grp, float* s_red, int ewarp, int lane) {
+  const int ncol = grp == 2 ? p.n2 : p.cout_n;
+  if (lane < 16) { s_red[(ewarp * 2 + 0) * 16 + lane] = 0.0f; s_red[(ewarp * 2 + 1) * 16 + lane] = 0.0f; }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8 + N2; ++k) {
+    float s = k < 8 ? sum[k < 8 ? k : 0] : sum2[k < 8 ? 0 : (k - 8) % N2];
+    float q = k < 8 ? sq[k < 8 ? k : 0] : sq2[k < 8 ? 0 : (k - 8) % N2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0 && k < ncol) { s_red[(ewarp * 2 + 0) * 16 + k] = s; s_red[(ewarp * 2 + 1) * 16 + k] = q; }
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+  if (ewarp == 0 && lane < ncol) {
+    float s = 0.0f, q = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { s += s_red[(w * 2 + 0) * 16 + lane]; q += s_red[(w * 2 + 1) * 16 + lane]; }
+    double* st = (grp == 2 ? p.stats2 : p.stats);
+    if (st) {
+      st += (size_t)(blockIdx.x % p.stats_reps) * p.stats_rep_stride;
+      const int cbase = grp == 2 ? 0 : p.cout_base, ctot = grp == 2 ? p.Cout2 : p.Cout;
+      atomicAdd(st + cbase + lane, (double)s);
+      atomicAdd(st + ctot + cbase + lane, (double)q);
+    }
+  }
+}
+
 // One 16-byte cell of the chunk-planar (cell index inside the plane, which = 0) or parity-split (which = 1) output;
 // boundary planes go to the neighbouring slabs' halo planes as well (peer memory over NVLink).
 template <bool PEER>
@@ -288,12 +353,13 @@ __device__ __forceinline__ void issue_ops(const uint4* s_ops, int ob, int oe, ui
 // XFC = 0: classic epilogue (CP accumulator columns per row block); XFC = 1 / 2 / 4: x-fold epilogue for launches of
 // 8 * XFC output channels (Cout = 1 uses XFC = 1)
 // FLAGS bit 0: D-slab mode over peer memory (flag wait in the prologue, boundary planes mirrored to the neighbours);
-// bit 1: the single-channel layer (Cout = 1, fp32 output, optional fused soft-argmin).  Separate instantiations, so
-// that neither costs the common path registers or instructions.
+// bit 1: the single-channel layer (Cout = 1, fp32 output, optional fused soft-argmin); bit 2: the rider launch
+// (3dconv0_1 with 3dconv1_0's channels riding on the odd planes; XFC = 2: up to 16 channels of statistics per warp).  Separate
+// instantiations, so that none of them costs the common path registers or instructions.
 template <int CP, int XFC, int FLAGS>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_constant__ Params p) {
   constexpr bool XF = XFC != 0;
-  constexpr bool PEER = (FLAGS & 1) != 0, C1 = (FLAGS & 2) != 0;
+  constexpr bool PEER = (FLAGS & 1) != 0, C1 = (FLAGS & 2) != 0, RIDER = (FLAGS & 4) != 0;
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [B image][R slots][skip slots][op table][plane op ranges][barriers][tmem ptr]
   unsigned char* s_b = smem;
@@ -347,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.R; ++i) { mbar_init(&bar_land[i], 1); mbar_init(&bar_ready[i], kXfWarps); mbar_init(&bar_empty[i], 1); }
     for (int i = 0; i < kMaxSkipRing; ++i) { mbar_init(&bar_sland[i], 1); mbar_init(&bar_sempty[i], kXfWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], RIDER ? kEpiWarps + kXfWarps : kEpiWarps); }
     mbar_init(bar_b, 1);
     fence_mbar_init();
   }
@@ -472,7 +538,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         }
       }
       if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[9] = clock64() - pw_t0; p.prof[10] = pw_empty; p.prof[11] = pw_sempty; p.prof[5 + 11] = pw_issue; }
-    } else if (warp >= kXfWarp0 && warp < kProdWarp) {
+    } else if (!RIDER && warp >= kXfWarp0 && warp < kProdWarp) {
       // ===================================== transform =====================================
       if (p.transform) {
         const int xt = threadIdx.x - kXfWarp0 * 32;
@@ -642,13 +708,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     } else {
       // ===================================== epilogue =====================================
       if (XF) {
+        // rider launch: the input needs no transform, so the 8 transform warps are epilogue warps too.  Warp w reads
+        // TMEM sub-partition w % 4; group w / 4 takes one kind of item: 0 = stride-1 layer, even plane, 1 = stride-1
+        // layer, odd plane, 2 = the rider's chunks (odd plane) -- two items per row block each, 8 / 8 / 16 channels of
+        // statistics, so every group can keep its next TMEM load in flight.
+        const int ewarp = RIDER ? (warp & 3) : warp, egrp = RIDER ? (warp >> 2) : 0;
         // x-fold: columns [j][kw][co]; output (yy, xx-1) = P[kw=0] of lane-1 + P[kw=1] + P[kw=2] of lane+1.
         // A warp's 32 TMEM lanes are 32 / PX whole tile rows, so the shuffles (width PX) never leave a row; the
         // halo columns xx = 0 and PX-1 only supply partial sums.
-        constexpr int NST = XF ? XFC * 8 : 8;
-        float sum[NST], sq[NST];
+        // (rider launch: the rider's second chunk has arrays of its own -- with one array the compiler turned the
+        // chunk selection into a run-time index and moved the statistics to local memory)
+        constexpr int NST = XF ? (RIDER ? 8 : XFC * 8) : 8;
+        float sum[NST], sq[NST], sum2[RIDER ? 8 : 1], sq2[RIDER ? 8 : 1];
 #pragma unroll
         for (int k = 0; k < NST; ++k) { sum[k] = 0.0f; sq[k] = 0.0f; }
+#pragma unroll
+        for (int k = 0; k < (RIDER ? 8 : 1); ++k) { sum2[k] = 0.0f; sq2[k] = 0.0f; }
         const int grp = 3 * p.cout_n, nchunk = p.cout_n >> 3;
         const size_t zpitch = (size_t)p.Ho * p.Wo;
         const int chunk0 = p.cout_base >> 3;
@@ -674,11 +749,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
 #pragma unroll
             for (int b = 0; b < kMaxMB; ++b) {
               if (b >= p.MB) break;
-              const int m = b * 128 + warp * 32 + lane;
+              const int m = b * 128 + ewarp * 32 + lane;
               const int yy = m >> px_shift, xx = m & (p.PX - 1);
               const bool valid = xx >= 1 && xx <= TXe && yy < TYe && !(p.dbg & 4);
               const int oy = y0 + yy, ox = x0 + xx - 1;
-              const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((stage * p.MB + b) * p.NB);
+              const uint32_t tb = tmem_base + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)((stage * p.MB + b) * p.NB);
               uint32_t r[16];
               tmem_ld16(tb, r);
               tmem_ld_wait();
@@ -716,32 +791,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           if (!C1) {
             // items (row block, output plane j, 8-channel chunk): the three TMEM loads of the next item are in flight
             // while this one is shuffled, reduced and stored
-            const int nitems = p.MB * p.zf * nchunk;
-            uint32_t r0[24], r1[24];
-            const uint32_t tstage = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(stage * p.MB * p.NB);
+            // rider launch: plane j = 0 (even) has the stride-1 layer's chunk only, plane j = 1 (odd) that chunk and
+            // the rider's n2 / 8 chunks; its columns start after the 3 * cout_n columns of plane 0
+            const int nrid = p.n2 >> 3;
+            const int nitems = RIDER ? (egrp == 2 ? p.MB * nrid : p.MB) : p.MB * p.zf * nchunk;
+            uint32_t r[24];
+            const uint32_t tstage = tmem_base + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)(stage * p.MB * p.NB);
             auto issue = [&](int b, int j, int ck, uint32_t* r) {
+              const uint32_t kws = RIDER ? (uint32_t)(j ? p.cout_n + p.n2 : p.cout_n) : (uint32_t)p.cout_n;
               const uint32_t col = tstage + (uint32_t)(b * p.NB + j * grp + ck * 8);
               tmem_ld8(col, r);
-              tmem_ld8(col + (uint32_t)p.cout_n, r + 8);
-              tmem_ld8(col + 2u * (uint32_t)p.cout_n, r + 16);
+              tmem_ld8(col + kws, r + 8);
+              tmem_ld8(col + 2u * kws, r + 16);
             };
-            // (with 32 channels of statistics the registers do not allow a load in flight: the asynchronous TMEM load
-            // must not be caught by a spill, so that variant loads, waits, then works)
-            constexpr bool kPrefetch = XFC < 4;
-            int b = 0, j = 0, ck = 0;                 // current item; (nb, nj, nck) = the next one
-            if (kPrefetch) issue(0, 0, 0, r0);
-            for (int it0 = 0; it0 < nitems; it0 += 2) {
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const int it = it0 + half;
-                if (it >= nitems) break;
-                uint32_t* r = half ? r1 : r0;
+            // ONE register buffer: the three partial sums of an item are folded into v[8] by the shuffles first, then
+            // the next item's TMEM loads are issued into the same registers and fly while this item is reduced, packed
+            // and stored (a second buffer cost 24 registers and pushed the statistics into local memory)
+            int b = 0, j = RIDER && egrp > 0 ? 1 : 0, ck = RIDER && egrp == 2 ? 1 : 0;      // current item; (nb, nj, nck) = the next one
+            if (nitems > 0) issue(0, j, ck, r);
+            for (int it = 0; it < nitems; ++it) {
+              {
                 int nck = ck + 1, nj = j, nb = b;
-                if (nck == nchunk) { nck = 0; if (++nj == p.zf) { nj = 0; ++nb; } }
-                if (!kPrefetch) issue(b, j, ck, r);
+                if (RIDER) {
+                  if (egrp < 2) { nck = 0; ++nb; }
+                  else if (nck > nrid) { nck = 1; ++nb; }
+                } else if (nck == nchunk) { nck = 0; if (++nj == p.zf) { nj = 0; ++nb; } }
                 tmem_ld_wait();
-                if (kPrefetch && it + 1 < nitems) issue(nb, nj, nck, half ? r0 : r1);
-                const int m = b * 128 + warp * 32 + lane;
+                const int m = b * 128 + ewarp * 32 + lane;
                 const int yy = m >> px_shift, xx = m & (p.PX - 1);
                 const bool valid = xx >= 1 && xx <= TXe && yy < TYe && !(p.dbg & 4);
                 const int oy = y0 + yy, ox = x0 + xx - 1;
@@ -752,11 +828,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(r[16 + k]), 1, p.PX);
                   v[k] = lft + __uint_as_float(r[8 + k]) + rgt;
                 }
-                if (valid && j < nlive) {
+                if (it + 1 < nitems) issue(nb, nj, nck, r);
+                if (RIDER && ck > 0) {
+                  // rider chunk ck - 1 (plane j = 1 only): the stride-2 conv's output (oz, oy, ox) >> 1 lives at the odd
+                  // positions; its own statistics (registers 8 ..) and its own output tensors
+                  if (valid && (oy & ox & 1)) {
+                    if (RIDER) {
+                      if (ck == 1) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { sum[k] += v[k]; sq[k] = fmaf(v[k], v[k], sq[k]); }
+                      } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { sum2[k] += v[k]; sq2[k] = fmaf(v[k], v[k], sq2[k]); }
+                      }
+                    }
+                    uint4 pk;
+                    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+                    pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+                    const int oz2 = (mz + 1) >> 1, oy2 = oy >> 1, ox2 = ox >> 1;
+                    const size_t zc = (size_t)oz2 * (p.Cout2 >> 3) + (ck - 1);
+                    if (p.y2_cp8 && !(p.dbg & 16))
+                      *reinterpret_cast<uint4*>(p.y2_cp8 + ((zc * p.Ho2 + oy2) * p.Wo2 + ox2) * 8) = pk;
+                    if (p.y2_ps8 && !(p.dbg & 16))
+                      *reinterpret_cast<uint4*>(p.y2_ps8 + ((((zc * 4 + (oy2 & 1) * 2 + (ox2 & 1)) * p.Hso2) + (oy2 >> 1)) * p.Wso2 +
+                                                            (ox2 >> 1)) * 8) = pk;
+                  }
+                } else if (valid && j < nlive) {
                   // channel chunk ck of this launch: statistics registers are indexed at compile time
 #pragma unroll
-                  for (int c4 = 0; c4 < (XF ? XFC : 1); ++c4)
-                    if (c4 == ck) {
+                  for (int c4 = 0; c4 < (XF ? (RIDER ? 1 : XFC) : 1); ++c4)
+                    if (c4 == ck && !(p.dbg & 64)) {
 #pragma unroll
                       for (int k = 0; k < 8; ++k) { sum[c4 * 8 + k] += v[k]; sq[c4 * 8 + k] = fmaf(v[k], v[k], sq[c4 * 8 + k]); }
                     }
@@ -770,8 +871,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                     uint4 pk;
                     pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
                     pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-                    if (p.y_cp8) store_cell<PEER>(p, 0, oz, chunk0 + ck, zpitch, (size_t)oy * p.Wo + ox, pk);
-                    if (p.y_ps8) {
+                    if (p.y_cp8 && !(p.dbg & 32)) store_cell<PEER>(p, 0, oz, chunk0 + ck, zpitch, (size_t)oy * p.Wo + ox, pk);
+                    if (p.y_ps8 && !(p.dbg & 32)) {
                       const size_t pcell = ((size_t)((oy & 1) * 2 + (ox & 1)) * p.Hso + (oy >> 1)) * p.Wso + (ox >> 1);
                       store_cell<PEER>(p, 1, oz, chunk0 + ck, 4 * (size_t)p.Hso * p.Wso, pcell, pk);
                     }
@@ -800,7 +901,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           }
         }
         if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
-        if (p.stats && !(p.dbg & 8)) flush_stats<NST>(p, sum, sq, p.cout_n, false, s_red, warp, lane);
+        if constexpr (RIDER) {
+          flush_stats_rider(p, sum, sq, sum2, sq2, egrp, s_red + egrp * 128, ewarp, lane);
+        } else {
+          if (p.stats && !(p.dbg & 8)) flush_stats<NST>(p, sum, sq, p.cout_n, false, s_red, warp, lane);
+        }
       } else {
       float sum[CP], sq[CP];
 #pragma unroll
@@ -1055,10 +1160,14 @@ double mma_clk(int n) { const double a = 32.0 + n / 4.0, b = n / 2.0; return (a 
 
 // Build the op table for one (mode, Cin, cout slice) and the slot geometry for tile (TX, TY), z-fold zf.
 bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base, int cout_n, int TX, int TY, int zf,
-                bool xfold, bool has_skip, bool transform, Plan* pl) {
+                bool xfold, bool has_skip, bool transform, int n2, Plan* pl) {
   Params& c = pl->cp;
   PackParams& pk = pl->pp;
   if (mode != MODE_CONV1) zf = 1;
+  // rider launch: x-folded stride-1 conv, steps of one even and one odd output plane, even extents (the stride-2 conv's
+  // SAME padding then has nothing before the volume: its outputs sit at the odd positions)
+  if (n2 && (mode != MODE_CONV1 || !xfold || zf != 2 || cin < 16 || (n2 & 7) || (cout_n & 7) || ((D | H | W) & 1) || has_skip ||
+             transform)) return false;
   if (xfold) {
     // x-fold: the padded tile is 8 / 16 / 32 cells wide and fills whole 128-row blocks
     if (mode != MODE_CONV1 || !(cout_n == 1 || cout_n % 8 == 0)) return false;
@@ -1066,10 +1175,12 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
     if ((px != 8 && px != 16 && px != 32) || (TY * px) % 128 != 0) return false;
   }
   if (zf > 1 && !xfold && ((cout_n & (cout_n - 1)) != 0)) return false;     // the epilogue splits folded columns by shift
-  const int kwn = xfold ? 3 : 1, grp = kwn * cout_n, ncols = zf * grp;
+  const int kwn = xfold ? 3 : 1, grp = kwn * cout_n, ncols = n2 ? grp + 3 * (cout_n + n2) : zf * grp;
   if (ncols > (xfold ? 128 : 32) || zf + 2 > kMaxSpan) return false;
   const int CP = xfold ? (ncols + 15) / 16 * 16 : (ncols <= 16 ? 16 : 32);
-  const bool master = zf > 1 && ncols == CP && cin >= 16;
+  const bool master = zf > 1 && ncols == CP && cin >= 16 && !n2;
+  c.n2 = n2; c.Cout2 = n2; c.Ho2 = H / 2; c.Wo2 = W / 2; c.Hso2 = (H / 2 + 1) / 2; c.Wso2 = (W / 2 + 1) / 2;
+  c.y2_cp8 = nullptr; c.y2_ps8 = nullptr; c.stats2 = nullptr;
   c.CP = CP;
   c.zf = zf;
   c.xfold = xfold ? 1 : 0;
@@ -1255,6 +1366,7 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   pk.zf = zf; pk.master = master ? 1 : 0; pk.xfold = xfold ? 1 : 0; pk.dmerge = c.dmerge; pk.cw = c.cw;
   pk.nops = nimg; pk.Cin = cin; pk.Cout = cout; pk.cout_base = cout_base; pk.cout_n = cout_n; pk.CP = CP;
   pk.CinT = cin; pk.CoutT = cout;
+  pk.kernel_tf2 = nullptr; pk.n2 = n2; pk.CoutT2 = n2;
   pk.transposed = mode == MODE_DECONV;
   const size_t fixed = (size_t)c.b_bytes + (size_t)c.ring_pad + (size_t)kMaxOps * 16 + 32 + 2048 + (3 * kMaxRing + 2 * kMaxSkipRing + 5) * sizeof(uint64_t) + 16;
   c.RS = has_skip ? kMinSkipRing : 0;
@@ -1287,7 +1399,8 @@ double estimate_clk(const Params& c, int sm_count) {
   const double plane_bytes = (double)c.nsub * c.NCH * c.RY * c.PX * 16.0 * (c.has_skip ? 2.0 : 1.0);
   const double load = plane_bytes * c.zstep / 18.0;                       // ~HBM share of one SM, B/clk
   const int ncls = c.mode == MODE_DECONV ? 8 : 1;
-  const double epi = c.xfold ? (c.cout_n == 1 ? (double)c.MB * 300.0 : (double)c.MB * c.zf * (c.cout_n / 8) * 420.0)
+  const double epi = c.xfold ? (c.cout_n == 1 ? (double)c.MB * 300.0
+                                              : (double)c.MB * (c.n2 ? 2 : c.zf * (c.cout_n / 8)) * 420.0)      // rider: three warp groups side by side
                              : (double)c.MB * ncls * (c.CP * 4.0 * 128.0 / 110.0 + 12.0 * c.CP + 80.0);
   const double tma_issue = (c.one_box ? 1.0 : (double)c.nsub * c.NCH) * (c.has_skip ? 2.0 : 1.0) * 250.0 * c.zstep;
   const double xf = c.transform ? (double)c.xf_k * c.zstep * (c.has_skip ? 70.0 : 45.0) : 0.0;
@@ -1306,7 +1419,7 @@ double estimate_clk(const Params& c, int sm_count) {
   return waves * cta;
 }
 
-std::map<std::array<int, 14>, Plan> g_plan_cache;
+std::map<std::array<int, 15>, Plan> g_plan_cache;
 std::mutex g_plan_mutex;
 
 PFN_encodeTiled get_encode() {
@@ -1343,7 +1456,7 @@ using namespace tc;
 
 // Plan (tile, folds, z split, op table) of one launch: output channels [cb, cb+cn) of a layer.  Cached per shape.
 static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, int cn, bool has_skip, bool transform,
-                      int sm_count, Plan* out, int* dbg_out) {
+                      int sm_count, Plan* out, int* dbg_out, int n2 = 0) {
   // tuning / debugging switches (mvsb200_set_tuning); TC_LAYER="cin,cout,mode" restricts them to one layer shape
   const Tuning& tn = tuning();
   const bool mine = !tn.tc_layer_set || (tn.tc_layer[0] == cin && tn.tc_layer[1] == cout && tn.tc_layer[2] == mode);
@@ -1354,8 +1467,8 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
   const int dbg_forced = mine ? tn.tc_dbg : 0;
     const int Mx = mode == MODE_CONV2 ? ceil_div(W, 2) : W, My = mode == MODE_CONV2 ? ceil_div(H, 2) : H,
               Mz = mode == MODE_CONV2 ? ceil_div(D, 2) : D;
-    const std::array<int, 14> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_forced > 0 ? zf_forced : 0,
-                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0)};
+    const std::array<int, 15> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_forced > 0 ? zf_forced : 0,
+                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0), n2};
     Plan best;
     bool found = false;
     {
@@ -1368,8 +1481,9 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
       for (int zi = 0; zi < 3; ++zi) {
         const int zf = zf_cands[zi];
         if (mode != MODE_CONV1 && zf != 1) continue;
-        if (zf_forced > 0 && zf_forced != zf && mode == MODE_CONV1) continue;
+        if (zf_forced > 0 && zf_forced != zf && mode == MODE_CONV1 && !n2) continue;
         if (zf > 1 && zf_forced <= 0 && Mz < 2 * zf) continue;
+        if (n2 && zf != 2) continue;
         for (int xf = (mode == MODE_CONV1 && !no_xfold) ? 1 : 0; xf >= 0; --xf)
         for (int TX = 4; TX <= 30; ++TX) {
           if (xf && TX != 6 && TX != 14 && TX != 30) continue;
@@ -1379,7 +1493,7 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
           for (int TY = 1; TY <= 64 && (TY <= My || xf); ++TY) {
             if (force_ty && TY != (force_ty < My || xf ? force_ty : My)) continue;
             Plan pl;
-            if (!build_plan(mode, D, H, W, cin, cout, cb, cn, tx_eff, TY, zf, xf != 0, has_skip, transform, &pl)) continue;
+            if (!build_plan(mode, D, H, W, cin, cout, cb, cn, tx_eff, TY, zf, xf != 0, has_skip, transform, n2, &pl)) continue;
             if (pl.smem > kSmemBudget) continue;
             Params& c = pl.cp;
             const int tiles = c.tiles_x * c.tiles_y;
@@ -1424,6 +1538,7 @@ struct PackAll { int n; PackParams job[kMaxPackJobs]; };
 
 __global__ void pack_all_kernel(const __grid_constant__ PackAll a) {
   const PackParams& p = a.job[blockIdx.y];
+  if (p.n2) { pack_rider(p); return; }
   if (p.dmerge) {
     // transposed conv, classes merged: image = [2 halves][8 classes x cw rows][8]; the op's tap code is its input
     // shift (bit 2: z-1, bit 1: y-1, bit 0: x-1); class (pz,py,px) takes filter tap k = parity + 2 on a shifted axis
@@ -1495,7 +1610,7 @@ int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStr
       const int cn = jb.cout - cb < 32 ? jb.cout - cb : 32;
       Plan pl;
       if (!find_plan(mode, jb.D, jb.H, jb.W, jb.cin, jb.cout, cb, cn, jb.has_skip != 0, jb.transform != 0, sm_count, &pl,
-                     nullptr)) {
+                     nullptr, jb.cout2)) {
         set_error("conv3d(bf16/tcgen05): no tile fits (Cin=%d Cout=%d mode=%d)", jb.cin, jb.cout, mode);
         return MVSB200_ERR_UNSUPPORTED;
       }
@@ -1504,6 +1619,10 @@ int conv3d_tc_pack_all(const TcPackJob* jobs, int njobs, void* dst_base, cudaStr
       a.job[a.n].kernel_tf = jb.kernel_tf;
       if (jb.cin_true > 0) a.job[a.n].CinT = jb.cin_true;
       if (jb.cout_true > 0) a.job[a.n].CoutT = jb.cout_true;
+      if (jb.cout2 > 0) {
+        a.job[a.n].kernel_tf2 = jb.kernel_tf2;
+        a.job[a.n].CoutT2 = jb.cout2_true > 0 ? jb.cout2_true : jb.cout2;
+      }
       a.job[a.n].out = (uint16_t*)((unsigned char*)dst_base + (size_t)slot * conv3d_tc_pack_slot_bytes());
       ++a.n;
     }
@@ -1522,7 +1641,8 @@ static TcKernel kernel_variant(int k, bool peer_mode) {
     case 2: return peer_mode ? conv3d_tc_kernel<32, 1, 1> : conv3d_tc_kernel<32, 1, 0>;
     case 3: return peer_mode ? conv3d_tc_kernel<32, 2, 1> : conv3d_tc_kernel<32, 2, 0>;
     case 4: return peer_mode ? conv3d_tc_kernel<32, 4, 1> : conv3d_tc_kernel<32, 4, 0>;
-    default: return peer_mode ? conv3d_tc_kernel<32, 1, 3> : conv3d_tc_kernel<32, 1, 2>;
+    case 5: return peer_mode ? conv3d_tc_kernel<32, 1, 3> : conv3d_tc_kernel<32, 1, 2>;
+    default: return conv3d_tc_kernel<32, 2, 4>;      // rider launch (no peer-memory flavour)
   }
 }
 
@@ -1533,7 +1653,11 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
                      const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
                      int stats_rep_stride, const TcSlab* slab, const TcPeer* peer, TcRegress* regress,
-                     cudaStream_t s) {
+                     cudaStream_t s, const TcRider* rider) {
+  if (rider && (peer || (slab && slab->halo) || transposed || stride != 1 || cout > 32 || y_f32 || skip || xs || (x_bn && x_bn->stats))) {
+    set_error("conv3d(bf16/tcgen05): a rider needs a plain stride-1 conv on a raw input, one launch, one GPU");
+    return MVSB200_ERR_UNSUPPORTED;
+  }
   if (cin != 8 && cin != 16 && cin != 32 && cin != 64) {
     set_error("conv3d(bf16/tcgen05): Cin=%d unsupported (need 8, 16, 32 or 64)", cin);
     return MVSB200_ERR_UNSUPPORTED;
@@ -1558,7 +1682,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
   static std::atomic<uint64_t> attr_done{0};
   if (!(attr_done.load(std::memory_order_acquire) >> (dev & 63) & 1u)) {
     for (int peer_mode = 0; peer_mode < 2; ++peer_mode)
-      for (int k = 0; k < 6; ++k)
+      for (int k = 0; k < 7; ++k)
         MVS_CUDA(cudaFuncSetAttribute((const void*)kernel_variant(k, peer_mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemBudget));
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
@@ -1569,7 +1693,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     const int cn = cout - cb < 32 ? cout - cb : 32;
     Plan best;
     int dbg_flags = 0;
-    if (!find_plan(mode, D, H, W, cin, cout, cb, cn, has_skip, transform, sm_count, &best, &dbg_flags)) {
+    if (!find_plan(mode, D, H, W, cin, cout, cb, cn, has_skip, transform, sm_count, &best, &dbg_flags, rider ? rider->cout2 : 0)) {
       set_error("conv3d(bf16/tcgen05): no tile fits (Cin=%d Cout=%d mode=%d)", cin, cout, mode);
       return MVSB200_ERR_UNSUPPORTED;
     }
@@ -1594,6 +1718,10 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       }
     }
     c.y_cp8 = (__nv_bfloat16*)y_cp8; c.y_ps8 = (__nv_bfloat16*)y_ps8; c.y_f32 = y_f32; c.stats = stats;
+    if (rider) {
+      c.y2_cp8 = (__nv_bfloat16*)rider->y2_cp8; c.y2_ps8 = (__nv_bfloat16*)rider->y2_ps8; c.stats2 = rider->stats2;
+      best.pp.kernel_tf2 = rider->kernel_tf2;
+    }
     // D-slab mode: the tensors hold D + 2 planes (halo before / after), local plane l is extended plane l + 1
     const int Dt = slab && slab->halo ? D + 2 : D;
     c.zv_lo = 0; c.zv_hi = D;
@@ -1611,9 +1739,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       c.dbg = dbg_flags;
       if (tuning().tc_verbose)
         fprintf(stderr, "[tc] mode=%d Cin=%d Cout=%d(+%d) tile %dx%d PX=%d RY=%d MB=%d N=%d R=%d zf=%d xf=%d zsplit=%d grid=%d smem=%zu "
-                "RS=%d nops=%d b=%dB xf=%d/%d est=%.0f clk\n",
+                "RS=%d nops=%d b=%dB xf=%d/%d est=%.0f clk rider=%d\n",
                 mode, cin, cn, cb, c.TX, c.TY, c.PX, c.RY, c.MB, c.CP, c.R, c.zf, c.xfold, c.zsplit, c.tiles_x * c.tiles_y * c.zsplit,
-                best.smem, c.RS, c.nops, c.b_bytes, c.transform, c.xf_k, best.est_clk);
+                best.smem, c.RS, c.nops, c.b_bytes, c.transform, c.xf_k, best.est_clk, c.n2);
     }
     if (prepacked) {
       // weights were packed for the whole network in one launch (conv3d_tc_pack_all), one slot per launch
@@ -1648,7 +1776,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     cfg.attrs = attr; cfg.numAttrs = c.pdl ? 1 : 0;
     cudaError_t lerr = cudaSuccess;
     // instantiation: epilogue shape x (peer-memory D-slab mode or not)
-    const int variant = c.xfold ? (c.cout_n == 1 ? 5 : c.cout_n <= 8 ? 2 : c.cout_n <= 16 ? 3 : 4) : (c.CP == 16 ? 0 : 1);
+    const int variant = c.n2 ? 6 : c.xfold ? (c.cout_n == 1 ? 5 : c.cout_n <= 8 ? 2 : c.cout_n <= 16 ? 3 : 4) : (c.CP == 16 ? 0 : 1);
     auto launch = [&]() { lerr = cudaLaunchKernelEx(&cfg, kernel_variant(variant, peer != nullptr), c); };
     launch();
     if (lerr != cudaSuccess) {
@@ -1815,7 +1943,7 @@ int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, cons
   else if (via_f32) MVS_CUDA(tmp.alloc((void**)&yf, (size_t)Do * Ho * Wo * cout * sizeof(float)));
   else MVS_CUDA(tmp.alloc(&yp, planar_bytes(Do, Ho, Wo, cout, 0)));
   rc = launch_conv3d_tc(xp, xs, xb, kp, ss, sb, kernel_tf, D, H, W, cin, cout, stride, transposed, yp, nullptr, yf, stats,
-                        scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, nullptr, nullptr, s);
+                        scratch, nullptr, nullptr, nullptr, 1, 0, nullptr, nullptr, nullptr, s, nullptr);
   if (rc) return rc;
   if (yp) rc = launch_planar_to_ndhwc(yp, Do, Ho, Wo, cout, y, s);
   else if (via_f32) rc = launch_f32_to_bf16(yf, (size_t)Do * Ho * Wo * cout, y, s);

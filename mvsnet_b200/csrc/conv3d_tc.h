@@ -34,7 +34,15 @@ struct TcRegress { float* partial; float start, step; int fused; };
 // One job per layer of a network for conv3d_tc_pack_all; its launches (output-channel slices of 32) take
 // consecutive weight slots starting at slot0.
 // cin_true / cout_true > 0: channel counts of kernel_tf itself when the layer runs with channels padded to whole cells.
-struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0, cin_true, cout_true; };
+// kernel_tf2 / cout2 (> 0): the stride-2 conv riding on this stride-1 conv's launch (TcRider).
+struct TcPackJob { const float* kernel_tf; int D, H, W, cin, cout, stride, transposed, has_skip, transform, slot0, cin_true, cout_true;
+                   const float* kernel_tf2; int cout2, cout2_true; };
+
+// Rider of a stride-1 conv on a raw input (3dconv0_1 + 3dconv1_0: one pass over the cost volume): the stride-2 conv
+// with filter kernel_tf2 [3,3,3,cin,cout2] on the same input is the stride-1 conv of that filter at the odd (z, y, x)
+// positions (TF SAME padding, even extents); its raw output goes to y2_cp8 / y2_ps8 ([D/2,H/2,W/2,cout2] in the planar
+// layouts), its statistics to stats2.
+struct TcRider { const float* kernel_tf2; int cout2; void* y2_cp8; void* y2_ps8; double* stats2; };
 
 // x: CP8 for stride-1 convs and transposed convs, PS8 for stride-2 convs.  skip: CP8.
 // Outputs: y_cp8 and / or y_ps8 (bf16, Cout % 8 == 0), or y_f32 (NDHWC fp32, any Cout).
@@ -43,7 +51,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
                      int transposed, void* y_cp8, void* y_ps8, float* y_f32, double* stats, void* scratch,
                      const TcBnSrc* x_bn, const TcBnSrc* s_bn, const void* prepacked, int stats_reps,
                      int stats_rep_stride, const TcSlab* slab, const TcPeer* peer, TcRegress* regress,
-                     cudaStream_t s);
+                     cudaStream_t s, const TcRider* rider = nullptr);
 int launch_conv3d_tc_ndhwc(const void* x, const float* xs, const float* xb, const void* skip, const float* ss,
                            const float* sb, const float* kernel_tf, int D, int H, int W, int cin, int cout,
                            int stride, int transposed, void* y, int y_dtype, double* stats, cudaStream_t s);

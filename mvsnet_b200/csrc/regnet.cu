@@ -49,8 +49,21 @@ int launch_conv3d_layer(const void* x, int x_dtype, const float* x_scale, const 
   return MVSB200_ERR_INVALID;
 }
 
-// cost_planar != 0 (bf16 mode only): the caller has already written the cost volume in both planar
-// layouts at regnet_cost_planar() inside the workspace and `cost` is ignored.
+// bf16 mode: 3dconv0_1 and 3dconv1_0 both read the cost volume; when the shapes allow it they run as ONE launch (the
+// stride-2 layer rides on the stride-1 layer's MMAs, conv3d_tc.h TcRider): the volume is read once, and its parity-split
+// copy is never needed (the cost-volume kernel then writes the chunk-planar copy only).  Tuning TC_FUSE01=0 turns it off.
+bool regnet_fuse01(int D, int H, int W, int cin, int b) {
+  if (tuning().tc_fuse01 == 0) return false;
+  RegnetPlan p;
+  make_plan(D, H, W, cin, b, MVSB200_PRECISION_BF16, &p);
+  const LayerDesc& a = p.layer[MVSB200_L_3DCONV0_1];
+  const LayerDesc& r = p.layer[MVSB200_L_3DCONV1_0];
+  return a.cin == r.cin && a.cin % 16 == 0 && a.cin <= 64 && a.cout == 8 && (r.cout == 8 || r.cout == 16) && !((D | H | W) & 1);
+}
+
+// cost_planar != 0 (bf16 mode only): the caller has already written the cost volume in the planar layouts
+// (chunk-planar always; parity-split unless regnet_fuse01()) at regnet_cost_planar() inside the workspace and `cost`
+// is ignored.
 int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const mvsb200_regnet_params* params, int D,
                         int H, int W, int cin, int b, float eps, int precision, float* filtered, void* workspace,
                         size_t workspace_bytes, cudaStream_t s, TcRegress* regress = nullptr, bool inspect = true) {
@@ -76,9 +89,10 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
   float* shift = (float*)(ws + p.shift_off);
   const int act_dtype = bf16 ? MVSB200_BF16 : MVSB200_F32;
   MVS_CUDA(cudaMemsetAsync(stats, 0, p.stats_bytes, s));
+  const bool fuse01 = bf16 && regnet_fuse01(D, H, W, cin, b);
   if (bf16 && !cost_planar) {
     MVS_CHECK_ARG(cost_dtype == MVSB200_BF16, "regnet_forward: precision bf16 needs a bf16 cost volume");
-    rc = launch_ndhwc_to_planar(cost, D, H, W, cin, ws + p.cost_cp8_off, ws + p.cost_ps8_off, s);
+    rc = launch_ndhwc_to_planar(cost, D, H, W, cin, ws + p.cost_cp8_off, fuse01 ? nullptr : ws + p.cost_ps8_off, s);
     if (rc) return rc;
   }
   // development aid: MVSB200_REGNET_PROFILE=1 prints per-layer device times (synchronises; not for timed runs)
@@ -102,12 +116,38 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
       jobs[i] = {params->kernel[i], d[0], d[1], d[2], L.cin, L.cout, L.stride, L.transposed, L.skip >= 0 ? 1 : 0,
                  (L.src >= 0 || L.skip >= 0) ? 1 : 0, 2 * i, L.cin_true, L.cout_true};
     }
+    if (fuse01) {
+      // slot of 3dconv1_0 = the rider launch: 3dconv0_1's filter with 3dconv1_0's riding on it
+      const LayerDesc& A = p.layer[MVSB200_L_3DCONV0_1];
+      const LayerDesc& R = p.layer[MVSB200_L_3DCONV1_0];
+      jobs[MVSB200_L_3DCONV1_0] = {params->kernel[MVSB200_L_3DCONV0_1], D, H, W, A.cin, A.cout, 1, 0, 0, 0,
+                                   2 * MVSB200_L_3DCONV1_0, A.cin_true, A.cout_true, params->kernel[MVSB200_L_3DCONV1_0],
+                                   R.cout, R.cout_true};
+    }
     rc = conv3d_tc_pack_all(jobs, MVSB200_REGNET_LAYERS, ws + p.scratch_off, s);
     if (rc) return rc;
   }
   for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
     const LayerDesc& L = p.layer[i];
     const bool last = i == MVSB200_L_3DCONV6_2;
+    if (fuse01 && (i == MVSB200_L_3DCONV1_0 || i == MVSB200_L_3DCONV0_1)) {
+      if (i == MVSB200_L_3DCONV1_0) {
+        const LayerDesc& A = p.layer[MVSB200_L_3DCONV0_1];
+        const int* o = p.dims[L.out_level];
+        if ((o[1] | o[2]) & 1) MVS_CUDA(cudaMemsetAsync(ws + p.ps8_off[i], 0, planar_bytes(o[0], o[1], o[2], L.cout, 1), s));
+        const int rep_stride = MVSB200_REGNET_LAYERS * 2 * cpad;
+        const TcRider rider = {params->kernel[i], L.cout, ws + p.raw_off[i], p.has_ps8[i] ? ws + p.ps8_off[i] : nullptr,
+                               stats + (size_t)i * 2 * cpad};
+        rc = launch_conv3d_tc(ws + p.cost_cp8_off, nullptr, nullptr, nullptr, nullptr, nullptr, params->kernel[MVSB200_L_3DCONV0_1],
+                              D, H, W, A.cin, A.cout, 1, 0, ws + p.raw_off[MVSB200_L_3DCONV0_1], nullptr, nullptr,
+                              stats + (size_t)MVSB200_L_3DCONV0_1 * 2 * cpad, nullptr, nullptr, nullptr,
+                              ws + p.scratch_off + (size_t)2 * i * conv3d_tc_pack_slot_bytes(), kStatsReps, rep_stride, nullptr,
+                              nullptr, nullptr, s, &rider);
+        if (rc) return rc;
+      }
+      if (profile) cudaEventRecord(pev[i + 1], s);
+      continue;
+    }
     const float* xs = L.src < 0 ? nullptr : scale + (size_t)L.src * cpad;
     const float* xb = L.src < 0 ? nullptr : shift + (size_t)L.src * cpad;
     const void* sk = L.skip < 0 ? nullptr : (const void*)(ws + p.raw_off[L.skip]);
@@ -742,6 +782,7 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   if (planar) {
     void *cp8 = nullptr, *ps8 = nullptr;
     regnet_cost_planar(ws + ip.regnet_off, depth_num, hf, wf, channels, base_filter, &cp8, &ps8);
+    if (regnet_fuse01(depth_num, hf, wf, channels, base_filter)) ps8 = nullptr;      // nobody reads the parity-split copy
     const bool fp32_taps = tuning().cv_fp32_taps != 0;
     rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8,
                                    fp32_taps ? nullptr : ws + ip.pair_off, coefs, s);

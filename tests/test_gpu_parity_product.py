@@ -89,7 +89,9 @@ def test_product_cost_volume_vs_oracle_small(small_problem, tuning, blend32):
     ratio = np.abs(got - ref) / tol
     print(f"small, blend32={blend32}: max |err| / tolerance = {ratio.max():.3f}, mean = {ratio.mean():.4f}")
     assert ratio.max() <= 1.0
-    # the parity-split copy holds the same cells
+    # the parity-split copy (only written when 3dconv1_0 runs as a launch of its own) holds the same cells
+    tuning("TC_FUSE01", 0)
+    cp8, ps8 = eng.cost_volume_planar(to_dev(p["feats"]), to_dev(p["cams"]), p["depth_start"], p["depth_interval"])
     b = ps8.view(D, 4, 2, 2, hf // 2, wf // 2, 8).permute(0, 4, 2, 5, 3, 1, 6).reshape(D, hf, wf, 32).float()
     assert torch.equal(b.cpu(), torch.from_numpy(got))
 

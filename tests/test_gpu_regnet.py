@@ -251,3 +251,46 @@ def test_bf16_layer_bf16_output_layouts(ops, O, case):
     assert tuple(y.shape) == ref.shape
     err = np.abs(y.float().cpu().numpy() - ref).max()
     assert err <= 1e-2 * max(1.0, np.abs(ref).max()), f"{case}: max abs err {err}"
+
+
+@pytest.mark.parametrize("base_filter", [8, 4])
+def test_regnet_bf16_first_layers_in_one_launch(O, small_problem, tuning, base_filter):
+    """3dconv0_1 and 3dconv1_0 as ONE launch over the cost volume (the stride-2 layer rides on the odd positions of
+    the stride-1 layer's MMAs; default) against the two separate launches (tuning TC_FUSE01=0): same raw layer outputs up
+    to the bf16 rounding of differently ordered fp32 sums, same batch-norm scale / shift, same filtered volume."""
+    import ctypes
+    from mvsnet_b200 import synthetic
+    from mvsnet_b200.engine import HotPath
+    p = small_problem
+    weights = p["weights"] if base_filter == 8 else synthetic.make_regnet_weights(32, base_filter, seed=7)
+    D, hf, wf = p["depth_num"], p["hf"], p["wf"]
+    rng = np.random.RandomState(5)
+    cost = to_dev(np.abs(rng.randn(D, hf, wf, 32)).astype(np.float32)).to(torch.bfloat16)
+    eng = HotPath(p["n_views"], D, hf, wf, weights, precision="bf16")
+    got = {}
+    for fuse in (0, 1):
+        tuning("TC_FUSE01", fuse)
+        out = eng.regnet(cost).clone()
+        ws = eng._last_regnet_ws
+        layers = {}
+        for name, layer, lvl, c in (("3dconv1_0", 0, 1, max(2 * base_filter, 8)), ("3dconv0_1", 3, 0, 8)):
+            raw, sc, sh = eng.regnet_layer_raw(layer, D, hf, wf)
+            off = raw - ws.data_ptr()
+            n = (D >> lvl) * (hf >> lvl) * (wf >> lvl) * c
+            t = ws[off:off + 2 * n].view(torch.bfloat16).float().clone()
+            soff, hoff = sc - ws.data_ptr(), sh - ws.data_ptr()
+            layers[name] = (t, ws[soff:soff + 4 * c].view(torch.float32).clone(), ws[hoff:hoff + 4 * c].view(torch.float32).clone())
+        got[fuse] = (out, layers)
+    for name in ("3dconv1_0", "3dconv0_1"):
+        a, b = got[0][1][name], got[1][1][name]
+        err = (a[0] - b[0]).abs()
+        assert float(a[0].abs().max()) > 0.1
+        assert float((err <= 2.0 ** -7 * a[0].abs() + 1e-3).float().mean()) == 1.0, (name, float(err.max()))
+        assert float((err == 0).float().mean()) >= 0.98, name
+        ct = base_filter * (2 if name == "3dconv1_0" else 1)        # the layer's own channels (the rest is padding)
+        assert torch.allclose(a[1][:ct], b[1][:ct], rtol=2e-3, atol=1e-5), name
+        assert torch.allclose(a[2][:ct], b[2][:ct], rtol=2e-3, atol=2e-4), name
+    # the filtered volumes differ by what the one-ulp flips above grow into through nine more bf16 layers
+    scale = float(got[0][0].abs().max())
+    diff = got[0][0] - got[1][0]
+    assert float(diff.abs().max()) <= 2e-2 * scale and float(diff.pow(2).mean().sqrt()) <= 2e-3 * scale

@@ -228,9 +228,12 @@ def stage_times(eng, feats, cams, ds, di, iters):
 
 def cost_volume_variants(eng, feats, cams, ds, di):
     """The cost-volume stage under its arithmetic variants, side by side (device ms, config of this run): the shipped
-    kernel reads fp16-rounded features and blends in packed fp16; north_star's arithmetic is fp32 features."""
+    kernel reads fp16-rounded features, blends the difference to the reference pixel in packed fp16 and sums in fp32;
+    north_star's arithmetic is fp32 features.  (The variants are timed inside the whole pass: with the gather kernel the
+    two first regularizer layers still run as one launch.)"""
     from mvsnet_b200 import _lib
-    variants = (("window_fp16_taps_fp16_blend (shipped)", {}),
+    variants = (("window_fp16_taps_fp16_blend_fp32_sums (shipped)", {}),
+                ("window_fp16_taps_fp16_blend_fp16_sums", {"CV_FP32_BLEND": 2}),
                 ("window_fp16_taps_fp32_blend", {"CV_FP32_BLEND": 1}),
                 ("gather_fp16_taps_fp16_blend (round 1)", {"CV_KERNEL": 1}),
                 ("gather_fp32_taps_fp32_blend (north_star arithmetic)", {"CV_KERNEL": 1, "CV_FP32_TAPS": 1}))
@@ -363,9 +366,11 @@ def run_ours(args, rank, world, local_rank):
                    ">2.5 GB of intermediates through HBM (L2 is 126 MB)", "parallelism": f"view-sharded x{world}",
                    "stage_ms": {"homographies": float(stage_ms[0]), "cost_volume": cv_ms,
                                 "regularizer": float(stage_ms[2]), "regression": rg_ms},
-                   "arithmetic": "source views and reference view read as fp16, 4-tap blend in packed fp16, running sums "
-                                 "and variance fp32, bf16 volume; regularizer bf16 operands / fp32 accumulation "
-                                 "(tcgen05); parity of exactly this mode vs the oracle: tests/test_gpu_parity_product.py"},
+                   "arithmetic": "source views and reference view read as fp16, 4-tap blend of (warped - reference) in "
+                                 "packed fp16, sums of the differences and their squares and the variance in fp32, bf16 "
+                                 "volume (chunk-planar copy only); regularizer bf16 operands / fp32 accumulation (tcgen05), "
+                                 "3dconv0_1 + 3dconv1_0 in one launch; parity of exactly this mode vs the oracle: "
+                                 "tests/test_gpu_parity_product.py"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes,
                 "d2h_bytes_per_step": eng.d2h_bytes, "ms_per_step": ms_e2e / args.steps, "depth_checksum": checksum},
         "gpu_launches": int(launches),
@@ -374,9 +379,9 @@ def run_ours(args, rank, world, local_rank):
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes": cv_bytes, "avg_launch_ms": cv_ms},
-        # the second stage as a whole (13 launches of conv3d_tc_kernel): SURVEY 8(d) unfused compulsory bytes 230 B
+        # the second stage as a whole (12 launches of conv3d_tc_kernel): SURVEY 8(d) unfused compulsory bytes 230 B
         # per voxel and 22 896 FLOP per voxel, against the same measured HBM peak
-        "roofline_regularizer": {"kernel": "conv3d_tc_kernel x13 (RegNetUS0, bf16 tcgen05)", "bound": "hbm",
+        "roofline_regularizer": {"kernel": "conv3d_tc_kernel x12 (RegNetUS0, bf16 tcgen05)", "bound": "hbm",
                                  "achieved": 230.0 * V / (float(stage_ms[2]) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": 230.0 * V / (float(stage_ms[2]) * 1e-3) / 1e9 / peak,
                                  "algorithmic_bytes": 230 * V, "tflops": 22896.0 * V / (float(stage_ms[2]) * 1e-3) / 1e12,

@@ -8,7 +8,7 @@ timeout 300 python tools/infer_once.py > gpurun_out/once.log 2>&1 || exit 1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:cost_volume_window -c 1 -o gpurun_out/prof_cv python tools/infer_once.py > gpurun_out/ncu_cv.log 2>&1
 ncu -i gpurun_out/prof_cv.ncu-rep --page raw --csv > gpurun_out/prof_cv_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_cv.ncu-rep --page details > gpurun_out/prof_cv_details.txt 2>/dev/null
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:conv3d_tc_kernel -c 13 -o gpurun_out/prof_conv python tools/infer_once.py > gpurun_out/ncu_conv.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:conv3d_tc_kernel -c 12 -o gpurun_out/prof_conv python tools/infer_once.py > gpurun_out/ncu_conv.log 2>&1
 ncu -i gpurun_out/prof_conv.ncu-rep --page raw --csv > gpurun_out/prof_conv_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_conv.ncu-rep --page details > gpurun_out/prof_conv_details.txt 2>/dev/null
 # tensor-pipe counters that see tcgen05 (UTCHMMA): whatever this ncu names them

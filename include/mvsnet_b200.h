@@ -326,6 +326,19 @@ int mvsb200_unet_forward(const float* images, const mvsb200_unet_params* params,
 int mvsb200_unet_layer_output(int n_views, int height, int width, int base_filter, int layer, size_t* offset,
                               int* dims);
 
+/* The same tower in bf16 on the tensor cores (csrc/feature2d_tc.cu: tcgen05 implicit GEMM per layer, raw activations
+ * bf16 chunk-planar [N][C/8][H][W][8], group normalisation applied by the consuming layer from fp64 statistics).  Same
+ * arguments and result as mvsb200_unet_forward; base_filter must be 8 (network mode "normal"); its own workspace size. */
+size_t mvsb200_unet_tc_workspace_bytes(int n_views, int height, int width, int base_filter);
+int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_params* params, int n_views, int height,
+                            int width, int base_filter, float gn_eps, float* feats, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* After mvsb200_unet_tc_forward: byte offset of a layer's RAW (pre-normalisation) bf16 chunk-planar output in the
+ * workspace, its dims {Ho, Wo, C}, and the byte offset of its statistics [N][C/8][2] (sum, sum of squares; fp64).
+ * Layers 0 .. 30 (the last layer is written to `feats`). */
+int mvsb200_unet_tc_layer_raw(int n_views, int height, int width, int base_filter, int layer, size_t* offset,
+                              int* dims, size_t* stats_offset);
+
 /* ---- training step of the path (BASELINE config 4; train.py:314-315 `inference` inside get_loss, loss.py:190-220
  * mvsnet_regression_loss with loss_type 'original', train.py:429 opt.compute_gradients) ------------------------------
  * Gradient buffers in the layout of the variables they belong to (fp32, device memory); gamma/beta[10] unused. */

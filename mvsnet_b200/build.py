@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmvsnet_b200.so")
 SOURCES = ["api.cu", "homography.cu", "warp.cu", "cost_volume.cu", "cost_volume_win.cu", "regress.cu", "conv3d_direct.cu",
-           "conv3d_tc.cu", "umma_probe.cu", "regnet.cu", "feature2d.cu", "refine.cu", "backward.cu"]
+           "conv3d_tc.cu", "umma_probe.cu", "regnet.cu", "feature2d.cu", "feature2d_tc.cu", "refine.cu", "backward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -102,9 +102,13 @@ class UNetDS2GN:
     `image` is [B,H,W,3] fp32 (centred).  Group normalisation has no batch dependence, so a batch of B images is B
     independent towers (upstream builds one tower per view and batch_size 1)."""
 
-    def __init__(self, inputs, trainable=True, training=True, mode="normal", reuse=False, epsilon=1e-5, **kwargs):
+    def __init__(self, inputs, trainable=True, training=True, mode="normal", reuse=False, epsilon=1e-5, precision="fp32",
+                 **kwargs):
         if mode not in NETWORK_MODE_DIVISOR:
             raise ValueError(f"unknown network mode {mode!r}")
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision          # "bf16": the tensor-core tower (csrc/feature2d_tc.cu)
         if regnet_base_filter(mode) % 8:
             raise NotImplementedError(f"UNetDS2GN mode {mode!r}: groups of fewer than 8 channels are not built")
         self.base_divisor = NETWORK_MODE_DIVISOR[mode]
@@ -121,9 +125,9 @@ class UNetDS2GN:
                 raise ValueError("Improper input rank for layer: 2dconv1_0")
             if not _UNET_VARIABLES:
                 raise RuntimeError("UNetDS2GN variables not set: call mvsnetworks.set_unet_variables(weights)")
-            key = (str(image.device), self.epsilon)
+            key = (str(image.device), self.epsilon, self.precision)
             if key not in _UNET_CACHE:
-                _UNET_CACHE[key] = FeatureTower(_UNET_VARIABLES, self.epsilon, image.device)
+                _UNET_CACHE[key] = FeatureTower(_UNET_VARIABLES, self.epsilon, image.device, precision=self.precision)
             tower = _UNET_CACHE[key]
             if tower.weights.base_filter != self.base_filter:
                 raise ValueError(f"variables are for base_filter {tower.weights.base_filter}, mode needs {self.base_filter}")

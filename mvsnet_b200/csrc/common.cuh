@@ -30,6 +30,8 @@ struct Tuning {
   int tc_fuse01 = -1;         // TC_FUSE01: 0 = 3dconv0_1 and 3dconv1_0 as two launches (and a parity-split cost volume)
   int tc_layer_set = 0, tc_layer[3] = {0, 0, 0};                     // TC_LAYER="cin,cout,mode": restrict the tc_* switches
   int regnet_profile = 0, unet_no_tile = 0, unet_profile = 0, unet_fp32 = 0;
+  int unet_dbg = 0;
+  int unet_mb = 0;            // UNET_MB: 1 / 2 = 128-row blocks per tile of the tensor-core tower (0: by tile count)
 };
 const Tuning& tuning();
 

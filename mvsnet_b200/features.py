@@ -1,7 +1,8 @@
-"""Image feature tower UNetDS2GN on the GPU (fp32 parity mode): images [N,H,W,3] -> features [N,H/4,W/4,32].
+"""Image feature tower UNetDS2GN on the GPU: images [N,H,W,3] -> features [N,H/4,W/4,32].
 
-The step before the hot path (mvsnet/model.py:392-406: one UNetDS2GN per view, shared variables).  Everything runs in
-libmvsnet_b200.so (csrc/feature2d.cu); there is no fallback.
+The step before the hot path (mvsnet/model.py:392-406: one UNetDS2GN per view, shared variables).  Two implementations
+in libmvsnet_b200.so, no fallback: precision "fp32" = CUDA-core parity mode (csrc/feature2d.cu), precision "bf16" =
+tensor cores (csrc/feature2d_tc.cu: bf16 operands, fp32 accumulation, group normalisation folded into the consumer).
 """
 from __future__ import annotations
 
@@ -46,7 +47,10 @@ class UnetWeights:
 class FeatureTower:
     """images [N,H,W,3] fp32 (centred) -> features [N,H/4,W/4,4*base_filter] fp32, all views in one call."""
 
-    def __init__(self, weights, epsilon=1e-5, device="cuda"):
+    def __init__(self, weights, epsilon=1e-5, device="cuda", precision="fp32"):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
         self.lib = L.load()
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:
@@ -58,7 +62,8 @@ class FeatureTower:
 
     def _workspace(self, n, h, w):
         if self._shape != (n, h, w):
-            nbytes = self.lib.mvsb200_unet_workspace_bytes(n, h, w, self.weights.base_filter)
+            size_fn = self.lib.mvsb200_unet_tc_workspace_bytes if self.precision == "bf16" else self.lib.mvsb200_unet_workspace_bytes
+            nbytes = size_fn(n, h, w, self.weights.base_filter)
             if nbytes == 0:
                 raise L.MVSB200Error(f"unet_workspace_bytes rejected the shape: {L.last_error()}")
             self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
@@ -76,14 +81,30 @@ class FeatureTower:
         n, h, w, _ = images.shape
         ws = self._workspace(n, h, w)
         feats = torch.empty((n, h // 4, w // 4, 4 * self.weights.base_filter), dtype=torch.float32, device=images.device)
-        rc = self.lib.mvsb200_unet_forward(L.ptr(images.contiguous()), ctypes.byref(self.weights.params), n, h, w,
-                                           self.weights.base_filter, self.epsilon, L.ptr(feats), L.ptr(ws), ws.numel(),
-                                           L.stream_ptr())
+        fwd = self.lib.mvsb200_unet_tc_forward if self.precision == "bf16" else self.lib.mvsb200_unet_forward
+        rc = fwd(L.ptr(images.contiguous()), ctypes.byref(self.weights.params), n, h, w, self.weights.base_filter,
+                 self.epsilon, L.ptr(feats), L.ptr(ws), ws.numel(), L.stream_ptr())
         L.check(rc, "unet_forward")
         return feats
 
+    def layer_raw(self, layer: int):
+        """bf16 mode, after forward(): (raw output [N,C/8,Ho,Wo,8] bf16, statistics [N,C/8,2] fp64) of a layer, views of
+        the workspace (tests)."""
+        if self.precision != "bf16":
+            raise ValueError("layer_raw is the bf16 tower's inspection call; use layer_output in fp32 mode")
+        n, h, w = self._shape
+        off, soff, dims = ctypes.c_size_t(), ctypes.c_size_t(), (ctypes.c_int * 3)()
+        L.check(self.lib.mvsb200_unet_tc_layer_raw(n, h, w, self.weights.base_filter, layer, ctypes.byref(off), dims,
+                                                   ctypes.byref(soff)), "unet_tc_layer_raw")
+        ho, wo, c = list(dims)
+        raw = self._ws[off.value:off.value + n * ho * wo * c * 2].view(torch.bfloat16).view(n, c // 8, ho, wo, 8)
+        stats = self._ws[soff.value:soff.value + n * (c // 8) * 16].view(torch.float64).view(n, c // 8, 2)
+        return raw, stats
+
     def layer_output(self, layer: int) -> torch.Tensor:
-        """After forward(): the (normalised) output [N,Ho,Wo,C] of a layer, a view of the workspace (tests)."""
+        """After forward() in fp32 mode: the (normalised) output [N,Ho,Wo,C] of a layer, a view of the workspace (tests)."""
+        if self.precision != "fp32":
+            raise ValueError("layer_output is the fp32 tower's inspection call; use layer_raw in bf16 mode")
         n, h, w = self._shape
         off, dims = ctypes.c_size_t(), (ctypes.c_int * 3)()
         L.check(self.lib.mvsb200_unet_layer_output(n, h, w, self.weights.base_filter, layer, ctypes.byref(off), dims),

@@ -17,8 +17,11 @@ from .cnn_wrapper import mvsnetworks
 from .engine import HotPath, RegnetWeights, regnet_base_filter
 
 # stand-in for tf.app.flags.FLAGS; the reference reads these inside the path (model.py:28,275,381-382,431)
+# precision: arithmetic of the hot path ("bf16" = tensor cores, "fp32" = parity mode); tower_precision: arithmetic of the
+# image feature towers when images are given ("fp32" = CUDA-core parity mode, the default: the regularizer's input then
+# matches the reference to 1e-5; "bf16" = tensor cores, 4x faster, features within ~2 % rms of the fp32 ones)
 FLAGS = types.SimpleNamespace(view_num=None, batch_size=1, height=None, width=None, reuse_vars=False,
-                              precision="bf16")
+                              precision="bf16", tower_precision="fp32")
 
 _feature_extractor = None
 _engines = {}
@@ -63,7 +66,8 @@ def _towers(images, network_mode="normal"):
     # one tower per view with shared variables (model.py:392-406); the views of a batch are independent, so they
     # go through the tower together
     b, _, h, w, _ = images.shape
-    tower = mvsnetworks.UNetDS2GN({"data": images.reshape(b * n, h, w, 3)}, mode=network_mode, reuse=True)
+    tower = mvsnetworks.UNetDS2GN({"data": images.reshape(b * n, h, w, 3)}, mode=network_mode, reuse=True,
+                                  precision=FLAGS.tower_precision)
     f = tower.get_output()
     return f.reshape(b, n, f.shape[1], f.shape[2], f.shape[3])
 

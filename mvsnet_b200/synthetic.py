@@ -103,6 +103,20 @@ def make_images(n_views, height, width, seed=91):
     return np.stack(imgs).astype(F32)
 
 
+def make_scene_images(cams, height, width, seed=97, noise=0.02):
+    """Centred images [N,H,W,3] of ONE scene: the textured plane make_features renders, seen through every camera of
+    `cams` at full resolution (cams carry the intrinsics of the H/4 x W/4 feature maps, scale_camera in
+    mvs_data_generation/utils.py:64-73, so K is scaled back by 4).  Unlike make_images the views are photo-consistent:
+    the cost volume built from their feature towers has a real minimum at the plane."""
+    full = np.array(cams, dtype=F32, copy=True)
+    full[:, 1, :2, :3] *= 4.0
+    im = make_features(full, height, width, channels=3, seed=seed, noise=noise)
+    out = []
+    for v in range(im.shape[0]):
+        out.append((im[v] - im[v].mean()) / np.sqrt(im[v].var() + 1e-8))
+    return np.stack(out).astype(F32)
+
+
 def _look_at(cam_pos, target, roll_deg):
     """World->camera rotation for a camera at cam_pos looking at target (z forward, y down)."""
     z = target - cam_pos

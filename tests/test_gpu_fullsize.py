@@ -39,11 +39,13 @@ def test_cost_volume_crop_against_oracle(big):
         assert np.abs(got - ref[:, y0:y0 + 8, x0:x0 + 8]).max() <= 2e-5
 
 
-def test_planar_cost_volume_matches_ndhwc(big):
-    """Product mode writes the volume chunk-planar and parity-split with fp16 taps: both copies hold the same cells and
-    agree with the fp32-tap bf16 volume within the bf16 + fp16-blend tolerance."""
+def test_planar_cost_volume_matches_ndhwc(big, tuning):
+    """Product mode writes the volume chunk-planar (and, when 3dconv1_0 runs as a launch of its own, parity-split) with
+    fp16 taps: both copies hold the same cells and agree with the fp32-tap bf16 volume within the bf16 + fp16-blend
+    tolerance."""
     from mvsnet_b200 import ops
     from mvsnet_b200.engine import HotPath
+    tuning("TC_FUSE01", 0)
     eng = HotPath(N, D, HF, WF, synthetic.make_regnet_weights(), precision="bf16")
     H = ops.homographies(big["cams"], D, big["ds"], big["di"])
     ref = ops.cost_volume(big["feats"], H, out_dtype=torch.bfloat16).float()

@@ -250,6 +250,37 @@ def cost_volume_variants(eng, feats, cams, ds, di):
     return out
 
 
+def images_in(eng, synthetic, cfg, cams, ds, di, dev, iters=10):
+    """The step BEFORE the path in front of it: images [N,H,W,3] resident in HBM -> UNetDS2GN towers ->
+    hot path -> depth map, device-timed, with the tensor-core tower (bf16) and the CUDA-core parity tower (fp32).  Not the
+    headline metric (BASELINE.json defines it from feature maps); random tower weights."""
+    import torch
+    from mvsnet_b200.features import FeatureTower
+    n, h, w = cfg["n_views"], cfg["height"], cfg["width"]
+    images = torch.randn((n, h, w, 3), device=dev)
+    wts = synthetic.make_unet_weights(8)
+    out = {}
+    for prec in ("bf16", "fp32"):
+        tower = FeatureTower(wts, precision=prec, device=dev)
+        for _ in range(3):
+            eng.infer(tower(images), cams, ds, di)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_tower, t_all = [], []
+        for _ in range(iters):
+            ev[0].record()
+            f = tower(images)
+            ev[1].record()
+            eng.infer(f, cams, ds, di)
+            ev[2].record()
+            torch.cuda.synchronize()
+            t_tower.append(ev[0].elapsed_time(ev[1]))
+            t_all.append(ev[0].elapsed_time(ev[2]))
+        out[f"tower_{prec}_ms"] = float(np.median(t_tower))
+        out[f"depth_maps_per_s_{prec}_tower"] = 1e3 / float(np.median(t_all))
+        del tower
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -396,6 +427,7 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1:
         line["detail"]["cost_volume_variants_ms"] = cost_volume_variants(eng, feats_d[0], cams_d[0], ds, di)
+        line["detail"]["from_images"] = images_in(eng, synthetic, cfg, cams_d[0], ds, di, dev)
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         problem = synthetic.make_problem(args.config)

@@ -89,7 +89,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __host__ __device__ inline int align128(int v) { return (v + 127) & ~127; }
 
-__global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int nch = p.nch_a + p.nch_b;
   const int win_cells = p.RYin * p.PXin;                       // cells of one chunk of the staged window

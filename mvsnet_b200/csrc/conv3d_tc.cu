@@ -109,6 +109,7 @@ struct Params {
   int one_box;                   // chunk planes are dense in the slot: one TMA box loads all chunks of a plane
   int ring_pad;                  // zeroed bytes after the last slot (rows of the last block may read past their plane)
   int xf_k;                      // cells per transform thread and plane
+  int xf_groups;                 // transform warp groups, each taking every xf_groups-th plane (1 or 2)
   int dz_begin[kMaxSpan + 1];    // ops [dz_begin[d], dz_begin[d+1]) read input plane d of the step
   float* rg_out; float rg_start, rg_step;   // fused soft-argmin partials of the last layer (NULL: off)
   // "rider" (3dconv0_1 + 3dconv1_0 in one pass over the cost volume): a stride-2 conv with the same input is the
@@ -411,8 +412,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.R; ++i) { mbar_init(&bar_land[i], 1); mbar_init(&bar_ready[i], kXfWarps); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < kMaxSkipRing; ++i) { mbar_init(&bar_sland[i], 1); mbar_init(&bar_sempty[i], kXfWarps); }
+    const int xfw = kXfWarps / p.xf_groups;         // transform warps per plane
+    for (int i = 0; i < p.R; ++i) { mbar_init(&bar_land[i], 1); mbar_init(&bar_ready[i], xfw); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < kMaxSkipRing; ++i) { mbar_init(&bar_sland[i], 1); mbar_init(&bar_sempty[i], xfw); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], RIDER ? kEpiWarps + kXfWarps : kEpiWarps); }
     mbar_init(bar_b, 1);
     fence_mbar_init();
@@ -541,8 +543,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     } else if (!RIDER && warp >= kXfWarp0 && warp < kProdWarp) {
       // ===================================== transform =====================================
       if (p.transform) {
-        const int xt = threadIdx.x - kXfWarp0 * 32;
-        const int tpc = kXfThreads / p.NCH;           // threads per channel chunk (chunk is warp-uniform)
+        // the planes of a step are independent: with two groups of four warps, each taking every other plane, two
+        // planes are in flight (a plane is a latency chain: barrier wait, loads, ~60 dependent instructions per cell,
+        // stores, proxy fence, arrive -- measured 1 570 clk per plane of 3dconv6_2 for ~260 issue slots of work)
+        const int xt_all = threadIdx.x - kXfWarp0 * 32;
+        const int gthreads = kXfThreads / p.xf_groups;
+        const int xgrp = xt_all / gthreads, xt = xt_all - xgrp * gthreads;
+        const int tpc = gthreads / p.NCH;             // threads per channel chunk
         const int ch = xt / tpc, ti = xt - ch * tpc;
         const int npos = p.nsub * p.RY * p.PX;
         // loop-invariant cell list of this thread: byte offset in the slot, -1 = outside the volume / none
@@ -569,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         }
         long long xw = 0, xt0 = 0;
         if (p.prof) xt0 = clock64();
-        for (int seq = 0; seq < nplanes; ++seq) {
+        for (int seq = xgrp; seq < nplanes; seq += p.xf_groups) {
           const int slot = seq % p.R, ss = seq % p.RS;
           long long xa = 0;
           if (p.prof) xa = clock64();
@@ -635,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
             if (p.has_skip) mbar_arrive(&bar_sempty[ss]);
           }
         }
-        if (p.prof && blockIdx.x == 0 && xt == 0) { p.prof[12] = clock64() - xt0; p.prof[13] = xw; }
+        if (p.prof && blockIdx.x == 0 && xt_all == 0) { p.prof[12] = clock64() - xt0; p.prof[13] = xw; }
       }
     } else if (warp == kMmaWarp) {
       // ===================================== MMA issuer =====================================
@@ -1221,7 +1228,13 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   if (2 * c.MB * c.NB > 512 || c.MB > kMaxMB) return false;
   c.tmem_cols = pow2_at_least(2 * c.MB * c.NB);
   c.xf_k = ceil_div(c.nsub * c.RY * c.PX, kXfThreads / c.NCH);
+  c.xf_groups = 1;
   if (transform && c.xf_k > kMaxK) return false;
+  // (measured at config 2: no gain -- 3dconv6_2 0.218 -> 0.214 ms, the coarse layers slightly slower -- so only on request)
+  if (transform && tuning().tc_xf_groups == 2 && 2 * c.NCH <= kXfThreads / 16) {
+    const int k2 = ceil_div(c.nsub * c.RY * c.PX, (kXfThreads / 2) / c.NCH);
+    if (k2 <= kMaxK) { c.xf_groups = 2; c.xf_k = k2; }
+  }
 
   // ---- taps ---------------------------------------------------------------------------------------
   struct Tap { int dz, pos, widx, cls; };
@@ -1403,7 +1416,7 @@ double estimate_clk(const Params& c, int sm_count) {
                                               : (double)c.MB * (c.n2 ? 2 : c.zf * (c.cout_n / 8)) * 420.0)      // rider: three warp groups side by side
                              : (double)c.MB * ncls * (c.CP * 4.0 * 128.0 / 110.0 + 12.0 * c.CP + 80.0);
   const double tma_issue = (c.one_box ? 1.0 : (double)c.nsub * c.NCH) * (c.has_skip ? 2.0 : 1.0) * 250.0 * c.zstep;
-  const double xf = c.transform ? (double)c.xf_k * c.zstep * (c.has_skip ? 70.0 : 45.0) : 0.0;
+  const double xf = c.transform ? (double)c.xf_k / c.xf_groups * c.zstep * (c.has_skip ? 70.0 : 45.0) : 0.0;
   double step = mma;
   if (load > step) step = load;
   if (epi > step) step = epi;

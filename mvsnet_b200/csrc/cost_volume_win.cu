@@ -44,7 +44,8 @@ constexpr int kRowBytes = WX * 16;
 constexpr int kMaxStages = 4, kMaxSrc = 7;
 constexpr size_t kSmemBudget = 200 * 1024;
 
-struct Meta { int wx0, wy0, rows, pad; };                // window origin (source pixels) and rows landed (0 / 8 / 16)
+struct Meta { int wx0, wy0, rows, pad; };                // window origin (source pixels) and rows landed (8 / 16)
+struct Item { int x0, y0, l0, pad; };                    // first reference pixel and first local plane of a work item
 
 struct Params {
   alignas(64) CUtensorMap tmap;      // fp16 chunk-planar features as (4*Wf, Hf, 4*N) fp32 elements, box (4*WX, 8, 1)
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
   unsigned char* s_ring = smem;
   Meta* s_meta = reinterpret_cast<Meta*>(smem + (size_t)p.nstages * stage_bytes);      // [2][kMaxSrc]
   float4* s_coef = reinterpret_cast<float4*>(s_meta + 2 * kMaxSrc);                     // [2][kMaxSrc][PL][2]: transform rows
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_coef + 2 * kMaxSrc * PL * 2);
+  Item* s_item = reinterpret_cast<Item*>(s_coef + 2 * kMaxSrc * PL * 2);                // [2]
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_item + 2);
   uint64_t* bar_empty = bar_full + kMaxStages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
       if (it >= nmine) return;
       const int wi = (int)blockIdx.x + it * (int)gridDim.x;
       const int tx = wi % p.tiles_x, ty = (wi / p.tiles_x) % p.tiles_y, dc = wi / (p.tiles_x * p.tiles_y);
+      if (lane == 31) s_item[it & 1] = Item{tx * TXP, ty * TYP, dc * PL, 0};      // (the consumers skip the divisions)
       if (lane < NV) {
         // bounding box of the work item's samples in source view `lane`: the 8 corners of (x, y, plane)
         const int xl = tx * TXP, xh = min(xl + TXP - 1, p.Wf - 1);
@@ -227,25 +230,11 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
   int stage = 0;
   uint32_t round = 0;
   for (int it = 0; it < nmine; ++it) {
-    const int wi = (int)blockIdx.x + it * (int)gridDim.x;
-    const int tx = wi % p.tiles_x, ty = (wi / p.tiles_x) % p.tiles_y, dc = wi / (p.tiles_x * p.tiles_y);
-    const int x = tx * TXP + px, y = ty * TYP + py;
-    const int xc = min(x, p.Wf - 1), yc = min(y, p.Hf - 1);
     uint32_t fo[IPT][NV];              // per (voxel, view): byte offset of the top-left tap in the view's window, or
                                        // bit 31 | (y0 + 2) << 15 | (x0 + 2) when the footprint is outside the window
     uint32_t wa[IPT][NV], wb[IPT][NV]; // fp16 blend: half2 (w00, w01), (w10, w11); fp32 blend: wxr, wyr bits
     bool live[IPT];
     uint32_t cell_cp8[IPT], cell_ps8[IPT];       // chunk-0 cell index of the voxel in the two output layouts
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const int l = dc * PL + pl0 + i * (PL / IPT);
-      live[i] = x < p.Wf && y < p.Hf && l < p.Dloc && (unsigned)(p.d0g + l) < (unsigned)p.D;
-      cell_cp8[i] = (uint32_t)(((size_t)l * 4 * p.Hf + y) * p.Wf + x);
-      cell_ps8[i] = (uint32_t)((((size_t)l * 16 + (y & 1) * 2 + (x & 1)) * Hs + (y >> 1)) * Ws + (x >> 1));
-    }
-    // reference cell of chunk 0 (in flight while the window of the item is awaited)
-    const uint4* rptr = p.feats16 + (size_t)yc * p.Wf + xc;
-    uint4 rcell = __ldg(rptr);
     bool slow_warp = false;            // some voxel of this warp reads a view from global memory
 
     // ---- chunk 0's stage carries the item's window and transform rows (published before the barrier was armed):
@@ -254,6 +243,20 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_window_kernel(const _
     // land on the bound: "outside", as the reference's zero fill has it).  A footprint whose four taps sit inside
     // the landed rows of the window becomes a shared-memory offset.
     mbar_wait(&bar_full[stage], round & 1u);
+    const Item item = s_item[it & 1];
+    const int x = item.x0 + px, y = item.y0 + py;
+    const int xc = min(x, p.Wf - 1), yc = min(y, p.Hf - 1);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const int l = item.l0 + pl0 + i * (PL / IPT);
+      live[i] = x < p.Wf && y < p.Hf && l < p.Dloc && (unsigned)(p.d0g + l) < (unsigned)p.D;
+      cell_cp8[i] = ((uint32_t)l * 4u * (uint32_t)p.Hf + (uint32_t)y) * (uint32_t)p.Wf + (uint32_t)x;       // (< 2^31: launch check)
+      cell_ps8[i] = (((uint32_t)l * 16u + (uint32_t)((y & 1) * 2 + (x & 1))) * (uint32_t)Hs + (uint32_t)(y >> 1)) * (uint32_t)Ws +
+                    (uint32_t)(x >> 1);
+    }
+    // reference cell of chunk 0
+    const uint4* rptr = p.feats16 + (size_t)yc * p.Wf + xc;
+    uint4 rcell = __ldg(rptr);
     {
       bool slow = false;
 #pragma unroll
@@ -511,7 +514,7 @@ int launch_cost_volume_window(const float* feats, const float* coef_table, int n
   MVS_CHECK_ARG(p.nstages >= 2, "cost_volume(window): shared-memory ring too small");
   p.stats = stats ? stats : (tuning().cv_stats ? window_stats_buffer() : nullptr);
   const size_t smem = (size_t)p.nstages * stage_bytes + 2 * kMaxSrc * sizeof(Meta) + 2 * kMaxSrc * PL * 2 * sizeof(float4) +
-                      2 * kMaxStages * sizeof(uint64_t);
+                      2 * sizeof(Item) + 2 * kMaxStages * sizeof(uint64_t);
   MVS_CHECK_ARG((size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) < ((size_t)1 << 31) && (size_t)dloc * 4 * hf * wf < ((size_t)1 << 31),
                 "cost_volume(window): volume too large for 32-bit cell indices");
   Kernel k = blend32 == 1 ? pick<1>(nv) : (blend32 == 2 ? pick<2>(nv) : pick<0>(nv));

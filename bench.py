@@ -487,6 +487,10 @@ def run_cfg3(args, rank, world, local_rank):
 
     for _ in range(max(1, min(args.warmup, 2))):
         one_pass()
+    if world > 1:
+        # the gather's first call builds NCCL's channels (> 1 s): part of the warm-up, like the first kernel launches
+        torch.cuda.synchronize()
+        sharding.gather_maps(mine, [d.to(dev) for d in depth_out], n_ref)
     barrier()
     launches0 = ops.launch_count()
     sampler = ClockSampler(local_rank)

@@ -46,8 +46,10 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <array>
+#include <algorithm>
 #include <map>
 #include <mutex>
+#include <vector>
 
 namespace mvsb200 {
 using namespace umma;
@@ -1478,10 +1480,11 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
   const int force_zs = mine ? tn.tc_zsplit : 0;
   const bool no_xfold = mine && tn.tc_xfold == 0;
   const int dbg_forced = mine ? tn.tc_dbg : 0;
+  const int rank = mine && tn.tc_rank > 0 ? tn.tc_rank : 0;      // development: the rank-th best plan of the cycle model
     const int Mx = mode == MODE_CONV2 ? ceil_div(W, 2) : W, My = mode == MODE_CONV2 ? ceil_div(H, 2) : H,
               Mz = mode == MODE_CONV2 ? ceil_div(D, 2) : D;
     const std::array<int, 15> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_forced > 0 ? zf_forced : 0,
-                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0), n2};
+                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0) + 64 * rank, n2};
     Plan best;
     bool found = false;
     {
@@ -1489,6 +1492,7 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
       auto it = g_plan_cache.find(key);
       if (it != g_plan_cache.end()) { best = it->second; found = true; }
     }
+    std::vector<Plan> ranked;
     if (!found) {
       const int zf_cands[] = {4, 2, 1};
       for (int zi = 0; zi < 3; ++zi) {
@@ -1525,10 +1529,24 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
               const int sseg = ceil_div(steps_all, zcands[zi2]);
               c.zsplit = ceil_div(steps_all, sseg);           // drops empty trailing segments
               pl.est_clk = estimate_clk(c, sm_count);
+              if (rank > 0) ranked.push_back(pl);
               if (!found || pl.est_clk < best.est_clk) { best = pl; found = true; }
             }
           }
         }
+      }
+      if (found && rank > 0) {
+        // distinct plans in the model's order (z-split candidates repeat)
+        std::stable_sort(ranked.begin(), ranked.end(), [](const Plan& a, const Plan& b) { return a.est_clk < b.est_clk; });
+        std::vector<Plan> uniq;
+        for (const Plan& q : ranked) {
+          bool dup = false;
+          for (const Plan& u : uniq)
+            dup = dup || (u.cp.TX == q.cp.TX && u.cp.TY == q.cp.TY && u.cp.zf == q.cp.zf && u.cp.xfold == q.cp.xfold && u.cp.zsplit == q.cp.zsplit);
+          if (!dup) uniq.push_back(q);
+          if ((int)uniq.size() > rank) break;
+        }
+        best = uniq[(size_t)rank < uniq.size() ? rank : uniq.size() - 1];
       }
       if (found) {
         std::lock_guard<std::mutex> lock(g_plan_mutex);

@@ -7,17 +7,15 @@
 // Transform coefficients: one 8-float row per (view, plane) in global memory, staged per block in
 // shared memory.  The whole-path entry points pass the table the homography kernel wrote into the
 // caller's workspace (so calls on different streams do not share state); the stand-alone entry point
-// derives it from the homographies into a library-owned table (one call in flight at a time).
+// derives it from the homographies into a stream-ordered temporary of its own (cudaMallocAsync / cudaFreeAsync on the
+// caller's stream: calls in flight on different streams share nothing).
 #include "geometry.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace mvsb200 {
 
-constexpr int kTableFloats = 14336;  // 56 KB: (N-1)*D*8 for N=8, D=256 (inference.py:29-31 defaults)
-__device__ float g_table[kTableFloats];  // table of the stand-alone entry point
-
-__global__ void prepare_table_kernel(const float* __restrict__ homographies, int count) {
+__global__ void prepare_table_kernel(const float* __restrict__ homographies, int count, float* __restrict__ table) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count) return;
   float h[9], t[8];
@@ -25,7 +23,7 @@ __global__ void prepare_table_kernel(const float* __restrict__ homographies, int
   for (int i = 0; i < 9; ++i) h[i] = homographies[idx * 9 + i];
   transform_coefs(h, t);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) g_table[idx * 8 + i] = t[i];
+  for (int i = 0; i < 8; ++i) table[idx * 8 + i] = t[i];
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -463,17 +461,17 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
   const int rows = (n_views - 1) * depth_num;
   const bool bf16 = out_dtype == MVSB200_BF16;
   const float* coef = coef_table;
+  // stand-alone call: the coefficient rows live in a stream-ordered temporary, released (in stream order) on every
+  // exit path of this function
+  struct Temp {
+    cudaStream_t s; void* p = nullptr;
+    ~Temp() { if (p) cudaFreeAsync(p, s); }
+  } temp{s};
   if (sampler == MVSB200_SAMPLER_TRANSFORM && !coef) {
-    if (rows * 8 > kTableFloats) {
-      set_error("cost_volume: (n_views-1)*depth_num = %d exceeds the %d-row coefficient table", rows,
-                kTableFloats / 8);
-      return MVSB200_ERR_UNSUPPORTED;
-    }
-    prepare_table_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(homographies, rows);
+    MVS_CUDA(cudaMallocAsync(&temp.p, (size_t)rows * 8 * sizeof(float), s));
+    prepare_table_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(homographies, rows, (float*)temp.p);
     MVS_LAUNCH_CHECK("prepare_table_kernel");
-    void* g_ptr = nullptr;
-    MVS_CUDA(cudaGetSymbolAddress(&g_ptr, g_table));
-    coef = (const float*)g_ptr;
+    coef = (const float*)temp.p;
   }
   // variant: 0 auto, 1 generic, 2 fast path with a 32x1 pixel tile, 3 fast path with a 16x2 tile
   bool fast_ok = sampler == MVSB200_SAMPLER_TRANSFORM && channels == 32 && n_views - 1 <= kMaxSrcViews &&

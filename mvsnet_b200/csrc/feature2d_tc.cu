@@ -59,7 +59,7 @@ struct Params {
   float eps;
   int H, W, Ho, Wo, Cout;
   int stride, transposed, ksize;
-  int TX, TY, MB, tiles_x, tiles_y, n_views, grid_dbg;   // tile = TY = 8 * MB rows of TX positions (MB 128-row MMA blocks)
+  int TX, TY, MB, tiles_x, tiles_y, n_views, grid_dbg, variant_dbg;   // tile = TY = 8 * MB rows of TX positions (MB 128-row MMA blocks)
   int px_shift;                            // log2(PXin)
   int org_mul, org_off;                    // staged window origin = org_mul * (x0, y0) + org_off
   int PXin, RYin;                          // staged window: RYin rows of PXin cells per chunk
@@ -72,6 +72,7 @@ struct Params {
   __nv_bfloat16* y_cp8; float* y_f32; double* stats_out;
   long long* prof;                         // development (tuning UNET_PROFILE=2): phase clocks of CTA 0, thread 0
   int nops, dbg;                           // dbg (tuning UNET_DBG): 1 = no MMAs
+  int obuf;                                // operand buffers: 2 = the next item is transformed while this item's MMAs run
   Op ops[kMaxOps];
 };
 
@@ -89,15 +90,39 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __host__ __device__ inline int align128(int v) { return (v + 127) & ~127; }
 
-__global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_constant__ Params p) {
+// KIND = 0: every shape from the kernel parameters.  KIND = 1 (3x3 stride 1), 2 (3x3 stride 2), 3 (5x5 stride 2), 4 (transposed)
+// with NCH input chunks, NCS output chunks (one slice) and MBT row blocks per tile: the same code with the shape as
+// compile-time constants, for the layers that carry most of the pixels (the generic code spent 3 400 warp instructions per
+// tile on run-time loop bounds, divisions and parameter reads: ncu, issue slots 58 %; 0.125 -> 0.07 ms per full-resolution
+// layer).  The geometry below restates plan_layer(); the launch checks a plan against it before it picks a variant.
+struct Shape { int MB, ncls, N, CS, PXin, pxs, RYin, nsub, subc, nchp, TX, TY, omul, ooff, trans, split; };
+__host__ __device__ constexpr Shape shape_of(int kind, int nch, int ncs, int mb) {
+  const bool s2 = kind == 2 || kind == 3;
+  const int ryin = kind == 1 ? 8 * mb + 2 : (kind == 2 ? 16 * mb + 2 : (kind == 3 ? 16 * mb + 4 : 8 * mb + 1));
+  return Shape{mb, kind == 4 ? 4 : 1, (ncs * 8 + 15) / 16 * 16, ncs * 8, s2 ? 32 : 16, s2 ? 5 : 4, ryin, s2 ? 4 : 1,
+               (s2 ? ryin / 2 : ryin) * 16, nch == 1 ? 1 : nch, (kind == 1 || kind == 3) ? 14 : 15, 8 * mb, s2 ? 2 : 1,
+               kind == 2 ? 0 : (kind == 3 ? -2 : -1), kind == 4 ? 1 : 0, s2 ? 1 : 0};
+}
+
+template <int KIND, int NCH, int NCS, int MBT>
+__global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int nch = p.nch_a + p.nch_b;
-  const int win_cells = p.RYin * p.PXin;                       // cells of one chunk of the staged window
+  constexpr bool H = KIND != 0;
+  constexpr Shape SH = shape_of(H ? KIND : 1, H ? NCH : 1, H ? NCS : 1, H ? MBT : 1);
+  const int nch = H ? NCH : p.nch_a + p.nch_b;
+  const int c_MB = H ? SH.MB : p.MB, c_ncls = H ? SH.ncls : p.ncls, c_N = H ? SH.N : p.N, c_CS = H ? SH.CS : p.CS;
+  const int c_PXin = H ? SH.PXin : p.PXin, c_pxs = H ? SH.pxs : p.px_shift, c_RYin = H ? SH.RYin : p.RYin;
+  const int c_nsub = H ? SH.nsub : p.nsub, c_subc = H ? SH.subc : p.sub_cells, c_nchp = H ? SH.nchp : p.nchp;
+  const int c_nsl = H ? 1 : p.nslices, c_obuf = H ? 1 : p.obuf, c_TX = H ? SH.TX : p.TX, c_TY = H ? SH.TY : p.TY;
+  const bool c_trans = H ? SH.trans != 0 : p.transposed != 0;
+  const int c_omul = H ? SH.omul : p.org_mul, c_ooff = H ? SH.ooff : p.org_off;
+  const int win_cells = c_RYin * c_PXin;                       // cells of one chunk of the staged window
   const int s_bytes = nch * win_cells * 16;
-  const int chunk_o = p.nsub * p.sub_cells * 16;               // bytes of one chunk of the operand buffer
+  const int chunk_o = c_nsub * c_subc * 16;               // bytes of one chunk of the operand buffer
   unsigned char* s_S = smem;
   unsigned char* s_O = s_S + align128(s_bytes);
-  unsigned char* s_W = s_O + align128(p.nchp * chunk_o + 128);
+  const int o_stride = align128(c_nchp * chunk_o + 128);      // bytes of one operand buffer
+  unsigned char* s_W = s_O + (size_t)c_obuf * o_stride;
   float* s_aff = reinterpret_cast<float*>(s_W + align128(p.w_slice_bytes));     // [scale | shift][kMaxCin]
   float* s_red = s_aff + 2 * kMaxCin;                                           // [4 warps][sum(8) | sumsq(8)]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 64);                     // window landed, weights landed, MMAs done
@@ -121,16 +146,17 @@ __global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_con
   const uint32_t tmem_base = *s_tmem;
 
   // the zero chunk of an odd Cin / 8 (K = 16 takes chunks in pairs) and the pad behind the buffer are written once
-  for (int i = tid; i < ((p.nchp - nch) * chunk_o + 128) / 16; i += kThreads)
-    reinterpret_cast<uint4*>(s_O + (size_t)nch * chunk_o)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int ob = 0; ob < c_obuf; ++ob)
+    for (int i = tid; i < ((c_nchp - nch) * chunk_o + 128) / 16; i += kThreads)
+      reinterpret_cast<uint4*>(s_O + (size_t)ob * o_stride + (size_t)nch * chunk_o)[i] = make_uint4(0u, 0u, 0u, 0u);
   // The CTA is persistent: items (view, tile) blockIdx.x, + gridDim.x, ...  The window of the NEXT item is fetched as
   // soon as the transform has emptied the staging buffer, i.e. under the MMAs and the drain of the current item;
   // TMEM, barriers, the weights of single-slice layers and the scale / shift table of a view are set up once.
   const int tiles = p.tiles_x * p.tiles_y, total = tiles * p.n_views;
   auto fetch = [&](int item) {           // one thread
     const int n = item / tiles, t = item - n * tiles;
-    const int x0 = (t % p.tiles_x) * p.TX, y0 = (t / p.tiles_x) * p.TY;
-    const int ix0 = p.org_mul * x0 + p.org_off, iy0 = p.org_mul * y0 + p.org_off;
+    const int x0 = (t % p.tiles_x) * c_TX, y0 = (t / p.tiles_x) * c_TY;
+    const int ix0 = c_omul * x0 + c_ooff, iy0 = c_omul * y0 + c_ooff;
     mbar_arrive_expect_tx(bar_in, (uint32_t)s_bytes);
     tma_load_4d(s_S, &p.tmap_a, ix0 * 4, iy0, 0, n, bar_in);
     if (p.nch_b) tma_load_4d(s_S + (size_t)p.nch_a * win_cells * 16, &p.tmap_b, ix0 * 4, iy0, 0, n, bar_in);
@@ -143,13 +169,15 @@ __global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_con
   };
   if (tid == 0 && (int)blockIdx.x < total) { fetch((int)blockIdx.x); fetch_weights(0); }
 
-  const uint32_t idesc = make_idesc_bf16_f32(128, p.N);
+  const uint32_t idesc = make_idesc_bf16_f32(128, c_N);
   const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;          // version 1, SBO = 128 B
   const int xx = lane & 15, yy0 = warp * 2 + (lane >> 4);      // GEMM row of block b: (yy0 + 8 b, xx)
-  const bool row_ok = xx < p.TX;
-  const int nck = p.CS >> 3, ncho = p.Cout >> 3;
-  const bool split = p.stride == 2 && !p.transposed;
-  const bool one_slice = p.nslices == 1;
+  const bool row_ok = xx < c_TX;
+  const int nck = c_CS >> 3, ncho = p.Cout >> 3;
+  const bool split = H ? SH.split != 0 : (p.stride == 2 && !c_trans);
+  const int cls_shift = c_ncls == 4 ? 2 : 0;                    // (1 or 4 output classes)
+  const int lim_y = c_trans ? p.H : p.Ho, lim_x = c_trans ? p.W : p.Wo;
+  const bool one_slice = c_nsl == 1;
   uint32_t ph_in = 0, ph_w = 0, ph_mma = 0;
   bool w_ready = false;                  // single-slice layers: the weights stay
   int cur_view = -1;
@@ -202,14 +230,14 @@ __global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_con
 
   // transform: staged window -> operand buffer (normalise, ReLU, zero outside the image = SAME padding, parity split for
   // the stride-2 convolutions).  A thread owns window positions and walks the chunks of each.
-  auto transform = [&](int ix0, int iy0) {
+  auto transform = [&](int ix0, int iy0, int ob) {
     for (int pos = tid; pos < win_cells; pos += kThreads) {
-      const int r = pos >> p.px_shift, j = pos & (p.PXin - 1);
+      const int r = pos >> c_pxs, j = pos & (c_PXin - 1);
       const int ay = iy0 + r, ax = ix0 + j;
       const bool inside = ay >= 0 && ay < p.H && ax >= 0 && ax < p.W;
       int sub = 0, rr = r, jj = j;
       if (split) { sub = (r & 1) * 2 + (j & 1); rr = r >> 1; jj = j >> 1; }
-      unsigned char* dst = s_O + ((size_t)sub * p.sub_cells + rr * 16 + jj) * 16;
+      unsigned char* dst = s_O + (size_t)ob * o_stride + ((size_t)sub * c_subc + rr * 16 + jj) * 16;
       const unsigned char* src = s_S + (size_t)pos * 16;
       for (int ch = 0; ch < nch; ++ch) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -243,8 +271,8 @@ __global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_con
   };
 
   // the MMAs of one slice into accumulator buffer `buf` (warp 0; one elected lane issues, then commits on bar_mma)
-  const int acc_cols = p.MB * p.ncls * p.N;
-  auto issue = [&](int buf) {
+  const int acc_cols = c_MB * c_ncls * c_N;
+  auto issue = [&](int buf, int ob) {
     if (warp == 0) {
       if (!w_ready) { mbar_wait(bar_w, ph_w); w_ready = one_slice; }
       tc_fence_after();
@@ -252,12 +280,13 @@ __global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_con
         // one 16-byte shared-memory record per MMA (read ahead by the unrolled loop: an indexed read of the kernel
         // parameters per MMA cost ~250 clk each); row block b = the same descriptors 128 cells further down
         const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols);
+        const uint32_t oofs = (uint32_t)(ob * o_stride) >> 4;
 #pragma unroll 4
         for (int o = 0; o < p.nops; ++o) {
           const uint4 e = s_ops[o];
-          for (int b = 0; b < p.MB; ++b) {
+          for (int b = 0; b < c_MB; ++b) {
             if (p.dbg & 1) continue;
-            mma_bf16(d0 + e.z + (uint32_t)(b * p.ncls * p.N), desc_hi | (uint64_t)(e.x + (uint32_t)(b * 128)),
+            mma_bf16(d0 + e.z + (uint32_t)(b * c_ncls * c_N), desc_hi | (uint64_t)(e.x + oofs + (uint32_t)(b * 128)),
                      desc_hi | (uint64_t)e.y, idesc, e.w);
           }
         }
@@ -271,18 +300,52 @@ __global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_con
   // drain of one slice of item (n, x0, y0): group statistics + stores
   auto drain = [&](int n, int x0, int y0, int sl, int buf) {
     const int gx = x0 + xx;                // GEMM-row position (output; input for the transposed conv)
-    const int nbc = p.MB * p.ncls;
+    const int nbc = c_MB * c_ncls;
+    if (c_CS == 8) {
+      // 8-channel layers: one chunk per (row block, class) pair; two pairs per TMEM round trip (a round trip costs
+      // ~1 000 clk while MMAs are queued)
+      for (int bc0 = 0; bc0 < nbc; bc0 += 2) {
+        uint32_t r[16];
+        const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * acc_cols + bc0 * c_N);
+        tmem_ld8(tb, r);
+        if (bc0 + 1 < nbc) tmem_ld8(tb + (uint32_t)c_N, r + 8);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int bc = bc0 + u;
+          if (bc >= nbc) break;
+          const int b = bc >> cls_shift, cls = bc & (c_ncls - 1);
+          const int gy = y0 + yy0 + 8 * b;
+          int oy = gy, ox = gx;
+          const bool ok = row_ok && gy < lim_y && gx < lim_x;
+          if (c_trans) { oy = 2 * gy + (cls >> 1); ox = 2 * gx + (cls & 1); }
+          if (!ok) continue;
+          float s_ = 0.0f, q_ = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const float v = __uint_as_float(r[8 * u + k]); s_ += v; q_ = fmaf(v, v, q_); }
+          gs[0] += s_; gq[0] += q_;
+          uint4 pk;
+          pk.x = pack2(__uint_as_float(r[8 * u]), __uint_as_float(r[8 * u + 1]));
+          pk.y = pack2(__uint_as_float(r[8 * u + 2]), __uint_as_float(r[8 * u + 3]));
+          pk.z = pack2(__uint_as_float(r[8 * u + 4]), __uint_as_float(r[8 * u + 5]));
+          pk.w = pack2(__uint_as_float(r[8 * u + 6]), __uint_as_float(r[8 * u + 7]));
+          *reinterpret_cast<uint4*>(p.y_cp8 + ((((size_t)n * ncho + sl) * p.Ho + oy) * p.Wo + ox) * 8) = pk;
+        }
+      }
+      tc_fence_before();
+      return;
+    }
     for (int bc = 0; bc < nbc; ++bc) {
-      const int b = bc / p.ncls, cls = bc - b * p.ncls;
+      const int b = bc >> cls_shift, cls = bc & (c_ncls - 1);
       const int gy = y0 + yy0 + 8 * b;
       int oy = gy, ox = gx;
-      const bool ok = row_ok && gy < (p.transposed ? p.H : p.Ho) && gx < (p.transposed ? p.W : p.Wo);
-      if (p.transposed) { oy = 2 * gy + (cls >> 1); ox = 2 * gx + (cls & 1); }
+      const bool ok = row_ok && gy < lim_y && gx < lim_x;
+      if (c_trans) { oy = 2 * gy + (cls >> 1); ox = 2 * gx + (cls & 1); }
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 16) {
-        if (c0 < p.N) {
+        if (c0 < c_N) {
           uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * acc_cols + bc * p.N + c0), r);
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * acc_cols + bc * c_N + c0), r);
           tmem_ld_wait();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -315,10 +378,56 @@ __global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_con
     tc_fence_before();
   };
 
-  {
+  if (c_obuf == 2) {
+    // Single-slice layers with room for two operand buffers: while the MMAs of item i run (issue + commit round trip
+    // ~2 300 clk), the threads transform item i + 1 into the other buffer; then drain i.  The scale / shift table
+    // follows the item being TRANSFORMED, the statistics registers the item being DRAINED.
+    const int G = (int)gridDim.x;
+    int item = (int)blockIdx.x, it = 0, stat_view = -1;
+    // (view, tile row, tile column) of the item and of the next one, advanced by the grid stride without divisions
+    const int step_x = G % p.tiles_x, step_y = (G / p.tiles_x) % p.tiles_y, step_n = G / tiles;
+    int n = item / tiles, ty = (item - n * tiles) / p.tiles_x, tx = item - n * tiles - ty * p.tiles_x;
+    auto advance = [&](int& vn, int& vy, int& vx) {
+      vx += step_x;
+      if (vx >= p.tiles_x) { vx -= p.tiles_x; ++vy; }
+      vy += step_y;
+      if (vy >= p.tiles_y) { vy -= p.tiles_y; ++vn; }
+      vn += step_n;
+    };
+    int n1 = n, ty1 = ty, tx1 = tx;
+    if (item < total) {
+      set_view(n); cur_view = n;
+      mbar_wait(bar_in, ph_in); ph_in ^= 1u;
+      transform(c_omul * tx * c_TX + c_ooff, c_omul * ty * c_TY + c_ooff, 0);
+      if (tid == 0 && item + G < total) fetch(item + G);
+    }
+    for (; item < total; item += G, ++it) {
+      n = n1; ty = ty1; tx = tx1;
+      const int x0 = tx * c_TX, y0 = ty * c_TY;
+      tc_fence_after();
+      issue(0, it & 1);
+      if (item + G < total) {
+        advance(n1, ty1, tx1);
+        const int x1 = tx1 * c_TX, y1 = ty1 * c_TY;
+        if (n1 != cur_view) { set_view(n1); cur_view = n1; }
+        mbar_wait(bar_in, ph_in); ph_in ^= 1u;
+        transform(c_omul * x1 + c_ooff, c_omul * y1 + c_ooff, (it + 1) & 1);
+        if (tid == 0 && item + 2 * G < total) fetch(item + 2 * G);
+      }
+      mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
+      tc_fence_after();
+      if (p.stats_out && n != stat_view) {
+        if (stat_view >= 0) flush_stats(stat_view, 0);
+        stat_view = n;
+      }
+      drain(n, x0, y0, 0, 0);
+      __syncthreads();                     // accumulators drained before the next MMAs overwrite them
+    }
+    if (p.stats_out && stat_view >= 0) flush_stats(stat_view, 0);
+  } else {
     for (int item = (int)blockIdx.x; item < total; item += (int)gridDim.x) {
       const int n = item / tiles, t = item - n * tiles;
-      const int x0 = (t % p.tiles_x) * p.TX, y0 = (t / p.tiles_x) * p.TY;
+      const int x0 = (t % p.tiles_x) * c_TX, y0 = (t / p.tiles_x) * c_TY;
       if (n != cur_view) {
         if (p.stats_out && one_slice && cur_view >= 0) flush_stats(cur_view, 0);
         set_view(n);
@@ -329,20 +438,20 @@ __global__ void __launch_bounds__(kThreads, 7) conv2d_tc_kernel(const __grid_con
       mbar_wait(bar_in, ph_in);
       ph_in ^= 1u;
       if (p.prof) t1 = clock64();
-      transform(p.org_mul * x0 + p.org_off, p.org_mul * y0 + p.org_off);
+      transform(c_omul * x0 + c_ooff, c_omul * y0 + c_ooff, 0);
       if (p.prof) t2 = clock64();
       // the staging buffer is free: the next item's window lands under this item's MMAs and drain
       if (tid == 0 && item + (int)gridDim.x < total) fetch(item + (int)gridDim.x);
-      for (int sl = 0; sl < p.nslices; ++sl) {
-        issue(0);
+      for (int sl = 0; sl < c_nsl; ++sl) {
+        issue(0, 0);
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1u;
         tc_fence_after();
         if (p.prof) t3 = clock64();
         // multi-slice layers: the weight buffer is free, the images of the next (item, slice) land while this one drains
         if (!one_slice && tid == 0) {
-          const bool more = sl + 1 < p.nslices || item + (int)gridDim.x < total;
-          if (more) fetch_weights(sl + 1 < p.nslices ? sl + 1 : 0);
+          const bool more = sl + 1 < c_nsl || item + (int)gridDim.x < total;
+          if (more) fetch_weights(sl + 1 < c_nsl ? sl + 1 : 0);
         }
         drain(n, x0, y0, sl, 0);
         __syncthreads();                   // accumulators drained: the next MMAs may overwrite them (and the operand buffer)
@@ -499,7 +608,10 @@ static int plan_layer(int ksize, int stride, int transposed, int cin, int cout, 
   const int npairs = 1;
   nt = nops;                               // (weights: one image per op)
   // slice of output channels: weights of a slice <= 74 KB, accumulators of all classes <= 256 columns
-  const size_t fixed = (size_t)align128(nch * c->RYin * c->PXin * 16) + align128(c->nchp * c->nsub * c->sub_cells * 16 + 128) +
+  const size_t o_bytes = (size_t)align128(c->nchp * c->nsub * c->sub_cells * 16 + 128);
+  // a second operand buffer where it is cheap (the big-resolution layers: a few KB): transform under the MMAs
+  c->obuf = (o_bytes <= 20 * 1024 && tuning().unet_obuf == 2) ? 2 : 1;       // (measured: no gain at config 2; on request)
+  const size_t fixed = (size_t)align128(nch * c->RYin * c->PXin * 16) + c->obuf * o_bytes +
                        2 * kMaxCin * sizeof(float) + 64 * sizeof(float) + 4 * sizeof(uint64_t) + kMaxOps * sizeof(uint4);
   int CS = cout < 64 ? cout : 64;
   for (;;) {
@@ -511,6 +623,7 @@ static int plan_layer(int ksize, int stride, int transposed, int cin, int cout, 
   }
   c->CS = CS; c->nslices = cout / CS; c->N = (CS + 15) / 16 * 16;
   c->w_slice_bytes = nt * npairs * 2 * c->N * 16;
+  if (c->nslices > 1) c->obuf = 1;         // (multi-slice layers keep the sequential loop; their buffer is large anyway)
   for (int o = 0; o < nops; ++o) {
     c->ops[o].col *= (uint32_t)c->N;
     c->ops[o].b_lo = (uint32_t)((o * 2 * c->N * 16) >> 4) | ((uint32_t)((c->N * 16) >> 4) << 16);
@@ -653,18 +766,31 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
     for (int i = 0; i <= MVSB200_UNET_LAYERS; ++i) cudaEventCreate(&pev[i]);
     cudaEventRecord(pev[0], s);
   }
+  using Kernel = void (*)(const Params);
+  struct Variant { int kind, nch, ncs, mb; Kernel fn; };
+#define F2V(K, C, S, M) {K, C, S, M, conv2d_tc_kernel<K, C, S, M>}
+  static const Variant kVariants[] = {
+      {0, 0, 0, 0, conv2d_tc_kernel<0, 0, 0, 0>},
+      F2V(1, 1, 1, 2), F2V(1, 2, 1, 2), F2V(1, 2, 2, 2), F2V(1, 4, 2, 2),          // full resolution and level 1, 3x3 stride 1
+      F2V(1, 4, 4, 1), F2V(1, 8, 4, 1), F2V(1, 8, 8, 1),                           // levels 2 and 3
+      F2V(2, 1, 2, 2), F2V(2, 2, 4, 1), F2V(2, 4, 8, 1),                           // 3x3 stride 2
+      F2V(3, 1, 2, 2), F2V(3, 2, 4, 1),                                            // 5x5 stride 2
+      F2V(4, 2, 1, 1), F2V(4, 2, 1, 2), F2V(4, 4, 2, 1), F2V(4, 8, 4, 1),          // transposed
+  };
+#undef F2V
+  constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
   static std::atomic<uint64_t> attr_done{0};
+  static int kernel_regs_of[kNumVariants];
   int dev = 0;
   MVS_CUDA(cudaGetDevice(&dev));
   if (!(attr_done.load(std::memory_order_acquire) >> (dev & 63) & 1u)) {
-    MVS_CUDA(cudaFuncSetAttribute((const void*)conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    for (int k = 0; k < kNumVariants; ++k) {
+      MVS_CUDA(cudaFuncSetAttribute((const void*)kVariants[k].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+      cudaFuncAttributes fa;
+      MVS_CUDA(cudaFuncGetAttributes(&fa, (const void*)kVariants[k].fn));
+      kernel_regs_of[k] = fa.numRegs;
+    }
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
-  }
-  int kernel_regs = 128;
-  {
-    cudaFuncAttributes fa;
-    MVS_CUDA(cudaFuncGetAttributes(&fa, (const void*)conv2d_tc_kernel));
-    kernel_regs = fa.numRegs;
   }
   for (int l = 0; l < MVSB200_UNET_LAYERS; ++l) {
     const F2Layer& L = kUnet[l];
@@ -691,6 +817,22 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
     c.stats_out = L.gn ? stats + (size_t)l * n_views * tp.gmax * 2 : nullptr;
     // NOTE the statistics of a layer are laid out [N][C/8][2] with ITS OWN group count
     cudaLaunchConfig_t cfg = {};
+    // a compile-time variant when there is one whose geometry IS the plan's (one slice, one operand buffer)
+    int variant = 0;
+    if (tuning().unet_hot != 0 && c.nslices == 1 && c.obuf == 1) {
+      const int kind = L.transposed ? 4 : (L.stride == 1 ? 1 : (L.k == 3 ? 2 : 3));
+      const int nchl = c.nch_a + c.nch_b;
+      for (int k = 1; k < kNumVariants; ++k) {
+        const Variant& v = kVariants[k];
+        if (v.kind != kind || v.nch != nchl || v.ncs * 8 != c.CS || v.mb != c.MB) continue;
+        const Shape sh = shape_of(v.kind, v.nch, v.ncs, v.mb);
+        if (sh.ncls == c.ncls && sh.N == c.N && sh.PXin == c.PXin && sh.pxs == c.px_shift && sh.RYin == c.RYin && sh.nsub == c.nsub &&
+            sh.subc == c.sub_cells && sh.nchp == c.nchp && sh.TX == c.TX && sh.TY == c.TY && sh.omul == c.org_mul &&
+            sh.ooff == c.org_off && (sh.trans != 0) == (c.transposed != 0))
+          variant = k;
+      }
+    }
+    const int kernel_regs = kernel_regs_of[variant];
     // persistent CTAs: as many as fit an SM (shared memory, 512 TMEM columns, 16 x 128 threads), each walks its items
     c.n_views = n_views;
     // (registers, shared memory with its 1 KB per-block reserve, 512 TMEM columns, 16 x 128 threads)
@@ -707,6 +849,7 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = tuning().tc_no_pdl ? 0 : 1;
     c.grid_dbg = (int)cfg.gridDim.x;
+    c.variant_dbg = variant;
     c.dbg = tuning().unet_dbg;
     static long long* prof_buf = nullptr;
     c.prof = nullptr;
@@ -715,7 +858,7 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
       MVS_CUDA(cudaMemsetAsync(prof_buf, 0, 64, s));
       c.prof = prof_buf;
     }
-    const cudaError_t lerr = cudaLaunchKernelEx(&cfg, conv2d_tc_kernel, c);
+    const cudaError_t lerr = cudaLaunchKernelEx(&cfg, kVariants[variant].fn, c);
     if (lerr != cudaSuccess) {
       set_error("launch of conv2d_tc_kernel (%s) failed: %s", L.name, cudaGetErrorString(lerr));
       return MVSB200_ERR_CUDA;
@@ -737,8 +880,8 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
       float ms = 0.f;
       cudaEventElapsedTime(&ms, pev[l], pev[l + 1]);
       total += ms;
-      fprintf(stderr, "[unet-tc] %-10s %4dx%-4d C=%-3d items %5d grid %4d smem %6zu slices %d N %3d  %.3f ms\n", kUnet[l].name, tp.h[l],
-              tp.w[l], tp.c[l], plans[l].tiles_x * plans[l].tiles_y * n_views, plans[l].grid_dbg, smems[l], plans[l].nslices, plans[l].N, ms);
+      fprintf(stderr, "[unet-tc] %-10s %4dx%-4d C=%-3d items %5d grid %4d smem %6zu slices %d N %3d var %d  %.3f ms\n", kUnet[l].name, tp.h[l],
+              tp.w[l], tp.c[l], plans[l].tiles_x * plans[l].tiles_y * n_views, plans[l].grid_dbg, smems[l], plans[l].nslices, plans[l].N, plans[l].variant_dbg, ms);
     }
     fprintf(stderr, "[unet-tc] total %.3f ms\n", total);
     for (int i = 0; i <= MVSB200_UNET_LAYERS; ++i) cudaEventDestroy(pev[i]);

@@ -97,11 +97,15 @@ json.dump({"kernel": cv[0]["kernel"], "config": "cfg2", "dram_bytes_per_launch":
            "source": f"profiles/{tag}_cost_volume_ncu.json (ncu --set full, one launch at cfg2: dram__bytes_read.sum + "
                      "dram__bytes_write.sum)"},
           open(os.path.join(P, "cost_volume_traffic.json"), "w"), indent=1)
-layers = ["3dconv1_0", "3dconv2_0", "3dconv3_0[0:32]", "3dconv3_0[32:64]", "3dconv0_1", "3dconv1_1", "3dconv2_1",
+layers = ["3dconv0_1 + 3dconv1_0 (one launch)", "3dconv2_0", "3dconv3_0[0:32]", "3dconv3_0[32:64]", "3dconv1_1", "3dconv2_1",
           "3dconv3_1[0:32]", "3dconv3_1[32:64]", "3dconv4_0", "3dconv5_0", "3dconv6_0", "3dconv6_2"]
 if os.path.exists(os.path.join(G, "prof_conv_raw.csv")):
     summarise(os.path.join(G, "prof_conv_raw.csv"), os.path.join(P, f"{tag}_conv3d_ncu.json"), layers)
-for f in ("prof_cv_details.txt", "prof_conv_details.txt"):
+if os.path.exists(os.path.join(G, "prof_tower_raw.csv")):
+    summarise(os.path.join(G, "prof_tower_raw.csv"), os.path.join(P, f"{tag}_tower_layer_ncu.json"), ["a full-resolution 8 -> 8 layer"])
+if os.path.exists(os.path.join(G, "tower_bench.json")):
+    open(os.path.join(P, f"{tag}_tower_bench.json"), "w").write(open(os.path.join(G, "tower_bench.json")).read())
+for f in ("prof_cv_details.txt", "prof_conv_details.txt", "prof_tower_details.txt"):
     if os.path.exists(os.path.join(G, f)):
         open(os.path.join(P, f"{tag}_{f}"), "w").write(open(os.path.join(G, f), errors="replace").read())
 print("wrote summaries under profiles/")

@@ -200,32 +200,74 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ xs, const fl
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
   const size_t nb = (size_t)Db * Hb * Wb;
   const size_t b_begin = (size_t)blockIdx.x * chunk, b_end = b_begin + chunk < nb ? b_begin + chunk : nb;
+  // voxel offsets of the tile (X element offset / R element offset, -1 = outside), worked out once per voxel and tap
+  __shared__ long long s_off[2][kWgTile];
+  const bool vec4 = (cin & 3) == 0 && (cout & 3) == 0;
   for (size_t t0 = b_begin; t0 < b_end; t0 += kWgTile) {
     __syncthreads();
-    // stage the tile: thread -> (voxel, channel) pairs, channels fastest
-    for (int i = threadIdx.x; i < kWgTile * (cin + cout); i += 256) {
-      const bool is_x = i < kWgTile * cin;
-      const int j = is_x ? i : i - kWgTile * cin, C = is_x ? cin : cout;
-      const int v = j / C, c = j - v * C;
-      const size_t b = t0 + v;
-      float val = 0.0f;
+    if (threadIdx.x < kWgTile) {
+      const size_t b = t0 + threadIdx.x;
+      long long ox = -1, orr = -1;
       if (b < b_end) {
         const int bx = (int)(b % Wb), by = (int)((b / Wb) % Hb), bz = (int)(b / ((size_t)Wb * Hb));
         int xz, xy, xx, rz, ry, rx;
         if (TRANSPOSED) { xz = bz; xy = by; xx = bx; rz = 2 * bz + kd; ry = 2 * by + kh; rx = 2 * bx + kw; }
         else { xz = bz * stride + kd - pad_d; xy = by * stride + kh - pad_h; xx = bx * stride + kw - pad_w; rz = bz; ry = by; rx = bx; }
-        const bool ok = xz >= 0 && xz < Dx && xy >= 0 && xy < Hx && xx >= 0 && xx < Wx && rz < Dr && ry < Hr && rx < Wr;
-        if (ok) {
-          if (is_x) {
-            const size_t off = (((size_t)xz * Hx + xy) * Wx + xx) * cin + c;
-            val = act_in(x, xs, xb, off, c);
-            if (skip) val += act_in(skip, ss, sb, off, c);
-          } else {
-            val = __ldg(r + (((size_t)rz * Hr + ry) * Wr + rx) * cout + c);
-          }
+        if (xz >= 0 && xz < Dx && xy >= 0 && xy < Hx && xx >= 0 && xx < Wx && rz < Dr && ry < Hr && rx < Wr) {
+          ox = (long long)((((size_t)xz * Hx + xy) * Wx + xx) * cin);
+          orr = (long long)((((size_t)rz * Hr + ry) * Wr + rx) * cout);
         }
       }
-      (is_x ? s_x : s_r)[j] = val;
+      s_off[0][threadIdx.x] = ox; s_off[1][threadIdx.x] = orr;
+    }
+    __syncthreads();
+    // stage the tile: thread -> (voxel, group of 4 channels), channels fastest (scalar channels when Cin / Cout % 4 != 0)
+    if (vec4) {
+      const int gx4 = cin >> 2, gr4 = cout >> 2;
+      for (int i = threadIdx.x; i < kWgTile * (gx4 + gr4); i += 256) {
+        const bool is_x = i < kWgTile * gx4;
+        const int j = is_x ? i : i - kWgTile * gx4, G4 = is_x ? gx4 : gr4;
+        const int v = j / G4, c = (j - v * G4) * 4;
+        const long long off = s_off[is_x ? 0 : 1][v];
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (off >= 0) {
+          if (is_x) {
+            val = __ldg(reinterpret_cast<const float4*>(x + off + c));
+            if (xs) {
+              val.x = fmaxf(fmaf(val.x, xs[c], xb[c]), 0.0f); val.y = fmaxf(fmaf(val.y, xs[c + 1], xb[c + 1]), 0.0f);
+              val.z = fmaxf(fmaf(val.z, xs[c + 2], xb[c + 2]), 0.0f); val.w = fmaxf(fmaf(val.w, xs[c + 3], xb[c + 3]), 0.0f);
+            }
+            if (skip) {
+              float4 k = __ldg(reinterpret_cast<const float4*>(skip + off + c));
+              if (ss) {
+                k.x = fmaxf(fmaf(k.x, ss[c], sb[c]), 0.0f); k.y = fmaxf(fmaf(k.y, ss[c + 1], sb[c + 1]), 0.0f);
+                k.z = fmaxf(fmaf(k.z, ss[c + 2], sb[c + 2]), 0.0f); k.w = fmaxf(fmaf(k.w, ss[c + 3], sb[c + 3]), 0.0f);
+              }
+              val.x += k.x; val.y += k.y; val.z += k.z; val.w += k.w;
+            }
+          } else {
+            val = __ldg(reinterpret_cast<const float4*>(r + off + c));
+          }
+        }
+        *reinterpret_cast<float4*>((is_x ? s_x + v * cin : s_r + v * cout) + c) = val;
+      }
+    } else {
+      for (int i = threadIdx.x; i < kWgTile * (cin + cout); i += 256) {
+        const bool is_x = i < kWgTile * cin;
+        const int j = is_x ? i : i - kWgTile * cin, C = is_x ? cin : cout;
+        const int v = j / C, c = j - v * C;
+        const long long off = s_off[is_x ? 0 : 1][v];
+        float val = 0.0f;
+        if (off >= 0) {
+          if (is_x) {
+            val = act_in(x, xs, xb, (size_t)off + c, c);
+            if (skip) val += act_in(skip, ss, sb, (size_t)off + c, c);
+          } else {
+            val = __ldg(r + off + c);
+          }
+        }
+        (is_x ? s_x : s_r)[j] = val;
+      }
     }
     __syncthreads();
     if (worker) {

@@ -177,7 +177,7 @@ __device__ __forceinline__ float act_in(const float* x, const float* scale, cons
 // dW[tap][co][ci] (transposed) += sum_b X[x index][ci] * R[r index][co], X = relu(bn(raw)) (+ the skip activation).
 // grid = (voxel chunks, 27 taps); a block stages tiles of 64 base voxels (X and R rows) in shared memory; a thread owns a
 // 4 x TCO patch of the Cin x Cout matrix, the groups of threads that cover the matrix split the tile's voxels.
-constexpr int kWgTile = 64;
+constexpr int kWgTile = 256;      // (64: three block barriers per 64 voxels paced the kernel)
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ x, const float* __restrict__ xs, const float* __restrict__ xb,
@@ -512,11 +512,14 @@ extern "C" int mvsb200_train_step(const float* feats, const float* cams, const f
     {
       const int* db = L.transposed ? di : dout;          // base voxels: transposed conv walks its input volume
       const size_t nb = (size_t)db[0] * db[1] * db[2];
-      const int chunk = 2048;
+      const int chunk = 4096;
       dim3 grid((unsigned)((nb + chunk - 1) / chunk), 27);
       const size_t smem = (size_t)kWgTile * (L.cin + L.cout) * sizeof(float);
       const int pd = L.transposed ? 0 : tf_same_pad_before(di[0], 3, L.stride), ph = L.transposed ? 0 : tf_same_pad_before(di[1], 3, L.stride),
                 pw = L.transposed ? 0 : tf_same_pad_before(di[2], 3, L.stride);
+      // (a tile of 256 voxels x up to 128 channels exceeds the 48 KB default; the attribute is per function and device)
+      MVS_CUDA(cudaFuncSetAttribute((const void*)(L.transposed ? wgrad_kernel<true> : wgrad_kernel<false>),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       if (L.transposed)
         wgrad_kernel<true><<<grid, 256, smem, s>>>(x, xs, xb, sk, ss, sb, R, di[0], di[1], di[2], dout[0], dout[1], dout[2], db[0],
                                                    db[1], db[2], L.cin, L.cout, 2, 0, 0, 0, chunk, grads->kernel[i]);

@@ -45,6 +45,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peak():
+    """Dense bf16 tensor throughput for a kernel timed inside a long step: the sustained cuBLAS figure the driver measured."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 2250.0, "nominal (2.25 PFLOP/s dense bf16)"
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled WHILE the timed region runs: NVML polled from a thread every few
     milliseconds (the timed region of 20 steps is ~60 ms, too short for `nvidia-smi -lms`), nvidia-smi as a fallback."""
@@ -416,6 +426,10 @@ def run_ours(args, rank, world, local_rank):
                                  "achieved": 230.0 * V / (float(stage_ms[2]) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": 230.0 * V / (float(stage_ms[2]) * 1e-3) / 1e9 / peak,
                                  "algorithmic_bytes": 230 * V, "tflops": 22896.0 * V / (float(stage_ms[2]) * 1e-3) / 1e12,
+                                 "tensor_peak_tflops": tensor_peak()[0], "tensor_peak_source": tensor_peak()[1],
+                                 "tensor_frac": 22896.0 * V / (float(stage_ms[2]) * 1e-3) / 1e12 / tensor_peak()[0],
+                                 "tensor_pipe_active_per_launch": "profiles/r2c_conv3d_ncu.json (ncu sm__pipe_tensor_cycles_active: "
+                                                                  "48.6 % in the 3dconv0_1 + 3dconv1_0 launch, 3-18 % elsewhere)",
                                  "stage_ms": float(stage_ms[2])},
         # K4: in bf16 mode the soft-argmin runs inside 3dconv6_2's epilogue (the filtered volume is not re-read for it);
         # what is timed here is regress_combine_kernel (three partial maps in, four probability gathers, two maps out).

@@ -339,6 +339,12 @@ int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_params* para
 int mvsb200_unet_tc_layer_raw(int n_views, int height, int width, int base_filter, int layer, size_t* offset,
                               int* dims, size_t* stats_offset);
 
+/* Host-only view of the tensor-core tower's launch plan of one layer (no device work): out[0..11] = {kind (1: 3x3 stride 1,
+ * 2: 3x3 stride 2, 3: 5x5 stride 2, 4: transposed), input chunks of 8 channels, output channels per slice, slices, MMA N,
+ * 128-row blocks per tile, MMAs per row block and slice, shared-memory bytes, TMEM columns, tiles per view, weight bytes
+ * per slice, operand buffers}. */
+int mvsb200_unet_tc_plan(int n_views, int height, int width, int base_filter, int layer, int* out);
+
 /* ---- training step of the path (BASELINE config 4; train.py:314-315 `inference` inside get_loss, loss.py:190-220
  * mvsnet_regression_loss with loss_type 'original', train.py:429 opt.compute_gradients) ------------------------------
  * Gradient buffers in the layout of the variables they belong to (fp32, device memory); gamma/beta[10] unused. */

@@ -90,6 +90,7 @@ SIGNATURES = {
     "mvsb200_unet_layer_output": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_int)]),
     "mvsb200_unet_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mvsb200_unet_tc_forward": (c_int, [_P, POINTER(UnetParams), c_int, c_int, c_int, c_int, c_float, _P, _P, c_size_t, _P]),
+    "mvsb200_unet_tc_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int)]),
     "mvsb200_unet_tc_layer_raw": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_int),
                                           POINTER(c_size_t)]),
     "mvsb200_depth_regress": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, _P, _P, _P]),

@@ -681,11 +681,50 @@ static int make_tower_plan(int n, int H, int W, int bf, TowerPlan* p) {
   return MVSB200_OK;
 }
 
+// Plan of layer l at this problem size: geometry, ops, slices -- with two 128-row blocks per tile where there are plenty of
+// tiles (the per-item latency chain is paid once per tile; ops and weight images do not depend on it).
+static int choose_plan(int l, int n_views, int height, int width, const TowerPlan& tp, Params* plan, size_t* smem, OpSrc* srcs) {
+  const F2Layer& L = kUnet[l];
+  const int ca = L.src_a < 0 ? 8 : tp.c[L.src_a], cb = L.src_b >= 0 ? tp.c[L.src_b] : 0;
+  const int ih = L.src_a < 0 ? height : tp.h[L.src_a], iw = L.src_a < 0 ? width : tp.w[L.src_a];
+  int rc = plan_layer(L.k, L.stride, L.transposed, ca + cb, tp.c[l], ih, iw, 1, plan, smem, srcs);
+  if (rc) { set_error("unet(bf16): no plan for layer %s", L.name); return rc; }
+  const int mb_forced = tuning().unet_mb;
+  if ((mb_forced == 2 || (mb_forced == 0 && plan->tiles_x * plan->tiles_y * n_views >= 6000)) && plan->nslices == 1) {
+    Params two;
+    size_t smem2;
+    if (plan_layer(L.k, L.stride, L.transposed, ca + cb, tp.c[l], ih, iw, 2, &two, &smem2, nullptr) == MVSB200_OK &&
+        two.nslices == 1 && two.CS == plan->CS && two.nops == plan->nops) { *plan = two; *smem = smem2; }
+  }
+  plan->nch_a = ca / 8; plan->nch_b = cb / 8;
+  return MVSB200_OK;
+}
+
 }  // namespace f2
 }  // namespace mvsb200
 
 using namespace mvsb200;
 using namespace mvsb200::f2;
+
+/* Host-only view of the tower's launch plans (no device work; tests/test_planner.py): out[0..11] = {kind (1: 3x3 stride 1,
+ * 2: 3x3 stride 2, 3: 5x5 stride 2, 4: transposed), input chunks, output channels per slice, slices, MMA N, row blocks per
+ * tile, MMAs per row block and slice, shared memory bytes, TMEM columns, tiles per view, weight bytes per slice, operand
+ * buffers} of layer `layer` at this problem size. */
+extern "C" int mvsb200_unet_tc_plan(int n_views, int height, int width, int base_filter, int layer, int* out) {
+  MVS_CHECK_ARG(out && layer >= 0 && layer < MVSB200_UNET_LAYERS, "unet_tc_plan: bad layer %d", layer);
+  TowerPlan tp;
+  int rc = make_tower_plan(n_views, height, width, base_filter, &tp);
+  if (rc) return rc;
+  static thread_local Params plan;
+  size_t smem = 0;
+  rc = choose_plan(layer, n_views, height, width, tp, &plan, &smem, nullptr);
+  if (rc) return rc;
+  const F2Layer& L = kUnet[layer];
+  const int v[12] = {L.transposed ? 4 : (L.stride == 1 ? 1 : (L.k == 3 ? 2 : 3)), plan.nch_a + plan.nch_b, plan.CS, plan.nslices, plan.N,
+                     plan.MB, plan.nops, (int)smem, plan.tmem_cols, plan.tiles_x * plan.tiles_y, plan.w_slice_bytes, plan.obuf};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  return MVSB200_OK;
+}
 
 extern "C" size_t mvsb200_unet_tc_workspace_bytes(int n_views, int height, int width, int base_filter) {
   TowerPlan p;
@@ -742,17 +781,8 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
     if (L.src_b >= 0)
       MVS_CHECK_ARG(tp.h[L.src_b] == ih && tp.w[L.src_b] == iw, "unet_tc_forward: concat extents differ at %s", L.name);
     PackJob& j = jobs[l];
-    rc = plan_layer(L.k, L.stride, L.transposed, ca + cb, tp.c[l], ih, iw, 1, &plans[l], &smems[l], j.src);
-    if (rc) { set_error("unet(bf16): no plan for layer %s", L.name); return rc; }
-    // two 128-row blocks per tile where there are plenty of tiles (the per-item latency chain is paid once per tile);
-    // ops and weight images do not depend on it
-    const int mb_forced = tuning().unet_mb;
-    if ((mb_forced == 2 || (mb_forced == 0 && plans[l].tiles_x * plans[l].tiles_y * n_views >= 6000)) && plans[l].nslices == 1) {
-      Params two;
-      size_t smem2;
-      if (plan_layer(L.k, L.stride, L.transposed, ca + cb, tp.c[l], ih, iw, 2, &two, &smem2, nullptr) == MVSB200_OK &&
-          two.nslices == 1 && two.CS == plans[l].CS && two.nops == plans[l].nops) { plans[l] = two; smems[l] = smem2; }
-    }
+    rc = choose_plan(l, n_views, height, width, tp, &plans[l], &smems[l], j.src);
+    if (rc) return rc;
     j.kernel_tf = params->kernel[l]; j.out = (uint16_t*)(ws + tp.woff[l]);
     j.nops = plans[l].nops; j.N = plans[l].N; j.CS = plans[l].CS;
     j.nslices = plans[l].nslices; j.Cout = tp.c[l]; j.CinT = L.src_a < 0 ? 3 : ca + cb; j.transposed = L.transposed;

@@ -55,3 +55,42 @@ def test_headline_layer_folds():
 def test_plan_rejects_unsupported_channels():
     with pytest.raises(L.MVSB200Error, match="Cin"):
         plan(8, 16, 16, 24, 8, 1, False, False, False)
+
+
+# ---- tensor-core image tower (csrc/feature2d_tc.cu): host-side plans of the 32 layers ------------------------------
+TOWER = ["kind", "nch", "cs", "slices", "n", "mb", "ops", "smem", "tmem", "tiles", "wbytes", "obuf"]
+
+
+@pytest.mark.parametrize("config", ["cfg1", "cfg2", "cfg5"])
+def test_tower_plans_fit_the_sm(config):
+    import oracle.feature_oracle as FO
+    cfg = synthetic.CONFIGS[config]
+    lib = L.load()
+    specs = FO.unet_layer_specs(8)
+    assert len(specs) == 32
+    for i, (name, op, k, stride, cin, cout, srcs, gn, relu) in enumerate(specs):
+        nums = (ctypes.c_int * 12)()
+        L.check(lib.mvsb200_unet_tc_plan(cfg["n_views"], cfg["height"], cfg["width"], 8, i, nums), "unet_tc_plan")
+        p = dict(zip(TOWER, list(nums)))
+        kind = 4 if op == "deconv" else (1 if stride == 1 else (2 if k == 3 else 3))
+        assert p["kind"] == kind, (name, p)
+        assert p["nch"] == max(cin, 8) // 8 and p["cs"] * p["slices"] == cout, (name, p)      # the 3-channel images fill one chunk
+        assert p["n"] % 16 == 0 and p["n"] >= p["cs"] and p["mb"] in (1, 2), (name, p)
+        assert 0 < p["smem"] <= 220 * 1024 and p["wbytes"] <= 75776, (name, p)
+        assert p["tmem"] in (32, 64, 128, 256, 512) and p["tmem"] >= p["mb"] * (4 if kind == 4 else 1) * p["n"], (name, p)
+        assert p["ops"] <= 72 and p["wbytes"] == p["ops"] * 2 * p["n"] * 16, (name, p)
+        # one MMA per (tap, channel pair) -- or per pair of taps when the input is a single chunk
+        taps = {1: 9, 2: 9, 3: 25, 4: 9}[kind]
+        if p["nch"] == 1:
+            assert p["ops"] == ({1: 5, 2: 5, 3: 13}[kind] if kind != 4 else 2 + 1 + 1 + 1), (name, p)
+        else:
+            assert p["ops"] == taps * p["nch"] // 2, (name, p)
+
+
+def test_tower_plan_rejects_bad_shapes():
+    lib = L.load()
+    nums = (ctypes.c_int * 12)()
+    assert lib.mvsb200_unet_tc_plan(5, 100, 160, 8, 0, nums) != 0          # H not a multiple of 16
+    assert lib.mvsb200_unet_tc_plan(5, 96, 160, 4, 0, nums) != 0           # groups of 8 channels need base_filter % 8 == 0
+    assert lib.mvsb200_unet_tc_workspace_bytes(5, 100, 160, 8) == 0
+    assert lib.mvsb200_unet_tc_workspace_bytes(5, 96, 160, 8) > 0

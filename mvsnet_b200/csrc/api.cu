@@ -27,7 +27,7 @@ const TuningField kTuningInts[] = {
     {"TC_ZSPLIT", &Tuning::tc_zsplit}, {"TC_DBG", &Tuning::tc_dbg}, {"TC_VERBOSE", &Tuning::tc_verbose},
     {"TC_PROF", &Tuning::tc_prof}, {"TC_EXACT_SMEM", &Tuning::tc_exact_smem}, {"TC_NO_PDL", &Tuning::tc_no_pdl},
     {"REGNET_PROFILE", &Tuning::regnet_profile}, {"UNET_NO_TILE", &Tuning::unet_no_tile},
-    {"UNET_PROFILE", &Tuning::unet_profile}, {"UNET_FP32", &Tuning::unet_fp32}, {"UNET_MB", &Tuning::unet_mb}, {"UNET_DBG", &Tuning::unet_dbg}, {"UNET_OBUF", &Tuning::unet_obuf}, {"UNET_HOT", &Tuning::unet_hot},
+    {"UNET_PROFILE", &Tuning::unet_profile}, {"UNET_FP32", &Tuning::unet_fp32}, {"UNET_MB", &Tuning::unet_mb}, {"UNET_DBG", &Tuning::unet_dbg}, {"UNET_OBUF", &Tuning::unet_obuf}, {"UNET_HOT", &Tuning::unet_hot}, {"UNET_INPLACE", &Tuning::unet_inplace},
 };
 std::atomic<const Tuning*> g_tuning{nullptr};
 std::mutex g_tuning_mutex;

@@ -34,6 +34,7 @@ struct Tuning {
   int regnet_profile = 0, unet_no_tile = 0, unet_profile = 0, unet_fp32 = 0;
   int unet_dbg = 0;
   int unet_obuf = 0;          // UNET_OBUF: 2 = a second operand buffer where it is cheap (transform under the MMAs)
+  int unet_inplace = -1;      // UNET_INPLACE: 0 = never transform in place
   int unet_hot = -1;          // UNET_HOT: 0 = no compile-time variants of the tower kernel
   int unet_mb = 0;            // UNET_MB: 1 / 2 = 128-row blocks per tile of the tensor-core tower (0: by tile count)
 };

@@ -73,6 +73,7 @@ struct Params {
   long long* prof;                         // development (tuning UNET_PROFILE=2): phase clocks of CTA 0, thread 0
   int nops, dbg;                           // dbg (tuning UNET_DBG): 1 = no MMAs
   int obuf;                                // operand buffers: 2 = the next item is transformed while this item's MMAs run
+  int inplace;                             // the transform rewrites the staged window in place (no operand buffer of its own)
   Op ops[kMaxOps];
 };
 
@@ -120,9 +121,10 @@ __global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_con
   const int s_bytes = nch * win_cells * 16;
   const int chunk_o = c_nsub * c_subc * 16;               // bytes of one chunk of the operand buffer
   unsigned char* s_S = smem;
-  unsigned char* s_O = s_S + align128(s_bytes);
+  const bool c_inplace = H ? false : p.inplace != 0;
+  unsigned char* s_O = c_inplace ? s_S : s_S + align128(s_bytes);
   const int o_stride = align128(c_nchp * chunk_o + 128);      // bytes of one operand buffer
-  unsigned char* s_W = s_O + (size_t)c_obuf * o_stride;
+  unsigned char* s_W = c_inplace ? s_S + o_stride : s_O + (size_t)c_obuf * o_stride;
   float* s_aff = reinterpret_cast<float*>(s_W + align128(p.w_slice_bytes));     // [scale | shift][kMaxCin]
   float* s_red = s_aff + 2 * kMaxCin;                                           // [4 warps][sum(8) | sumsq(8)]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 64);                     // window landed, weights landed, MMAs done
@@ -440,8 +442,9 @@ __global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_con
       if (p.prof) t1 = clock64();
       transform(c_omul * x0 + c_ooff, c_omul * y0 + c_ooff, 0);
       if (p.prof) t2 = clock64();
-      // the staging buffer is free: the next item's window lands under this item's MMAs and drain
-      if (tid == 0 && item + (int)gridDim.x < total) fetch(item + (int)gridDim.x);
+      // the staging buffer is free: the next item's window lands under this item's MMAs and drain (in-place layers: the
+      // window IS the operand buffer, so the fetch waits for the last MMAs)
+      if (!c_inplace && tid == 0 && item + (int)gridDim.x < total) fetch(item + (int)gridDim.x);
       for (int sl = 0; sl < c_nsl; ++sl) {
         issue(0, 0);
         mbar_wait(bar_mma, ph_mma);
@@ -458,6 +461,7 @@ __global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_con
         tc_fence_after();
         if (p.stats_out && !one_slice) flush_stats(n, sl);
       }
+      if (c_inplace && tid == 0 && item + (int)gridDim.x < total) fetch(item + (int)gridDim.x);
       if (p.prof && blockIdx.x == 0 && tid == 0) {
         t4 = clock64();
         p.prof[0] += t1 - t0; p.prof[1] += t2 - t1; p.prof[2] += t3 - t2; p.prof[3] += t4 - t3; p.prof[4] += 1;
@@ -530,7 +534,7 @@ static bool make_map(CUtensorMap* tm, const void* base, int n, int nch, int H, i
 
 // geometry + tap table of one layer; cin = channels of the concatenated input as stored (image: 8)
 static int plan_layer(int ksize, int stride, int transposed, int cin, int cout, int H, int W, int MB, Params* c, size_t* smem,
-                      OpSrc* srcs) {
+                      OpSrc* srcs, bool inplace = false) {
   memset(c, 0, sizeof(*c));
   Tap taps[kMaxTaps];
   const int kTY = 8 * MB;
@@ -611,13 +615,17 @@ static int plan_layer(int ksize, int stride, int transposed, int cin, int cout, 
   const size_t o_bytes = (size_t)align128(c->nchp * c->nsub * c->sub_cells * 16 + 128);
   // a second operand buffer where it is cheap (the big-resolution layers: a few KB): transform under the MMAs
   c->obuf = (o_bytes <= 20 * 1024 && tuning().unet_obuf == 2) ? 2 : 1;       // (measured: no gain at config 2; on request)
-  const size_t fixed = (size_t)align128(nch * c->RYin * c->PXin * 16) + c->obuf * o_bytes +
+  // in place: the staged window is the operand buffer (same geometry: one array per chunk, an even chunk count)
+  if (inplace && !(c->nsub == 1 && c->nchp == nch)) return MVSB200_ERR_UNSUPPORTED;
+  c->inplace = inplace ? 1 : 0;
+  if (inplace) c->obuf = 1;
+  const size_t fixed = (inplace ? o_bytes : (size_t)align128(nch * c->RYin * c->PXin * 16) + c->obuf * o_bytes) +
                        2 * kMaxCin * sizeof(float) + 64 * sizeof(float) + 4 * sizeof(uint64_t) + kMaxOps * sizeof(uint4);
   int CS = cout < 64 ? cout : 64;
   for (;;) {
     const int N = (CS + 15) / 16 * 16;
     const size_t wb = (size_t)nt * npairs * 2 * N * 16;
-    if (wb <= 75776 && fixed + align128((int)wb) <= kSmemMax && MB * c->ncls * N <= 256) break;
+    if (wb <= (inplace ? (size_t)160 * 1024 : (size_t)75776) && fixed + align128((int)wb) <= kSmemMax && MB * c->ncls * N <= 256) break;
     if (CS <= 8) return MVSB200_ERR_UNSUPPORTED;
     CS /= 2;
   }
@@ -695,6 +703,15 @@ static int choose_plan(int l, int n_views, int height, int width, const TowerPla
     size_t smem2;
     if (plan_layer(L.k, L.stride, L.transposed, ca + cb, tp.c[l], ih, iw, 2, &two, &smem2, nullptr) == MVSB200_OK &&
         two.nslices == 1 && two.CS == plan->CS && two.nops == plan->nops) { *plan = two; *smem = smem2; }
+  }
+  // layers whose weights do not fit beside window + operand buffer: transform in place if that saves slices (each slice
+  // re-fetches 74 KB of weights per tile)
+  if (plan->nslices > 1 && tuning().unet_inplace != 0) {
+    Params ip;
+    size_t smem3;
+    static thread_local OpSrc src3[kMaxOps];
+    if (plan_layer(L.k, L.stride, L.transposed, ca + cb, tp.c[l], ih, iw, 1, &ip, &smem3, src3, true) == MVSB200_OK &&
+        ip.nslices < plan->nslices && ip.nops == plan->nops) { *plan = ip; *smem = smem3; }
   }
   plan->nch_a = ca / 8; plan->nch_b = cb / 8;
   return MVSB200_OK;
@@ -849,7 +866,7 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
     cudaLaunchConfig_t cfg = {};
     // a compile-time variant when there is one whose geometry IS the plan's (one slice, one operand buffer)
     int variant = 0;
-    if (tuning().unet_hot != 0 && c.nslices == 1 && c.obuf == 1) {
+    if (tuning().unet_hot != 0 && c.nslices == 1 && c.obuf == 1 && !c.inplace) {
       const int kind = L.transposed ? 4 : (L.stride == 1 ? 1 : (L.k == 3 ? 2 : 3));
       const int nchl = c.nch_a + c.nch_b;
       for (int k = 1; k < kNumVariants; ++k) {

@@ -105,7 +105,7 @@ __host__ __device__ constexpr Shape shape_of(int kind, int nch, int ncs, int mb)
                kind == 2 ? 0 : (kind == 3 ? -2 : -1), kind == 4 ? 1 : 0, s2 ? 1 : 0};
 }
 
-template <int KIND, int NCH, int NCS, int MBT>
+template <int KIND, int NCH, int NCS, int MBT, bool IP>
 __global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr bool H = KIND != 0;
@@ -114,14 +114,14 @@ __global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_con
   const int c_MB = H ? SH.MB : p.MB, c_ncls = H ? SH.ncls : p.ncls, c_N = H ? SH.N : p.N, c_CS = H ? SH.CS : p.CS;
   const int c_PXin = H ? SH.PXin : p.PXin, c_pxs = H ? SH.pxs : p.px_shift, c_RYin = H ? SH.RYin : p.RYin;
   const int c_nsub = H ? SH.nsub : p.nsub, c_subc = H ? SH.subc : p.sub_cells, c_nchp = H ? SH.nchp : p.nchp;
-  const int c_nsl = H ? 1 : p.nslices, c_obuf = H ? 1 : p.obuf, c_TX = H ? SH.TX : p.TX, c_TY = H ? SH.TY : p.TY;
+  const int c_nsl = (H && !IP) ? 1 : p.nslices, c_obuf = H ? 1 : p.obuf, c_TX = H ? SH.TX : p.TX, c_TY = H ? SH.TY : p.TY;
   const bool c_trans = H ? SH.trans != 0 : p.transposed != 0;
   const int c_omul = H ? SH.omul : p.org_mul, c_ooff = H ? SH.ooff : p.org_off;
   const int win_cells = c_RYin * c_PXin;                       // cells of one chunk of the staged window
   const int s_bytes = nch * win_cells * 16;
   const int chunk_o = c_nsub * c_subc * 16;               // bytes of one chunk of the operand buffer
   unsigned char* s_S = smem;
-  const bool c_inplace = H ? false : p.inplace != 0;
+  const bool c_inplace = H ? IP : p.inplace != 0;
   unsigned char* s_O = c_inplace ? s_S : s_S + align128(s_bytes);
   const int o_stride = align128(c_nchp * chunk_o + 128);      // bytes of one operand buffer
   unsigned char* s_W = c_inplace ? s_S + o_stride : s_O + (size_t)c_obuf * o_stride;
@@ -814,17 +814,20 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
     cudaEventRecord(pev[0], s);
   }
   using Kernel = void (*)(const Params);
-  struct Variant { int kind, nch, ncs, mb; Kernel fn; };
-#define F2V(K, C, S, M) {K, C, S, M, conv2d_tc_kernel<K, C, S, M>}
+  struct Variant { int kind, nch, ncs, mb, ip; Kernel fn; };
+#define F2V(K, C, S, M) {K, C, S, M, 0, conv2d_tc_kernel<K, C, S, M, false>}
+#define F2I(K, C, S, M) {K, C, S, M, 1, conv2d_tc_kernel<K, C, S, M, true>}
   static const Variant kVariants[] = {
-      {0, 0, 0, 0, conv2d_tc_kernel<0, 0, 0, 0>},
+      {0, 0, 0, 0, 0, conv2d_tc_kernel<0, 0, 0, 0, false>},
       F2V(1, 1, 1, 2), F2V(1, 2, 1, 2), F2V(1, 2, 2, 2), F2V(1, 4, 2, 2),          // full resolution and level 1, 3x3 stride 1
       F2V(1, 4, 4, 1), F2V(1, 8, 4, 1), F2V(1, 8, 8, 1),                           // levels 2 and 3
       F2V(2, 1, 2, 2), F2V(2, 2, 4, 1), F2V(2, 4, 8, 1),                           // 3x3 stride 2
       F2V(3, 1, 2, 2), F2V(3, 2, 4, 1),                                            // 5x5 stride 2
       F2V(4, 2, 1, 1), F2V(4, 2, 1, 2), F2V(4, 4, 2, 1), F2V(4, 8, 4, 1),          // transposed
+      F2I(1, 16, 8, 1), F2I(4, 16, 8, 1),                                          // deep layers, transform in place
   };
 #undef F2V
+#undef F2I
   constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
   static std::atomic<uint64_t> attr_done{0};
   static int kernel_regs_of[kNumVariants];
@@ -866,12 +869,12 @@ extern "C" int mvsb200_unet_tc_forward(const float* images, const mvsb200_unet_p
     cudaLaunchConfig_t cfg = {};
     // a compile-time variant when there is one whose geometry IS the plan's (one slice, one operand buffer)
     int variant = 0;
-    if (tuning().unet_hot != 0 && c.nslices == 1 && c.obuf == 1 && !c.inplace) {
+    if (tuning().unet_hot != 0 && c.obuf == 1 && (c.nslices == 1 || c.inplace)) {       // (fixed-shape code: one slice unless in place)
       const int kind = L.transposed ? 4 : (L.stride == 1 ? 1 : (L.k == 3 ? 2 : 3));
       const int nchl = c.nch_a + c.nch_b;
       for (int k = 1; k < kNumVariants; ++k) {
         const Variant& v = kVariants[k];
-        if (v.kind != kind || v.nch != nchl || v.ncs * 8 != c.CS || v.mb != c.MB) continue;
+        if (v.kind != kind || v.nch != nchl || v.ncs * 8 != c.CS || v.mb != c.MB || v.ip != c.inplace) continue;
         const Shape sh = shape_of(v.kind, v.nch, v.ncs, v.mb);
         if (sh.ncls == c.ncls && sh.N == c.N && sh.PXin == c.PXin && sh.pxs == c.px_shift && sh.RYin == c.RYin && sh.nsub == c.nsub &&
             sh.subc == c.sub_cells && sh.nchp == c.nchp && sh.TX == c.TX && sh.TY == c.TY && sh.omul == c.org_mul &&

@@ -1484,7 +1484,7 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
     const int Mx = mode == MODE_CONV2 ? ceil_div(W, 2) : W, My = mode == MODE_CONV2 ? ceil_div(H, 2) : H,
               Mz = mode == MODE_CONV2 ? ceil_div(D, 2) : D;
     const std::array<int, 15> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_forced > 0 ? zf_forced : 0,
-                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0) + 64 * rank, n2};
+                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0) + 64 * rank + (mine && tn.tc_xfold == 2 ? 32 : 0), n2};
     Plan best;
     bool found = false;
     {
@@ -1501,7 +1501,7 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
         if (zf_forced > 0 && zf_forced != zf && mode == MODE_CONV1 && !n2) continue;
         if (zf > 1 && zf_forced <= 0 && Mz < 2 * zf) continue;
         if (n2 && zf != 2) continue;
-        for (int xf = (mode == MODE_CONV1 && !no_xfold) ? 1 : 0; xf >= 0; --xf)
+        for (int xf = (mode == MODE_CONV1 && !no_xfold) ? 1 : 0; xf >= (mine && tn.tc_xfold == 2 && mode == MODE_CONV1 ? 1 : 0); --xf)
         for (int TX = 4; TX <= 30; ++TX) {
           if (xf && TX != 6 && TX != 14 && TX != 30) continue;
           if (!xf && TX > Mx && TX != 4 && TX - 1 >= Mx) break;        // one clipped candidate is enough

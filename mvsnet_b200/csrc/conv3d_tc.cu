@@ -71,7 +71,8 @@ enum { MODE_CONV1 = 0, MODE_CONV2 = 1, MODE_DECONV = 2 };
 struct UmmaOp {
   uint32_t a_lo;   // [0,14) a_off>>4 | [16,30) a_lbo>>4
   uint32_t b_lo;   // [0,14) b_off>>4 | [16,30) b_lbo>>4
-  uint32_t meta;   // [0,16) tmem column offset in the block | [16] first (overwrite) | [20,24) dz
+  uint32_t meta;   // [0,16) tmem column offset in the block | [16] first (overwrite) | [20,24) dz |
+                   // [24,30) (N of the launch - N of this op) / 8: an op spans only the column blocks it has weights for
   uint32_t pad;
 };
 
@@ -230,9 +231,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// (one instruction per half: the library conversion moves the high half down and shifts it up again)
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
-  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
-  return __bfloat1622float2(h);
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+// packed fp32 pairs (sm_100): one FFMA2 / FADD2 for two channels
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)), "l"(reinterpret_cast<const uint64_t&>(c)));
+  return reinterpret_cast<const float2&>(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return reinterpret_cast<const float2&>(d);
+}
+// max(., 0) and the rounding to bf16 in one instruction
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
 }
 
 // scale / shift of channel c from batch statistics: the arithmetic of bn_finalize_kernel (conv3d_direct.cu), i.e.
@@ -341,15 +361,16 @@ __device__ __forceinline__ void store_cell(const Params& p, int which, int oz, i
 // prefetches them), the MB row blocks of an op reuse its descriptors (A start + 2 KB, next TMEM column group).
 template <int MB>
 __device__ __forceinline__ void issue_ops(const uint4* s_ops, int ob, int oe, uint32_t sl, uint32_t d_base, uint32_t nb,
-                                          uint64_t desc_hi, uint32_t idesc) {
+                                          uint64_t desc_hi) {
 #pragma unroll(MB == 1 ? 6 : (MB == 2 ? 3 : 2))
   for (int o = ob; o < oe; ++o) {
     const uint4 e = s_ops[o];
-    const uint32_t a_lo = e.x + sl, d_col = d_base + e.z;
+    // record: A start | B start | accumulator column [0,16) + accumulate flag [16] | instruction descriptor (N of the op)
+    const uint32_t a_lo = e.x + sl, d_col = d_base + (e.z & 0xFFFFu);
     const uint64_t db = desc_hi | (uint64_t)e.y;
 #pragma unroll
     for (int b = 0; b < MB; ++b)
-      mma_bf16(d_col + (uint32_t)b * nb, desc_hi | (uint64_t)(a_lo + (uint32_t)b * (2048u >> 4)), db, idesc, e.w);
+      mma_bf16(d_col + (uint32_t)b * nb, desc_hi | (uint64_t)(a_lo + (uint32_t)b * (2048u >> 4)), db, e.w, e.z >> 16);
   }
 }
 
@@ -403,7 +424,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     const uint32_t b16 = smem_u32(s_b) >> 4;
     for (int i = threadIdx.x; i < p.nops; i += blockDim.x) {
       const UmmaOp e = p.ops[i];
-      s_ops[i] = make_uint4(e.a_lo, e.b_lo + b16, e.meta & 0xFFFFu, ((e.meta >> 16) & 1u) ^ 1u);
+      s_ops[i] = make_uint4(e.a_lo, e.b_lo + b16, (e.meta & 0xFFFFu) | ((((e.meta >> 16) & 1u) ^ 1u) << 16),
+                            make_idesc_bf16_f32(128, p.mma_n - (int)((e.meta >> 24) << 3)));
     }
     if (threadIdx.x <= kMaxSpan) s_dzb[threadIdx.x] = p.dz_begin[threadIdx.x];
   }
@@ -496,11 +518,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       const int nbox = p.nsub * p.NCH;
       long long pw_empty = 0, pw_sempty = 0, pw_t0 = 0, pw_issue = 0;
       if (p.prof) pw_t0 = clock64();
+      int slot = 0, ss = 0;                 // ring positions; phases of the "empty" barriers = (lap - 1) & 1
+      uint32_t ph = 1u, sph = 1u;
       for (int seq = 0; seq < nplanes; ++seq) {
-        const int slot = seq % p.R;
         long long pa = 0;
         if (p.prof) pa = clock64();
-        if (seq >= p.R) mbar_wait(&bar_empty[slot], (uint32_t)((seq / p.R) - 1) & 1u);
+        if (seq >= p.R) mbar_wait(&bar_empty[slot], ph);
         long long pc0 = 0;
         if (p.prof) { pc0 = clock64(); pw_empty += pc0 - pa; }
         const int iz = p.zmul * zb + p.zoff + seq;
@@ -522,10 +545,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         }
         if (p.prof) pw_issue += clock64() - pc0;
         if (p.has_skip) {
-          const int ss = seq % p.RS;
           long long pb = 0;
           if (p.prof) pb = clock64();
-          if (seq >= p.RS) mbar_wait(&bar_sempty[ss], (uint32_t)((seq / p.RS) - 1) & 1u);
+          if (seq >= p.RS) mbar_wait(&bar_sempty[ss], sph);
           if (p.prof) pw_sempty += clock64() - pb;
           unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
           if (!(p.dbg & 1)) {
@@ -539,7 +561,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           } else if (lane == 0) {
             mbar_arrive(&bar_sland[ss]);
           }
+          if (++ss == p.RS) { ss = 0; sph ^= 1u; }
         }
+        if (++slot == p.R) { slot = 0; ph ^= 1u; }
       }
       if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[9] = clock64() - pw_t0; p.prof[10] = pw_empty; p.prof[11] = pw_sempty; p.prof[5 + 11] = pw_issue; }
     } else if (!RIDER && warp >= kXfWarp0 && warp < kProdWarp) {
@@ -569,23 +593,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
             if (ix >= 0 && ix < p.W && iy >= 0 && iy < p.H) off[k] = ch * p.PS + (sub * p.SUBP + r * p.PX + c) * 16;
           }
         }
-        float xsc[8], xsh[8], ssc[8], ssh[8];
+        float2 xsc[4], xsh[4], ssc[4], ssh[4];      // channel pairs
         const bool x_act = p.xs != nullptr || p.xbn.stats != nullptr, s_act = p.ss != nullptr || p.sbn.stats != nullptr;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          xsc[k] = s_aff[ch * 8 + k]; xsh[k] = s_aff[64 + ch * 8 + k];
-          ssc[k] = s_aff[128 + ch * 8 + k]; ssh[k] = s_aff[192 + ch * 8 + k];
+        for (int k = 0; k < 4; ++k) {
+          xsc[k] = *reinterpret_cast<const float2*>(&s_aff[ch * 8 + 2 * k]); xsh[k] = *reinterpret_cast<const float2*>(&s_aff[64 + ch * 8 + 2 * k]);
+          ssc[k] = *reinterpret_cast<const float2*>(&s_aff[128 + ch * 8 + 2 * k]); ssh[k] = *reinterpret_cast<const float2*>(&s_aff[192 + ch * 8 + 2 * k]);
         }
         long long xw = 0, xt0 = 0;
         if (p.prof) xt0 = clock64();
+        // ring positions and barrier phases are carried along (a modulo by a run-time ring depth costs ~50
+        // instructions per plane and warp: measured a third of this loop at 3dconv6_2)
+        int slot = xgrp, ss = p.has_skip ? xgrp % p.RS : 0;
+        uint32_t ph = 0u, sph = p.has_skip ? (uint32_t)(xgrp / p.RS) & 1u : 0u;
+        const int iz0 = p.zmul * zb + p.zoff;
         for (int seq = xgrp; seq < nplanes; seq += p.xf_groups) {
-          const int slot = seq % p.R, ss = seq % p.RS;
           long long xa = 0;
           if (p.prof) xa = clock64();
-          mbar_wait(&bar_land[slot], (uint32_t)(seq / p.R) & 1u);
-          if (p.has_skip) mbar_wait(&bar_sland[ss], (uint32_t)(seq / p.RS) & 1u);
+          mbar_wait(&bar_land[slot], ph);
+          if (p.has_skip) mbar_wait(&bar_sland[ss], sph);
           if (p.prof) xw += clock64() - xa;
-          const int iz = p.zmul * zb + p.zoff + seq;
+          const int iz = iz0 + seq;
           if (iz >= p.zv_lo && iz < p.zv_hi) {
             unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
             const unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
@@ -613,22 +641,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   for (int j = 0; j < 4; ++j) {
                     float2 f = unpack_bf16x2(vw[j]), g = unpack_bf16x2(sw[j]);
                     if (x_act) {
-                      f.x = fmaxf(fmaf(f.x, xsc[2 * j], xsh[2 * j]), 0.0f);
-                      f.y = fmaxf(fmaf(f.y, xsc[2 * j + 1], xsh[2 * j + 1]), 0.0f);
+                      f = ffma2(f, xsc[j], xsh[j]);
+                      f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f);
                     }
                     if (s_act) {
-                      g.x = fmaxf(fmaf(g.x, ssc[2 * j], ssh[2 * j]), 0.0f);
-                      g.y = fmaxf(fmaf(g.y, ssc[2 * j + 1], ssh[2 * j + 1]), 0.0f);
+                      g = ffma2(g, ssc[j], ssh[j]);
+                      g.x = fmaxf(g.x, 0.0f); g.y = fmaxf(g.y, 0.0f);
                     }
-                    vw[j] = pack_bf16x2(f.x + g.x, f.y + g.y);
+                    f = fadd2(f, g);
+                    vw[j] = pack_bf16x2(f.x, f.y);
                   }
                 } else {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    float2 f = unpack_bf16x2(vw[j]);
-                    f.x = fmaxf(fmaf(f.x, xsc[2 * j], xsh[2 * j]), 0.0f);
-                    f.y = fmaxf(fmaf(f.y, xsc[2 * j + 1], xsh[2 * j + 1]), 0.0f);
-                    vw[j] = pack_bf16x2(f.x, f.y);
+                    const float2 f = ffma2(unpack_bf16x2(vw[j]), xsc[j], xsh[j]);
+                    vw[j] = pack_bf16x2_relu(f.x, f.y);
                   }
                 }
                 *reinterpret_cast<uint4*>(sl + off[k0 + u]) = v[u];
@@ -643,13 +670,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
             mbar_arrive(&bar_ready[slot]);
             if (p.has_skip) mbar_arrive(&bar_sempty[ss]);
           }
+          slot += p.xf_groups;
+          if (slot >= p.R) { slot -= p.R; ph ^= 1u; }
+          if (p.has_skip) {
+            ss += p.xf_groups;
+            if (ss >= p.RS) { ss -= p.RS; sph ^= 1u; }
+          }
         }
         if (p.prof && blockIdx.x == 0 && xt_all == 0) { p.prof[12] = clock64() - xt0; p.prof[13] = xw; }
       }
     } else if (warp == kMmaWarp) {
       // ===================================== MMA issuer =====================================
       mbar_wait(bar_b, 0);
-      const uint32_t idesc = make_idesc_bf16_f32(128, p.mma_n);
       const uint32_t slots16 = smem_u32(s_slots) >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
       const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;   // version 1, SBO = 128 B
       uint64_t* bar_in = p.transform ? bar_ready : bar_land;
@@ -686,10 +718,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
               if (++sl_idx == p.R) sl_idx = 0;
               const int ob = s_dzb[dz], oe = s_dzb[dz + 1];
               switch (p.MB) {
-                case 1: issue_ops<1>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi, idesc); break;
-                case 2: issue_ops<2>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi, idesc); break;
-                case 3: issue_ops<3>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi, idesc); break;
-                default: issue_ops<4>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi, idesc); break;
+                case 1: issue_ops<1>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi); break;
+                case 2: issue_ops<2>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi); break;
+                case 3: issue_ops<3>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi); break;
+                default: issue_ops<4>(s_ops, ob, oe, sl, d_base, (uint32_t)p.NB, desc_hi); break;
               }
             }
           }
@@ -1299,11 +1331,22 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
   int nops = 0, nimg = 0;
   const int b_op_bytes = 2 * CP * 16;
   const int m_rows = (2 * zf + 1) * grp, m_bytes = 2 * m_rows * 16;      // master image
-  auto add_op = [&](int dz, uint32_t a_off, uint32_t a_lbo, uint32_t b_off, uint32_t b_lbo, int col, bool first) {
+  // [c_lo, c_hi): the columns of the image this op has weights for (the others are zero rows: the op skips them,
+  // except the first op of a step, which has to overwrite every accumulator column).  N stays a multiple of 16 and
+  // the first column a multiple of 16 (the B window then starts on a whole 8-row core matrix).
+  const bool trim = tuning().tc_trim != 0;
+  auto add_op = [&](int dz, uint32_t a_off, uint32_t a_lbo, uint32_t b_off, uint32_t b_lbo, int col, bool first,
+                    int c_lo = 0, int c_hi = 1 << 20) {
     UmmaOp& o = c.ops[nops++];
+    int lo = 0, n_op = c.mma_n;
+    if (trim && !first) {
+      lo = max(0, c_lo) / 16 * 16;
+      n_op = (min(c.mma_n, c_hi) - lo + 15) / 16 * 16;
+      if (lo + n_op > c.mma_n) { lo = 0; n_op = c.mma_n; }
+    }
     o.a_lo = (a_off >> 4) | ((a_lbo >> 4) << 16);
-    o.b_lo = (b_off >> 4) | ((b_lbo >> 4) << 16);
-    o.meta = (uint32_t)col | ((first ? 1u : 0u) << 16) | ((uint32_t)dz << 20);
+    o.b_lo = ((b_off + (uint32_t)lo * 16u) >> 4) | ((b_lbo >> 4) << 16);
+    o.meta = (uint32_t)(col + lo) | ((first ? 1u : 0u) << 16) | ((uint32_t)dz << 20) | ((uint32_t)((c.mma_n - n_op) >> 3) << 24);
     o.pad = 0;
   };
   auto add_img = [&](int tap0, int cb0, int tap1, int cb1) {
@@ -1332,8 +1375,10 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
       for (int j = 0; j < cin / 16; ++j) {
         const bool first = nops == 0;
         const int img = add_img(taps[i].widx, 16 * j, taps[i].widx, 16 * j + 8);
+        int cls_hi = 0;                              // classes that use input shift sh: cls & sh == 0
+        for (int cls = 0; cls < 8; ++cls) if ((cls & taps[i].widx) == 0) cls_hi = cls + 1;
         add_op(taps[i].dz, (uint32_t)(2 * j * c.PS + taps[i].pos * 16), (uint32_t)c.PS, (uint32_t)(img * img_bytes),
-               (uint32_t)(c.mma_n * 16), 0, first);
+               (uint32_t)(c.mma_n * 16), 0, first, 0, cls_hi * c.cw);
       }
     c.b_bytes = nimg * img_bytes;
   } else if (cin >= 16) {
@@ -1342,8 +1387,11 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
         const bool first = !seen_cls[taps[i].cls];
         seen_cls[taps[i].cls] = true;
         const int img = add_img(taps[i].widx, 16 * j, taps[i].widx, 16 * j + 8);
+        // rider launch: input plane 0 of the step only feeds the even output plane (columns [0, grp)), plane 3 only the
+        // odd one (columns [grp, ncols))
+        const int c_lo = n2 && taps[i].dz == 3 ? grp : 0, c_hi = n2 && taps[i].dz == 0 ? grp : 1 << 20;
         add_op(taps[i].dz, (uint32_t)(2 * j * c.PS + taps[i].pos * 16), (uint32_t)c.PS, (uint32_t)(img * b_op_bytes),
-               (uint32_t)(CP * 16), taps[i].cls * CP, first);
+               (uint32_t)(CP * 16), taps[i].cls * CP, first, c_lo, c_hi);
       }
     c.b_bytes = nimg * b_op_bytes;
   } else {
@@ -1484,7 +1532,7 @@ static bool find_plan(int mode, int D, int H, int W, int cin, int cout, int cb, 
     const int Mx = mode == MODE_CONV2 ? ceil_div(W, 2) : W, My = mode == MODE_CONV2 ? ceil_div(H, 2) : H,
               Mz = mode == MODE_CONV2 ? ceil_div(D, 2) : D;
     const std::array<int, 15> key = {mode, D, H, W, cin, cout, cb, has_skip, transform, zf_forced > 0 ? zf_forced : 0,
-                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0) + 64 * rank + (mine && tn.tc_xfold == 2 ? 32 : 0), n2};
+                                     force_tx, force_ty, sm_count, force_zs * 2 + (no_xfold ? 1 : 0) + 64 * rank + (mine && tn.tc_xfold == 2 ? 32 : 0) + (tn.tc_trim == 0 ? 1 << 20 : 0), n2};
     Plan best;
     bool found = false;
     {

@@ -978,30 +978,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           uint32_t ra[32], rb[32];
           tmem_ld16(tbase, ra);
           if (!narrow) tmem_ld16(tbase + 16, ra + 16);
-          for (int i = 0; i < npair; i += 2) {
+          // (position and output address once per row block: the four class pairs of a block differ by one output
+          // plane / one output row -- the division and the 64-bit address chain per pair were half of this loop)
+          const size_t pr_z = (size_t)ncho * zpitch * 8, pr_y = (size_t)p.Wo * 8;      // elements per output plane / row
+          for (int b = 0; b < p.MB; ++b) {
+            const int m = b * 128 + warp * 32 + lane;
+            const int yy = m / p.PX, xx = m - yy * p.PX;
+            const bool valid = xx < TXe && yy < TYe && !(p.dbg & 4);
+            const int oy0 = 2 * (y0 + yy), ox = 2 * (x0 + xx);
+            const size_t cell0 = (size_t)oy0 * p.Wo + ox;
+            __nv_bfloat16* const base = p.y_cp8 + (((size_t)(2 * mz) * ncho + chunk0) * zpitch + cell0) * 8;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int ii = i + half;
-              uint32_t* r = half ? rb : ra;
-              uint32_t* rn = half ? ra : rb;
+            for (int pr = 0; pr < 4; ++pr) {                    // pair pr = classes 2*pr, 2*pr+1 (pz, py fixed)
+              uint32_t* r = (pr & 1) ? rb : ra;
+              uint32_t* rn = (pr & 1) ? ra : rb;
               tmem_ld_wait();
-              if (ii + 1 < npair) {
-                const int bn = (ii + 1) >> 2, pn = (ii + 1) & 3;
-                const uint32_t ta = tbase + (uint32_t)(bn * p.NB + pn * 2 * p.cw);
+              if (b * 4 + pr + 1 < npair) {
+                const uint32_t ta = tbase + (uint32_t)((pr == 3 ? b + 1 : b) * p.NB + ((pr + 1) & 3) * 2 * p.cw);
                 tmem_ld16(ta, rn);
                 if (!narrow) tmem_ld16(ta + 16, rn + 16);
               }
-              const int b = ii >> 2, pr = ii & 3;               // pair pr = classes 2*pr, 2*pr+1 (pz, py fixed)
-              const int m = b * 128 + warp * 32 + lane;
-              const int yy = m / p.PX, xx = m - yy * p.PX;
-              if (!(xx < TXe && yy < TYe) || (p.dbg & 4)) continue;
-              const int oz = 2 * mz + (pr >> 1), oy = 2 * (y0 + yy) + (pr & 1), ox = 2 * (x0 + xx);
-              const size_t cell = ((size_t)oy * p.Wo + ox);
+              if (!valid) continue;
+              const int oz = 2 * mz + (pr >> 1);
+              const size_t cell = cell0 + (size_t)(pr & 1) * p.Wo;
+              __nv_bfloat16* const dst0 = base + (pr >> 1) * pr_z + (pr & 1) * pr_y;
+              const float2* f = reinterpret_cast<const float2*>(r);
+              float2* sum2 = reinterpret_cast<float2*>(sum);
+              float2* sq2 = reinterpret_cast<float2*>(sq);
               if (narrow) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const float v0 = __uint_as_float(r[k]), v1 = __uint_as_float(r[8 + k]);
-                  sum[k] += v0 + v1; sq[k] = fmaf(v1, v1, fmaf(v0, v0, sq[k]));
+                for (int k = 0; k < 4; ++k) {
+                  sum2[k] = fadd2(sum2[k], fadd2(f[k], f[4 + k]));
+                  sq2[k] = ffma2(f[4 + k], f[4 + k], ffma2(f[k], f[k], sq2[k]));
                 }
                 uint4 c0, c1;
                 c0.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
@@ -1016,15 +1024,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   store_cell<true>(p, 0, oz, chunk0, zpitch, cell, c0);
                   store_cell<true>(p, 0, oz, chunk0, zpitch, cell + 1, c1);
                 } else {
-                  const size_t zc = (size_t)oz * ncho + chunk0;
-                  uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
+                  uint4* dst = reinterpret_cast<uint4*>(dst0);
                   dst[0] = c0; dst[1] = c1;
                 }
               } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                  const float v0 = __uint_as_float(r[k]), v1 = __uint_as_float(r[16 + k]);
-                  sum[k] += v0 + v1; sq[k] = fmaf(v1, v1, fmaf(v0, v0, sq[k]));
+                for (int k = 0; k < 8; ++k) {
+                  sum2[k] = fadd2(sum2[k], fadd2(f[k], f[8 + k]));
+                  sq2[k] = ffma2(f[8 + k], f[8 + k], ffma2(f[k], f[k], sq2[k]));
                 }
 #pragma unroll
                 for (int k = 0; k < 16; k += 8) {
@@ -1042,8 +1049,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                       store_cell<true>(p, 0, oz, chunk0 + (k >> 3), zpitch, cell, c0);
                       store_cell<true>(p, 0, oz, chunk0 + (k >> 3), zpitch, cell + 1, c1);
                     } else {
-                      const size_t zc = (size_t)oz * ncho + chunk0 + (k >> 3);
-                      uint4* dst = reinterpret_cast<uint4*>(p.y_cp8 + (zc * zpitch + cell) * 8);
+                      uint4* dst = reinterpret_cast<uint4*>(dst0 + (size_t)(k >> 3) * zpitch * 8);
                       dst[0] = c0; dst[1] = c1;
                     }
                   }

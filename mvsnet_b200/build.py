@@ -38,6 +38,8 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
     obj_dir = os.path.join(LIB_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
+    # development builds: e.g. MVSB200_NVCC_EXTRA="-DMVSB200_TC_PROF_BUILD=1" for the per-role counters of MVSB200_TC_PROF
+    extra_flags = (*extra_flags, *os.environ.get("MVSB200_NVCC_EXTRA", "").split())
     procs = []
     objs = []
     for src in SOURCES:

@@ -59,6 +59,13 @@ using namespace umma;
 namespace tc {
 
 constexpr int kMaxOps = 108;            // 27 taps x (64 channels / 16)
+// Per-role cycle counters of MVSB200_TC_PROF live behind a build switch (-DMVSB200_TC_PROF_BUILD=1): even as a
+// not-taken branch per plane they were ~5 % of the transform warps' instructions.  Without it MVSB200_TC_PROF=1 still
+// prints every launch's stand-alone time.
+#ifndef MVSB200_TC_PROF_BUILD
+#define MVSB200_TC_PROF_BUILD 0
+#endif
+constexpr bool kProf = MVSB200_TC_PROF_BUILD != 0;
 constexpr int kEpiWarps = 4, kXfWarps = 8;
 constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kThreads = (kEpiWarps + 2 + kXfWarps) * 32;
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long pr_entry = 0;
-  if (p.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_entry));
+  if (kProf && p.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_entry));
   int bid = blockIdx.x;
   const int tx = bid % p.tiles_x; bid /= p.tiles_x;
   const int ty = bid % p.tiles_y; bid /= p.tiles_y;
@@ -517,15 +524,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       const int cx = (x0 + p.cx_off) * 8, cy = y0 + p.cy_off;
       const int nbox = p.nsub * p.NCH;
       long long pw_empty = 0, pw_sempty = 0, pw_t0 = 0, pw_issue = 0;
-      if (p.prof) pw_t0 = clock64();
+      if (kProf && p.prof) pw_t0 = clock64();
       int slot = 0, ss = 0;                 // ring positions; phases of the "empty" barriers = (lap - 1) & 1
       uint32_t ph = 1u, sph = 1u;
       for (int seq = 0; seq < nplanes; ++seq) {
         long long pa = 0;
-        if (p.prof) pa = clock64();
+        if (kProf && p.prof) pa = clock64();
         if (seq >= p.R) mbar_wait(&bar_empty[slot], ph);
         long long pc0 = 0;
-        if (p.prof) { pc0 = clock64(); pw_empty += pc0 - pa; }
+        if (kProf && p.prof) { pc0 = clock64(); pw_empty += pc0 - pa; }
         const int iz = p.zmul * zb + p.zoff + seq;
         unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
         if (!(p.dbg & 1)) {
@@ -543,12 +550,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         } else if (lane == 0) {
           mbar_arrive(&bar_land[slot]);
         }
-        if (p.prof) pw_issue += clock64() - pc0;
+        if (kProf && p.prof) pw_issue += clock64() - pc0;
         if (p.has_skip) {
           long long pb = 0;
-          if (p.prof) pb = clock64();
+          if (kProf && p.prof) pb = clock64();
           if (seq >= p.RS) mbar_wait(&bar_sempty[ss], sph);
-          if (p.prof) pw_sempty += clock64() - pb;
+          if (kProf && p.prof) pw_sempty += clock64() - pb;
           unsigned char* sk = s_skip + (size_t)ss * p.slot_bytes;
           if (!(p.dbg & 1)) {
             if (lane == 0) mbar_arrive_expect_tx(&bar_sland[ss], plane_bytes);
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         }
         if (++slot == p.R) { slot = 0; ph ^= 1u; }
       }
-      if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[9] = clock64() - pw_t0; p.prof[10] = pw_empty; p.prof[11] = pw_sempty; p.prof[5 + 11] = pw_issue; }
+      if (kProf && p.prof && blockIdx.x == 0 && lane == 0) { p.prof[9] = clock64() - pw_t0; p.prof[10] = pw_empty; p.prof[11] = pw_sempty; p.prof[5 + 11] = pw_issue; }
     } else if (!RIDER && warp >= kXfWarp0 && warp < kProdWarp) {
       // ===================================== transform =====================================
       if (p.transform) {
@@ -601,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           ssc[k] = *reinterpret_cast<const float2*>(&s_aff[128 + ch * 8 + 2 * k]); ssh[k] = *reinterpret_cast<const float2*>(&s_aff[192 + ch * 8 + 2 * k]);
         }
         long long xw = 0, xt0 = 0;
-        if (p.prof) xt0 = clock64();
+        if (kProf && p.prof) xt0 = clock64();
         // ring positions and barrier phases are carried along (a modulo by a run-time ring depth costs ~50
         // instructions per plane and warp: measured a third of this loop at 3dconv6_2)
         int slot = xgrp, ss = p.has_skip ? xgrp % p.RS : 0;
@@ -609,10 +616,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         const int iz0 = p.zmul * zb + p.zoff;
         for (int seq = xgrp; seq < nplanes; seq += p.xf_groups) {
           long long xa = 0;
-          if (p.prof) xa = clock64();
+          if (kProf && p.prof) xa = clock64();
           mbar_wait(&bar_land[slot], ph);
           if (p.has_skip) mbar_wait(&bar_sland[ss], sph);
-          if (p.prof) xw += clock64() - xa;
+          if (kProf && p.prof) xw += clock64() - xa;
           const int iz = iz0 + seq;
           if (iz >= p.zv_lo && iz < p.zv_hi) {
             unsigned char* sl = s_slots + (size_t)slot * p.slot_bytes;
@@ -677,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
             if (ss >= p.RS) { ss -= p.RS; sph ^= 1u; }
           }
         }
-        if (p.prof && blockIdx.x == 0 && xt_all == 0) { p.prof[12] = clock64() - xt0; p.prof[13] = xw; }
+        if (kProf && p.prof && blockIdx.x == 0 && xt_all == 0) { p.prof[12] = clock64() - xt0; p.prof[13] = xw; }
       }
     } else if (warp == kMmaWarp) {
       // ===================================== MMA issuer =====================================
@@ -689,11 +696,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       uint32_t wphase = 0;
       int slot_lo = 0;                                  // ring slot of the first plane of the step
       long long pr_t0 = 0, pr_in = 0, pr_acc = 0, pr_issue = 0, pr_g0 = 0;
-      if (p.prof) { pr_t0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_g0)); }
+      if (kProf && p.prof) { pr_t0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_g0)); }
       for (int t = 0; t < nsteps; ++t) {
         const int seq_lo = p.zstep * t, seq_hi = seq_lo + p.span - 1;
         long long pr_a = 0;
-        if (p.prof) pr_a = clock64();
+        if (kProf && p.prof) pr_a = clock64();
         while (waited <= seq_hi) {
           mbar_wait(&bar_in[wslot], wphase);
           ++waited;
@@ -701,11 +708,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         }
         const int stage = t & 1;
         long long pr_b = 0;
-        if (p.prof) pr_b = clock64();
+        if (kProf && p.prof) pr_b = clock64();
         mbar_wait(&bar_acc_empty[stage], ((uint32_t)(t >> 1) & 1u) ^ 1u);
         tc_fence_after();
         long long pr_c = 0;
-        if (p.prof) { pr_c = clock64(); pr_in += pr_b - pr_a; pr_acc += pr_c - pr_b; }
+        if (kProf && p.prof) { pr_c = clock64(); pr_in += pr_b - pr_a; pr_acc += pr_c - pr_b; }
         if (elect_one()) {
           if (!(p.dbg & 2)) {
             // plane-major, op-major order.  One 16-byte shared-memory record per op (prefetched by the
@@ -734,11 +741,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           }
         }
         __syncwarp();
-        if (p.prof) pr_issue += clock64() - pr_c;
+        if (kProf && p.prof) pr_issue += clock64() - pr_c;
         slot_lo += p.zstep;
         if (slot_lo >= p.R) slot_lo -= p.R;
       }
-      if (p.prof && blockIdx.x == 0 && lane == 0) {
+      if (kProf && p.prof && blockIdx.x == 0 && lane == 0) {
         long long g1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
         p.prof[0] = clock64() - pr_t0; p.prof[1] = g1 - pr_g0; p.prof[2] = pr_in; p.prof[3] = pr_acc; p.prof[4] = pr_issue;
@@ -770,23 +777,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         const int chunk0 = p.cout_base >> 3;
         const int px_shift = 31 - __clz(p.PX);
         long long ew = 0, et0 = 0;
-        if (p.prof) et0 = clock64();
+        if (kProf && p.prof) et0 = clock64();
         float rg_m[kMaxMB], rg_s[kMaxMB], rg_w[kMaxMB];     // fused soft-argmin state of this thread's pixels
 #pragma unroll
         for (int b = 0; b < kMaxMB; ++b) { rg_m[b] = -INFINITY; rg_s[b] = 0.0f; rg_w[b] = 0.0f; }
         for (int t = 0; t < nsteps; ++t) {
           const int stage = t & 1;
           long long ea = 0;
-          if (p.prof) ea = clock64();
+          if (kProf && p.prof) ea = clock64();
           mbar_wait(&bar_acc_full[stage], (uint32_t)(t >> 1) & 1u);
           tc_fence_after();
-          if (p.prof) ew += clock64() - ea;
+          if (kProf && p.prof) ew += clock64() - ea;
           const int mz = zb + t * p.zf;
           const int nlive = min(p.zf, ze - mz);
           if (C1) {
             // Cout = 1 (3dconv6_2): N = 3*zf <= 12 columns, fp32 [D,H,W] output.  When the CTA covers the whole depth
             // range the soft-argmin of the regression (model.py:472-495) is folded in: every thread keeps the running
             // (max of -F, sum of exp, depth-weighted sum) of its pixels, rescaled when the maximum moves.
+            // two register buffers of 3 * zf <= 12 columns: the next row block's accumulators are on their way while this
+            // one is shuffled, stored and folded into the soft-argmin (a TMEM round trip per block was most of this loop)
+            const uint32_t tb0 = tmem_base + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)(stage * p.MB * p.NB);
+            uint32_t rbuf[2][12];
+            tmem_ld8(tb0, rbuf[0]);
+            tmem_ld4(tb0 + 8, rbuf[0] + 8);
 #pragma unroll
             for (int b = 0; b < kMaxMB; ++b) {
               if (b >= p.MB) break;
@@ -794,10 +807,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
               const int yy = m >> px_shift, xx = m & (p.PX - 1);
               const bool valid = xx >= 1 && xx <= TXe && yy < TYe && !(p.dbg & 4);
               const int oy = y0 + yy, ox = x0 + xx - 1;
-              const uint32_t tb = tmem_base + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)((stage * p.MB + b) * p.NB);
-              uint32_t r[16];
-              tmem_ld16(tb, r);
+              uint32_t* r = rbuf[b & 1];
               tmem_ld_wait();
+              if (b + 1 < p.MB) {
+                tmem_ld8(tb0 + (uint32_t)((b + 1) * p.NB), rbuf[(b + 1) & 1]);
+                tmem_ld4(tb0 + (uint32_t)((b + 1) * p.NB) + 8, rbuf[(b + 1) & 1] + 8);
+              }
               float xj[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -941,7 +956,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
             }
           }
         }
-        if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
+        if (kProf && p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
         if constexpr (RIDER) {
           flush_stats_rider(p, sum, sq, sum2, sq2, egrp, s_red + egrp * 128, ewarp, lane);
         } else {
@@ -958,14 +973,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       const int chunk0 = p.cout_base >> 3;
       const int ncho = p.Cout >> 3;
       long long ew = 0, et0 = 0;
-      if (p.prof) et0 = clock64();
+      if (kProf && p.prof) et0 = clock64();
       for (int t = 0; t < nsteps; ++t) {
         const int stage = t & 1;
         long long ea = 0;
-        if (p.prof) ea = clock64();
+        if (kProf && p.prof) ea = clock64();
         mbar_wait(&bar_acc_full[stage], (uint32_t)(t >> 1) & 1u);
         tc_fence_after();
-        if (p.prof) ew += clock64() - ea;
+        if (kProf && p.prof) ew += clock64() - ea;
         const int mz = zb + t * p.zf;
         const int nlive = min(p.zf, ze - mz);          // output planes of this step inside the volume
         if (CP == 16 && deconv && !p.y_f32) {
@@ -1080,10 +1095,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
             // columns [j*cout_n, (j+1)*cout_n) belong to output plane mz + j (z-fold); planes past the
             // end of the volume are computed but neither stored nor counted.  Unused columns are exact zeros.
             if (nlive == p.zf) {
+              // packed fp32 pairs: the accumulator columns of a TMEM load sit in consecutive registers
+              const float2* f = reinterpret_cast<const float2*>(r);
+              float2* sum2 = reinterpret_cast<float2*>(sum);
+              float2* sq2 = reinterpret_cast<float2*>(sq);
 #pragma unroll
-              for (int k = 0; k < CP; ++k) {
-                const float v = __uint_as_float(r[k]);
-                sum[k] += v; sq[k] = fmaf(v, v, sq[k]);
+              for (int k = 0; k < CP / 2; ++k) {
+                sum2[k] = fadd2(sum2[k], f[k]);
+                sq2[k] = ffma2(f[k], f[k], sq2[k]);
               }
             } else {
 #pragma unroll
@@ -1126,7 +1145,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_acc_empty[stage]);
       }
-      if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
+      if (kProf && p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[14] = clock64() - et0; p.prof[15] = ew; }
       if (p.stats && !(p.dbg & 8)) flush_stats<CP>(p, sum, sq, ncol, p.zf != 1, s_red, warp, lane);
       }
     }
@@ -1135,7 +1154,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   __syncthreads();
   if (p.pdl == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-  if (p.prof && threadIdx.x == 0) {
+  if (kProf && p.prof && threadIdx.x == 0) {
     long long g2;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g2));
     if (blockIdx.x == 0) p.prof[8] = g2 - pr_entry;             // whole CTA
@@ -1842,7 +1861,8 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     const int grid = c.tiles_x * c.tiles_y * c.zsplit;
     static long long* prof_buf = nullptr;
     c.prof = nullptr;
-    if (tuning().tc_prof) {
+    const bool prof = tuning().tc_prof != 0;
+    if (prof && kProf) {
       if (!prof_buf) MVS_CUDA(cudaMalloc(&prof_buf, 256 + 16 * 4096));
       c.prof = prof_buf;
     }
@@ -1869,7 +1889,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       return MVSB200_ERR_CUDA;
     }
     MVS_LAUNCH_CHECK("conv3d_tc_kernel");
-    if (c.prof) {
+    if (prof) {
       long long h[17];
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1883,6 +1903,10 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       cudaEventElapsedTime(&kms, e0, e1);
       cudaEventDestroy(e0); cudaEventDestroy(e1);
       fprintf(stderr, "[tc-prof] kernel alone %.1f us (grid %d); ", kms * 1e3, grid);
+      if (!kProf) {
+        fprintf(stderr, "mode=%d Cin=%d Cout=%d (per-role counters: build with -DMVSB200_TC_PROF_BUILD=1)\n", mode, cin, cn);
+        continue;
+      }
       cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "CTA 0: prologue %.1f us, MMA warp done at %.1f us, CTA end %.1f us\n", h[6] * 1e-3, h[7] * 1e-3, h[8] * 1e-3);
       fprintf(stderr, "[tc-prof] producer %lld clk (wait empty %lld, wait skip-empty %lld); transform %lld clk (wait landed %lld); "

@@ -266,18 +266,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float a, float b) {
 // fp64 moments rounded once, then tf.nn.batch_normalization in fp32 (network.py:496-506, Appendix A.6)
 __device__ __forceinline__ void bn_scale_shift(const TcBnSrc& b, int c, float& scale, float& shift) {
   if (b.channels_true > 0 && c >= b.channels_true) { scale = 0.0f; shift = 0.0f; return; }     // padding channel: stays 0
+  // all loads of a batch of partial copies are issued before the first add (one L2 round trip per batch instead of one
+  // per copy: measured 1.2 - 4.4 us of every launch's prologue); the order of the fp64 adds is unchanged
+  const float gam = b.gamma[c], bet = b.beta[c];
   double sm = 0.0, sq = 0.0;
-  for (int r = 0; r < b.reps; ++r) {
-    sm += b.stats[(size_t)r * b.rep_stride + c];
-    sq += b.stats[(size_t)r * b.rep_stride + b.channels + c];
+  for (int r0 = 0; r0 < b.reps; r0 += 8) {
+    double a[8], q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool in = r0 + u < b.reps;
+      a[u] = in ? b.stats[(size_t)(r0 + u) * b.rep_stride + c] : 0.0;
+      q[u] = in ? b.stats[(size_t)(r0 + u) * b.rep_stride + b.channels + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { sm += a[u]; sq += q[u]; }
   }
   const double mean = sm / b.count;
   double var = sq / b.count - mean * mean;
   if (var < 0.0) var = 0.0;
   const float meanf = (float)mean, varf = (float)var;
-  const float inv = __fmul_rn(__fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(varf, b.eps))), b.gamma[c]);
+  const float inv = __fmul_rn(__fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(varf, b.eps))), gam);
   scale = inv;
-  shift = __fsub_rn(b.beta[c], __fmul_rn(meanf, inv));
+  shift = __fsub_rn(bet, __fmul_rn(meanf, inv));
 }
 
 // Batch statistics of a CTA: per-thread partials -> warp reduce -> the 4 epilogue warps combine in shared memory ->
@@ -439,9 +449,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   // Every cell of the ring starts finite: halo rows of the GEMM read a few cells past the landed boxes
   // (their results are dropped, but 0 * NaN from stale shared memory must not reach a zero-weighted
   // K half of a valid row).
-  for (int i = threadIdx.x; i < (p.R * p.slot_bytes + p.ring_pad) / 16; i += blockDim.x)
+  // With dense chunk planes every byte of a slot is rewritten by the plane's TMA box before it is read (out-of-image
+  // cells arrive as zeros), and a valid row never reads past its plane (x-fold, or whole K = 16 cells): only the pad
+  // behind the ring has to be cleared (the clear of ~200 KB was 1 us of every CTA's prologue).
+  const int clear_from = (p.one_box && (p.xfold || p.Cin >= 16)) ? p.R * p.slot_bytes / 16 : 0;
+  for (int i = clear_from + threadIdx.x; i < (p.R * p.slot_bytes + p.ring_pad) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
+  auto stamp = [&](int slot) {
+    if (kProf && p.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+      long long g;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+      p.prof[slot] = g - pr_entry;
+    }
+  };
+  stamp(17);                                        // op table + ring clear
   if (threadIdx.x == 0) {
     const int xfw = kXfWarps / p.xf_groups;         // transform warps per plane
     for (int i = 0; i < p.R; ++i) { mbar_init(&bar_land[i], 1); mbar_init(&bar_ready[i], xfw); mbar_init(&bar_empty[i], 1); }
@@ -457,10 +479,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   // Programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; from
   // here on its outputs (statistics, activations) are read.  A single-wave grid lets the next kernel's CTAs take
   // over SMs as they free up; a multi-wave grid only triggers at CTA end (its own waiting CTAs must get the SMs).
+  stamp(18);                                        // barriers initialised
   if (p.pdl) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
+  stamp(19);                                        // previous grid complete
   // D-slab mode over peer memory: the layers this one consumes must have been published by EVERY rank (their
   // statistics) -- which covers the two neighbours whose boundary planes landed in our halo planes.  One flag word
   // per (layer, rank) holds the sequence number of the last published inference.  The spin is bounded.
@@ -503,9 +527,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       s_aff[which * 128 + 64 + c] = sh;
     }
   }
+  stamp(20);                                        // statistics -> scale / shift (thread 0's channel)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  stamp(21);                                        // every warp through the prologue
   const uint32_t tmem_base = *s_tmem;
 
   if (nsteps > 0) {
@@ -709,6 +735,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         const int stage = t & 1;
         long long pr_b = 0;
         if (kProf && p.prof) pr_b = clock64();
+        if (kProf && p.prof && t == 0 && blockIdx.x == 0 && lane == 0) {
+          long long g;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+          p.prof[22] = g - pr_entry;                 // input planes of the first step ready
+        }
         mbar_wait(&bar_acc_empty[stage], ((uint32_t)(t >> 1) & 1u) ^ 1u);
         tc_fence_after();
         long long pr_c = 0;
@@ -1890,7 +1921,7 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
     }
     MVS_LAUNCH_CHECK("conv3d_tc_kernel");
     if (prof) {
-      long long h[17];
+      long long h[24];
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaStreamSynchronize(s);
@@ -1912,6 +1943,9 @@ int launch_conv3d_tc(const void* x, const float* xs, const float* xb, const void
       fprintf(stderr, "[tc-prof] producer %lld clk (wait empty %lld, wait skip-empty %lld); transform %lld clk (wait landed %lld); "
               "epilogue %lld clk (wait acc %lld)\n", h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
       fprintf(stderr, "[tc-prof] producer: %lld clk in expect_tx + TMA issue\n", h[16]);
+      fprintf(stderr, "[tc-prof] CTA 0 timeline (us from entry): ring cleared %.2f, barriers %.2f, grid dependency %.2f, scale/shift %.2f, "
+              "prologue barrier %.2f, weights %.2f, first step's planes %.2f\n", h[17] * 1e-3, h[18] * 1e-3, h[19] * 1e-3,
+              h[20] * 1e-3, h[21] * 1e-3, h[6] * 1e-3, h[22] * 1e-3);
       if (grid <= 4096) {
         static long long hh[2 * 4096];
         cudaMemcpy(hh, prof_buf + 32, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);

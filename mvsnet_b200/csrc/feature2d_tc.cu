@@ -248,21 +248,22 @@ __global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_con
           const bool b = ch >= p.nch_a;
           if (b ? p.stats_b != nullptr : p.stats_a != nullptr) {
             const bool relu = (b ? p.relu_b : p.relu_a) != 0;
+            // channel pairs: one shift / mask per half to unpack, one packed FMA per pair, ReLU folded into the rounding
+            // (the kernel is bound by issue slots)
             const float4 s0 = *reinterpret_cast<const float4*>(s_aff + ch * 8), s1 = *reinterpret_cast<const float4*>(s_aff + ch * 8 + 4);
             const float4 h0 = *reinterpret_cast<const float4*>(s_aff + kMaxCin + ch * 8),
                          h1 = *reinterpret_cast<const float4*>(s_aff + kMaxCin + ch * 8 + 4);
             uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-            float2 f0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[0]));
-            float2 f1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[1]));
-            float2 f2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[2]));
-            float2 f3 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[3]));
-            f0.x = fmaf(f0.x, s0.x, h0.x); f0.y = fmaf(f0.y, s0.y, h0.y); f1.x = fmaf(f1.x, s0.z, h0.z); f1.y = fmaf(f1.y, s0.w, h0.w);
-            f2.x = fmaf(f2.x, s1.x, h1.x); f2.y = fmaf(f2.y, s1.y, h1.y); f3.x = fmaf(f3.x, s1.z, h1.z); f3.y = fmaf(f3.y, s1.w, h1.w);
+            const float2 f0 = ffma2(unpack_bf16x2(w[0]), make_float2(s0.x, s0.y), make_float2(h0.x, h0.y));
+            const float2 f1 = ffma2(unpack_bf16x2(w[1]), make_float2(s0.z, s0.w), make_float2(h0.z, h0.w));
+            const float2 f2 = ffma2(unpack_bf16x2(w[2]), make_float2(s1.x, s1.y), make_float2(h1.x, h1.y));
+            const float2 f3 = ffma2(unpack_bf16x2(w[3]), make_float2(s1.z, s1.w), make_float2(h1.z, h1.w));
             if (relu) {
-              f0.x = fmaxf(f0.x, 0.0f); f0.y = fmaxf(f0.y, 0.0f); f1.x = fmaxf(f1.x, 0.0f); f1.y = fmaxf(f1.y, 0.0f);
-              f2.x = fmaxf(f2.x, 0.0f); f2.y = fmaxf(f2.y, 0.0f); f3.x = fmaxf(f3.x, 0.0f); f3.y = fmaxf(f3.y, 0.0f);
+              w[0] = pack_bf16x2_relu(f0.x, f0.y); w[1] = pack_bf16x2_relu(f1.x, f1.y);
+              w[2] = pack_bf16x2_relu(f2.x, f2.y); w[3] = pack_bf16x2_relu(f3.x, f3.y);
+            } else {
+              w[0] = pack2(f0.x, f0.y); w[1] = pack2(f1.x, f1.y); w[2] = pack2(f2.x, f2.y); w[3] = pack2(f3.x, f3.y);
             }
-            w[0] = pack2(f0.x, f0.y); w[1] = pack2(f1.x, f1.y); w[2] = pack2(f2.x, f2.y); w[3] = pack2(f3.x, f3.y);
           }
         }
         *reinterpret_cast<uint4*>(dst + (size_t)ch * chunk_o) = v;
@@ -322,10 +323,12 @@ __global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_con
           const bool ok = row_ok && gy < lim_y && gx < lim_x;
           if (c_trans) { oy = 2 * gy + (cls >> 1); ox = 2 * gx + (cls & 1); }
           if (!ok) continue;
-          float s_ = 0.0f, q_ = 0.0f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { const float v = __uint_as_float(r[8 * u + k]); s_ += v; q_ = fmaf(v, v, q_); }
-          gs[0] += s_; gq[0] += q_;
+          {
+            const float2* f = reinterpret_cast<const float2*>(r + 8 * u);
+            const float2 s2 = fadd2(fadd2(f[0], f[1]), fadd2(f[2], f[3]));
+            const float2 q2 = ffma2(f[3], f[3], ffma2(f[2], f[2], ffma2(f[1], f[1], ffma2(f[0], f[0], make_float2(0.0f, 0.0f)))));
+            gs[0] += s2.x + s2.y; gq[0] += q2.x + q2.y;
+          }
           uint4 pk;
           pk.x = pack2(__uint_as_float(r[8 * u]), __uint_as_float(r[8 * u + 1]));
           pk.y = pack2(__uint_as_float(r[8 * u + 2]), __uint_as_float(r[8 * u + 3]));
@@ -353,10 +356,12 @@ __global__ void __launch_bounds__(kThreads, 6) conv2d_tc_kernel(const __grid_con
           for (int h = 0; h < 2; ++h) {
             const int ck = (c0 >> 3) + h;                          // chunk of the slice (compile-time index)
             if (ck < nck && ok) {
-              float s_ = 0.0f, q_ = 0.0f;
-#pragma unroll
-              for (int k = 0; k < 8; ++k) { const float v = __uint_as_float(r[8 * h + k]); s_ += v; q_ = fmaf(v, v, q_); }
-              gs[ck] += s_; gq[ck] += q_;
+              {
+                const float2* f = reinterpret_cast<const float2*>(r + 8 * h);
+                const float2 s2 = fadd2(fadd2(f[0], f[1]), fadd2(f[2], f[3]));
+                const float2 q2 = ffma2(f[3], f[3], ffma2(f[2], f[2], ffma2(f[1], f[1], ffma2(f[0], f[0], make_float2(0.0f, 0.0f)))));
+                gs[ck] += s2.x + s2.y; gq[ck] += q2.x + q2.y;
+              }
               const int gch = sl * nck + ck;
               if (p.y_f32) {
                 float4* yo = reinterpret_cast<float4*>(p.y_f32 + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.Cout + gch * 8);

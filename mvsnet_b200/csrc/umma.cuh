@@ -114,6 +114,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
+// ----------------------------------------------------------------------------- bf16 pairs / packed fp32 pairs
+// (one instruction per half: the library conversion moves the high half down and shifts it up again)
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+// packed fp32 pairs (sm_100): one FFMA2 / FADD2 for two channels
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)), "l"(reinterpret_cast<const uint64_t&>(c)));
+  return reinterpret_cast<const float2&>(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return reinterpret_cast<const float2&>(d);
+}
+// max(., 0) and the rounding to bf16 in one instruction
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
 // ----------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave"): the operand is a grid of
 // 8-row x 16-byte core matrices, each stored as 128 contiguous bytes;

@@ -1397,8 +1397,11 @@ bool build_plan(int mode, int D, int H, int W, int cin, int cout, int cout_base,
         const bool first = !seen_cls[0];
         seen_cls[0] = true;
         const int img = ((taps[i].widx % 9) / kwn) * (cin / 16) + j;
+        // input plane dz of the step feeds the output planes max(0, dz - 2) .. min(zf - 1, dz) only
+        const int j_lo = taps[i].dz > 2 ? taps[i].dz - 2 : 0, j_hi = taps[i].dz < zf - 1 ? taps[i].dz : zf - 1;
         add_op(taps[i].dz, (uint32_t)(2 * j * c.PS + taps[i].pos * 16), (uint32_t)c.PS,
-               (uint32_t)(img * m_bytes + (zf + 1 - taps[i].dz) * grp * 16), (uint32_t)(m_rows * 16), 0, first);
+               (uint32_t)(img * m_bytes + (zf + 1 - taps[i].dz) * grp * 16), (uint32_t)(m_rows * 16), 0, first,
+               j_lo * grp, (j_hi + 1) * grp);
       }
     c.b_bytes = nimg * m_bytes;
   } else if (c.dmerge) {

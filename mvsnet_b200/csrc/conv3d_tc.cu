@@ -1973,11 +1973,22 @@ int conv3d_tc_describe(int D, int H, int W, int cin, int cout, int stride, int t
       const int v[12] = {0, c.TX, c.TY, c.PX, c.RY, c.MB, c.mma_n, c.zf, c.xfold, c.R, (int)pl.smem, c.tmem_cols};
       for (int i = 0; i < 12; ++i) out[i] = v[i];
     }
+    // columns the ops of one step span (ops skip their all-zero column blocks; first op full width) / nops * N; ok = every
+    // op keeps N a multiple of 16 inside [0, N), starts on a multiple of 16, and the step's first op is full width
+    int cols = 0, ok = 1;
+    for (int o = 0; o < c.nops; ++o) {
+      const int n_op = c.mma_n - (int)((c.ops[o].meta >> 24) << 3), first = (int)((c.ops[o].meta >> 16) & 1u);
+      const int col = (int)(c.ops[o].meta & 0xFFFFu) % (c.NB > 0 ? c.NB : 1);
+      cols += n_op;
+      if (n_op < 16 || n_op % 16 || n_op > c.mma_n || (n_op != c.mma_n && (col % 16 || first))) ok = 0;
+    }
+    if (c.nops > 0 && !((c.ops[0].meta >> 16) & 1u)) ok = 0;
     if (text && written < text_len)
       written += snprintf(text + written, (size_t)(text_len - written),
                           "cout[%d:%d] tile %dx%d cells %dx%d blocks %d N %d zfold %d xfold %d ring %d+%d grid %dx%dx%d ops %d "
-                          "smem %zu tmem %d one_box %d\n", cb, cb + cn, c.TX, c.TY, c.PX, c.RY, c.MB, c.mma_n, c.zf, c.xfold,
-                          c.R, c.RS, c.tiles_x, c.tiles_y, c.zsplit, c.nops, pl.smem, c.tmem_cols, c.one_box);
+                          "smem %zu tmem %d one_box %d cols %d/%d ok %d\n", cb, cb + cn, c.TX, c.TY, c.PX, c.RY, c.MB, c.mma_n,
+                          c.zf, c.xfold, c.R, c.RS, c.tiles_x, c.tiles_y, c.zsplit, c.nops, pl.smem, c.tmem_cols, c.one_box,
+                          cols, c.nops * c.mma_n, ok);
   }
   if (out) out[0] = launches;
   return MVSB200_OK;

@@ -52,6 +52,44 @@ def test_headline_layer_folds():
     assert p["xfold"] == 1 and p["zf"] == 4 and p["mma_n"] == 96, text
 
 
+@pytest.mark.parametrize("config", ["cfg1", "cfg2", "cfg5"])
+def test_ops_skip_only_zero_column_blocks(config):
+    """Every MMA of a step keeps N a multiple of 16 inside the launch's N and starts on a 16-column boundary, the first
+    op of a step is full width (it overwrites the accumulators); layers whose B images have all-zero column blocks
+    (z-folded convs, merged transposed-conv classes) issue fewer columns than ops x N, and MVSB200_TC_TRIM=0 turns the
+    skipping off."""
+    import re
+    cfg = synthetic.CONFIGS[config]
+    D, hf, wf = cfg["depth_num"], cfg["height"] // 4, cfg["width"] // 4
+    seen_less = 0
+    for name, (cin, cout, op, stride) in synthetic.regnet_channels(32, 8).items():
+        lv = LEVEL[name]
+        args = (D >> lv, hf >> lv, wf >> lv, cin, cout, stride, op == "deconv", name in SKIP,
+                name != "3dconv0_1" and name != "3dconv1_0")
+        p, text = plan(*args)
+        for line in text.strip().splitlines():
+            m = re.search(r"ops (\d+) .* cols (\d+)/(\d+) ok (\d)", line)
+            assert m, line
+            nops, cols, full, ok = map(int, m.groups())
+            assert ok == 1, (name, line)
+            assert full == nops * p["mma_n"] and 16 * nops <= cols <= full, (name, line)
+            zfold = int(re.search(r"zfold (\d+)", line).group(1))
+            merged = op == "deconv" and cout <= 16
+            if zfold > 1 and p["mma_n"] >= 32 or merged:
+                assert cols < full, (name, line)
+                seen_less += 1
+            else:
+                assert cols == full, (name, line)
+    assert seen_less >= 2
+    L.set_tuning("TC_TRIM", 0)
+    try:
+        p, text = plan(D >> 1, hf >> 1, wf >> 1, 16, 8, 2, True, True, True)       # 3dconv6_0
+        m = re.search(r"cols (\d+)/(\d+) ok (\d)", text)
+        assert m and m.group(1) == m.group(2) and m.group(3) == "1", text
+    finally:
+        L.set_tuning("TC_TRIM", None)
+
+
 def test_plan_rejects_unsupported_channels():
     with pytest.raises(L.MVSB200Error, match="Cin"):
         plan(8, 16, 16, 24, 8, 1, False, False, False)

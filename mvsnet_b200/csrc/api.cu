@@ -23,7 +23,7 @@ const TuningField kTuningInts[] = {
     {"NO_FUSED_REGRESS", &Tuning::no_fused_regress}, {"CV_FP32_TAPS", &Tuning::cv_fp32_taps},
     {"CV_KERNEL", &Tuning::cv_kernel}, {"CV_FP32_BLEND", &Tuning::cv_fp32_blend}, {"CV_MINB", &Tuning::cv_minb},
     {"CV_REC16", &Tuning::cv_rec16}, {"CV_KDC", &Tuning::cv_kdc}, {"CV_PLANES", &Tuning::cv_planes},
-    {"CV_STATS", &Tuning::cv_stats}, {"CV_DBG", &Tuning::cv_dbg}, {"TC_ZF", &Tuning::tc_zf}, {"TC_FUSE01", &Tuning::tc_fuse01}, {"TC_RANK", &Tuning::tc_rank}, {"TC_TRIM", &Tuning::tc_trim}, {"TC_XF_GROUPS", &Tuning::tc_xf_groups}, {"TC_XFOLD", &Tuning::tc_xfold},
+    {"CV_STATS", &Tuning::cv_stats}, {"CV_DBG", &Tuning::cv_dbg}, {"TC_ZF", &Tuning::tc_zf}, {"TC_FUSE01", &Tuning::tc_fuse01}, {"TC_RANK", &Tuning::tc_rank}, {"INFER_SIDE", &Tuning::infer_side}, {"TC_TRIM", &Tuning::tc_trim}, {"TC_XF_GROUPS", &Tuning::tc_xf_groups}, {"TC_XFOLD", &Tuning::tc_xfold},
     {"TC_ZSPLIT", &Tuning::tc_zsplit}, {"TC_DBG", &Tuning::tc_dbg}, {"TC_VERBOSE", &Tuning::tc_verbose},
     {"TC_PROF", &Tuning::tc_prof}, {"TC_EXACT_SMEM", &Tuning::tc_exact_smem}, {"TC_NO_PDL", &Tuning::tc_no_pdl},
     {"REGNET_PROFILE", &Tuning::regnet_profile}, {"UNET_NO_TILE", &Tuning::unet_no_tile},

@@ -31,7 +31,7 @@ int launch_cost_volume_coef(const float* feats, const float* homographies, const
                             void* out, cudaStream_t s);
 int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const mvsb200_regnet_params* params, int D,
                         int H, int W, int cin, int b, float eps, int precision, float* filtered, void* workspace,
-                        size_t workspace_bytes, cudaStream_t s, TcRegress* regress, bool inspect);
+                        size_t workspace_bytes, cudaStream_t s, TcRegress* regress, bool inspect, bool prepared);
 
 constexpr int kMaxViewsBw = 7;       // source views (as the forward kernels)
 
@@ -447,7 +447,7 @@ extern "C" int mvsb200_train_step(const float* feats, const float* cams, const f
                                MVSB200_F32, cost, s);
   if (rc) return rc;
   rc = regnet_forward_impl(cost, MVSB200_F32, 0, params, depth_num, hf, wf, channels, base_filter, bn_eps,
-                           MVSB200_PRECISION_FP32, filtered, rws, tp.regnet_bytes, s, nullptr, true);
+                           MVSB200_PRECISION_FP32, filtered, rws, tp.regnet_bytes, s, nullptr, true, false);
   if (rc) return rc;
   rc = launch_depth_regress(filtered, depth_num, hf, wf, depth_start, depth_interval, 0, 4, depth_map, pmap, prob, s);
   if (rc) return rc;

@@ -30,6 +30,7 @@ struct Tuning {
   int tc_xf_groups = 0;       // TC_XF_GROUPS: 2 = two groups of transform warps on alternate planes (default: all warps on one plane)
   int tc_rank = 0;            // TC_RANK: take the rank-th best plan of the cycle model (development: is the model's order right?)
   int tc_trim = -1;           // TC_TRIM: 0 = every MMA of a launch spans all N columns (default: ops skip their all-zero column blocks)
+  int infer_side = -1;        // INFER_SIDE: 0 = statistics clear + weight packing on the compute stream (default: side stream beside K2)
   int tc_fuse01 = -1;         // TC_FUSE01: 0 = 3dconv0_1 and 3dconv1_0 as two launches (and a parity-split cost volume)
   int tc_layer_set = 0, tc_layer[3] = {0, 0, 0};                     // TC_LAYER="cin,cout,mode": restrict the tc_* switches
   int regnet_profile = 0, unet_no_tile = 0, unet_profile = 0, unet_fp32 = 0;

@@ -61,12 +61,44 @@ bool regnet_fuse01(int D, int H, int W, int cin, int b) {
   return a.cin == r.cin && a.cin % 16 == 0 && a.cin <= 64 && a.cout == 8 && (r.cout == 8 || r.cout == 16) && !((D | H | W) & 1);
 }
 
+// What a forward pass needs that does not depend on the cost volume: cleared statistics and (bf16 mode) every layer's
+// weights as bf16 B images, one launch (slot 2*i, 2*i+1 = the <= 2 output-channel slices of layer i).  mvsb200_infer
+// runs it on a side stream beside the cost-volume kernel.
+static int regnet_prepare(const RegnetPlan& p, const mvsb200_regnet_params* params, int D, int H, int W, int cin, int b,
+                          bool bf16, char* ws, cudaStream_t s) {
+  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+    MVS_CHECK_ARG(params->kernel[i] != nullptr, "regnet_forward: kernel[%d] is NULL", i);
+    if (i != MVSB200_L_3DCONV6_2)
+      MVS_CHECK_ARG(params->gamma[i] && params->beta[i], "regnet_forward: gamma/beta[%d] is NULL", i);
+  }
+  MVS_CUDA(cudaMemsetAsync(ws + p.stats_off, 0, p.stats_bytes, s));
+  if (!bf16) return MVSB200_OK;
+  TcPackJob jobs[MVSB200_REGNET_LAYERS];
+  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
+    const LayerDesc& L = p.layer[i];
+    const int* d = p.dims[L.in_level];
+    jobs[i] = {params->kernel[i], d[0], d[1], d[2], L.cin, L.cout, L.stride, L.transposed, L.skip >= 0 ? 1 : 0,
+               (L.src >= 0 || L.skip >= 0) ? 1 : 0, 2 * i, L.cin_true, L.cout_true};
+  }
+  if (regnet_fuse01(D, H, W, cin, b)) {
+    // slot of 3dconv1_0 = the rider launch: 3dconv0_1's filter with 3dconv1_0's riding on it
+    const LayerDesc& A = p.layer[MVSB200_L_3DCONV0_1];
+    const LayerDesc& R = p.layer[MVSB200_L_3DCONV1_0];
+    jobs[MVSB200_L_3DCONV1_0] = {params->kernel[MVSB200_L_3DCONV0_1], D, H, W, A.cin, A.cout, 1, 0, 0, 0,
+                                 2 * MVSB200_L_3DCONV1_0, A.cin_true, A.cout_true, params->kernel[MVSB200_L_3DCONV1_0],
+                                 R.cout, R.cout_true};
+  }
+  return conv3d_tc_pack_all(jobs, MVSB200_REGNET_LAYERS, ws + p.scratch_off, s);
+}
+
 // cost_planar != 0 (bf16 mode only): the caller has already written the cost volume in the planar layouts
 // (chunk-planar always; parity-split unless regnet_fuse01()) at regnet_cost_planar() inside the workspace and `cost`
 // is ignored.
 int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const mvsb200_regnet_params* params, int D,
                         int H, int W, int cin, int b, float eps, int precision, float* filtered, void* workspace,
-                        size_t workspace_bytes, cudaStream_t s, TcRegress* regress = nullptr, bool inspect = true) {
+                        size_t workspace_bytes, cudaStream_t s, TcRegress* regress = nullptr, bool inspect = true,
+                        bool prepared = false) {
+  // prepared: regnet_prepare() has already run for this pass (ordered before `s` reaches this call)
   // inspect: also materialise every layer's BN scale / shift for mvsb200_regnet_layer_raw (the whole-path entry
   // points do not need them: one launch less on the critical path)
   MVS_CHECK_ARG((cost || cost_planar) && params && filtered && workspace, "regnet_forward: NULL pointer");
@@ -88,7 +120,10 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
   float* scale = (float*)(ws + p.scale_off);
   float* shift = (float*)(ws + p.shift_off);
   const int act_dtype = bf16 ? MVSB200_BF16 : MVSB200_F32;
-  MVS_CUDA(cudaMemsetAsync(stats, 0, p.stats_bytes, s));
+  if (!prepared) {
+    rc = regnet_prepare(p, params, D, H, W, cin, b, bf16, ws, s);
+    if (rc) return rc;
+  }
   const bool fuse01 = bf16 && regnet_fuse01(D, H, W, cin, b);
   if (bf16 && !cost_planar) {
     MVS_CHECK_ARG(cost_dtype == MVSB200_BF16, "regnet_forward: precision bf16 needs a bf16 cost volume");
@@ -101,31 +136,6 @@ int regnet_forward_impl(const void* cost, int cost_dtype, int cost_planar, const
   if (profile) {
     for (int i = 0; i <= MVSB200_REGNET_LAYERS; ++i) cudaEventCreate(&pev[i]);
     cudaEventRecord(pev[0], s);
-  }
-  for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
-    MVS_CHECK_ARG(params->kernel[i] != nullptr, "regnet_forward: kernel[%d] is NULL", i);
-    if (i != MVSB200_L_3DCONV6_2)
-      MVS_CHECK_ARG(params->gamma[i] && params->beta[i], "regnet_forward: gamma/beta[%d] is NULL", i);
-  }
-  if (bf16) {
-    // every layer's weights -> bf16 B images, one launch (slot 2*i, 2*i+1 = the <=2 output-channel slices of layer i)
-    TcPackJob jobs[MVSB200_REGNET_LAYERS];
-    for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
-      const LayerDesc& L = p.layer[i];
-      const int* d = p.dims[L.in_level];
-      jobs[i] = {params->kernel[i], d[0], d[1], d[2], L.cin, L.cout, L.stride, L.transposed, L.skip >= 0 ? 1 : 0,
-                 (L.src >= 0 || L.skip >= 0) ? 1 : 0, 2 * i, L.cin_true, L.cout_true};
-    }
-    if (fuse01) {
-      // slot of 3dconv1_0 = the rider launch: 3dconv0_1's filter with 3dconv1_0's riding on it
-      const LayerDesc& A = p.layer[MVSB200_L_3DCONV0_1];
-      const LayerDesc& R = p.layer[MVSB200_L_3DCONV1_0];
-      jobs[MVSB200_L_3DCONV1_0] = {params->kernel[MVSB200_L_3DCONV0_1], D, H, W, A.cin, A.cout, 1, 0, 0, 0,
-                                   2 * MVSB200_L_3DCONV1_0, A.cin_true, A.cout_true, params->kernel[MVSB200_L_3DCONV1_0],
-                                   R.cout, R.cout_true};
-    }
-    rc = conv3d_tc_pack_all(jobs, MVSB200_REGNET_LAYERS, ws + p.scratch_off, s);
-    if (rc) return rc;
   }
   for (int i = 0; i < MVSB200_REGNET_LAYERS; ++i) {
     const LayerDesc& L = p.layer[i];
@@ -746,6 +756,24 @@ extern "C" int mvsb200_infer_filtered_offset(int n_views, int depth_num, int hf,
   return MVSB200_OK;
 }
 
+// A side stream per (host thread, device) with its fork / join events, created on first use and kept for the life of
+// the thread: work that does not depend on the cost volume (cleared statistics, packed weights: ~15 us) runs there,
+// beside the cost-volume kernel, instead of between it and the first layer of the regularizer.
+struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; };
+static int side_lane(SideLane** out) {
+  static thread_local SideLane pool[64] = {};
+  int dev = 0;
+  MVS_CUDA(cudaGetDevice(&dev));
+  SideLane& l = pool[dev & 63];
+  if (!l.stream) {
+    MVS_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    MVS_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    MVS_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+  }
+  *out = &l;
+  return MVSB200_OK;
+}
+
 extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views, int depth_num, int hf, int wf,
                              int channels, float depth_start, float depth_interval, int inverse_depth, int order,
                              int sampler, const mvsb200_regnet_params* params, int base_filter, float bn_eps,
@@ -771,6 +799,22 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   volatile float prod = dm1 * depth_interval;
   volatile float depth_end = depth_start + prod;
   MVS_STAGE_EVENT(0);
+  // fork: everything enqueued on `s` so far (the previous inference on this workspace) precedes the side lane's work
+  SideLane* lane = nullptr;
+  const bool side = tuning().infer_side != 0;
+  if (side) {
+    rc = side_lane(&lane);
+    if (rc) return rc;
+    RegnetPlan rp;
+    make_plan(depth_num, hf, wf, channels, base_filter, precision, &rp);
+    MVS_CUDA(cudaEventRecord(lane->fork, s));
+    MVS_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+    rc = regnet_prepare(rp, params, depth_num, hf, wf, channels, base_filter, precision == MVSB200_PRECISION_BF16,
+                        ws + ip.regnet_off, lane->stream);
+    // (join even after an error: the side stream must not be left waiting inside a capture)
+    cudaEventRecord(lane->join, lane->stream);
+    if (rc) { cudaStreamWaitEvent(s, lane->join, 0); return rc; }
+  }
   float* coefs = (float*)(ws + ip.coef_off);      // pixel-coordinate transform rows, private to this call's workspace
   rc = launch_homographies(cams, n_views, depth_num, depth_start, inverse_depth ? (float)depth_end : depth_interval,
                            inverse_depth, homs, coefs, s);
@@ -800,8 +844,10 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   const bool no_fused_regress = tuning().no_fused_regress != 0;      // tests compare the two paths
   TcRegress rg = {(float*)(ws + ip.partial_off), depth_start, (float)lin_step, 0};
   const bool try_fuse = precision == MVSB200_PRECISION_BF16 && !inverse_depth && !no_fused_regress;
+  if (side) MVS_CUDA(cudaStreamWaitEvent(s, lane->join, 0));
   rc = regnet_forward_impl(cost, cost_dtype, planar ? 1 : 0, params, depth_num, hf, wf, channels, base_filter, bn_eps,
-                           precision, filtered, ws + ip.regnet_off, ip.regnet_bytes, s, try_fuse ? &rg : nullptr, false);
+                           precision, filtered, ws + ip.regnet_off, ip.regnet_bytes, s, try_fuse ? &rg : nullptr, false,
+                           side);
   if (rc) return rc;
   MVS_STAGE_EVENT(3);
   if (try_fuse && rg.fused)

@@ -428,8 +428,8 @@ def run_ours(args, rank, world, local_rank):
                                  "algorithmic_bytes": 230 * V, "tflops": 22896.0 * V / (float(stage_ms[2]) * 1e-3) / 1e12,
                                  "tensor_peak_tflops": tensor_peak()[0], "tensor_peak_source": tensor_peak()[1],
                                  "tensor_frac": 22896.0 * V / (float(stage_ms[2]) * 1e-3) / 1e12 / tensor_peak()[0],
-                                 "tensor_pipe_active_per_launch": "profiles/r2c_conv3d_ncu.json (ncu sm__pipe_tensor_cycles_active: "
-                                                                  "48.6 % in the 3dconv0_1 + 3dconv1_0 launch, 3-18 % elsewhere)",
+                                 "tensor_pipe_active_per_launch": "profiles/r2d_conv3d_ncu.json (ncu sm__pipe_tensor_cycles_active: "
+                                                                  "41.3 % in the 3dconv0_1 + 3dconv1_0 launch, 3-19 % elsewhere)",
                                  "stage_ms": float(stage_ms[2])},
         # K4: in bf16 mode the soft-argmin runs inside 3dconv6_2's epilogue (the filtered volume is not re-read for it);
         # what is timed here is regress_combine_kernel (three partial maps in, four probability gathers, two maps out).

@@ -442,13 +442,22 @@ size_t cost_volume_window_scratch_bytes(int n_views, int hf, int wf);
 bool cost_volume_window_ok(int n_views, int hf, int wf, int channels, int sampler);
 int launch_cost_volume_window(const float* feats, const float* coef_table, int n_views, int depth_num, int d0g, int dloc,
                               int hf, int wf, int order, void* cp8, void* ps8, void* feats16, int blend32,
-                              unsigned long long* stats, cudaStream_t s);
+                              unsigned long long* stats, cudaStream_t s, bool feats16_ready = false);
+
+// product mode (planar output, coefficient table, fp16 taps): is it the shared-memory window kernel (cost_volume_win.cu)
+// that runs, i.e. is its planar fp16 feature copy the one to prepare?  (Not when the round-1 gather kernel is asked for.)
+bool cost_volume_uses_window(int n_views, int dloc, int hf, int wf, int channels, int sampler) {
+  const bool fast_ok = sampler == MVSB200_SAMPLER_TRANSFORM && channels == 32 && n_views - 1 <= kMaxSrcViews &&
+                       hf < 65536 && wf < 32768;
+  return fast_ok && tuning().cv_kernel == 0 && cost_volume_window_ok(n_views, hf, wf, channels, sampler) &&
+         (size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) < ((size_t)1 << 31);      // 32-bit cell indices
+}
 
 // planar_ps8 != NULL or planar != 0: write the bf16 planar layouts (out = CP8, planar_ps8 = PS8); fast path only
 static int launch_cost_volume_any(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                                   int wf, int channels, int order, int sampler, int out_dtype, void* out, int variant,
                                   int planar, void* planar_ps8, void* feats16, const float* coef_table,
-                                  cudaStream_t s, int d0g = 0, int dloc = -1) {
+                                  cudaStream_t s, int d0g = 0, int dloc = -1, bool feats16_ready = false) {
   // (d0g, dloc): plane window of the D-slab mode; the coefficient table always covers all depth_num planes
   if (dloc < 0) dloc = depth_num;
   MVS_CHECK_ARG(feats && homographies && (out || planar_ps8), "cost_volume: NULL pointer");
@@ -487,11 +496,10 @@ static int launch_cost_volume_any(const float* feats, const float* homographies,
     return MVSB200_ERR_UNSUPPORTED;
   }
   // product mode: the shared-memory window kernel (cost_volume_win.cu) unless the round-1 gather kernel is asked for
-  if (planar && feats16 && coef && variant == 3 && tuning().cv_kernel == 0 &&
-      cost_volume_window_ok(n_views, hf, wf, channels, sampler) &&
-      (size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) < ((size_t)1 << 31))      // 32-bit cell indices
+  if (planar && feats16 && coef && variant == 3 && cost_volume_uses_window(n_views, dloc, hf, wf, channels, sampler))
     return launch_cost_volume_window(feats, coef, n_views, depth_num, d0g, dloc, hf, wf, order, out, planar_ps8, feats16,
-                                     tuning().cv_fp32_blend, nullptr, s);
+                                     tuning().cv_fp32_blend, nullptr, s, feats16_ready);
+  MVS_CHECK_ARG(!feats16_ready, "cost_volume: the prepared feature copy belongs to the window kernel");
   if (variant >= 2) {
     const bool wide = variant == 2;
     const int tx = wide ? 32 : 16, ty = wide ? 1 : 2;
@@ -601,9 +609,9 @@ size_t cost_volume_pair_bytes(int n_views, int hf, int wf) { return (size_t)n_vi
 
 int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                               int wf, int channels, int order, int sampler, void* cp8, void* ps8, void* feats16,
-                              const float* coef_table, cudaStream_t s) {
+                              const float* coef_table, cudaStream_t s, bool feats16_ready) {
   return launch_cost_volume_any(feats, homographies, n_views, depth_num, hf, wf, channels, order, sampler,
-                                MVSB200_BF16, cp8, 0, 1, ps8, feats16, coef_table, s);
+                                MVSB200_BF16, cp8, 0, 1, ps8, feats16, coef_table, s, 0, -1, feats16_ready);
 }
 
 // D-slab mode: local planes [0, dloc) = global planes [d0g, d0g + dloc) of the depth_num-plane sweep

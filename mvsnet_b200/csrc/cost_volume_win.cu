@@ -472,20 +472,30 @@ bool cost_volume_window_ok(int n_views, int hf, int wf, int channels, int sample
 // feats16: scratch of cost_volume_window_scratch_bytes() for the fp16 chunk-planar copy of the features.
 // Local planes [0, dloc) = global planes [d0g, d0g + dloc) of the depth_num-plane sweep (D-slab mode; whole volume:
 // d0g = 0, dloc = depth_num); planes whose global index falls outside [0, depth_num) are left alone.
+// the window kernel's source: the feature maps as fp16, 8-channel groups planar per view (what its TMA boxes read)
+int launch_planar_half_features(const float* feats, int n_views, int hf, int wf, void* feats16, cudaStream_t s) {
+  using namespace cvw;
+  MVS_CHECK_ARG(feats && feats16, "cost_volume(window): NULL pointer");
+  const size_t npix = (size_t)n_views * hf * wf;
+  const size_t want = (npix + 255) / 256, cap = (size_t)sm_count_current() * 16;
+  planar_half_features_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(feats, n_views, hf, wf, (uint4*)feats16);
+  MVS_LAUNCH_CHECK("planar_half_features_kernel");
+  return MVSB200_OK;
+}
+
+// feats16_ready: launch_planar_half_features() has already run for these feature maps (ordered before `s` gets here)
 int launch_cost_volume_window(const float* feats, const float* coef_table, int n_views, int depth_num, int d0g, int dloc,
                               int hf, int wf, int order, void* cp8, void* ps8, void* feats16, int blend32,
-                              unsigned long long* stats, cudaStream_t s) {
+                              unsigned long long* stats, cudaStream_t s, bool feats16_ready) {
   using namespace cvw;
   MVS_CHECK_ARG(feats && coef_table && feats16 && (cp8 || ps8), "cost_volume(window): NULL pointer");
   MVS_CHECK_ARG(cost_volume_window_ok(n_views, hf, wf, 32, MVSB200_SAMPLER_TRANSFORM),
                 "cost_volume(window): needs 2..8 views, 32 channels, Hf, Wf < 32000 and a driver with TMA descriptors");
   const int nv = n_views - 1;
   const int sm = sm_count_current();
-  {
-    const size_t npix = (size_t)n_views * hf * wf;
-    const size_t want = (npix + 255) / 256, cap = (size_t)sm * 16;
-    planar_half_features_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(feats, n_views, hf, wf, (uint4*)feats16);
-    MVS_LAUNCH_CHECK("planar_half_features_kernel");
+  if (!feats16_ready) {
+    const int rc = launch_planar_half_features(feats, n_views, hf, wf, feats16, s);
+    if (rc) return rc;
   }
   if (ps8 && ((hf | wf) & 1)) MVS_CUDA(cudaMemsetAsync(ps8, 0, (size_t)dloc * 16 * ((hf + 1) / 2) * ((wf + 1) / 2) * 16, s));
   Params p;

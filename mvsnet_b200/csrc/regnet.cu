@@ -669,7 +669,9 @@ namespace mvsb200 {
 bool cost_volume_planar_ok(int n_views, int hf, int wf, int channels, int sampler);
 int launch_cost_volume_planar(const float* feats, const float* homographies, int n_views, int depth_num, int hf,
                               int wf, int channels, int order, int sampler, void* cp8, void* ps8, void* feats16,
-                              const float* coef_table, cudaStream_t s);
+                              const float* coef_table, cudaStream_t s, bool feats16_ready = false);
+bool cost_volume_uses_window(int n_views, int dloc, int hf, int wf, int channels, int sampler);
+int launch_planar_half_features(const float* feats, int n_views, int hf, int wf, void* feats16, cudaStream_t s);
 int launch_cost_volume_coef(const float* feats, const float* homographies, const float* coef_table, int n_views,
                             int depth_num, int hf, int wf, int channels, int order, int sampler, int out_dtype,
                             void* out, cudaStream_t s);
@@ -759,7 +761,7 @@ extern "C" int mvsb200_infer_filtered_offset(int n_views, int depth_num, int hf,
 // A side stream per (host thread, device) with its fork / join events, created on first use and kept for the life of
 // the thread: work that does not depend on the cost volume (cleared statistics, packed weights: ~15 us) runs there,
 // beside the cost-volume kernel, instead of between it and the first layer of the regularizer.
-struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; };
+struct SideLane { cudaStream_t stream; cudaEvent_t fork, feats, join; };
 static int side_lane(SideLane** out) {
   static thread_local SideLane pool[64] = {};
   int dev = 0;
@@ -769,6 +771,7 @@ static int side_lane(SideLane** out) {
     MVS_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     MVS_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
     MVS_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    MVS_CUDA(cudaEventCreateWithFlags(&l.feats, cudaEventDisableTiming));
   }
   *out = &l;
   return MVSB200_OK;
@@ -802,6 +805,7 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
   // fork: everything enqueued on `s` so far (the previous inference on this workspace) precedes the side lane's work
   SideLane* lane = nullptr;
   const bool side = tuning().infer_side != 0;
+  bool feats_early = false;
   if (side) {
     rc = side_lane(&lane);
     if (rc) return rc;
@@ -809,6 +813,15 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
     make_plan(depth_num, hf, wf, channels, base_filter, precision, &rp);
     MVS_CUDA(cudaEventRecord(lane->fork, s));
     MVS_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+    // first what the cost-volume kernel itself waits for: the fp16 copy of the feature maps (beside the homographies)
+    feats_early = precision == MVSB200_PRECISION_BF16 && sampler == MVSB200_SAMPLER_TRANSFORM &&
+                  cost_volume_planar_ok(n_views, hf, wf, channels, sampler) && tuning().cv_fp32_taps == 0 &&
+                  cost_volume_uses_window(n_views, depth_num, hf, wf, channels, sampler);
+    if (feats_early) {
+      rc = launch_planar_half_features(feats, n_views, hf, wf, ws + ip.pair_off, lane->stream);
+      if (rc) feats_early = false;
+      cudaEventRecord(lane->feats, lane->stream);
+    }
     rc = regnet_prepare(rp, params, depth_num, hf, wf, channels, base_filter, precision == MVSB200_PRECISION_BF16,
                         ws + ip.regnet_off, lane->stream);
     // (join even after an error: the side stream must not be left waiting inside a capture)
@@ -828,8 +841,9 @@ extern "C" int mvsb200_infer(const float* feats, const float* cams, int n_views,
     regnet_cost_planar(ws + ip.regnet_off, depth_num, hf, wf, channels, base_filter, &cp8, &ps8);
     if (regnet_fuse01(depth_num, hf, wf, channels, base_filter)) ps8 = nullptr;      // nobody reads the parity-split copy
     const bool fp32_taps = tuning().cv_fp32_taps != 0;
+    if (feats_early) MVS_CUDA(cudaStreamWaitEvent(s, lane->feats, 0));
     rc = launch_cost_volume_planar(feats, homs, n_views, depth_num, hf, wf, channels, order, sampler, cp8, ps8,
-                                   fp32_taps ? nullptr : ws + ip.pair_off, coefs, s);
+                                   fp32_taps ? nullptr : ws + ip.pair_off, coefs, s, feats_early);
   } else {
     rc = launch_cost_volume_coef(feats, homs, coefs, n_views, depth_num, hf, wf, channels, order, sampler, cost_dtype,
                                  cost, s);

@@ -885,11 +885,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                 const bool valid = xx >= 1 && xx <= TXe && yy < TYe && !(p.dbg & 4);
                 const int oy = y0 + yy, ox = x0 + xx - 1;
                 float v[8];
+                float2* v2 = reinterpret_cast<float2*>(v);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(r[k]), 1, p.PX);
-                  const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(r[16 + k]), 1, p.PX);
-                  v[k] = lft + __uint_as_float(r[8 + k]) + rgt;
+                for (int k = 0; k < 8; k += 2) {
+                  float2 lft, rgt;
+                  lft.x = __shfl_up_sync(0xffffffffu, __uint_as_float(r[k]), 1, p.PX);
+                  lft.y = __shfl_up_sync(0xffffffffu, __uint_as_float(r[k + 1]), 1, p.PX);
+                  rgt.x = __shfl_down_sync(0xffffffffu, __uint_as_float(r[16 + k]), 1, p.PX);
+                  rgt.y = __shfl_down_sync(0xffffffffu, __uint_as_float(r[16 + k + 1]), 1, p.PX);
+                  v2[k >> 1] = fadd2(fadd2(lft, make_float2(__uint_as_float(r[8 + k]), __uint_as_float(r[8 + k + 1]))), rgt);
                 }
                 if (it + 1 < nitems) issue(nb, nj, nck, r);
                 if (RIDER && ck > 0) {
@@ -922,7 +926,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   for (int c4 = 0; c4 < (XF ? (RIDER ? 1 : XFC) : 1); ++c4)
                     if (c4 == ck && !(p.dbg & 64)) {
 #pragma unroll
-                      for (int k = 0; k < 8; ++k) { sum[c4 * 8 + k] += v[k]; sq[c4 * 8 + k] = fmaf(v[k], v[k], sq[c4 * 8 + k]); }
+                      for (int k = 0; k < 4; ++k) {
+                        float2* s2 = reinterpret_cast<float2*>(sum + c4 * 8) + k;
+                        float2* q2 = reinterpret_cast<float2*>(sq + c4 * 8) + k;
+                        *s2 = fadd2(*s2, v2[k]);
+                        *q2 = ffma2(v2[k], v2[k], *q2);
+                      }
                     }
                   const int oz = mz + j;
                   if (p.y_f32) {
